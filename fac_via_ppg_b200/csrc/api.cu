@@ -1,0 +1,62 @@
+// extern "C" surface of libfacb200.so (declared in include/fac_b200.h).
+#include "fac_common.cuh"
+#include <atomic>
+#include <cstring>
+
+namespace fac {
+
+static thread_local char g_error[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int launch_conv_gemm_f32(const fac_conv_src*, int, const float*, const float*, int, int, int, const fac_conv_epilogue*,
+                         int, long long, long long, cudaStream_t);
+int wg_upsample_squeeze(const fac_wg_model*, const float*, float*, int, int, cudaStream_t);
+int wg_start(const fac_wg_model*, int, const float*, float*, int, int, cudaStream_t);
+int wg_layer(const fac_wg_model*, int, int, const fac_wg_workspace*, int, int, cudaStream_t);
+int wg_end(const fac_wg_model*, int, const float*, float*, int, int, cudaStream_t);
+int wg_infer(const fac_wg_model*, const float*, float*, const fac_wg_workspace*, int, int, cudaStream_t);
+
+}  // namespace fac
+
+extern "C" {
+
+int fac_version(void) { return 100; }
+const char* fac_last_error(void) { return fac::g_error; }
+long long fac_launch_count(void) { return fac::g_launches.load(); }
+void fac_reset_launch_count(void) { fac::g_launches.store(0); }
+
+int fac_conv_gemm_f32(const fac_conv_src* srcs, int n_srcs, const float* w_packed, const float* bias, int B, int T_out,
+                      int N, const fac_conv_epilogue* epi, int n_phases, long long w_phase_stride,
+                      long long out_phase_stride, void* stream) {
+  return fac::launch_conv_gemm_f32(srcs, n_srcs, w_packed, bias, B, T_out, N, epi, n_phases, w_phase_stride,
+                                   out_phase_stride, (cudaStream_t)stream);
+}
+int fac_waveglow_upsample_squeeze_f32(const fac_wg_model* m, const float* mel_cl, float* spect, int B, int F,
+                                      void* stream) {
+  return fac::wg_upsample_squeeze(m, mel_cl, spect, B, F, (cudaStream_t)stream);
+}
+int fac_wn_start_f32(const fac_wg_model* m, int flow, const float* audio, float* x, int B, int Tg, void* stream) {
+  return fac::wg_start(m, flow, audio, x, B, Tg, (cudaStream_t)stream);
+}
+int fac_wn_layer_f32(const fac_wg_model* m, int flow, int layer, const fac_wg_workspace* ws, int B, int Tg,
+                     void* stream) {
+  return fac::wg_layer(m, flow, layer, ws, B, Tg, (cudaStream_t)stream);
+}
+int fac_wn_end_coupling_f32(const fac_wg_model* m, int flow, const float* skip, float* audio, int B, int Tg,
+                            void* stream) {
+  return fac::wg_end(m, flow, skip, audio, B, Tg, (cudaStream_t)stream);
+}
+int fac_waveglow_infer_f32(const fac_wg_model* m, const float* mel_cl, float* audio, const fac_wg_workspace* ws, int B,
+                           int F, void* stream) {
+  return fac::wg_infer(m, mel_cl, audio, ws, B, F, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+// Shared helpers for the fac_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include "../../include/fac_b200.h"
+
+namespace fac {
+
+// Error text returned by fac_last_error(); set by every failing entry point.
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+#define FAC_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      fac::set_error(__VA_ARGS__);        \
+      return 1;                           \
+    }                                     \
+  } while (0)
+
+__device__ __forceinline__ float sigmoidf_exact(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+}  // namespace fac

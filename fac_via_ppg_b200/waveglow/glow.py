@@ -1,0 +1,208 @@
+"""Drop-in for the reference ``src/waveglow/glow.py`` (inference side).
+
+Same class names, constructor arguments, attribute / parameter names and
+``infer`` signature as the reference, so pickled ``{'model': WaveGlow}``
+checkpoints (reference src/script/train_waveglow.py:56-64) and state dicts load
+unchanged and the callers in src/common/utils.py:142-152,177-181,
+src/waveglow/denoiser.py:44-61 and src/waveglow/inference.py:33-56 keep working.
+The modules below are parameter containers only: every FLOP of ``infer`` runs in
+the hand-written sm_100a kernels of libfacb200.so through the C ABI of
+include/fac_b200.h.  There is no PyTorch or CPU fallback; the training direction
+(``forward`` / ``WaveGlowLoss``) is out of scope and raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from fac_via_ppg_b200 import _ext
+from fac_via_ppg_b200.packing import PackedWaveGlow
+
+
+class Invertible1x1Conv(torch.nn.Module):
+    """Parameter holder for the invertible 1x1 convolution (reference glow.py:62-102).
+
+    Initialised to a random rotation (orthonormal, det +1) like the reference."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv = torch.nn.Conv1d(c, c, kernel_size=1, bias=False)
+        q, _ = torch.linalg.qr(torch.randn(c, c))
+        if torch.det(q) < 0:
+            q[:, 0].neg_()
+        self.conv.weight.data = q.contiguous().view(c, c, 1)
+
+    def forward(self, z, reverse=False):
+        raise NotImplementedError("fac_via_ppg_b200: Invertible1x1Conv runs fused inside WaveGlow.infer "
+                                  "(fac_wn_end_coupling_f32); the standalone/training call is out of scope")
+
+
+class WN(torch.nn.Module):
+    """Parameter holder for the WaveNet-like coupling network (reference glow.py:105-152)."""
+
+    def __init__(self, n_in_channels, n_mel_channels, n_layers, n_channels, kernel_size):
+        super().__init__()
+        if kernel_size % 2 != 1 or n_channels % 2 != 0:
+            raise ValueError("WN needs an odd kernel size and an even channel count")
+        wnorm = torch.nn.utils.weight_norm
+        self.n_layers, self.n_channels = n_layers, n_channels
+        self.start = wnorm(torch.nn.Conv1d(n_in_channels, n_channels, 1), name="weight")
+        self.end = torch.nn.Conv1d(n_channels, 2 * n_in_channels, 1)
+        torch.nn.init.zeros_(self.end.weight)
+        torch.nn.init.zeros_(self.end.bias)
+        self.in_layers = torch.nn.ModuleList()
+        self.res_skip_layers = torch.nn.ModuleList()
+        self.cond_layers = torch.nn.ModuleList()
+        for i in range(n_layers):
+            d = 2 ** i
+            self.in_layers.append(wnorm(torch.nn.Conv1d(n_channels, 2 * n_channels, kernel_size, dilation=d,
+                                                        padding=d * (kernel_size - 1) // 2), name="weight"))
+            self.cond_layers.append(wnorm(torch.nn.Conv1d(n_mel_channels, 2 * n_channels, 1), name="weight"))
+            width = 2 * n_channels if i < n_layers - 1 else n_channels
+            self.res_skip_layers.append(wnorm(torch.nn.Conv1d(n_channels, width, 1), name="weight"))
+
+    def forward(self, forward_input):
+        raise NotImplementedError("fac_via_ppg_b200: WN runs inside WaveGlow.infer (fac_wn_layer_f32 ...)")
+
+
+def _plain_weight(conv):
+    """Effective weight of a conv with or without weight-norm (both checkpoint
+    flavours reach infer(): generate_synthesis.py:58 vs utils.py:177-181)."""
+    if hasattr(conv, "weight_g") and hasattr(conv, "weight_v"):
+        v, g = conv.weight_v, conv.weight_g
+        return v * (g / v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1))))
+    return conv.weight
+
+
+class WaveGlow(torch.nn.Module):
+    """Reference-compatible WaveGlow (reference glow.py:178-303) whose ``infer`` is CUDA-native."""
+
+    def __init__(self, n_mel_channels, hop_length, n_flows, n_group, n_early_every, n_early_size, WN_config):
+        super().__init__()
+        if n_group % 2 != 0:
+            raise ValueError("n_group must be even")
+        self.upsample = torch.nn.ConvTranspose1d(n_mel_channels, n_mel_channels, 1024, stride=hop_length)
+        self.n_flows, self.n_group = n_flows, n_group
+        self.n_early_every, self.n_early_size = n_early_every, n_early_size
+        self.WN = torch.nn.ModuleList()
+        self.convinv = torch.nn.ModuleList()
+        n_half, n_rem = n_group // 2, n_group
+        for k in range(n_flows):
+            if k > 0 and k % n_early_every == 0:
+                n_half -= n_early_size // 2
+                n_rem -= n_early_size
+            self.convinv.append(Invertible1x1Conv(n_rem))
+            self.WN.append(WN(n_half, n_mel_channels * n_group, **WN_config))
+        self.n_remaining_channels = n_rem
+
+    # ------------------------------------------------------------------ config / packing
+    def config(self):
+        wn0 = self.WN[0]
+        return {
+            "n_mel_channels": self.upsample.in_channels,
+            "hop_length": self.upsample.stride[0],
+            "n_flows": self.n_flows,
+            "n_group": self.n_group,
+            "n_early_every": self.n_early_every,
+            "n_early_size": self.n_early_size,
+            "WN_config": {"n_layers": wn0.n_layers, "n_channels": wn0.n_channels,
+                          "kernel_size": wn0.in_layers[0].kernel_size[0]},
+        }
+
+    def plain_state(self):
+        """Weight-norm-free state dict (what remove_weightnorm would leave)."""
+        sd = {"upsample.weight": self.upsample.weight, "upsample.bias": self.upsample.bias}
+        for k, wn in enumerate(self.WN):
+            p = f"WN.{k}."
+            sd[p + "start.weight"], sd[p + "start.bias"] = _plain_weight(wn.start), wn.start.bias
+            sd[p + "end.weight"], sd[p + "end.bias"] = wn.end.weight, wn.end.bias
+            for i in range(wn.n_layers):
+                for name, layers in (("in_layers", wn.in_layers), ("cond_layers", wn.cond_layers),
+                                     ("res_skip_layers", wn.res_skip_layers)):
+                    sd[p + f"{name}.{i}.weight"] = _plain_weight(layers[i])
+                    sd[p + f"{name}.{i}.bias"] = layers[i].bias
+            sd[f"convinv.{k}.conv.weight"] = self.convinv[k].conv.weight
+        return sd
+
+    def _weights_signature(self):
+        return tuple((p.data_ptr(), p._version, p.dtype) for p in self.parameters())
+
+    def packed(self) -> PackedWaveGlow:
+        """Packed fp32 weights on the module's device, rebuilt when a parameter changes."""
+        sig = self._weights_signature()
+        cache = getattr(self, "_fac_packed", None)
+        if cache is None or cache[0] != sig:
+            dev = self.upsample.weight.device
+            _ext.require_cuda(self.upsample.weight, "WaveGlow parameters")
+            cache = (sig, PackedWaveGlow.from_state(self.plain_state(), self.config(), dev))
+            object.__setattr__(self, "_fac_packed", cache)
+        return cache[1]
+
+    def use_packed(self, packed: PackedWaveGlow):
+        """Adopt externally provided packed weights (e.g. received by NCCL broadcast)."""
+        object.__setattr__(self, "_fac_packed", (self._weights_signature(), packed))
+
+    # ------------------------------------------------------------------ inference
+    def noise_like_reference(self, batch, n_cols, device, dtype):
+        """The N(0,1) draws of reference infer() in its order (glow.py:261-270, 285-290)."""
+        draws = [torch.empty(batch, self.n_remaining_channels, n_cols, device=device, dtype=dtype).normal_()]
+        for k in reversed(range(self.n_flows)):
+            if k % self.n_early_every == 0 and k > 0:
+                draws.append(torch.empty(batch, self.n_early_size, n_cols, device=device, dtype=dtype).normal_())
+        return draws
+
+    @torch.no_grad()
+    def infer(self, spect, sigma=1.0, noise=None):
+        """mel (B, n_mel, F) -> audio (B, F*hop); reference glow.py:252-293.
+
+        ``noise`` optionally supplies the unit-normal draws (list in reference draw
+        order); by default they come from torch's generator on spect's device with
+        the reference's shapes and order, so seeding reproduces the reference."""
+        _ext.require_cuda(spect, "spect")
+        lib = _ext.load()
+        packed = self.packed()
+        B, n_mel, F = spect.shape
+        hop, G = self.upsample.stride[0], self.n_group
+        if n_mel != self.upsample.in_channels:
+            raise ValueError("spect has %d mel channels, model expects %d" % (n_mel, self.upsample.in_channels))
+        out_dtype = spect.dtype
+        if B == 0 or F == 0:
+            return spect.new_zeros(B, F * hop)
+        Tg = F * hop // G
+        dev = spect.device
+        if noise is None:
+            noise = self.noise_like_reference(B, Tg, dev, out_dtype)
+        # lay the draws out per slot: the flow with n_rem live channels owns the last n_rem slots
+        audio = torch.empty(B, Tg, G, device=dev, dtype=torch.float32)
+        hi = G
+        for z in noise:
+            lo = hi - z.shape[1]
+            audio[:, :, lo:hi] = (sigma * z).float().transpose(1, 2)
+            hi = lo
+        if hi != 0:
+            raise ValueError("noise draws do not cover n_group channels")
+        mel_cl = spect.float().transpose(1, 2).contiguous()
+        Cn = self.WN[0].n_channels
+        ws_spect = torch.empty(B, Tg, n_mel * G, device=dev, dtype=torch.float32)
+        ws_x = torch.empty(B, Tg, Cn, device=dev, dtype=torch.float32)
+        ws_acts = torch.empty_like(ws_x)
+        ws_skip = torch.empty_like(ws_x)
+        ws = _ext.WgWorkspace(ws_spect.data_ptr(), ws_x.data_ptr(), ws_acts.data_ptr(), ws_skip.data_ptr())
+        import ctypes as C
+        rc = lib.fac_waveglow_infer_f32(C.byref(packed.cmodel), mel_cl.data_ptr(), audio.data_ptr(), C.byref(ws),
+                                        B, F, _ext.current_stream())
+        _ext.check(rc, "fac_waveglow_infer_f32")
+        return audio.view(B, Tg * G).to(out_dtype)
+
+    def forward(self, forward_input):
+        raise NotImplementedError("fac_via_ppg_b200 covers the inference path only (WaveGlow.infer); "
+                                  "the training direction of reference glow.py:209-250 is out of scope")
+
+    @staticmethod
+    def remove_weightnorm(model):
+        """reference glow.py:295-311: fold weight_g * v / |v| into plain weights."""
+        rm = torch.nn.utils.remove_weight_norm
+        for wn in model.WN:
+            wn.start = rm(wn.start)
+            for name in ("in_layers", "cond_layers", "res_skip_layers"):
+                setattr(wn, name, torch.nn.ModuleList([rm(c) for c in getattr(wn, name)]))
+        return model

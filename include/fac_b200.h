@@ -1,0 +1,134 @@
+/*
+ * fac_b200.h -- C ABI of the B200-native PPG -> Mel -> WaveGlow inference path.
+ *
+ * The reference (guanlongzhao/fac-via-ppg) has no FFI layer: its boundary is two
+ * Python methods, WaveGlow.infer (src/waveglow/glow.py:252-293) and
+ * Tacotron2.inference (src/common/model.py:597-610).  The drop-in Python classes
+ * of this repository keep those signatures and call the entry points below
+ * through ctypes.  Conventions:
+ *   - every pointer is a DEVICE pointer into caller-owned (PyTorch-owned) memory;
+ *     nothing is allocated or freed across the boundary;
+ *   - every call takes the cudaStream_t to launch on (as void*), is asynchronous,
+ *     and returns 0 on success or a non-zero code; fac_last_error() gives text;
+ *   - activations are "channels-last": element (b, t, c) of a (B, T, C) tensor is
+ *     at ptr[b*T*C + t*C + c], so a time column is one contiguous vector;
+ *   - not thread-safe per stream; safe across streams/devices.
+ *
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ */
+#ifndef FAC_B200_H
+#define FAC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FAC_MAX_FLOWS 16
+#define FAC_MAX_LAYERS 16
+
+/* ---- bookkeeping ------------------------------------------------------- */
+int fac_version(void);
+const char* fac_last_error(void);
+/* Number of kernels launched by this library since load / since the last reset
+ * (bench.py reports it as gpu_launches). */
+long long fac_launch_count(void);
+void fac_reset_launch_count(void);
+
+/* ---- generic implicit-GEMM Conv1d / Linear (fp32 FFMA) ----------------- */
+/* One input of a K-concatenated implicit GEMM.  Output row m (time step) reads
+ * input rows m + tap*dilation - center for tap = 0..taps-1; rows outside [0, T_src)
+ * are zero (Conv1d zero padding).  Element (b, row, c) is at
+ * ptr[b*batch_stride + row*row_stride + c*ch_stride].  channels % 8 == 0. */
+typedef struct fac_conv_src {
+  const float* ptr;
+  long long batch_stride, row_stride, ch_stride;
+  int channels, taps, dilation, center;
+  int rows;            /* T_src: number of valid rows of this input */
+  int _pad;
+} fac_conv_src;
+
+enum { FAC_ACT_NONE = 0, FAC_ACT_RELU = 1, FAC_ACT_TANH = 2 };
+enum {
+  FAC_EPI_LINEAR = 0,   /* out = act(acc + bias) [* mask] [+ residual]                       */
+  FAC_EPI_GATE = 1,     /* packed columns (2c, 2c+1) = (tanh, sigmoid) pre-activations of
+                           channel c; out[:, c] = tanh(.)*sigmoid(.)  (glow.py:33-40)        */
+  FAC_EPI_RES_SKIP = 2  /* columns [0, n_split): out += v (residual stream, glow.py:166);
+                           columns [n_split, N): out2 (+)= v (skip sum, glow.py:167-174)     */
+};
+
+typedef struct fac_conv_epilogue {
+  int kind, act;
+  float* out;            /* (B, T_out, N_out) channels-last with the strides below */
+  long long out_batch_stride, out_row_stride;
+  const float* mask;     /* optional multiplicative mask, same addressing as out   */
+  const float* residual; /* optional additive input, same addressing as out        */
+  float* out2;           /* FAC_EPI_RES_SKIP: skip accumulator (same strides)       */
+  int n_split;           /* FAC_EPI_RES_SKIP: width of the residual part            */
+  int accumulate_out2;   /* 0: out2 = v, 1: out2 += v                               */
+} fac_conv_epilogue;
+
+/* Replaces torch.nn.Conv1d / torch.nn.Linear as used through ConvNorm / LinearNorm
+ * (reference src/common/layers.py:40-71) and the WN convolutions
+ * (src/waveglow/glow.py:156-164).  w_packed is [K_total][N_pad] row-major with
+ * K index = (source, tap, channel) and N_pad = N rounded up to 128 (zero filled);
+ * bias is [N_pad] or NULL.  n_phases > 1 runs that many independent GEMMs that
+ * differ only by w_packed += phase*w_phase_stride and out += phase*out_phase_stride
+ * (used by the transposed-conv upsampler). */
+int fac_conv_gemm_f32(const fac_conv_src* srcs, int n_srcs, const float* w_packed, const float* bias,
+                      int B, int T_out, int N, const fac_conv_epilogue* epi,
+                      int n_phases, long long w_phase_stride, long long out_phase_stride, void* stream);
+
+/* ---- WaveGlow reverse flow --------------------------------------------- */
+/* Weights of one WaveGlow after remove_weightnorm (glow.py:295-311), repacked by
+ * fac_via_ppg_b200/packing.py.  All fp32 device pointers. */
+typedef struct fac_wg_flow {
+  int n_half, n_rem;                 /* coupling half width, channels alive in this flow (glow.py:195-207) */
+  const float* start_w;              /* [n_half][C]  (transposed start.weight)                */
+  const float* start_b;              /* [C]                                                   */
+  const float* end_w;                /* [2*n_half][C]                                         */
+  const float* end_b;                /* [2*n_half]                                            */
+  const float* w_inv;                /* [n_rem][n_rem] = inverse of convinv weight (glow.py:89-95) */
+  const float* in_cond_w[FAC_MAX_LAYERS]; /* [3*C + n_cond][2*C] gate-interleaved columns     */
+  const float* in_cond_b[FAC_MAX_LAYERS]; /* [2*C] = in.bias + cond.bias, gate-interleaved    */
+  const float* res_skip_w[FAC_MAX_LAYERS];/* [C][N_pad]                                       */
+  const float* res_skip_b[FAC_MAX_LAYERS];/* [N_pad]                                          */
+} fac_wg_flow;
+
+typedef struct fac_wg_model {
+  int n_flows, n_layers, n_channels, n_group, n_mel, hop, n_early_every, n_early_size, upsample_taps;
+  int kernel_size;                   /* WN in_layers kernel size (3) */
+  const float* upsample_w;           /* [hop/n_group phases][taps*n_mel][n_mel*n_group (padded to 128)] */
+  const float* upsample_b;           /* [n_mel*n_group (padded)] bias replicated per group slot */
+  fac_wg_flow flows[FAC_MAX_FLOWS];
+} fac_wg_model;
+
+/* Scratch the caller allocates for B utterances of F frames (T_g = F*hop/n_group columns):
+ * spect (B,T_g,n_mel*n_group), x / acts / skip (B,T_g,C). */
+typedef struct fac_wg_workspace {
+  float* spect; float* x; float* acts; float* skip;
+} fac_wg_workspace;
+
+/* glow.py:253-259: ConvTranspose1d(n_mel,n_mel,1024,stride=hop) + trim + group squeeze,
+ * written directly in squeezed channels-last form.  mel_cl is (B, F, n_mel). */
+int fac_waveglow_upsample_squeeze_f32(const fac_wg_model* m, const float* mel_cl, float* spect,
+                                      int B, int F, void* stream);
+/* glow.py:156 : x = start(audio_0).  audio is (B, T_g, n_group) with the flow's live
+ * channels in the LAST n_rem slots of each column. */
+int fac_wn_start_f32(const fac_wg_model* m, int flow, const float* audio, float* x, int B, int Tg, void* stream);
+/* glow.py:158-174, one WN layer: gate(in_layer(x) + cond_layer(spect)) -> acts;
+ * res_skip(acts) -> x += res, skip (+)= skip. */
+int fac_wn_layer_f32(const fac_wg_model* m, int flow, int layer, const fac_wg_workspace* ws,
+                     int B, int Tg, void* stream);
+/* glow.py:175 + 278-283: end conv, affine coupling inverse, invertible 1x1 (reverse), in place. */
+int fac_wn_end_coupling_f32(const fac_wg_model* m, int flow, const float* skip, float* audio,
+                            int B, int Tg, void* stream);
+/* glow.py:252-293 without the RNG: `audio` (B, T_g, n_group) arrives holding sigma*z in
+ * every slot (the reference's three normal_() draws laid out per slot, see
+ * fac_via_ppg_b200/waveglow/glow.py) and leaves holding the waveform (B, T_g*n_group). */
+int fac_waveglow_infer_f32(const fac_wg_model* m, const float* mel_cl, float* audio,
+                           const fac_wg_workspace* ws, int B, int F, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAC_B200_H */

@@ -1,0 +1,38 @@
+"""The C-ABI library builds, loads and exports every symbol include/fac_b200.h declares
+(no compute calls: this runs without a GPU)."""
+import os
+import re
+
+from fac_via_ppg_b200 import _ext
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fac_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(fac_[a-z0-9_]+)\s*\(", text))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _ext.load()
+    names = declared_symbols()
+    assert names, "no declarations parsed"
+    for name in names:
+        assert hasattr(lib, name), name
+    assert names == set(_ext.SIGNATURES), names ^ set(_ext.SIGNATURES)
+
+
+def test_version_and_error_string():
+    lib = _ext.load()
+    assert lib.fac_version() >= 100
+    assert isinstance(lib.fac_last_error(), bytes)
+
+
+def test_struct_sizes_match_header():
+    import ctypes as C
+    # pointer tables: the C structs are plain pointers/ints, so sizes are predictable
+    assert C.sizeof(_ext.ConvSrc) == 8 + 3 * 8 + 6 * 4
+    assert C.sizeof(_ext.WgWorkspace) == 4 * 8
+    assert C.sizeof(_ext.WgFlow) == 8 + 5 * 8 + 4 * 16 * 8
+    assert C.sizeof(_ext.WgModel) == 10 * 4 + 2 * 8 + 16 * C.sizeof(_ext.WgFlow)

@@ -1,0 +1,44 @@
+"""Host logic without a GPU: the packed-weight formulation (phase-decomposed upsampler,
+gate-interleaved K-concatenated GEMM, slot layout of the audio buffer) reproduces the
+oracle when evaluated with torch on the CPU (tests/emulate.py mirrors the kernels)."""
+import os
+
+import pytest
+import torch
+
+import emulate
+from fac_via_ppg_b200 import synth
+from fac_via_ppg_b200.packing import PackedWaveGlow, waveglow_layout
+from oracle import waveglow_oracle
+
+
+@pytest.mark.parametrize("name", ["waveglow_small_b2_f6.pt", "waveglow_full_b2_f5.pt"])
+def test_packed_formulation_matches_golden(golden_dir, name):
+    g = torch.load(os.path.join(golden_dir, name))
+    cfg = g["cfg"]
+    packed = PackedWaveGlow.from_state(synth.waveglow_state(cfg=cfg), cfg, "cpu")
+    mel = synth.synthetic_mel(g["batch"], g["frames"], seed=g["mel_seed"])
+    audio0 = emulate.fill_audio_slots(g["noise"], g["sigma"], cfg["n_group"])
+    out = emulate.waveglow_infer(packed, mel, audio0)
+    assert (out - g["audio"]).abs().max().item() <= 5e-5
+
+
+def test_upsample_phase_decomposition_ragged_frames():
+    cfg = synth.WAVEGLOW_CONFIG_SMALL
+    sd = synth.waveglow_state(cfg=cfg, seed=3)
+    packed = PackedWaveGlow.from_state(sd, cfg, "cpu")
+    for frames in (1, 2, 7):        # fewer frames than taps exercises the zero fill
+        mel = synth.synthetic_mel(1, frames, seed=frames)
+        ref = waveglow_oracle.upsample_and_squeeze(sd, cfg, mel).transpose(1, 2)
+        mel_cl = mel.transpose(1, 2).contiguous()
+        w, b = packed.layout.view(packed.flat, "upsample_w"), packed.layout.view(packed.flat, "upsample_b")
+        out = torch.stack([emulate.conv_gemm([(mel_cl, 7, -1, 0)], w[p], b, 640) for p in range(20)], dim=2)
+        assert (out.reshape(1, frames * 20, 640) - ref).abs().max().item() <= 1e-5
+
+
+def test_layout_is_deterministic_and_aligned():
+    a, b = waveglow_layout(synth.WAVEGLOW_CONFIG), waveglow_layout(synth.WAVEGLOW_CONFIG)
+    assert list(a.entries.items()) == list(b.entries.items())
+    assert all(off % 64 == 0 for off, _ in a.entries.values())
+    # 87.7 M parameters + phase padding of the upsampler
+    assert 87e6 < a.size < 90e6
