@@ -51,6 +51,16 @@ class WgWorkspace(C.Structure):
     _fields_ = [("spect", _fp), ("x", _fp), ("acts", _fp), ("skip", _fp)]
 
 
+class TacoDecoderWeights(C.Structure):
+    _fields_ = [(n, _fp) for n in ("w_att", "b_att", "w_dec", "b_dec", "wq_t", "w_loc", "w_ld_t", "v", "w_proj",
+                                   "b_proj", "w_pre1_t", "w_pre2_t")]
+
+
+class TacoDecoderState(C.Structure):
+    _fields_ = [(n, _fp) for n in ("h_att", "c_att", "h_dec", "c_dec", "ctx", "pre", "w_prev", "w_cum", "done",
+                                   "out_len")]
+
+
 # name -> (restype, argtypes); every symbol include/fac_b200.h declares.
 _P = C.POINTER
 SIGNATURES = {
@@ -65,6 +75,9 @@ SIGNATURES = {
     "fac_wn_layer_f32": (C.c_int, [_P(WgModel), C.c_int, C.c_int, _P(WgWorkspace), C.c_int, C.c_int, _fp]),
     "fac_wn_end_coupling_f32": (C.c_int, [_P(WgModel), C.c_int, _fp, _fp, C.c_int, C.c_int, _fp]),
     "fac_waveglow_infer_f32": (C.c_int, [_P(WgModel), _fp, _fp, _P(WgWorkspace), C.c_int, C.c_int, _fp]),
+    "fac_lstm_bidir_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    "fac_taco_decoder_run": (C.c_int, [_P(TacoDecoderWeights), _fp, _fp, _fp, _fp, _P(TacoDecoderState), _fp, _fp,
+                                       _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),
 }
 
 _lib = None

@@ -1,0 +1,296 @@
+"""Drop-in for the reference ``src/common/model.py`` (inference side of the PPG->Mel model).
+
+Module tree, constructor arguments and parameter names mirror the reference so
+``load_state_dict(torch.load(ckpt)['state_dict'])`` (generate_synthesis.py:81-83) works
+unchanged; ``Tacotron2.inference(inputs)`` keeps its signature and return list
+``[mel, mel_postnet, gate, alignments]`` (reference model.py:597-610).  The modules hold
+parameters only.  All arithmetic runs in libfacb200.so:
+
+  encoder prenet / convs+BN / LSTM input projection / memory layer / postnet
+      -> fac_conv_gemm_f32 (implicit-GEMM Conv1d/Linear, BN folded, fused ReLU/tanh/dropout mask)
+  encoder BiLSTM recurrence -> fac_lstm_bidir_f32 (8-CTA clusters, W_hh resident in DSMEM)
+  decoder loop              -> fac_taco_decoder_run (one persistent cooperative kernel)
+
+Differences from the reference that a caller can observe:
+  * B > 1 works (the reference's stop test only supports B == 1, model.py:524): every
+    utterance stops on its own gate; frames after an utterance's stop are zeroed and the
+    per-utterance lengths are left in ``model.last_output_lengths``.
+  * the always-on prenet dropout (model.py:132-135) draws its masks from torch's generator
+    on the input's device.  ``rng_mode='reference'`` replays the reference's draw order
+    call by call (seed-exact); the default ``'fast'`` makes one draw per tensor kind.
+    A recorded tape can be injected with ``inference(inputs, dropout_tape=...)``.
+The training direction (``forward`` / ``parse_batch``) is out of scope and raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from fac_via_ppg_b200 import _ext, ops
+from fac_via_ppg_b200.packing import PackedTacotron
+from fac_via_ppg_b200.common.layers import ConvNorm, LinearNorm
+
+_HP_KEYS = ("n_symbols", "symbols_embedding_dim", "encoder_embedding_dim", "encoder_kernel_size",
+            "encoder_n_convolutions", "n_acoustic_feat_dims", "prenet_dim", "attention_rnn_dim", "decoder_rnn_dim",
+            "attention_dim", "attention_location_n_filters", "attention_location_kernel_size",
+            "attention_window_size", "postnet_embedding_dim", "postnet_kernel_size", "postnet_n_convolutions",
+            "gate_threshold", "max_decoder_steps", "p_attention_dropout", "p_decoder_dropout")
+
+
+def _no_forward(name):
+    def forward(self, *a, **k):
+        raise NotImplementedError("fac_via_ppg_b200: %s is a parameter holder; use Tacotron2.inference" % name)
+    return forward
+
+
+class LocationLayer(nn.Module):
+    def __init__(self, attention_n_filters, attention_kernel_size, attention_dim):
+        super().__init__()
+        self.location_conv = ConvNorm(2, attention_n_filters, kernel_size=attention_kernel_size,
+                                      padding=(attention_kernel_size - 1) // 2, bias=False)
+        self.location_dense = LinearNorm(attention_n_filters, attention_dim, bias=False, w_init_gain="tanh")
+
+    forward = _no_forward("LocationLayer")
+
+
+class Attention(nn.Module):
+    def __init__(self, attention_rnn_dim, embedding_dim, attention_dim, attention_location_n_filters,
+                 attention_location_kernel_size):
+        super().__init__()
+        self.query_layer = LinearNorm(attention_rnn_dim, attention_dim, bias=False, w_init_gain="tanh")
+        self.memory_layer = LinearNorm(embedding_dim, attention_dim, bias=False, w_init_gain="tanh")
+        self.v = LinearNorm(attention_dim, 1, bias=False)
+        self.location_layer = LocationLayer(attention_location_n_filters, attention_location_kernel_size,
+                                            attention_dim)
+        self.score_mask_value = -float("inf")
+
+    forward = _no_forward("Attention")
+
+
+class Prenet(nn.Module):
+    def __init__(self, in_dim, sizes):
+        super().__init__()
+        dims = [in_dim] + list(sizes)
+        self.layers = nn.ModuleList(LinearNorm(a, b, bias=False) for a, b in zip(dims[:-1], dims[1:]))
+
+    forward = _no_forward("Prenet")
+
+
+def _conv_bn(c_in, c_out, k, gain):
+    return nn.Sequential(ConvNorm(c_in, c_out, kernel_size=k, padding=(k - 1) // 2, w_init_gain=gain),
+                         nn.BatchNorm1d(c_out))
+
+
+class Postnet(nn.Module):
+    def __init__(self, hparams):
+        super().__init__()
+        n, k = hparams.postnet_n_convolutions, hparams.postnet_kernel_size
+        dims = [hparams.n_acoustic_feat_dims] + [hparams.postnet_embedding_dim] * (n - 1) + \
+               [hparams.n_acoustic_feat_dims]
+        self.convolutions = nn.ModuleList(
+            _conv_bn(dims[i], dims[i + 1], k, "tanh" if i < n - 1 else "linear") for i in range(n))
+
+    forward = _no_forward("Postnet")
+
+
+class Encoder(nn.Module):
+    def __init__(self, hparams):
+        super().__init__()
+        E = hparams.encoder_embedding_dim
+        self.prenet = Prenet(hparams.n_symbols, [hparams.symbols_embedding_dim, hparams.symbols_embedding_dim])
+        self.convolutions = nn.ModuleList(
+            _conv_bn(E, E, hparams.encoder_kernel_size, "relu") for _ in range(hparams.encoder_n_convolutions))
+        self.lstm = nn.LSTM(E, E // 2, 1, batch_first=True, bidirectional=True)
+
+    forward = _no_forward("Encoder")
+
+
+class Decoder(nn.Module):
+    def __init__(self, hparams):
+        super().__init__()
+        for key in ("n_acoustic_feat_dims", "encoder_embedding_dim", "attention_rnn_dim", "decoder_rnn_dim",
+                    "prenet_dim", "max_decoder_steps", "gate_threshold", "p_attention_dropout", "p_decoder_dropout",
+                    "attention_window_size"):
+            setattr(self, key, getattr(hparams, key))
+        E = hparams.encoder_embedding_dim
+        self.prenet = Prenet(hparams.n_acoustic_feat_dims, [hparams.prenet_dim, hparams.prenet_dim])
+        self.attention_rnn = nn.LSTMCell(hparams.prenet_dim + E, hparams.attention_rnn_dim)
+        self.attention_layer = Attention(hparams.attention_rnn_dim, E, hparams.attention_dim,
+                                         hparams.attention_location_n_filters,
+                                         hparams.attention_location_kernel_size)
+        self.decoder_rnn = nn.LSTMCell(hparams.attention_rnn_dim + E, hparams.decoder_rnn_dim, 1)
+        self.linear_projection = LinearNorm(hparams.decoder_rnn_dim + E, hparams.n_acoustic_feat_dims)
+        self.gate_layer = LinearNorm(hparams.decoder_rnn_dim + E, 1, bias=True, w_init_gain="sigmoid")
+
+    forward = _no_forward("Decoder")
+
+
+class Tacotron2(nn.Module):
+    """Reference-compatible PPG->Mel model (reference model.py:538-610), CUDA-native inference."""
+
+    rng_mode = "fast"            # 'fast' | 'reference'  (see module docstring)
+    return_alignments = True     # dense (B, T_out, T_in) like the reference; False saves memory on long inputs
+
+    def __init__(self, hparams):
+        super().__init__()
+        self.mask_padding = hparams.mask_padding
+        self.fp16_run = hparams.fp16_run
+        self.n_acoustic_feat_dims = hparams.n_acoustic_feat_dims
+        self.hp = {k: getattr(hparams, k) for k in _HP_KEYS}
+        self.encoder = Encoder(hparams)
+        self.decoder = Decoder(hparams)
+        self.postnet = Postnet(hparams)
+        self.last_output_lengths = None
+
+    # ------------------------------------------------------------------ packing
+    def _weights_signature(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def packed(self) -> PackedTacotron:
+        sig = self._weights_signature()
+        cache = getattr(self, "_fac_packed", None)
+        if cache is None or cache[0] != sig:
+            w = self.decoder.linear_projection.linear_layer.weight
+            _ext.require_cuda(w, "Tacotron2 parameters")
+            cache = (sig, PackedTacotron.from_state(self.state_dict(), self.hp, w.device))
+            object.__setattr__(self, "_fac_packed", cache)
+        return cache[1]
+
+    def empty_packed(self) -> PackedTacotron:
+        return PackedTacotron(self.hp, self.decoder.linear_projection.linear_layer.weight.device)
+
+    def use_packed(self, packed: PackedTacotron):
+        object.__setattr__(self, "_fac_packed", (self._weights_signature(), packed))
+
+    # ------------------------------------------------------------------ dropout masks
+    def _dropout_masks(self, B, T_in, n_steps, dev, tape):
+        """Returns (enc0, enc1) float masks in {0,2} of shape (B,T_in,E) and the decoder mask
+        tensor (n_steps, 2, B, P) uint8 in {0,1}; draw order = reference call order."""
+        E, P = self.hp["symbols_embedding_dim"], self.hp["prenet_dim"]
+        if tape is not None:
+            tape = [m.to(dev) for m in tape]
+            if len(tape) < 2 + 2 * n_steps:
+                raise ValueError("dropout tape holds %d masks, need %d" % (len(tape), 2 + 2 * n_steps))
+            enc = [(m.float() > 0).float().mul_(2.0).view(B, T_in, E).contiguous() for m in tape[:2]]
+            dec = torch.stack([(m.float() > 0).view(B, P) for m in tape[2:2 + 2 * n_steps]])
+            return enc[0], enc[1], dec.view(n_steps, 2, B, P).to(torch.uint8).contiguous()
+        if self.rng_mode == "reference":
+            ones_e = torch.ones(B, T_in, E, device=dev)
+            enc0, enc1 = F.dropout(ones_e, 0.5, True), F.dropout(ones_e, 0.5, True)
+            ones_d = torch.ones(B, P, device=dev)
+            dec = torch.stack([F.dropout(ones_d, 0.5, True) for _ in range(2 * n_steps)])
+            return enc0, enc1, (dec > 0).view(n_steps, 2, B, P).to(torch.uint8).contiguous()
+        enc = (torch.rand(2, B, T_in, E, device=dev) >= 0.5).float().mul_(2.0)
+        dec = (torch.rand(n_steps, 2, B, P, device=dev) >= 0.5).to(torch.uint8)
+        return enc[0], enc[1], dec
+
+    # ------------------------------------------------------------------ stages
+    def _encode(self, packed, inputs, enc0, enc1):
+        """reference model.py:237-249 (Encoder.inference): (B, D, T) -> memory (B, T, E)."""
+        hp = self.hp
+        B, D, T = inputs.shape
+        E, H = hp["encoder_embedding_dim"], hp["encoder_embedding_dim"] // 2
+        dev = inputs.device
+        new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        h = ops.conv_gemm([ops.conv_src(inputs, channel_major=True)], packed.view("enc.pre0_w"), None, E,
+                          new(B, T, E), batch=B, rows=T, act=_ext.ACT_RELU, mask=enc0)
+        h = ops.conv_gemm([ops.conv_src(h)], packed.view("enc.pre1_w"), None, E, new(B, T, E), batch=B, rows=T,
+                          act=_ext.ACT_RELU, mask=enc1)
+        k = hp["encoder_kernel_size"]
+        for i in range(hp["encoder_n_convolutions"]):
+            h = ops.conv_gemm([ops.conv_src(h, k, 1, (k - 1) // 2)], packed.view(f"enc.conv{i}_w"),
+                              packed.view(f"enc.conv{i}_b"), E, new(B, T, E), batch=B, rows=T, act=_ext.ACT_RELU)
+        xp = ops.conv_gemm([ops.conv_src(h)], packed.view("enc.lstm_ih_w"), packed.view("enc.lstm_ih_b"), 8 * H,
+                           new(B, T, 8 * H), batch=B, rows=T)
+        memory = new(B, T, E)
+        rc = _ext.load().fac_lstm_bidir_f32(xp.data_ptr(), packed.view("enc.lstm_hh").data_ptr(), memory.data_ptr(),
+                                            B, T, H, _ext.current_stream())
+        _ext.check(rc, "fac_lstm_bidir_f32")
+        return memory
+
+    def _decode(self, packed, memory, dec_masks, n_steps):
+        """reference model.py:489-535 (Decoder.inference) -> mel_cl (B, n_steps, M), gate, align, lengths."""
+        hp = self.hp
+        B, T, E = memory.shape
+        dev = memory.device
+        A, R, M = hp["attention_dim"], hp["attention_rnn_dim"], hp["n_acoustic_feat_dims"]
+        pmem = ops.conv_gemm([ops.conv_src(memory)], packed.view("dec.mem_w"), None, A,
+                             torch.empty(B, T, A, device=dev), batch=B, rows=T)
+        z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        st = {"h_att": z(2, B, R), "c_att": z(B, R), "h_dec": z(2, B, R), "c_dec": z(B, R), "ctx": z(B, E),
+              "pre": z(B, hp["prenet_dim"]), "w_prev": z(B, T), "w_cum": z(B, T),
+              "done": torch.zeros(4, dtype=torch.int32, device=dev),
+              "out_len": torch.zeros(B, dtype=torch.int32, device=dev)}
+        cstate = _ext.TacoDecoderState(*[st[n].data_ptr() for n, _ in _ext.TacoDecoderState._fields_])
+        lengths = torch.full((B,), T, dtype=torch.int32, device=dev)      # model.py:599
+        mel = z(B, n_steps, M)
+        gate = z(B, n_steps)
+        align = z(B, n_steps, T) if self.return_alignments else None
+        rc = _ext.load().fac_taco_decoder_run(
+            C.byref(packed.cdecoder), memory.data_ptr(), pmem.data_ptr(), lengths.data_ptr(), dec_masks.data_ptr(),
+            C.byref(cstate), mel.data_ptr(), gate.data_ptr(), _ext.ptr(align), B, T, n_steps,
+            hp["attention_window_size"], float(self.decoder.gate_threshold), _ext.current_stream())
+        _ext.check(rc, "fac_taco_decoder_run")
+        return mel, gate, align, st["out_len"], st["done"]
+
+    def _postnet(self, packed, mel_cl):
+        """reference model.py:178-184 + 604-605: mel_post = mel + postnet(mel), channels-last in/out."""
+        hp = self.hp
+        B, T, M = mel_cl.shape
+        n, k, Pe = hp["postnet_n_convolutions"], hp["postnet_kernel_size"], hp["postnet_embedding_dim"]
+        h = mel_cl
+        for i in range(n):
+            last = i == n - 1
+            width = M if last else Pe
+            h = ops.conv_gemm([ops.conv_src(h, k, 1, (k - 1) // 2)], packed.view(f"post.conv{i}_w"),
+                              packed.view(f"post.conv{i}_b"), width,
+                              torch.empty(B, T, width, device=mel_cl.device), batch=B, rows=T,
+                              act=_ext.ACT_NONE if last else _ext.ACT_TANH, residual=mel_cl if last else None)
+        return h
+
+    # ------------------------------------------------------------------ public API
+    def parse_input(self, inputs):
+        return inputs.half() if self.fp16_run else inputs            # fp16_optimizer.py:53-63
+
+    def parse_output(self, outputs, output_lengths=None):
+        return [o if o is None else o.float() for o in outputs] if self.fp16_run else outputs   # model.py:566-578 (no masking at inference)
+
+    @torch.no_grad()
+    def inference(self, inputs, dropout_tape=None):
+        """inputs (B, n_symbols, T_in) -> [mel (B,M,T_out), mel_postnet, gate (B,T_out,1), alignments (B,T_out,T_in)]."""
+        _ext.require_cuda(inputs, "inputs")
+        inputs = self.parse_input(inputs)
+        x = inputs.float().contiguous()
+        B, D, T = x.shape
+        if D != self.hp["n_symbols"]:
+            raise ValueError("inputs have %d symbols, model expects %d" % (D, self.hp["n_symbols"]))
+        if B == 0 or T == 0:
+            raise ValueError("empty input batch")
+        packed = self.packed()
+        n_steps = int(self.decoder.max_decoder_steps)
+        enc0, enc1, dec_masks = self._dropout_masks(B, T, n_steps, x.device, dropout_tape)
+        memory = self._encode(packed, x, enc0, enc1)
+        mel_cl, gate, align, out_len, done = self._decode(packed, memory, dec_masks, n_steps)
+        lens = out_len.cpu()                                          # the one device->host sync of the call
+        t_out = int(lens.max())
+        if int(done.cpu()[1]) > 0:
+            print("Warning! Reached max decoder steps")              # model.py:526-528
+        mel_cl = mel_cl[:, :t_out].contiguous()
+        if B > 1 and int(lens.min()) < t_out:                        # per-utterance stop: zero the tail
+            keep = (torch.arange(t_out, device=x.device)[None, :] < out_len[:, None]).unsqueeze(-1)
+            mel_cl = mel_cl * keep
+        self.last_output_lengths = lens
+        post_cl = self._postnet(packed, mel_cl)
+        outputs = [mel_cl.transpose(1, 2), post_cl.transpose(1, 2), gate[:, :t_out].unsqueeze(-1),
+                   align[:, :t_out] if align is not None else None]
+        return self.parse_output(outputs)
+
+    def forward(self, inputs):
+        raise NotImplementedError("fac_via_ppg_b200 covers Tacotron2.inference only; teacher-forced training "
+                                  "(reference model.py:580-595) is out of scope")
+
+    def parse_batch(self, batch):
+        raise NotImplementedError("training batches are out of scope (reference model.py:547-560)")

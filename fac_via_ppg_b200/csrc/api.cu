@@ -24,6 +24,10 @@ int wg_layer(const fac_wg_model*, int, int, const fac_wg_workspace*, int, int, c
 int wg_end(const fac_wg_model*, int, const float*, float*, int, int, cudaStream_t);
 int wg_infer(const fac_wg_model*, const float*, float*, const fac_wg_workspace*, int, int, cudaStream_t);
 
+int lstm_bidir(const float*, const float*, float*, int, int, int, cudaStream_t);
+int taco_decoder_run(const fac_taco_decoder_weights*, const float*, const float*, const int*, const unsigned char*,
+                     const fac_taco_decoder_state*, float*, float*, float*, int, int, int, int, float, cudaStream_t);
+
 }  // namespace fac
 
 extern "C" {
@@ -57,6 +61,16 @@ int fac_wn_end_coupling_f32(const fac_wg_model* m, int flow, const float* skip, 
 int fac_waveglow_infer_f32(const fac_wg_model* m, const float* mel_cl, float* audio, const fac_wg_workspace* ws, int B,
                            int F, void* stream) {
   return fac::wg_infer(m, mel_cl, audio, ws, B, F, (cudaStream_t)stream);
+}
+
+int fac_lstm_bidir_f32(const float* xp, const float* w_hh, float* out, int B, int T, int H, void* stream) {
+  return fac::lstm_bidir(xp, w_hh, out, B, T, H, (cudaStream_t)stream);
+}
+int fac_taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, const float* pmem, const int* lengths,
+                         const unsigned char* drop, const fac_taco_decoder_state* state, float* mel, float* gate,
+                         float* align, int B, int T_in, int max_steps, int window, float gate_threshold, void* stream) {
+  return fac::taco_decoder_run(w, memory, pmem, lengths, drop, state, mel, gate, align, B, T_in, max_steps, window,
+                               gate_threshold, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -17,9 +17,12 @@ def conv_src(t: torch.Tensor, taps: int = 1, dilation: int = 0, center: int = 0,
         raise _ext.FacError("conv sources must be contiguous fp32 tensors")
     if channel_major:
         B, Cc, T = t.shape
-        return _ext.ConvSrc(t.data_ptr(), Cc * T, 1, T, Cc, taps, dilation, center, T, 0)
-    B, T, Cc = t.shape
-    return _ext.ConvSrc(t.data_ptr(), T * Cc, Cc, 1, Cc, taps, dilation, center, T, 0)
+        src = _ext.ConvSrc(t.data_ptr(), Cc * T, 1, T, Cc, taps, dilation, center, T, 0)
+    else:
+        B, T, Cc = t.shape
+        src = _ext.ConvSrc(t.data_ptr(), T * Cc, Cc, 1, Cc, taps, dilation, center, T, 0)
+    src.keepalive = t   # the descriptor only holds a raw pointer: pin the tensor to it
+    return src
 
 
 def conv_gemm(srcs, w_packed, bias, n_out, out, *, batch, rows, kind=_ext.EPI_LINEAR, act=_ext.ACT_NONE,

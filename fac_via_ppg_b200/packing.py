@@ -186,3 +186,146 @@ class PackedWaveGlow:
     @classmethod
     def from_state(cls, sd, cfg, device):
         return cls(cfg, device).load_state(sd)
+
+
+# ===================================================================== Tacotron2 (PPG -> Mel)
+def _fold_bn(sd, prefix, dev, eps=1e-5):
+    """Conv1d + BatchNorm1d(eval) -> one conv: w' = w * g / sqrt(var + eps), b' = (b - mean) * g / sqrt(...) + beta
+    (reference src/common/model.py:143-176, 199-209; BatchNorm1d default eps)."""
+    f32 = dict(device=dev, dtype=torch.float32)
+    w = sd[prefix + "0.conv.weight"].detach().to(**f32)
+    b = sd[prefix + "0.conv.bias"].detach().to(**f32)
+    scale = sd[prefix + "1.weight"].detach().to(**f32) / torch.sqrt(sd[prefix + "1.running_var"].detach().to(**f32) + eps)
+    shift = sd[prefix + "1.bias"].detach().to(**f32) - sd[prefix + "1.running_mean"].detach().to(**f32) * scale
+    return w * scale[:, None, None], b * scale + shift
+
+
+def tacotron_layout(hp) -> FlatLayout:
+    E, D, M = hp["encoder_embedding_dim"], hp["n_symbols"], hp["n_acoustic_feat_dims"]
+    P, A, R = hp["prenet_dim"], hp["attention_dim"], hp["attention_rnn_dim"]
+    H = E // 2
+    ke, kp, Pe = hp["encoder_kernel_size"], hp["postnet_kernel_size"], hp["postnet_embedding_dim"]
+    pad = lambda n: _round_up(n, 128)  # noqa: E731
+    lay = FlatLayout()
+    lay.add("enc.pre0_w", (D, pad(E)))
+    lay.add("enc.pre1_w", (E, pad(E)))
+    for i in range(hp["encoder_n_convolutions"]):
+        lay.add(f"enc.conv{i}_w", (ke * E, pad(E)))
+        lay.add(f"enc.conv{i}_b", (pad(E),))
+    lay.add("enc.lstm_ih_w", (E, pad(8 * H)))
+    lay.add("enc.lstm_ih_b", (pad(8 * H),))
+    lay.add("enc.lstm_hh", (2, 4 * H, H))
+    lay.add("dec.mem_w", (E, pad(A)))
+    kin = P + E + R
+    lay.add("dec.w_att", (4 * R, kin))
+    lay.add("dec.b_att", (4 * R,))
+    lay.add("dec.w_dec", (4 * R, kin))
+    lay.add("dec.b_dec", (4 * R,))
+    lay.add("dec.wq_t", (R, A))
+    lay.add("dec.w_loc", (hp["attention_location_n_filters"], 2, hp["attention_location_kernel_size"]))
+    lay.add("dec.w_ld_t", (hp["attention_location_n_filters"], A))
+    lay.add("dec.v", (A,))
+    lay.add("dec.w_proj", (M + 1, R + E))
+    lay.add("dec.b_proj", (M + 1,))
+    lay.add("dec.w_pre1_t", (M, P))
+    lay.add("dec.w_pre2_t", (P, P))
+    n_post = hp["postnet_n_convolutions"]
+    dims = [M] + [Pe] * (n_post - 1) + [M]
+    for i in range(n_post):
+        lay.add(f"post.conv{i}_w", (kp * dims[i], pad(dims[i + 1])))
+        lay.add(f"post.conv{i}_b", (pad(dims[i + 1]),))
+    return lay
+
+
+def validate_tacotron_hparams(hp):
+    """The persistent decoder kernel is compiled for the geometry of create_hparams_stage()
+    (reference src/common/hparams.py:167-231); other sizes fail loudly instead of silently."""
+    want = {"encoder_embedding_dim": 600, "prenet_dim": 300, "attention_rnn_dim": 300, "decoder_rnn_dim": 300,
+            "attention_dim": 150, "attention_location_n_filters": 32, "attention_location_kernel_size": 31,
+            "n_acoustic_feat_dims": 80}
+    bad = {k: hp[k] for k, v in want.items() if hp[k] != v}
+    if bad:
+        raise _ext.FacError("decoder kernel is built for %s; got %s" % (want, bad))
+    if hp["n_symbols"] % 8 or hp["postnet_embedding_dim"] % 8:
+        raise _ext.FacError("n_symbols and postnet_embedding_dim must be multiples of 8")
+    w = hp["attention_window_size"]
+    if w is None or 2 * w + 1 > 64:
+        raise _ext.FacError("attention_window_size must be set and <= 31 (windowed attention kernel)")
+
+
+class PackedTacotron:
+    """Flat packed weights of the PPG->Mel model + the decoder pointer table."""
+
+    def __init__(self, hp, device):
+        validate_tacotron_hparams(hp)
+        self.hp = dict(hp)
+        self.layout = tacotron_layout(hp)
+        self.flat = torch.zeros(self.layout.size, dtype=torch.float32, device=device)
+        w = _ext.TacoDecoderWeights()
+        for name in ("w_att", "b_att", "w_dec", "b_dec", "wq_t", "w_loc", "w_ld_t", "v", "w_proj", "b_proj",
+                     "w_pre1_t", "w_pre2_t"):
+            setattr(w, name, self.layout.ptr(self.flat, "dec." + name))
+        self.cdecoder = w
+
+    def view(self, name):
+        return self.layout.view(self.flat, name)
+
+    @property
+    def nbytes(self):
+        return self.flat.numel() * 4
+
+    @torch.no_grad()
+    def load_state(self, sd):
+        hp, dev = self.hp, self.flat.device
+        E, M = hp["encoder_embedding_dim"], hp["n_acoustic_feat_dims"]
+        H = E // 2
+
+        def get(name):
+            return sd[name].detach().to(device=dev, dtype=torch.float32)
+
+        def put(name, t):
+            v = self.view(name)
+            if v.dim() == 2 and t.shape[1] != v.shape[1]:
+                t = _pad_cols(t, v.shape[1])
+            elif v.dim() == 1 and t.numel() != v.numel():
+                t = torch.cat([t, t.new_zeros(v.numel() - t.numel())])
+            v.copy_(t)
+
+        put("enc.pre0_w", get("encoder.prenet.layers.0.linear_layer.weight").t())
+        put("enc.pre1_w", get("encoder.prenet.layers.1.linear_layer.weight").t())
+        for i in range(hp["encoder_n_convolutions"]):
+            w, b = _fold_bn(sd, f"encoder.convolutions.{i}.", dev)
+            put(f"enc.conv{i}_w", w.permute(2, 1, 0).reshape(-1, w.shape[0]))      # rows (tap, c_in)
+            put(f"enc.conv{i}_b", b)
+        w_ih = torch.cat([get("encoder.lstm.weight_ih_l0"), get("encoder.lstm.weight_ih_l0_reverse")], dim=0)
+        b_ih = torch.cat([get("encoder.lstm.bias_ih_l0") + get("encoder.lstm.bias_hh_l0"),
+                          get("encoder.lstm.bias_ih_l0_reverse") + get("encoder.lstm.bias_hh_l0_reverse")])
+        put("enc.lstm_ih_w", w_ih.t())
+        put("enc.lstm_ih_b", b_ih)
+        self.view("enc.lstm_hh").copy_(torch.stack([get("encoder.lstm.weight_hh_l0"),
+                                                    get("encoder.lstm.weight_hh_l0_reverse")]))
+        al = "decoder.attention_layer."
+        put("dec.mem_w", get(al + "memory_layer.linear_layer.weight").t())
+        for cell, name in (("attention_rnn", "att"), ("decoder_rnn", "dec")):
+            p = f"decoder.{cell}."
+            put(f"dec.w_{name}", torch.cat([get(p + "weight_ih"), get(p + "weight_hh")], dim=1))
+            put(f"dec.b_{name}", get(p + "bias_ih") + get(p + "bias_hh"))
+        put("dec.wq_t", get(al + "query_layer.linear_layer.weight").t())
+        self.view("dec.w_loc").copy_(get(al + "location_layer.location_conv.conv.weight"))
+        put("dec.w_ld_t", get(al + "location_layer.location_dense.linear_layer.weight").t())
+        put("dec.v", get(al + "v.linear_layer.weight")[0])
+        put("dec.w_proj", torch.cat([get("decoder.linear_projection.linear_layer.weight"),
+                                     get("decoder.gate_layer.linear_layer.weight")], dim=0))
+        put("dec.b_proj", torch.cat([get("decoder.linear_projection.linear_layer.bias"),
+                                     get("decoder.gate_layer.linear_layer.bias")]))
+        put("dec.w_pre1_t", get("decoder.prenet.layers.0.linear_layer.weight").t())
+        put("dec.w_pre2_t", get("decoder.prenet.layers.1.linear_layer.weight").t())
+        for i in range(hp["postnet_n_convolutions"]):
+            w, b = _fold_bn(sd, f"postnet.convolutions.{i}.", dev)
+            put(f"post.conv{i}_w", w.permute(2, 1, 0).reshape(-1, w.shape[0]))
+            put(f"post.conv{i}_b", b)
+        return self
+
+    @classmethod
+    def from_state(cls, sd, hp, device):
+        return cls(hp, device).load_state(sd)

@@ -12,6 +12,8 @@ include/fac_b200.h.  There is no PyTorch or CPU fallback; the training direction
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from fac_via_ppg_b200 import _ext
@@ -137,6 +139,10 @@ class WaveGlow(torch.nn.Module):
             object.__setattr__(self, "_fac_packed", cache)
         return cache[1]
 
+    def empty_packed(self) -> PackedWaveGlow:
+        """Unfilled packed buffer of the right layout on the module's device (broadcast target)."""
+        return PackedWaveGlow(self.config(), self.upsample.weight.device)
+
     def use_packed(self, packed: PackedWaveGlow):
         """Adopt externally provided packed weights (e.g. received by NCCL broadcast)."""
         object.__setattr__(self, "_fac_packed", (self._weights_signature(), packed))
@@ -150,6 +156,40 @@ class WaveGlow(torch.nn.Module):
                 draws.append(torch.empty(batch, self.n_early_size, n_cols, device=device, dtype=dtype).normal_())
         return draws
 
+    precision = "fp32"     # exact-fp32 FFMA path
+
+    def _alloc_io(self, spect, sigma, noise):
+        """Allocates the audio slot buffer (pre-filled with sigma*z), mel in channels-last
+        form and the workspace.  Everything here is PyTorch plumbing around raw pointers."""
+        B, n_mel, F = spect.shape
+        hop, G = self.upsample.stride[0], self.n_group
+        Tg = F * hop // G
+        dev = spect.device
+        if noise is None:
+            noise = self.noise_like_reference(B, Tg, dev, spect.dtype)
+        # the flow with n_rem live channels owns the LAST n_rem slots of every column, so
+        # the first draw fills the last slots and each early draw the slots before them
+        audio = torch.empty(B, Tg, G, device=dev, dtype=torch.float32)
+        hi = G
+        for z in noise:
+            lo = hi - z.shape[1]
+            audio[:, :, lo:hi] = (sigma * z).float().transpose(1, 2)
+            hi = lo
+        if hi != 0:
+            raise ValueError("noise draws do not cover n_group channels")
+        mel_cl = spect.float().transpose(1, 2).contiguous()
+        Cn = self.WN[0].n_channels
+        bufs = {
+            "audio": audio, "mel_cl": mel_cl,
+            "spect": torch.empty(B, Tg, n_mel * G, device=dev, dtype=torch.float32),
+            "x": torch.empty(B, Tg, Cn, device=dev, dtype=torch.float32),
+            "acts": torch.empty(B, Tg, Cn, device=dev, dtype=torch.float32),
+            "skip": torch.empty(B, Tg, Cn, device=dev, dtype=torch.float32),
+        }
+        bufs["ws"] = _ext.WgWorkspace(bufs["spect"].data_ptr(), bufs["x"].data_ptr(), bufs["acts"].data_ptr(),
+                                      bufs["skip"].data_ptr())
+        return bufs, B, F, Tg
+
     @torch.no_grad()
     def infer(self, spect, sigma=1.0, noise=None):
         """mel (B, n_mel, F) -> audio (B, F*hop); reference glow.py:252-293.
@@ -161,37 +201,58 @@ class WaveGlow(torch.nn.Module):
         lib = _ext.load()
         packed = self.packed()
         B, n_mel, F = spect.shape
-        hop, G = self.upsample.stride[0], self.n_group
         if n_mel != self.upsample.in_channels:
             raise ValueError("spect has %d mel channels, model expects %d" % (n_mel, self.upsample.in_channels))
-        out_dtype = spect.dtype
         if B == 0 or F == 0:
-            return spect.new_zeros(B, F * hop)
-        Tg = F * hop // G
-        dev = spect.device
-        if noise is None:
-            noise = self.noise_like_reference(B, Tg, dev, out_dtype)
-        # lay the draws out per slot: the flow with n_rem live channels owns the last n_rem slots
-        audio = torch.empty(B, Tg, G, device=dev, dtype=torch.float32)
-        hi = G
-        for z in noise:
-            lo = hi - z.shape[1]
-            audio[:, :, lo:hi] = (sigma * z).float().transpose(1, 2)
-            hi = lo
-        if hi != 0:
-            raise ValueError("noise draws do not cover n_group channels")
-        mel_cl = spect.float().transpose(1, 2).contiguous()
-        Cn = self.WN[0].n_channels
-        ws_spect = torch.empty(B, Tg, n_mel * G, device=dev, dtype=torch.float32)
-        ws_x = torch.empty(B, Tg, Cn, device=dev, dtype=torch.float32)
-        ws_acts = torch.empty_like(ws_x)
-        ws_skip = torch.empty_like(ws_x)
-        ws = _ext.WgWorkspace(ws_spect.data_ptr(), ws_x.data_ptr(), ws_acts.data_ptr(), ws_skip.data_ptr())
-        import ctypes as C
-        rc = lib.fac_waveglow_infer_f32(C.byref(packed.cmodel), mel_cl.data_ptr(), audio.data_ptr(), C.byref(ws),
-                                        B, F, _ext.current_stream())
+            return spect.new_zeros(B, F * self.upsample.stride[0])
+        bufs, B, F, Tg = self._alloc_io(spect, sigma, noise)
+        rc = lib.fac_waveglow_infer_f32(C.byref(packed.cmodel), bufs["mel_cl"].data_ptr(), bufs["audio"].data_ptr(),
+                                        C.byref(bufs["ws"]), B, F, _ext.current_stream())
         _ext.check(rc, "fac_waveglow_infer_f32")
-        return audio.view(B, Tg * G).to(out_dtype)
+        return bufs["audio"].view(B, Tg * self.n_group).to(spect.dtype)
+
+    @torch.no_grad()
+    def profile_dominant_kernel(self, spect, peaks):
+        """Times the dominant kernel (the two WN-layer GEMM launches, glow.py:158-174) live with
+        CUDA events on the launching stream, one event pair per (flow, layer), and returns
+        the ``roofline`` object bench.py prints.  Algorithmic work per launch pair:
+        columns x (2C x (ks*C + n_cond) + n_rs x C) MACs."""
+        lib = _ext.load()
+        packed = self.packed()
+        bufs, B, F, Tg = self._alloc_io(spect, 0.6, None)
+        st = _ext.current_stream()
+        m = C.byref(packed.cmodel)
+        _ext.check(lib.fac_waveglow_upsample_squeeze_f32(m, bufs["mel_cl"].data_ptr(), bufs["spect"].data_ptr(),
+                                                         B, F, st), "upsample")
+        cfg = self.config()
+        Cn, L, ks = cfg["WN_config"]["n_channels"], cfg["WN_config"]["n_layers"], cfg["WN_config"]["kernel_size"]
+        n_cond = cfg["n_mel_channels"] * cfg["n_group"]
+        pairs, macs = [], 0
+        for k in reversed(range(self.n_flows)):
+            _ext.check(lib.fac_wn_start_f32(m, k, bufs["audio"].data_ptr(), bufs["x"].data_ptr(), B, Tg, st), "start")
+            for i in range(L):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _ext.check(lib.fac_wn_layer_f32(m, k, i, C.byref(bufs["ws"]), B, Tg, st), "layer")
+                e1.record()
+                pairs.append((e0, e1))
+                macs += B * Tg * (2 * Cn * (ks * Cn + n_cond) + (2 * Cn if i < L - 1 else Cn) * Cn)
+            _ext.check(lib.fac_wn_end_coupling_f32(m, k, bufs["skip"].data_ptr(), bufs["audio"].data_ptr(), B, Tg, st),
+                       "end")
+        torch.cuda.synchronize()
+        total_ms = sum(a.elapsed_time(b) for a, b in pairs)
+        n_launch = 2 * len(pairs)
+        achieved = 2.0 * macs / (total_ms / 1e3) / 1e12
+        peak = peaks["tflops_sustained"]
+        return {
+            "bound": "tensor", "kernel": "conv_gemm_f32_kernel (WN layer: in+cond GEMM -> gate, res/skip GEMM)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
+            "launches_timed": n_launch, "avg_launch_ms": total_ms / n_launch,
+            "flop_per_launch": 2.0 * macs / n_launch, "traffic": None,
+            "note": "exact-fp32 FFMA path: its own pipe peak is 74.4 TFLOP/s (148 SM x 128 lanes x 2 x 1.965 GHz), "
+                    "frac_of_ffma_peak=%.3f" % (achieved / 74.4),
+        }
 
     def forward(self, forward_input):
         raise NotImplementedError("fac_via_ppg_b200 covers the inference path only (WaveGlow.infer); "

@@ -128,6 +128,58 @@ int fac_wn_end_coupling_f32(const fac_wg_model* m, int flow, const float* skip, 
 int fac_waveglow_infer_f32(const fac_wg_model* m, const float* mel_cl, float* audio,
                            const fac_wg_workspace* ws, int B, int F, void* stream);
 
+/* ---- PPG -> Mel (Tacotron2 variant) ------------------------------------- */
+/* Recurrent part of the encoder's bidirectional LSTM (reference src/common/model.py:211-213,
+ * 246-247).  xp is (B, T, 2*4H): x W_ih^T + b_ih + b_hh of the forward direction in columns
+ * [0, 4H) and of the reverse direction in [4H, 8H) (gate order i, f, g, o), produced by
+ * fac_conv_gemm_f32.  w_hh is [2][4H][H] (weight_hh_l0, weight_hh_l0_reverse).  out is
+ * (B, T, 2H) = [forward h | reverse h], i.e. the encoder `memory`. */
+int fac_lstm_bidir_f32(const float* xp, const float* w_hh, float* out, int B, int T, int H, void* stream);
+
+/* Decoder weights (fp32 device pointers), packed by fac_via_ppg_b200/packing.py from the
+ * reference state-dict keys decoder.* (SURVEY.md section 8a). */
+typedef struct fac_taco_decoder_weights {
+  const float* w_att;    /* [1200][1200] attention_rnn: cat(weight_ih (prenet 300 | context 600), weight_hh 300) */
+  const float* b_att;    /* [1200] bias_ih + bias_hh                                                            */
+  const float* w_dec;    /* [1200][1200] decoder_rnn: cat(weight_ih (h_att 300 | context 600), weight_hh 300)   */
+  const float* b_dec;    /* [1200]                                                                              */
+  const float* wq_t;     /* [300][150]  attention_layer.query_layer weight, transposed                          */
+  const float* w_loc;    /* [32][2][31] attention_layer.location_layer.location_conv weight                     */
+  const float* w_ld_t;   /* [32][150]   location_dense weight, transposed                                       */
+  const float* v;        /* [150]       attention_layer.v weight                                                */
+  const float* w_proj;   /* [81][900]   rows 0..79 linear_projection, row 80 gate_layer                         */
+  const float* b_proj;   /* [81]                                                                                */
+  const float* w_pre1_t; /* [80][300]   decoder.prenet.layers.0 weight, transposed                              */
+  const float* w_pre2_t; /* [300][300]  decoder.prenet.layers.1 weight, transposed                              */
+} fac_taco_decoder_weights;
+
+/* Decoder state the caller allocates ZERO-FILLED (reference model.py:304-335 initialises every
+ * state to zero); the kernel owns it while running. */
+typedef struct fac_taco_decoder_state {
+  float* h_att;   /* [2][B][300] double-buffered attention_hidden            */
+  float* c_att;   /* [B][300]    attention_cell                              */
+  float* h_dec;   /* [2][B][300] decoder_hidden                              */
+  float* c_dec;   /* [B][300]    decoder_cell                                */
+  float* ctx;     /* [B][600]    attention_context                           */
+  float* pre;     /* [B][300]    prenet output feeding the next step         */
+  float* w_prev;  /* [B][T_in]   attention_weights                           */
+  float* w_cum;   /* [B][T_in]   attention_weights_cum                       */
+  int* done;      /* [4]: #utterances stopped by the gate, #stopped by max_steps, steps run, spare */
+  int* out_len;   /* [B] number of frames of each utterance (0 while running) */
+} fac_taco_decoder_state;
+
+/* The whole autoregressive loop of Decoder.inference (reference model.py:489-535 with decode
+ * :387-442, Attention :100-121, window mask utils.py:46-78) in one persistent kernel.
+ *   memory (B,T_in,600), pmem = memory_layer(memory) (B,T_in,150), lengths[B] (int32),
+ *   drop (max_steps, 2, B, 300) uint8 in {0,1}: the always-on prenet dropout masks
+ *   (model.py:132-135) of step t, layers 0/1;  outputs mel (B,max_steps,80), gate (B,max_steps),
+ *   align (B,max_steps,T_in) pre-zeroed or NULL.  Stops when every utterance's
+ *   sigmoid(gate) > gate_threshold has fired (model.py:524) or at max_steps (model.py:526-528). */
+int fac_taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, const float* pmem,
+                         const int* lengths, const unsigned char* drop, const fac_taco_decoder_state* state,
+                         float* mel, float* gate, float* align, int B, int T_in, int max_steps,
+                         int window, float gate_threshold, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,3 +87,74 @@ def fill_audio_slots(noise, sigma, G):
         hi = lo
     assert hi == 0
     return audio
+
+
+# ===================================================================== Tacotron2 from the packed buffer
+def tacotron_inference(packed, inputs, masks, n_steps, window, gate_threshold=2.0):
+    """Mirror of Tacotron2.inference in fac_via_ppg_b200/common/model.py + csrc/tacotron_*.cu:
+    BN-folded convs, hoisted LSTM input projection, windowed attention, packed decoder weights."""
+    hp = packed.hp
+    v = packed.view
+    B, D, T = inputs.shape
+    E, H, A, R, M = 600, 300, 150, 300, 80
+    x = inputs.transpose(1, 2).contiguous()
+    h = torch.relu(conv_gemm([(x, 1, 0, 0)], v("enc.pre0_w"), None, E)) * masks[0]
+    h = torch.relu(conv_gemm([(h, 1, 0, 0)], v("enc.pre1_w"), None, E)) * masks[1]
+    for i in range(hp["encoder_n_convolutions"]):
+        h = torch.relu(conv_gemm([(h, 5, 1, 2)], v(f"enc.conv{i}_w"), v(f"enc.conv{i}_b"), E))
+    xp = conv_gemm([(h, 1, 0, 0)], v("enc.lstm_ih_w"), v("enc.lstm_ih_b"), 8 * H)
+    w_hh = v("enc.lstm_hh")
+    memory = torch.zeros(B, T, E)
+    for d in range(2):
+        hh, cc = torch.zeros(B, H), torch.zeros(B, H)
+        for step in range(T):
+            t = step if d == 0 else T - 1 - step
+            g = xp[:, t, d * 4 * H:(d + 1) * 4 * H] + hh @ w_hh[d].t()
+            i_, f_, g_, o_ = g.chunk(4, dim=-1)
+            cc = torch.sigmoid(f_) * cc + torch.sigmoid(i_) * torch.tanh(g_)
+            hh = torch.sigmoid(o_) * torch.tanh(cc)
+            memory[:, t, d * H:(d + 1) * H] = hh
+    pmem = conv_gemm([(memory, 1, 0, 0)], v("dec.mem_w"), None, A)
+
+    def cell(w, b, xin, c):
+        g = xin @ w.t() + b
+        i_, f_, g_, o_ = g.chunk(4, dim=-1)
+        c = torch.sigmoid(f_) * c + torch.sigmoid(i_) * torch.tanh(g_)
+        return torch.sigmoid(o_) * torch.tanh(c), c
+
+    h_att, c_att, h_dec, c_dec = (torch.zeros(B, R) for _ in range(4))
+    ctx, pre = torch.zeros(B, E), torch.zeros(B, R)
+    w_prev, w_cum = torch.zeros(B, T), torch.zeros(B, T)
+    mel, gate, align = torch.zeros(B, n_steps, M), torch.zeros(B, n_steps), torch.zeros(B, n_steps, T)
+    w_loc = v("dec.w_loc")                       # (32, 2, 31)
+    for t in range(n_steps):
+        h_att, c_att = cell(v("dec.w_att"), v("dec.b_att"), torch.cat([pre, ctx, h_att], -1), c_att)
+        start, end = min(max(0, t - window), T - 1), min(t + window, T - 1)
+        nw = end - start + 1
+        pq = h_att @ v("dec.wq_t")
+        cat = torch.zeros(B, 2, nw + 30)
+        for q in range(nw + 30):
+            pos = start - 15 + q
+            if 0 <= pos < T:
+                cat[:, 0, q], cat[:, 1, q] = w_prev[:, pos], w_cum[:, pos]
+        loc = torch.stack([torch.einsum("fck,bck->bf", w_loc, cat[:, :, q:q + 31]) for q in range(nw)], dim=1)
+        e = torch.tanh(pq[:, None, :] + loc @ v("dec.w_ld_t") + pmem[:, start:end + 1]) @ v("dec.v")
+        w = torch.softmax(e, dim=1)
+        ctx = torch.einsum("bq,bqc->bc", w, memory[:, start:end + 1])
+        w_prev = torch.zeros(B, T)
+        w_prev[:, start:end + 1] = w
+        w_cum[:, start:end + 1] += w
+        align[:, t, start:end + 1] = w
+        h_dec, c_dec = cell(v("dec.w_dec"), v("dec.b_dec"), torch.cat([h_att, ctx, h_dec], -1), c_dec)
+        out = torch.cat([h_dec, ctx], -1) @ v("dec.w_proj").t() + v("dec.b_proj")
+        mel[:, t], gate[:, t] = out[:, :M], out[:, M]
+        if t + 1 < n_steps:
+            p1 = torch.relu(out[:, :M] @ v("dec.w_pre1_t")) * masks[2 + 2 * (t + 1)]
+            pre = torch.relu(p1 @ v("dec.w_pre2_t")) * masks[3 + 2 * (t + 1)]
+    hpost = mel
+    n = hp["postnet_n_convolutions"]
+    for i in range(n):
+        width = M if i == n - 1 else hp["postnet_embedding_dim"]
+        hpost = conv_gemm([(hpost, 5, 1, 2)], v(f"post.conv{i}_w"), v(f"post.conv{i}_b"), width)
+        hpost = torch.tanh(hpost) if i < n - 1 else hpost + mel
+    return [mel.transpose(1, 2), hpost.transpose(1, 2), gate.unsqueeze(-1), align]

@@ -42,3 +42,36 @@ def test_layout_is_deterministic_and_aligned():
     assert all(off % 64 == 0 for off, _ in a.entries.values())
     # 87.7 M parameters + phase padding of the upsampler
     assert 87e6 < a.size < 90e6
+
+
+def test_packed_tacotron_formulation_matches_golden(golden_dir):
+    """BN folding, hoisted LSTM projection, window-only attention and the packed decoder
+    tables reproduce the unmodified reference (golden) when evaluated with torch on CPU."""
+    from fac_via_ppg_b200.packing import PackedTacotron
+    g = torch.load(os.path.join(golden_dir, "tacotron_b1_t24.pt"))
+    packed = PackedTacotron.from_state(synth.tacotron_state(), synth.TACOTRON_HPARAMS, "cpu")
+    ppg = synth.synthetic_ppg(1, g["t_in"], seed=g["ppg_seed"])
+    masks = [m.float() for m in g["masks"]]
+    mel, mel_post, gate, align = emulate.tacotron_inference(packed, ppg, masks, g["t_in"], window=20)
+    # north-star tolerance on mel is 1e-3 max-abs; a different (but fp32) summation order stays well inside
+    assert (mel - g["mel"]).abs().max().item() <= 3e-4
+    assert (mel_post - g["mel_post"]).abs().max().item() <= 3e-4
+    assert (gate - g["gate"]).abs().max().item() <= 3e-4
+    assert (align - g["align"]).abs().max().item() <= 3e-4
+
+
+def test_window_only_attention_equals_dense_masked_attention():
+    """Longer than the window: positions outside [t-w, t+w] get exactly zero weight in the
+    reference (utils.py:46-78 + masked_fill(-inf)), so evaluating only the window is exact."""
+    from fac_via_ppg_b200.packing import PackedTacotron
+    from oracle import tacotron_oracle
+    sd = synth.tacotron_state(seed=5)
+    packed = PackedTacotron.from_state(sd, synth.TACOTRON_HPARAMS, "cpu")
+    T = 70
+    ppg = synth.synthetic_ppg(1, T, seed=8)
+    torch.manual_seed(4)
+    masks = tacotron_oracle.record_dropout_tape(1, T, T)
+    ref = tacotron_oracle.tacotron_inference(sd, synth.TACOTRON_HPARAMS, ppg, masks, 2.0, T)
+    out = emulate.tacotron_inference(packed, ppg, masks, T, window=20)
+    for a, b in zip(out, ref):
+        assert (a - b).abs().max().item() <= 3e-4

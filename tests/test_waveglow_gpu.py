@@ -40,8 +40,9 @@ def test_conv_gemm_two_sources_dilated(rows, batch):
     ref = torch.relu(emulate.conv_gemm([(x, 3, 4, 4), (s, 1, 0, 0)], w, bias, 200)) * mask + res
     wp, bp = ops.pack_gemm_weight(w.to(DEV), bias.to(DEV))
     out = torch.empty(batch, rows, 200, device=DEV)
-    ops.conv_gemm([ops.conv_src(x.to(DEV), 3, 4, 4), ops.conv_src(s.to(DEV))], wp, bp, 200, out, batch=batch,
-                  rows=rows, act=_ext.ACT_RELU, mask=mask.to(DEV), residual=res.to(DEV))
+    xd, sdv, md, rd = x.to(DEV), s.to(DEV), mask.to(DEV), res.to(DEV)
+    ops.conv_gemm([ops.conv_src(xd, 3, 4, 4), ops.conv_src(sdv)], wp, bp, 200, out, batch=batch,
+                  rows=rows, act=_ext.ACT_RELU, mask=md, residual=rd)
     assert (out.cpu() - ref).abs().max().item() <= 1e-4
 
 
@@ -52,7 +53,8 @@ def test_conv_gemm_channel_major_source_and_odd_width():
     ref = torch.tanh(emulate.conv_gemm([(x.transpose(1, 2).contiguous(), 5, 1, 2)], w, None, 150))
     wp, _ = ops.pack_gemm_weight(w.to(DEV))
     out = torch.empty(2, 37, 150, device=DEV)
-    ops.conv_gemm([ops.conv_src(x.to(DEV), 5, 1, 2, channel_major=True)], wp, None, 150, out, batch=2, rows=37,
+    xd = x.to(DEV)
+    ops.conv_gemm([ops.conv_src(xd, 5, 1, 2, channel_major=True)], wp, None, 150, out, batch=2, rows=37,
                   act=_ext.ACT_TANH)
     assert (out.cpu() - ref).abs().max().item() <= 1e-4
 
@@ -67,11 +69,12 @@ def test_gate_and_res_skip_epilogues():
     ref_gate = torch.tanh(pre[..., 0::2]) * torch.sigmoid(pre[..., 1::2])
     wp, bp = ops.pack_gemm_weight(w.to(DEV), b.to(DEV))
     acts = torch.empty(B, T, Cn, device=DEV)
-    ops.conv_gemm([ops.conv_src(x.to(DEV))], wp, bp, 2 * Cn, acts, batch=B, rows=T, kind=_ext.EPI_GATE)
+    xd = x.to(DEV)
+    ops.conv_gemm([ops.conv_src(xd)], wp, bp, 2 * Cn, acts, batch=B, rows=T, kind=_ext.EPI_GATE)
     assert (acts.cpu() - ref_gate).abs().max().item() <= 1e-5
     res0, skip0 = torch.randn(B, T, Cn, generator=g), torch.randn(B, T, Cn, generator=g)
     res, skip = res0.to(DEV), skip0.to(DEV)
-    ops.conv_gemm([ops.conv_src(x.to(DEV))], wp, bp, 2 * Cn, res, batch=B, rows=T, kind=_ext.EPI_RES_SKIP,
+    ops.conv_gemm([ops.conv_src(xd)], wp, bp, 2 * Cn, res, batch=B, rows=T, kind=_ext.EPI_RES_SKIP,
                   out2=skip, n_split=Cn, accumulate_out2=True)
     assert (res.cpu() - (res0 + pre[..., :Cn])).abs().max().item() <= 1e-4
     assert (skip.cpu() - (skip0 + pre[..., Cn:])).abs().max().item() <= 1e-4
@@ -85,8 +88,8 @@ def test_upsample_squeeze_matches_oracle(frames):
     mel = synth.synthetic_mel(2, frames, seed=frames)
     ref = waveglow_oracle.upsample_and_squeeze(sd, cfg, mel).transpose(1, 2)
     spect = torch.empty(2, frames * 20, 640, device=DEV)
-    rc = _ext.load().fac_waveglow_upsample_squeeze_f32(C.byref(model.packed().cmodel),
-                                                       mel.transpose(1, 2).contiguous().to(DEV).data_ptr(),
+    mel_cl = mel.transpose(1, 2).contiguous().to(DEV)
+    rc = _ext.load().fac_waveglow_upsample_squeeze_f32(C.byref(model.packed().cmodel), mel_cl.data_ptr(),
                                                        spect.data_ptr(), 2, frames, _ext.current_stream())
     _ext.check(rc, "upsample")
     assert (spect.cpu() - ref).abs().max().item() <= 2e-5
