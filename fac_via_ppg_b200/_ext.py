@@ -51,6 +51,20 @@ class WgWorkspace(C.Structure):
     _fields_ = [("spect", _fp), ("x", _fp), ("acts", _fp), ("skip", _fp)]
 
 
+class WgTcFlow(C.Structure):
+    _fields_ = [("w1_hi", _fp * FAC_MAX_LAYERS), ("w1_lo", _fp * FAC_MAX_LAYERS),
+                ("w2_hi", _fp * FAC_MAX_LAYERS), ("w2_lo", _fp * FAC_MAX_LAYERS)]
+
+
+class WgTcWeights(C.Structure):
+    _fields_ = [("flows", WgTcFlow * FAC_MAX_FLOWS)]
+
+
+class WgTcWorkspace(C.Structure):
+    _fields_ = [(n, _fp) for n in ("spect_f32", "spect_hi", "spect_lo", "x", "x_hi", "x_lo", "acts_hi", "acts_lo",
+                                   "skip")]
+
+
 class TacoDecoderWeights(C.Structure):
     _fields_ = [(n, _fp) for n in ("w_att", "b_att", "w_dec", "b_dec", "wq_t", "w_loc", "w_ld_t", "v", "w_proj",
                                    "b_proj", "w_pre1_t", "w_pre2_t")]
@@ -75,6 +89,12 @@ SIGNATURES = {
     "fac_wn_layer_f32": (C.c_int, [_P(WgModel), C.c_int, C.c_int, _P(WgWorkspace), C.c_int, C.c_int, _fp]),
     "fac_wn_end_coupling_f32": (C.c_int, [_P(WgModel), C.c_int, _fp, _fp, C.c_int, C.c_int, _fp]),
     "fac_waveglow_infer_f32": (C.c_int, [_P(WgModel), _fp, _fp, _P(WgWorkspace), C.c_int, C.c_int, _fp]),
+    "fac_waveglow_tc_prepare_spect": (C.c_int, [_P(WgModel), _P(WgTcWorkspace), _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    "fac_wn_start_tc": (C.c_int, [_P(WgModel), C.c_int, _fp, _P(WgTcWorkspace), C.c_int, C.c_int, C.c_int, _fp]),
+    "fac_wn_layer_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), C.c_int, C.c_int, _P(WgTcWorkspace), C.c_int,
+                                  C.c_int, C.c_int, _fp]),
+    "fac_waveglow_infer_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), _fp, _fp, _P(WgTcWorkspace), C.c_int, C.c_int,
+                                        C.c_int, _fp]),
     "fac_lstm_bidir_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "fac_taco_decoder_run": (C.c_int, [_P(TacoDecoderWeights), _fp, _fp, _fp, _fp, _P(TacoDecoderState), _fp, _fp,
                                        _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),

@@ -24,6 +24,12 @@ int wg_layer(const fac_wg_model*, int, int, const fac_wg_workspace*, int, int, c
 int wg_end(const fac_wg_model*, int, const float*, float*, int, int, cudaStream_t);
 int wg_infer(const fac_wg_model*, const float*, float*, const fac_wg_workspace*, int, int, cudaStream_t);
 
+int wg_tc_prepare_spect(const fac_wg_model*, const fac_wg_tc_workspace*, const float*, int, int, int, cudaStream_t);
+int wg_tc_start(const fac_wg_model*, int, const float*, const fac_wg_tc_workspace*, int, int, int, cudaStream_t);
+int wg_tc_layer(const fac_wg_model*, const fac_wg_tc_weights*, int, int, const fac_wg_tc_workspace*, int, int, int,
+                cudaStream_t);
+int wg_infer_tc(const fac_wg_model*, const fac_wg_tc_weights*, const float*, float*, const fac_wg_tc_workspace*, int,
+                int, int, cudaStream_t);
 int lstm_bidir(const float*, const float*, float*, int, int, int, cudaStream_t);
 int taco_decoder_run(const fac_taco_decoder_weights*, const float*, const float*, const int*, const unsigned char*,
                      const fac_taco_decoder_state*, float*, float*, float*, int, int, int, int, float, cudaStream_t);
@@ -63,6 +69,22 @@ int fac_waveglow_infer_f32(const fac_wg_model* m, const float* mel_cl, float* au
   return fac::wg_infer(m, mel_cl, audio, ws, B, F, (cudaStream_t)stream);
 }
 
+int fac_waveglow_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_workspace* ws, const float* mel_cl, int B,
+                                  int F, int nsplit, void* stream) {
+  return fac::wg_tc_prepare_spect(m, ws, mel_cl, B, F, nsplit, (cudaStream_t)stream);
+}
+int fac_wn_start_tc(const fac_wg_model* m, int flow, const float* audio, const fac_wg_tc_workspace* ws, int B, int Tg,
+                    int nsplit, void* stream) {
+  return fac::wg_tc_start(m, flow, audio, ws, B, Tg, nsplit, (cudaStream_t)stream);
+}
+int fac_wn_layer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int layer,
+                    const fac_wg_tc_workspace* ws, int B, int Tg, int nsplit, void* stream) {
+  return fac::wg_tc_layer(m, w, flow, layer, ws, B, Tg, nsplit, (cudaStream_t)stream);
+}
+int fac_waveglow_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* mel_cl, float* audio,
+                          const fac_wg_tc_workspace* ws, int B, int F, int nsplit, void* stream) {
+  return fac::wg_infer_tc(m, w, mel_cl, audio, ws, B, F, nsplit, (cudaStream_t)stream);
+}
 int fac_lstm_bidir_f32(const float* xp, const float* w_hh, float* out, int B, int T, int H, void* stream) {
   return fac::lstm_bidir(xp, w_hh, out, B, T, H, (cudaStream_t)stream);
 }

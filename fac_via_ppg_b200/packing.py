@@ -138,6 +138,7 @@ class PackedWaveGlow:
     @torch.no_grad()
     def load_state(self, sd):
         """Fill the flat buffer from a weight-norm-free WaveGlow state dict."""
+        self._tc = None
         cfg, lay, flat = self.cfg, self.layout, self.flat
         dev = flat.device
         wn = cfg["WN_config"]
@@ -182,6 +183,51 @@ class PackedWaveGlow:
                 b2 = get(p + f"res_skip_layers.{i}.bias")
                 lay.view(flat, f"{k}.{i}.res_skip_b")[: b2.numel()].copy_(b2)
         return self
+
+    # ------------------------------------------------------------------ tensor-core copies
+    def tc_layout(self):
+        """bf16 [N][K] copies of the WN GEMM weights (hi and lo halves of the split-bf16 scheme)."""
+        cfg = self.cfg
+        wn = cfg["WN_config"]
+        Cn, L, ks = wn["n_channels"], wn["n_layers"], wn["kernel_size"]
+        n_cond = cfg["n_mel_channels"] * cfg["n_group"]
+        lay = FlatLayout()
+        for k in range(cfg["n_flows"]):
+            for i in range(L):
+                n_rs = 2 * Cn if i < L - 1 else Cn
+                for part in ("hi", "lo"):
+                    lay.add(f"{k}.{i}.w1_{part}", (2 * Cn, ks * Cn + n_cond))
+                    lay.add(f"{k}.{i}.w2_{part}", (n_rs, Cn))
+        return lay
+
+    @torch.no_grad()
+    def tc_weights(self):
+        """Builds (once) the bf16 hi/lo weight buffer from the packed fp32 buffer and returns the
+        ``fac_wg_tc_weights`` pointer table.  Derived data: after a broadcast of ``flat`` every rank
+        derives its own copy locally."""
+        cached = getattr(self, "_tc", None)
+        if cached is not None:
+            return cached[1]
+        cfg, lay = self.cfg, self.layout
+        wn = cfg["WN_config"]
+        Cn, L = wn["n_channels"], wn["n_layers"]
+        tl = self.tc_layout()
+        flat16 = torch.zeros(tl.size, dtype=torch.bfloat16, device=self.flat.device)
+        table = _ext.WgTcWeights()
+        for k in range(cfg["n_flows"]):
+            for i in range(L):
+                n_rs = 2 * Cn if i < L - 1 else Cn
+                w1 = lay.view(self.flat, f"{k}.{i}.in_cond_w")[:, : 2 * Cn].t().contiguous()   # (2C, K1)
+                w2 = lay.view(self.flat, f"{k}.{i}.res_skip_w")[:, :n_rs].t().contiguous()     # (n_rs, C)
+                for name, w in (("w1", w1), ("w2", w2)):
+                    hi = w.to(torch.bfloat16)
+                    lo = (w - hi.float()).to(torch.bfloat16)
+                    tl.view(flat16, f"{k}.{i}.{name}_hi").copy_(hi)
+                    tl.view(flat16, f"{k}.{i}.{name}_lo").copy_(lo)
+                    getattr(table.flows[k], name + "_hi")[i] = tl.ptr(flat16, f"{k}.{i}.{name}_hi")
+                    getattr(table.flows[k], name + "_lo")[i] = tl.ptr(flat16, f"{k}.{i}.{name}_lo")
+        self._tc = (flat16, table)
+        return table
 
     @classmethod
     def from_state(cls, sd, cfg, device):

@@ -156,7 +156,24 @@ class WaveGlow(torch.nn.Module):
                 draws.append(torch.empty(batch, self.n_early_size, n_cols, device=device, dtype=dtype).normal_())
         return draws
 
-    precision = "fp32"     # exact-fp32 FFMA path
+    # Arithmetic of the WN layer GEMMs (>99 % of the FLOPs):
+    #   "fp32"   exact fp32 on the FFMA pipe (parity anchor)
+    #   "bf16x3" tcgen05 tensor cores, split-bf16 operands (hi+lo, 3 UMMAs per product), fp32
+    #            accumulate: fp32-grade result (<= 1e-5 RMS on the waveform vs the fp32 reference)
+    #   "bf16"   tcgen05 tensor cores, plain bf16 operands (BASELINE configs[2] precision)
+    PRECISIONS = ("fp32", "bf16x3", "bf16")
+    precision = "fp32"
+
+    def set_precision(self, precision):
+        if precision in (None, "auto"):
+            precision = "bf16x3"
+        if precision not in self.PRECISIONS:
+            raise ValueError("precision must be one of %s" % (self.PRECISIONS,))
+        self.precision = precision
+        return self
+
+    def _nsplit(self):
+        return {"fp32": 0, "bf16": 1, "bf16x3": 2}[self.precision]
 
     def _alloc_io(self, spect, sigma, noise):
         """Allocates the audio slot buffer (pre-filled with sigma*z), mel in channels-last
@@ -178,16 +195,23 @@ class WaveGlow(torch.nn.Module):
         if hi != 0:
             raise ValueError("noise draws do not cover n_group channels")
         mel_cl = spect.float().transpose(1, 2).contiguous()
-        Cn = self.WN[0].n_channels
-        bufs = {
-            "audio": audio, "mel_cl": mel_cl,
-            "spect": torch.empty(B, Tg, n_mel * G, device=dev, dtype=torch.float32),
-            "x": torch.empty(B, Tg, Cn, device=dev, dtype=torch.float32),
-            "acts": torch.empty(B, Tg, Cn, device=dev, dtype=torch.float32),
-            "skip": torch.empty(B, Tg, Cn, device=dev, dtype=torch.float32),
-        }
-        bufs["ws"] = _ext.WgWorkspace(bufs["spect"].data_ptr(), bufs["x"].data_ptr(), bufs["acts"].data_ptr(),
-                                      bufs["skip"].data_ptr())
+        Cn, n_cond = self.WN[0].n_channels, n_mel * G
+        f32 = lambda c: torch.empty(B, Tg, c, device=dev, dtype=torch.float32)      # noqa: E731
+        b16 = lambda c: torch.empty(B, Tg, c, device=dev, dtype=torch.bfloat16)     # noqa: E731
+        bufs = {"audio": audio, "mel_cl": mel_cl, "spect": f32(n_cond), "x": f32(Cn), "skip": f32(Cn)}
+        nsplit = self._nsplit()
+        if nsplit == 0:
+            bufs["acts"] = f32(Cn)
+            bufs["ws"] = _ext.WgWorkspace(bufs["spect"].data_ptr(), bufs["x"].data_ptr(), bufs["acts"].data_ptr(),
+                                          bufs["skip"].data_ptr())
+        else:
+            for name, c in (("spect_hi", n_cond), ("x_hi", Cn), ("acts_hi", Cn)):
+                bufs[name] = b16(c)
+                bufs[name[:-2] + "lo"] = b16(c) if nsplit == 2 else None
+            bufs["ws"] = _ext.WgTcWorkspace(
+                bufs["spect"].data_ptr(), bufs["spect_hi"].data_ptr(), _ext.ptr(bufs["spect_lo"]),
+                bufs["x"].data_ptr(), bufs["x_hi"].data_ptr(), _ext.ptr(bufs["x_lo"]),
+                bufs["acts_hi"].data_ptr(), _ext.ptr(bufs["acts_lo"]), bufs["skip"].data_ptr())
         return bufs, B, F, Tg
 
     @torch.no_grad()
@@ -206,9 +230,17 @@ class WaveGlow(torch.nn.Module):
         if B == 0 or F == 0:
             return spect.new_zeros(B, F * self.upsample.stride[0])
         bufs, B, F, Tg = self._alloc_io(spect, sigma, noise)
-        rc = lib.fac_waveglow_infer_f32(C.byref(packed.cmodel), bufs["mel_cl"].data_ptr(), bufs["audio"].data_ptr(),
-                                        C.byref(bufs["ws"]), B, F, _ext.current_stream())
-        _ext.check(rc, "fac_waveglow_infer_f32")
+        nsplit = self._nsplit()
+        if nsplit == 0:
+            rc = lib.fac_waveglow_infer_f32(C.byref(packed.cmodel), bufs["mel_cl"].data_ptr(),
+                                            bufs["audio"].data_ptr(), C.byref(bufs["ws"]), B, F,
+                                            _ext.current_stream())
+            _ext.check(rc, "fac_waveglow_infer_f32")
+        else:
+            rc = lib.fac_waveglow_infer_tc(C.byref(packed.cmodel), C.byref(packed.tc_weights()),
+                                           bufs["mel_cl"].data_ptr(), bufs["audio"].data_ptr(), C.byref(bufs["ws"]),
+                                           B, F, nsplit, _ext.current_stream())
+            _ext.check(rc, "fac_waveglow_infer_tc")
         return bufs["audio"].view(B, Tg * self.n_group).to(spect.dtype)
 
     @torch.no_grad()
@@ -222,18 +254,32 @@ class WaveGlow(torch.nn.Module):
         bufs, B, F, Tg = self._alloc_io(spect, 0.6, None)
         st = _ext.current_stream()
         m = C.byref(packed.cmodel)
-        _ext.check(lib.fac_waveglow_upsample_squeeze_f32(m, bufs["mel_cl"].data_ptr(), bufs["spect"].data_ptr(),
-                                                         B, F, st), "upsample")
+        ws = C.byref(bufs["ws"])
+        nsplit = self._nsplit()
+        if nsplit == 0:
+            _ext.check(lib.fac_waveglow_upsample_squeeze_f32(m, bufs["mel_cl"].data_ptr(), bufs["spect"].data_ptr(),
+                                                             B, F, st), "upsample")
+        else:
+            tcw = C.byref(packed.tc_weights())
+            _ext.check(lib.fac_waveglow_tc_prepare_spect(m, ws, bufs["mel_cl"].data_ptr(), B, F, nsplit, st),
+                       "prepare_spect")
         cfg = self.config()
         Cn, L, ks = cfg["WN_config"]["n_channels"], cfg["WN_config"]["n_layers"], cfg["WN_config"]["kernel_size"]
         n_cond = cfg["n_mel_channels"] * cfg["n_group"]
         pairs, macs = [], 0
         for k in reversed(range(self.n_flows)):
-            _ext.check(lib.fac_wn_start_f32(m, k, bufs["audio"].data_ptr(), bufs["x"].data_ptr(), B, Tg, st), "start")
+            if nsplit == 0:
+                _ext.check(lib.fac_wn_start_f32(m, k, bufs["audio"].data_ptr(), bufs["x"].data_ptr(), B, Tg, st),
+                           "start")
+            else:
+                _ext.check(lib.fac_wn_start_tc(m, k, bufs["audio"].data_ptr(), ws, B, Tg, nsplit, st), "start")
             for i in range(L):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                _ext.check(lib.fac_wn_layer_f32(m, k, i, C.byref(bufs["ws"]), B, Tg, st), "layer")
+                if nsplit == 0:
+                    _ext.check(lib.fac_wn_layer_f32(m, k, i, ws, B, Tg, st), "layer")
+                else:
+                    _ext.check(lib.fac_wn_layer_tc(m, tcw, k, i, ws, B, Tg, nsplit, st), "layer")
                 e1.record()
                 pairs.append((e0, e1))
                 macs += B * Tg * (2 * Cn * (ks * Cn + n_cond) + (2 * Cn if i < L - 1 else Cn) * Cn)
@@ -244,15 +290,25 @@ class WaveGlow(torch.nn.Module):
         n_launch = 2 * len(pairs)
         achieved = 2.0 * macs / (total_ms / 1e3) / 1e12
         peak = peaks["tflops_sustained"]
-        return {
-            "bound": "tensor", "kernel": "conv_gemm_f32_kernel (WN layer: in+cond GEMM -> gate, res/skip GEMM)",
+        executed = {0: 1, 1: 1, 2: 3}[nsplit]
+        kernel = {0: "conv_gemm_f32_kernel (FFMA)", 1: "wn_gemm_tc_kernel (tcgen05 bf16)",
+                  2: "wn_gemm_tc_kernel (tcgen05 split-bf16, 3 UMMAs per product)"}[nsplit]
+        roof = {
+            "bound": "tensor", "kernel": kernel + " -- WN layer: in+cond GEMM -> gate, res/skip GEMM",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
             "launches_timed": n_launch, "avg_launch_ms": total_ms / n_launch,
             "flop_per_launch": 2.0 * macs / n_launch, "traffic": None,
-            "note": "exact-fp32 FFMA path: its own pipe peak is 74.4 TFLOP/s (148 SM x 128 lanes x 2 x 1.965 GHz), "
-                    "frac_of_ffma_peak=%.3f" % (achieved / 74.4),
+            "executed_tensor_tflops": achieved * executed if nsplit else 0.0,
+            "executed_frac_of_peak": achieved * executed / peak if nsplit else 0.0,
         }
+        if nsplit == 0:
+            roof["note"] = ("exact-fp32 FFMA path: its own pipe peak is 74.4 TFLOP/s (148 SM x 128 lanes x 2 x "
+                            "1.965 GHz), frac_of_ffma_peak=%.3f" % (achieved / 74.4))
+        elif nsplit == 2:
+            roof["note"] = ("`achieved` counts ALGORITHMIC flops; the split-bf16 scheme executes 3 bf16 UMMAs per "
+                            "algorithmic product to reach fp32-grade results, so frac <= 1/3 by construction")
+        return roof
 
     def forward(self, forward_input):
         raise NotImplementedError("fac_via_ppg_b200 covers the inference path only (WaveGlow.infer); "

@@ -128,6 +128,38 @@ int fac_wn_end_coupling_f32(const fac_wg_model* m, int flow, const float* skip, 
 int fac_waveglow_infer_f32(const fac_wg_model* m, const float* mel_cl, float* audio,
                            const fac_wg_workspace* ws, int B, int F, void* stream);
 
+/* ---- WaveGlow WN layers on tcgen05 tensor cores -------------------------- */
+/* bf16 copies of the WN weights, [N][K] row-major (K contiguous): w1 = in_layer|cond_layer
+ * (N = 2C gate-interleaved like in_cond_w, K = 3C + n_cond ordered tap0|tap1|tap2|cond),
+ * w2 = res_skip (N = 2C or C, K = C).  *_hi = bf16(w), *_lo = bf16(w - hi) (split-bf16). */
+typedef struct fac_wg_tc_flow {
+  const void* w1_hi[FAC_MAX_LAYERS]; const void* w1_lo[FAC_MAX_LAYERS];
+  const void* w2_hi[FAC_MAX_LAYERS]; const void* w2_lo[FAC_MAX_LAYERS];
+} fac_wg_tc_flow;
+typedef struct fac_wg_tc_weights { fac_wg_tc_flow flows[FAC_MAX_FLOWS]; } fac_wg_tc_weights;
+
+/* Scratch of the tensor-core path for B utterances of T_g columns: fp32 masters (x, skip, the
+ * upsampler output) and the bf16 hi/lo operand copies the TMA loads read ((B,T_g,channels)
+ * channels-last).  The *_lo buffers may be NULL when nsplit == 1. */
+typedef struct fac_wg_tc_workspace {
+  float* spect_f32; void* spect_hi; void* spect_lo;
+  float* x; void* x_hi; void* x_lo;
+  void* acts_hi; void* acts_lo;
+  float* skip;
+} fac_wg_tc_workspace;
+
+/* nsplit = 1: bf16 operands; nsplit = 2: split-bf16 (3 UMMAs per product, fp32-grade result). */
+int fac_waveglow_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_workspace* ws, const float* mel_cl,
+                                  int B, int F, int nsplit, void* stream);
+int fac_wn_start_tc(const fac_wg_model* m, int flow, const float* audio, const fac_wg_tc_workspace* ws,
+                    int B, int Tg, int nsplit, void* stream);
+/* glow.py:158-174 for one layer: TMA-fed tcgen05 GEMM + gate epilogue, then res/skip GEMM. */
+int fac_wn_layer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int layer,
+                    const fac_wg_tc_workspace* ws, int B, int Tg, int nsplit, void* stream);
+/* Same contract as fac_waveglow_infer_f32 (glow.py:252-293), WN layers on the tensor cores. */
+int fac_waveglow_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* mel_cl, float* audio,
+                          const fac_wg_tc_workspace* ws, int B, int F, int nsplit, void* stream);
+
 /* ---- PPG -> Mel (Tacotron2 variant) ------------------------------------- */
 /* Recurrent part of the encoder's bidirectional LSTM (reference src/common/model.py:211-213,
  * 246-247).  xp is (B, T, 2*4H): x W_ih^T + b_ih + b_hh of the forward direction in columns

@@ -115,7 +115,8 @@ def test_infer_default_noise_follows_reference_draw_order():
     torch.manual_seed(123)
     a = model.infer(mel, sigma=0.7)
     torch.manual_seed(123)
-    noise = [torch.empty(2, 4, 80, device=DEV).normal_(), torch.empty(2, 2, 80, device=DEV).normal_()]
+    # small geometry: 4 flows, early output every 2 -> first draw has 6 channels, then 2 at k=2
+    noise = [torch.empty(2, 6, 80, device=DEV).normal_(), torch.empty(2, 2, 80, device=DEV).normal_()]
     b = model.infer(mel, sigma=0.7, noise=noise)
     assert torch.equal(a, b)
     ref = waveglow_oracle.waveglow_infer(synth.waveglow_state(cfg=cfg), cfg, mel.cpu(), 0.7,
@@ -132,7 +133,7 @@ def test_infer_with_weightnorm_checkpoint_flavour():
         torch.nn.init.normal_(wn.end.weight, std=0.05)
     model = model.to(DEV).eval()
     mel = synth.synthetic_mel(1, 3).to(DEV)
-    noise = [torch.randn(1, 4, 60, device=DEV), torch.randn(1, 2, 60, device=DEV)]
+    noise = [torch.randn(1, 6, 60, device=DEV), torch.randn(1, 2, 60, device=DEV)]
     a = model.infer(mel, 0.5, noise=noise)
     sd = {k: v.detach().cpu() for k, v in model.plain_state().items()}
     ref = waveglow_oracle.waveglow_infer(sd, cfg, mel.cpu(), 0.5, [z.cpu() for z in noise])

@@ -1,0 +1,109 @@
+"""GPU parity tests for the tensor-core (tcgen05 + TMA) WaveGlow path, through the C ABI.
+
+bf16x3 (split-bf16, fp32 accumulate) is held to the north-star tolerance for the fp32 config
+(<= 1e-4 RMS on the waveform vs the unmodified fp32 reference); plain bf16 is the precision
+BASELINE configs[2] names and is held to a stated looser bound."""
+import ctypes as C
+import os
+
+import pytest
+import torch
+
+from fac_via_ppg_b200 import _ext, synth
+from fac_via_ppg_b200.waveglow.glow import WaveGlow
+from oracle import waveglow_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RMS_TOL = {"bf16x3": 1e-4, "bf16": 3e-2}
+
+
+def rms(a, b):
+    return (a.double().cpu() - b.double().cpu()).pow(2).mean().sqrt().item()
+
+
+_models = {}
+
+
+def build_model(cfg, precision):
+    key = (id(cfg), precision)
+    if key not in _models:
+        model = WaveGlow.remove_weightnorm(WaveGlow(**cfg))
+        model.load_state_dict(synth.waveglow_state(cfg=cfg), strict=True)
+        _models[key] = model.to(DEV).eval().set_precision(precision)
+    return _models[key]
+
+
+@pytest.mark.parametrize("cfg_name,cols", [("small", 70), ("small", 300), ("full", 200)])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_tc_layer_matches_fp32_layer(cfg_name, cols, precision):
+    """One WN layer (flow 0, layers 0 and 3: dilation 1 and 8) on the tensor cores vs the exact-fp32
+    kernels on identical inputs: gated activations, residual stream and skip sum."""
+    cfg = synth.WAVEGLOW_CONFIG_SMALL if cfg_name == "small" else synth.WAVEGLOW_CONFIG
+    model = build_model(cfg, precision)
+    lib, packed = _ext.load(), model.packed()
+    nsplit = model._nsplit()
+    B, Cn, n_cond = 2, cfg["WN_config"]["n_channels"], 640
+    g = torch.Generator().manual_seed(cols)
+    x0 = torch.randn(B, cols, Cn, generator=g).to(DEV)
+    spect = (torch.randn(B, cols, n_cond, generator=g) * 2).to(DEV)
+    skip0 = torch.randn(B, cols, Cn, generator=g).to(DEV)
+    st = _ext.current_stream()
+    tol = 2e-4 if precision == "bf16x3" else 8e-2
+    for layer in (0, 3 if cfg["WN_config"]["n_layers"] > 3 else 2):
+        # exact fp32 reference kernels
+        xr, sr, ar = x0.clone(), skip0.clone(), torch.empty_like(x0)
+        ws = _ext.WgWorkspace(spect.data_ptr(), xr.data_ptr(), ar.data_ptr(), sr.data_ptr())
+        _ext.check(lib.fac_wn_layer_f32(C.byref(packed.cmodel), 0, layer, C.byref(ws), B, cols, st), "f32 layer")
+        # tensor-core kernels
+        xt, skt = x0.clone(), skip0.clone()
+        hi = lambda t: t.to(torch.bfloat16)                                   # noqa: E731
+        lo = lambda t: (t - t.to(torch.bfloat16).float()).to(torch.bfloat16)  # noqa: E731
+        x_hi, x_lo, s_hi, s_lo = hi(xt), lo(xt), hi(spect), lo(spect)
+        a_hi, a_lo = torch.zeros_like(x_hi), torch.zeros_like(x_hi)
+        wst = _ext.WgTcWorkspace(None, s_hi.data_ptr(), s_lo.data_ptr(), xt.data_ptr(), x_hi.data_ptr(),
+                                 x_lo.data_ptr(), a_hi.data_ptr(), a_lo.data_ptr(), skt.data_ptr())
+        rc = lib.fac_wn_layer_tc(C.byref(packed.cmodel), C.byref(packed.tc_weights()), 0, layer, C.byref(wst), B, cols,
+                                 nsplit, st)
+        _ext.check(rc, "tc layer")
+        torch.cuda.synchronize()
+        acts = a_hi.float() + (a_lo.float() if nsplit == 2 else 0)
+        assert (acts - ar).abs().max().item() <= tol, ("acts", layer)
+        assert (xt - xr).abs().max().item() <= tol, ("x", layer)
+        assert (skt - sr).abs().max().item() <= tol, ("skip", layer)
+        if layer < cfg["WN_config"]["n_layers"] - 1:        # the bf16 operand copies follow the fp32 master
+            back = x_hi.float() + (x_lo.float() if nsplit == 2 else 0)
+            assert (back - xt).abs().max().item() <= (1e-4 if nsplit == 2 else 5e-2)
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("name", ["waveglow_small_b2_f6.pt", "waveglow_full_b2_f5.pt",
+                                  "waveglow_full_b1_f88_sigma0.pt"])
+def test_tc_infer_matches_reference_golden(golden_dir, name, precision):
+    g = torch.load(os.path.join(golden_dir, name))
+    model = build_model(g["cfg"], precision)
+    mel = synth.synthetic_mel(g["batch"], g["frames"], seed=g["mel_seed"]).to(DEV)
+    audio = model.infer(mel, sigma=g["sigma"], noise=[z.to(DEV) for z in g["noise"]])
+    assert audio.shape == g["audio"].shape
+    err = rms(audio, g["audio"])
+    print("%s %s rms %.3e" % (name, precision, err))
+    assert err <= RMS_TOL[precision]
+
+
+def test_tc_full_size_prefix_locality_and_independence():
+    """BASELINE configs[1] size (8 x 10 s) on the tensor cores: batch rows are independent
+    (bit-identical alone vs in the batch) and the first columns match the fp32 oracle on a prefix."""
+    cfg = synth.WAVEGLOW_CONFIG
+    model = build_model(cfg, "bf16x3")
+    B, F, Fp = 8, synth.frames_for_seconds(10.0), 240
+    mel = synth.synthetic_mel(B, F, seed=31).to(DEV)
+    torch.manual_seed(17)
+    noise = model.noise_like_reference(B, F * 20, DEV, torch.float32)
+    full = model.infer(mel, 0.6, noise=noise)
+    assert full.shape == (B, F * 160) and torch.isfinite(full).all()
+    alone = model.infer(mel[:1].contiguous(), 0.6, noise=[z[:1].contiguous() for z in noise])
+    assert torch.equal(alone[0], full[0])
+    ref = waveglow_oracle.waveglow_infer(synth.waveglow_state(cfg=cfg), cfg, mel[:1, :, :Fp].cpu(), 0.6,
+                                         [z[:1, :, :Fp * 20].cpu() for z in noise])
+    safe_cols = Fp * 20 - 12 * 255 - 8 * 20
+    assert rms(full[0, :safe_cols * 8], ref[0, :safe_cols * 8]) <= 1e-4
