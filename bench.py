@@ -248,7 +248,9 @@ def main():
     if rank == 0:
         sampler.start()
     lib.fac_reset_launch_count()
+    torch.cuda.nvtx.range_push("fac_timed")      # ncu --nvtx --nvtx-include "fac_timed/" isolates this region
     ms = timed(step_resident, args.steps)
+    torch.cuda.nvtx.range_pop()
     launches = lib.fac_launch_count()
     clocks = sampler.stop() if rank == 0 else None
 

@@ -53,7 +53,8 @@ class WgWorkspace(C.Structure):
 
 class WgTcFlow(C.Structure):
     _fields_ = [("w1_hi", _fp * FAC_MAX_LAYERS), ("w1_lo", _fp * FAC_MAX_LAYERS),
-                ("w2_hi", _fp * FAC_MAX_LAYERS), ("w2_lo", _fp * FAC_MAX_LAYERS)]
+                ("w2_hi", _fp * FAC_MAX_LAYERS), ("w2_lo", _fp * FAC_MAX_LAYERS),
+                ("wc", _fp * FAC_MAX_LAYERS), ("res_b", _fp * FAC_MAX_LAYERS), ("out_bias", _fp)]
 
 
 class WgTcWeights(C.Structure):
@@ -61,8 +62,8 @@ class WgTcWeights(C.Structure):
 
 
 class WgTcWorkspace(C.Structure):
-    _fields_ = [(n, _fp) for n in ("spect_f32", "spect_hi", "spect_lo", "x", "x_hi", "x_lo", "acts_hi", "acts_lo",
-                                   "skip")]
+    _fields_ = [(n, _fp) for n in ("spect_f32", "spect_hi", "spect_lo", "x_hi", "x_lo", "acts_hi", "acts_lo",
+                                   "out8")]
 
 
 class TacoDecoderWeights(C.Structure):
@@ -93,8 +94,10 @@ SIGNATURES = {
     "fac_wn_start_tc": (C.c_int, [_P(WgModel), C.c_int, _fp, _P(WgTcWorkspace), C.c_int, C.c_int, C.c_int, _fp]),
     "fac_wn_layer_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), C.c_int, C.c_int, _P(WgTcWorkspace), C.c_int,
                                   C.c_int, C.c_int, _fp]),
+    "fac_wn_end_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), C.c_int, _fp, _fp, C.c_int, C.c_int, _fp]),
     "fac_waveglow_infer_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), _fp, _fp, _P(WgTcWorkspace), C.c_int, C.c_int,
                                         C.c_int, _fp]),
+    "fac_tc_set_profile_buffer": (None, [_fp]),
     "fac_lstm_bidir_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "fac_taco_decoder_run": (C.c_int, [_P(TacoDecoderWeights), _fp, _fp, _fp, _fp, _P(TacoDecoderState), _fp, _fp,
                                        _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),

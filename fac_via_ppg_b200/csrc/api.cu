@@ -30,6 +30,8 @@ int wg_tc_layer(const fac_wg_model*, const fac_wg_tc_weights*, int, int, const f
                 cudaStream_t);
 int wg_infer_tc(const fac_wg_model*, const fac_wg_tc_weights*, const float*, float*, const fac_wg_tc_workspace*, int,
                 int, int, cudaStream_t);
+int wg_tc_end(const fac_wg_model*, const fac_wg_tc_weights*, int, const float*, float*, int, int, cudaStream_t);
+void tc_set_prof(long long*);
 int lstm_bidir(const float*, const float*, float*, int, int, int, cudaStream_t);
 int taco_decoder_run(const fac_taco_decoder_weights*, const float*, const float*, const int*, const unsigned char*,
                      const fac_taco_decoder_state*, float*, float*, float*, int, int, int, int, float, cudaStream_t);
@@ -81,10 +83,15 @@ int fac_wn_layer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow,
                     const fac_wg_tc_workspace* ws, int B, int Tg, int nsplit, void* stream) {
   return fac::wg_tc_layer(m, w, flow, layer, ws, B, Tg, nsplit, (cudaStream_t)stream);
 }
+int fac_wn_end_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, const float* out8, float* audio, int B,
+                  int Tg, void* stream) {
+  return fac::wg_tc_end(m, w, flow, out8, audio, B, Tg, (cudaStream_t)stream);
+}
 int fac_waveglow_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* mel_cl, float* audio,
                           const fac_wg_tc_workspace* ws, int B, int F, int nsplit, void* stream) {
   return fac::wg_infer_tc(m, w, mel_cl, audio, ws, B, F, nsplit, (cudaStream_t)stream);
 }
+void fac_tc_set_profile_buffer(long long* device_buf) { fac::tc_set_prof(device_buf); }
 int fac_lstm_bidir_f32(const float* xp, const float* w_hh, float* out, int B, int T, int H, void* stream) {
   return fac::lstm_bidir(xp, w_hh, out, B, T, H, (cudaStream_t)stream);
 }

@@ -1,18 +1,22 @@
 // WaveGlow WN layer on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), reference
-// src/waveglow/glow.py:158-174.
+// src/waveglow/glow.py:158-175.
 //
 // Each layer is two implicit GEMMs over 128-column time tiles:
-//   G1: pre[128 x 2C]  = [x(t-d) | x(t) | x(t+d) | spect(t)] (K = 3C + n_cond) * W1^T, fused gate
-//                         tanh(.)*sigmoid(.) epilogue  -> acts
-//   G2: rs [128 x 2C|C] = acts (K = C) * W2^T, fused residual / skip epilogue -> x, skip
-// Operands are bf16 in channels-last HBM layout and reach shared memory through TMA (the
-// dilated taps are just shifted box coordinates; rows outside [0, T) are zero-filled by the
-// TMA unit, which is exactly Conv1d's zero padding).  Accumulation is fp32 in tensor memory:
-// one 128 x 512 tile fills the 512 TMEM columns.  Precision modes:
+//   G1: pre[128 x 2C] = [x(t-d) | x(t) | x(t+d) | spect(t)] (K = 3C + n_cond) * W1^T
+//       epilogue: gate tanh(.)*sigmoid(.) (glow.py:33-40) -> acts (bf16 hi/lo), and the skip path
+//       collapsed algebraically: `end` is linear in the skip sum (glow.py:171-175), so
+//       end(sum_i skip_i) = sum_i (W_end W_skip_i) acts_i + const; each layer adds its 8-channel
+//       contribution  out8 += Wc_i acts  (fp32 FFMA on the exact gate outputs).  The (B,T,C) skip
+//       tensor and half of the res_skip GEMM disappear.
+//   G2: x_new[128 x C] = [acts | x] (K = 2C) * [W_res | I]^T  -- the residual add (glow.py:166) is
+//       done BY the tensor core through an identity block, so the epilogue has no global loads: it only
+//       re-splits the fp32 accumulator into the bf16 hi/lo operand copies of the next layer.
+// Operands are bf16 in channels-last HBM layout and reach shared memory through TMA (dilated taps
+// are shifted box coordinates; rows outside [0, T) are zero-filled by the TMA unit = Conv1d padding).
+// Accumulation is fp32 in tensor memory.  Precision modes:
 //   nsplit = 1  plain bf16 operands                                  (1 UMMA per product)
 //   nsplit = 2  split-bf16: v = hi + lo, a*w ~= ah*wh + al*wh + ah*wl (3 UMMAs per product),
-//               ~2^-16 relative operand error, fp32 accumulate: matches the fp32 reference to
-//               ~1e-5 RMS on the waveform (tests/test_waveglow_tc_gpu.py).
+//               ~2^-16 relative operand error, fp32 accumulate: fp32-grade results.
 // Warp roles (192 threads, persistent over tiles, 1 CTA / SM): warp 0 = TMA producer,
 // warp 1 = UMMA issuer (one elected lane), warps 2-5 = epilogue (one TMEM lane quarter each).
 #include "fac_common.cuh"
@@ -30,12 +34,16 @@ constexpr int TC_STAGES = 5;
 constexpr int TC_NMAX = 512;     // accumulator columns per tile (all of TMEM)
 constexpr int TC_NHALF = 256;    // N of one UMMA
 constexpr int TC_THREADS = 192;
+constexpr int TC_NOUT = 8;       // channels of the collapsed skip path (= max 2*n_half)
+constexpr int TC_CMAX = 256;     // max WN channels (Wc staging)
 constexpr int A_BYTES = TC_BM * TC_ROWB;       // 4 KB
 constexpr int W_BYTES = TC_NMAX * TC_ROWB;     // 16 KB (two halves of 8 KB)
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;   // hi + lo of both operands = 40 KB
-constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int TC_BAR_BYTES = 256;
+constexpr int TC_WC_BYTES = TC_NOUT * TC_CMAX * 4;       // 8 KB
+constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + TC_BAR_BYTES + TC_WC_BYTES + 1024 /*alignment slack*/;
 
-enum { TC_GATE = 0, TC_RES_SKIP = 1 };
+enum { TC_GATE = 0, TC_RESIDUAL = 1 };
 
 struct TcSrc {
   int channels, taps, dilation, center;
@@ -44,15 +52,15 @@ struct TcSrc {
 struct TcParams {
   int n_src;
   TcSrc src[2];
-  int n_total, k_steps, T, B, tiles_per_batch, n_tiles, nsplit, mode, C;
+  int n_total, k_steps, wlo_k_steps;   // K steps [0, wlo_k_steps) also use the W_lo term (split mode)
+  int T, B, tiles_per_batch, n_tiles, nsplit, mode, C;
   const float* bias;
-  __nv_bfloat16* acts_hi;
-  __nv_bfloat16* acts_lo;
-  float* x;
-  __nv_bfloat16* x_hi;
-  __nv_bfloat16* x_lo;
-  float* skip;
-  int n_split_cols, accumulate_skip;
+  __nv_bfloat16* out_hi;   // gate: acts; residual: x   (B, T, C)
+  __nv_bfloat16* out_lo;
+  const float* wc;         // gate: [TC_NOUT][C] collapsed skip weights (fp32)
+  float* out8;             // gate: (B, T, TC_NOUT) running end() pre-activation
+  int accumulate_out8;
+  long long* prof;         // optional [grid][8] cycle counters
 };
 
 __device__ __forceinline__ float ex2_approx(float v) {
@@ -80,6 +88,7 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
   uint64_t* tmem_full = empty + TC_STAGES;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  float* wc_s = reinterpret_cast<float*>(smem + TC_STAGES * STAGE_BYTES + TC_BAR_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_halves = (p.n_total + TC_NHALF - 1) / TC_NHALF;
@@ -96,6 +105,8 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
     tma_prefetch_desc(&a0_hi);
     tma_prefetch_desc(&w_hi);
   }
+  if (p.mode == TC_GATE)
+    for (int i = threadIdx.x; i < TC_NOUT * p.C; i += TC_THREADS) wc_s[i] = __ldg(p.wc + i);
   if (warp == 1) tmem_alloc(tmem_slot, TC_NMAX);
   tc_fence_before();
   __syncthreads();
@@ -105,10 +116,10 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      const uint32_t stage_bytes =
-          (uint32_t)(p.nsplit * (A_BYTES + n_halves * n_half_cols * TC_ROWB));
+      const uint32_t w_bytes = (uint32_t)(n_halves * n_half_cols * TC_ROWB);
       int stage = 0;
       uint32_t phase = 0;
+      long long prod_wait = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_batch;
         const int t0 = (tile % p.tiles_per_batch) * TC_BM;
@@ -119,14 +130,17 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
           for (int tap = 0; tap < p.src[s].taps; ++tap) {
             const int row0 = t0 + tap * p.src[s].dilation - p.src[s].center;
             for (int c0 = 0; c0 < p.src[s].channels; c0 += TC_BK, ++ks) {
+              const bool use_wlo = p.nsplit == 2 && ks < p.wlo_k_steps;
+              const long long w0 = clock64();
               mbar_wait(&empty[stage], phase ^ 1);
+              prod_wait += clock64() - w0;
               uint8_t* st = smem + stage * STAGE_BYTES;
-              mbar_arrive_expect_tx(&full[stage], stage_bytes);
+              mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.nsplit * A_BYTES) + w_bytes * (use_wlo ? 2u : 1u));
               tma_load_3d(st, mh, &full[stage], c0, row0, b);
               if (p.nsplit == 2) tma_load_3d(st + A_BYTES, ml, &full[stage], c0, row0, b);
               for (int h = 0; h < n_halves; ++h) {
                 tma_load_2d(st + 2 * A_BYTES + h * (W_BYTES / 2), &w_hi, &full[stage], ks * TC_BK, h * TC_NHALF);
-                if (p.nsplit == 2)
+                if (use_wlo)
                   tma_load_2d(st + 2 * A_BYTES + W_BYTES + h * (W_BYTES / 2), &w_lo, &full[stage], ks * TC_BK,
                               h * TC_NHALF);
               }
@@ -135,6 +149,7 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
           }
         }
       }
+      if (p.prof) p.prof[blockIdx.x * 8 + 0] = prod_wait;
     }
   } else if (warp == 1) {
     // ===================================================== UMMA issuer
@@ -143,11 +158,17 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long wait_tmem = 0, wait_full = 0;
+      const long long k_start = clock64();
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        long long w0 = clock64();
         mbar_wait(tmem_empty, (uint32_t)((it & 1) ^ 1));   // epilogue has drained the previous tile
+        wait_tmem += clock64() - w0;
         tc_fence_after();
         for (int ks = 0; ks < p.k_steps; ++ks) {
+          w0 = clock64();
           mbar_wait(&full[stage], phase);
+          wait_full += clock64() - w0;
           tc_fence_after();
           const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t a_h = make_smem_desc(st, TC_ROWB);
@@ -157,9 +178,11 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
             const uint64_t w_h = make_smem_desc(st + 2 * A_BYTES + h * (W_BYTES / 2), TC_ROWB);
             umma_bf16(d, a_h, w_h, idesc, ks > 0 ? 1u : 0u);
             if (p.nsplit == 2) {
-              const uint64_t w_l = make_smem_desc(st + 2 * A_BYTES + W_BYTES + h * (W_BYTES / 2), TC_ROWB);
               umma_bf16(d, a_l, w_h, idesc, 1u);
-              umma_bf16(d, a_h, w_l, idesc, 1u);
+              if (ks < p.wlo_k_steps) {
+                const uint64_t w_l = make_smem_desc(st + 2 * A_BYTES + W_BYTES + h * (W_BYTES / 2), TC_ROWB);
+                umma_bf16(d, a_h, w_l, idesc, 1u);
+              }
             }
           }
           umma_commit(&empty[stage]);   // frees the smem slot when these UMMAs have read it
@@ -167,20 +190,32 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
         }
         umma_commit(tmem_full);         // accumulator complete -> epilogue
       }
+      if (p.prof) {
+        p.prof[blockIdx.x * 8 + 1] = wait_tmem;
+        p.prof[blockIdx.x * 8 + 2] = wait_full;
+        p.prof[blockIdx.x * 8 + 3] = clock64() - k_start;
+      }
     }
   } else {
     // ===================================================== epilogue (4 warps, one TMEM lane quarter each)
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int it = 0;
+    long long epi_wait = 0, epi_busy = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_per_batch;
       const int t = (tile % p.tiles_per_batch) * TC_BM + row;
       const bool valid = t < p.T;
       const long long col = (long long)b * p.T + t;
+      const long long e0 = clock64();
       mbar_wait(tmem_full, (uint32_t)(it & 1));
+      const long long e1 = clock64();
+      epi_wait += e1 - e0;
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+      float acc8[TC_NOUT];
+#pragma unroll
+      for (int o = 0; o < TC_NOUT; ++o) acc8[o] = 0.f;
       for (int n0 = 0; n0 < p.n_total; n0 += 32) {
         uint32_t r[32];
         tmem_ld32(trow + n0, r);
@@ -200,57 +235,71 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
           float g[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) g[j] = gate_act(v[2 * j], v[2 * j + 1]);
+          const int ch0 = n0 >> 1;
+          // collapsed skip path: out8 += Wc[:, ch0:ch0+16] g   (fp32, exact gate outputs)
+#pragma unroll
+          for (int o = 0; o < TC_NOUT; ++o) {
+            const float4* wrow = reinterpret_cast<const float4*>(wc_s + o * p.C + ch0);
+            float a = acc8[o];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 w4 = wrow[j4];
+              a = fmaf(w4.x, g[4 * j4 + 0], a);
+              a = fmaf(w4.y, g[4 * j4 + 1], a);
+              a = fmaf(w4.z, g[4 * j4 + 2], a);
+              a = fmaf(w4.w, g[4 * j4 + 3], a);
+            }
+            acc8[o] = a;
+          }
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) split2(g[2 * j], g[2 * j + 1], hi[j], lo[j]);
-          const long long off = col * p.C + (n0 >> 1);
-          uint4* dh = reinterpret_cast<uint4*>(p.acts_hi + off);
+          const long long off = col * p.C + ch0;
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
           dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
           if (p.nsplit == 2) {
-            uint4* dl = reinterpret_cast<uint4*>(p.acts_lo + off);
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
             dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
           }
-        } else if (n0 < p.n_split_cols) {
-          // residual stream: x += rs[:, :C] (glow.py:166) + refresh the bf16 operand copies
-          const long long off = col * p.C + n0;
-          float4* xp = reinterpret_cast<float4*>(p.x + off);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = xp[j];
-            o.x += v[4 * j + 0]; o.y += v[4 * j + 1]; o.z += v[4 * j + 2]; o.w += v[4 * j + 3];
-            xp[j] = o;
-            v[4 * j + 0] = o.x; v[4 * j + 1] = o.y; v[4 * j + 2] = o.z; v[4 * j + 3] = o.w;
-          }
+        } else {
+          // residual stream x_new = x + res (glow.py:166), already summed by the identity block:
+          // refresh the bf16 operand copies the next layer's TMA loads read
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-          uint4* dh = reinterpret_cast<uint4*>(p.x_hi + off);
+          const long long off = col * p.C + n0;
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
 #pragma unroll
           for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
           if (p.nsplit == 2) {
-            uint4* dl = reinterpret_cast<uint4*>(p.x_lo + off);
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
 #pragma unroll
             for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
           }
-        } else {
-          // skip sum (glow.py:167-174)
-          float4* sp = reinterpret_cast<float4*>(p.skip + col * p.C + (n0 - p.n_split_cols));
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (p.accumulate_skip) {
-              const float4 old = sp[j];
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            sp[j] = o;
-          }
         }
+      }
+      if (p.mode == TC_GATE && valid) {
+        float4* o8 = reinterpret_cast<float4*>(p.out8 + col * TC_NOUT);
+        float4 o0 = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
+        float4 o1 = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
+        if (p.accumulate_out8) {
+          const float4 p0 = o8[0], p1 = o8[1];
+          o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+          o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+        }
+        o8[0] = o0;
+        o8[1] = o1;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty);
+      epi_busy += clock64() - e1;
+    }
+    if (p.prof && warp == 2 && lane == 0) {
+      p.prof[blockIdx.x * 8 + 4] = epi_wait;
+      p.prof[blockIdx.x * 8 + 5] = epi_busy;
     }
   }
   tc_fence_before();
@@ -272,11 +321,11 @@ __global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* _
   if (lo) reinterpret_cast<uint2*>(lo)[i] = make_uint2(l0, l1);
 }
 
-// x = start(audio_0) (glow.py:156) in fp32 plus its bf16 operand copies.
+// x = start(audio_0) (glow.py:156), written as the bf16 operand copies of the first layer.
 __global__ void wn_start_tc_kernel(const float* __restrict__ audio, const float* __restrict__ w,
-                                   const float* __restrict__ bias, float* __restrict__ x,
-                                   __nv_bfloat16* __restrict__ x_hi, __nv_bfloat16* __restrict__ x_lo,
-                                   long long n_cols, int C, int n_group, int off, int n_half) {
+                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ x_hi,
+                                   __nv_bfloat16* __restrict__ x_lo, long long n_cols, int C, int n_group, int off,
+                                   int n_half) {
   const int c4 = C >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_cols * c4) return;
@@ -291,12 +340,54 @@ __global__ void wn_start_tc_kernel(const float* __restrict__ audio, const float*
     o.z = fmaf(a, wv.z, o.z);
     o.w = fmaf(a, wv.w, o.w);
   }
-  *reinterpret_cast<float4*>(x + col * C + c) = o;
   uint32_t h0, l0, h1, l1;
   split2(o.x, o.y, h0, l0);
   split2(o.z, o.w, h1, l1);
   *reinterpret_cast<uint2*>(x_hi + col * C + c) = make_uint2(h0, h1);
   if (x_lo) *reinterpret_cast<uint2*>(x_lo + col * C + c) = make_uint2(l0, l1);
+}
+
+// out = out8 + bias8 is end(skip sum) (glow.py:175); b, s = halves (glow.py:278-279);
+// a1 <- (a1 - b) / exp(s) (glow.py:280); z <- W^-1 [a0; a1] (glow.py:283, 96).  One thread per column.
+__global__ void wn_end_tc_kernel(const float* __restrict__ out8, const float* __restrict__ bias8,
+                                 const float* __restrict__ w_inv, float* __restrict__ audio, long long n_cols,
+                                 int n_group, int n_rem, int n_half) {
+  const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= n_cols) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(out8 + col * TC_NOUT));
+  const float4 bq = __ldg(reinterpret_cast<const float4*>(out8 + col * TC_NOUT) + 1);
+  const float o[TC_NOUT] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+  const int off = n_group - n_rem;
+  float* acol = audio + col * n_group + off;
+  float y[TC_NOUT];
+#pragma unroll
+  for (int j = 0; j < TC_NOUT; ++j) {
+    y[j] = 0.f;
+    if (j < n_rem) {
+      const float av = acol[j];
+      if (j < n_half) {
+        y[j] = av;
+      } else {
+        float bshift = 0.f, s = 0.f;
+#pragma unroll
+        for (int k = 0; k < TC_NOUT; ++k) {     // static indexing keeps o[] in registers
+          if (k == j - n_half) bshift = o[k] + __ldg(bias8 + k);
+          if (k == j) s = o[k] + __ldg(bias8 + k);
+        }
+        y[j] = (av - bshift) / expf(s);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TC_NOUT; ++i) {
+    if (i < n_rem) {
+      float z = 0.f;
+#pragma unroll
+      for (int j = 0; j < TC_NOUT; ++j)
+        if (j < n_rem) z = fmaf(__ldg(w_inv + i * n_rem + j), y[j], z);
+      acol[i] = z;
+    }
+  }
 }
 
 // ---------------------------------------------------------------- host side
@@ -371,27 +462,31 @@ int launch_tc(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st) {
   return check_launch("wn_gemm_tc_kernel");
 }
 
+long long* g_tc_prof = nullptr;
+
 }  // namespace
+
+void tc_set_prof(long long* p) { g_tc_prof = p; }
 
 int wg_check_model(const fac_wg_model* m);
 int wg_upsample_squeeze(const fac_wg_model* m, const float* mel_cl, float* spect, int B, int F, cudaStream_t st);
-int wg_end(const fac_wg_model* m, int flow, const float* skip, float* audio, int B, int Tg, cudaStream_t st);
 
 static int tc_check(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac_wg_tc_workspace* ws, int nsplit) {
   if (int rc = wg_check_model(m)) return rc;
   FAC_REQUIRE(w && ws, "tensor-core path: NULL weights/workspace");
   FAC_REQUIRE(nsplit == 1 || nsplit == 2, "tensor-core path: nsplit must be 1 (bf16) or 2 (split-bf16), got %d", nsplit);
   const int C = m->n_channels, n_cond = m->n_mel * m->n_group;
-  FAC_REQUIRE(C % 16 == 0 && n_cond % 16 == 0 && 2 * C <= TC_NMAX,
-              "tensor-core path: needs n_channels %% 16 == 0, n_cond %% 16 == 0 and 2*n_channels <= %d", TC_NMAX);
-  FAC_REQUIRE(ws->spect_hi && ws->x && ws->x_hi && ws->acts_hi && ws->skip, "tensor-core path: workspace incomplete");
+  FAC_REQUIRE(C % 16 == 0 && n_cond % 16 == 0 && 2 * C <= TC_NMAX && C <= TC_CMAX,
+              "tensor-core path: needs n_channels %% 16 == 0 (<= %d) and n_cond %% 16 == 0", TC_CMAX);
+  FAC_REQUIRE(m->n_group <= TC_NOUT, "tensor-core path: n_group %d > %d", m->n_group, TC_NOUT);
+  FAC_REQUIRE(ws->spect_hi && ws->x_hi && ws->acts_hi && ws->out8, "tensor-core path: workspace incomplete");
   if (nsplit == 2) FAC_REQUIRE(ws->spect_lo && ws->x_lo && ws->acts_lo, "tensor-core path: lo buffers missing");
   return 0;
 }
 
 int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_workspace* ws, const float* mel_cl, int B, int F,
                         int nsplit, cudaStream_t st) {
-  FAC_REQUIRE(ws && ws->spect_f32, "tensor-core path: spect_f32 scratch missing");
+  FAC_REQUIRE(ws && ws->spect_f32 && ws->spect_hi, "tensor-core path: spect scratch missing");
   if (int rc = wg_upsample_squeeze(m, mel_cl, ws->spect_f32, B, F, st)) return rc;
   const long long n4 = (long long)B * F * (m->hop / m->n_group) * m->n_mel * m->n_group / 4;
   split_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
@@ -403,15 +498,29 @@ int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_workspace* ws, co
 
 int wg_tc_start(const fac_wg_model* m, int flow, const float* audio, const fac_wg_tc_workspace* ws, int B, int Tg,
                 int nsplit, cudaStream_t st) {
+  if (int rc = wg_check_model(m)) return rc;
+  FAC_REQUIRE(flow >= 0 && flow < m->n_flows && ws && ws->x_hi, "wn_start_tc: bad arguments");
   const fac_wg_flow& f = m->flows[flow];
   const long long n_cols = (long long)B * Tg;
   const long long total = n_cols * (m->n_channels / 4);
   wn_start_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      audio, f.start_w, f.start_b, ws->x, reinterpret_cast<__nv_bfloat16*>(ws->x_hi),
+      audio, f.start_w, f.start_b, reinterpret_cast<__nv_bfloat16*>(ws->x_hi),
       nsplit == 2 ? reinterpret_cast<__nv_bfloat16*>(ws->x_lo) : nullptr, n_cols, m->n_channels, m->n_group,
       m->n_group - f.n_rem, f.n_half);
   count_launch();
   return check_launch("wn_start_tc_kernel");
+}
+
+int wg_tc_end(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, const float* out8, float* audio, int B,
+              int Tg, cudaStream_t st) {
+  if (int rc = wg_check_model(m)) return rc;
+  FAC_REQUIRE(flow >= 0 && flow < m->n_flows && w && out8 && audio, "wn_end_tc: bad arguments");
+  const fac_wg_flow& f = m->flows[flow];
+  const long long n_cols = (long long)B * Tg;
+  wn_end_tc_kernel<<<(unsigned)((n_cols + 255) / 256), 256, 0, st>>>(out8, w->flows[flow].out_bias, f.w_inv, audio,
+                                                                    n_cols, m->n_group, f.n_rem, f.n_half);
+  count_launch();
+  return check_launch("wn_end_tc_kernel");
 }
 
 int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int layer, const fac_wg_tc_workspace* ws,
@@ -431,7 +540,8 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
   p.n_tiles = B * p.tiles_per_batch;
   p.nsplit = nsplit;
   p.C = C;
-  // ---- G1: [x taps | spect] -> gate -> acts
+  p.prof = g_tc_prof;
+  // ---- G1: [x taps | spect] -> gate -> acts, out8 += Wc acts
   const int K1 = ks * C + n_cond;
   if (int rc = make_act_map(&maps[0], ws->x_hi, B, Tg, C)) return rc;
   if (int rc = make_act_map(&maps[1], nsplit == 2 ? ws->x_lo : ws->x_hi, B, Tg, C)) return rc;
@@ -444,31 +554,36 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
   p.src[1] = TcSrc{n_cond, 1, 0, 0};
   p.n_total = 2 * C;
   p.k_steps = K1 / TC_BK;
+  p.wlo_k_steps = p.k_steps;
   p.mode = TC_GATE;
   p.bias = f.in_cond_b[layer];
-  p.acts_hi = reinterpret_cast<__nv_bfloat16*>(ws->acts_hi);
-  p.acts_lo = reinterpret_cast<__nv_bfloat16*>(ws->acts_lo);
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(ws->acts_hi);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(ws->acts_lo);
+  p.wc = wf.wc[layer];
+  p.out8 = ws->out8;
+  p.accumulate_out8 = layer > 0;
   if (int rc = launch_tc(maps, p, st)) return rc;
-  // ---- G2: acts -> res/skip
-  const int n_rs = last ? C : 2 * C;
+  if (last) return 0;   // the last layer feeds the skip path only (glow.py:168-169)
+  // ---- G2: x <- [acts | x] [W_res | I]^T + b_res
   if (int rc = make_act_map(&maps[0], ws->acts_hi, B, Tg, C)) return rc;
   if (int rc = make_act_map(&maps[1], nsplit == 2 ? ws->acts_lo : ws->acts_hi, B, Tg, C)) return rc;
-  maps[2] = maps[0];
-  maps[3] = maps[1];
-  if (int rc = make_weight_map(&maps[4], wf.w2_hi[layer], n_rs, C)) return rc;
-  if (int rc = make_weight_map(&maps[5], nsplit == 2 ? wf.w2_lo[layer] : wf.w2_hi[layer], n_rs, C)) return rc;
-  p.n_src = 1;
+  if (int rc = make_act_map(&maps[2], ws->x_hi, B, Tg, C)) return rc;
+  if (int rc = make_act_map(&maps[3], nsplit == 2 ? ws->x_lo : ws->x_hi, B, Tg, C)) return rc;
+  if (int rc = make_weight_map(&maps[4], wf.w2_hi[layer], C, 2 * C)) return rc;
+  if (int rc = make_weight_map(&maps[5], nsplit == 2 ? wf.w2_lo[layer] : wf.w2_hi[layer], C, 2 * C)) return rc;
+  p.n_src = 2;
   p.src[0] = TcSrc{C, 1, 0, 0};
-  p.n_total = n_rs;
-  p.k_steps = C / TC_BK;
-  p.mode = TC_RES_SKIP;
-  p.bias = f.res_skip_b[layer];
-  p.x = ws->x;
-  p.x_hi = reinterpret_cast<__nv_bfloat16*>(ws->x_hi);
-  p.x_lo = reinterpret_cast<__nv_bfloat16*>(ws->x_lo);
-  p.skip = ws->skip;
-  p.n_split_cols = last ? 0 : C;
-  p.accumulate_skip = layer > 0;
+  p.src[1] = TcSrc{C, 1, 0, 0};
+  p.n_total = C;
+  p.k_steps = 2 * C / TC_BK;
+  p.wlo_k_steps = C / TC_BK;        // the identity block has no lo part
+  p.mode = TC_RESIDUAL;
+  p.bias = wf.res_b[layer];
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(ws->x_hi);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(ws->x_lo);
+  p.wc = nullptr;
+  p.out8 = nullptr;
+  if (p.prof) p.prof += 8 * 256;   // G2 counters follow G1's
   return launch_tc(maps, p, st);
 }
 
@@ -482,7 +597,7 @@ int wg_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* 
     if (int rc = wg_tc_start(m, k, audio, ws, B, Tg, nsplit, st)) return rc;
     for (int i = 0; i < m->n_layers; ++i)
       if (int rc = wg_tc_layer(m, w, k, i, ws, B, Tg, nsplit, st)) return rc;
-    if (int rc = wg_end(m, k, ws->skip, audio, B, Tg, st)) return rc;
+    if (int rc = wg_tc_end(m, w, k, ws->out8, audio, B, Tg, st)) return rc;
   }
   return 0;
 }

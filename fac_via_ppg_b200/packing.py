@@ -185,48 +185,74 @@ class PackedWaveGlow:
         return self
 
     # ------------------------------------------------------------------ tensor-core copies
-    def tc_layout(self):
-        """bf16 [N][K] copies of the WN GEMM weights (hi and lo halves of the split-bf16 scheme)."""
+    def tc_layouts(self):
+        """Layouts of the derived tensor-core weights: (bf16 operand matrices, fp32 side tables)."""
         cfg = self.cfg
         wn = cfg["WN_config"]
         Cn, L, ks = wn["n_channels"], wn["n_layers"], wn["kernel_size"]
         n_cond = cfg["n_mel_channels"] * cfg["n_group"]
-        lay = FlatLayout()
+        l16, l32 = FlatLayout(), FlatLayout()
         for k in range(cfg["n_flows"]):
+            l32.add(f"{k}.out_bias", (8,))
             for i in range(L):
-                n_rs = 2 * Cn if i < L - 1 else Cn
                 for part in ("hi", "lo"):
-                    lay.add(f"{k}.{i}.w1_{part}", (2 * Cn, ks * Cn + n_cond))
-                    lay.add(f"{k}.{i}.w2_{part}", (n_rs, Cn))
-        return lay
+                    l16.add(f"{k}.{i}.w1_{part}", (2 * Cn, ks * Cn + n_cond))
+                    if i < L - 1:
+                        l16.add(f"{k}.{i}.w2_{part}", (Cn, 2 * Cn))
+                l32.add(f"{k}.{i}.wc", (8, Cn))
+                if i < L - 1:
+                    l32.add(f"{k}.{i}.res_b", (Cn,))
+        return l16, l32
 
     @torch.no_grad()
     def tc_weights(self):
-        """Builds (once) the bf16 hi/lo weight buffer from the packed fp32 buffer and returns the
-        ``fac_wg_tc_weights`` pointer table.  Derived data: after a broadcast of ``flat`` every rank
-        derives its own copy locally."""
+        """Builds (once) the tensor-core weight buffers from the packed fp32 buffer and returns the
+        ``fac_wg_tc_weights`` pointer table (see include/fac_b200.h for the algebra).  Derived data:
+        after a broadcast of ``flat`` every rank derives its own copy locally."""
         cached = getattr(self, "_tc", None)
         if cached is not None:
-            return cached[1]
+            return cached[-1]
         cfg, lay = self.cfg, self.layout
         wn = cfg["WN_config"]
         Cn, L = wn["n_channels"], wn["n_layers"]
-        tl = self.tc_layout()
-        flat16 = torch.zeros(tl.size, dtype=torch.bfloat16, device=self.flat.device)
+        dev = self.flat.device
+        l16, l32 = self.tc_layouts()
+        flat16 = torch.zeros(l16.size, dtype=torch.bfloat16, device=dev)
+        flat32 = torch.zeros(l32.size, dtype=torch.float32, device=dev)
         table = _ext.WgTcWeights()
-        for k in range(cfg["n_flows"]):
+        eye = torch.eye(Cn, device=dev)
+
+        def put16(name, w, flow, i):
+            hi = w.to(torch.bfloat16)
+            lo = (w - hi.float()).to(torch.bfloat16)
+            stem = name.split(".")[-1]
+            l16.view(flat16, name + "_hi").copy_(hi)
+            l16.view(flat16, name + "_lo").copy_(lo)
+            getattr(flow, stem + "_hi")[i] = l16.ptr(flat16, name + "_hi")
+            getattr(flow, stem + "_lo")[i] = l16.ptr(flat16, name + "_lo")
+
+        for k, (n_rem, n_half) in enumerate(flow_channels(cfg)):
+            flow = table.flows[k]
+            end_w = lay.view(self.flat, f"{k}.end_w").double()                    # (2*n_half, C)
+            bias8 = lay.view(self.flat, f"{k}.end_b").double().clone()
             for i in range(L):
-                n_rs = 2 * Cn if i < L - 1 else Cn
-                w1 = lay.view(self.flat, f"{k}.{i}.in_cond_w")[:, : 2 * Cn].t().contiguous()   # (2C, K1)
-                w2 = lay.view(self.flat, f"{k}.{i}.res_skip_w")[:, :n_rs].t().contiguous()     # (n_rs, C)
-                for name, w in (("w1", w1), ("w2", w2)):
-                    hi = w.to(torch.bfloat16)
-                    lo = (w - hi.float()).to(torch.bfloat16)
-                    tl.view(flat16, f"{k}.{i}.{name}_hi").copy_(hi)
-                    tl.view(flat16, f"{k}.{i}.{name}_lo").copy_(lo)
-                    getattr(table.flows[k], name + "_hi")[i] = tl.ptr(flat16, f"{k}.{i}.{name}_hi")
-                    getattr(table.flows[k], name + "_lo")[i] = tl.ptr(flat16, f"{k}.{i}.{name}_lo")
-        self._tc = (flat16, table)
+                last = i == L - 1
+                n_rs = Cn if last else 2 * Cn
+                put16(f"{k}.{i}.w1", lay.view(self.flat, f"{k}.{i}.in_cond_w")[:, : 2 * Cn].t().contiguous(), flow, i)
+                w_rs = lay.view(self.flat, f"{k}.{i}.res_skip_w")[:, :n_rs].t()       # (n_rs, C)
+                b_rs = lay.view(self.flat, f"{k}.{i}.res_skip_b")[:n_rs]
+                w_skip, b_skip = (w_rs, b_rs) if last else (w_rs[Cn:], b_rs[Cn:])
+                wc = l32.view(flat32, f"{k}.{i}.wc")
+                wc[: 2 * n_half].copy_((end_w @ w_skip.double()).float())            # composed in fp64
+                flow.wc[i] = l32.ptr(flat32, f"{k}.{i}.wc")
+                bias8 += end_w @ b_skip.double()
+                if not last:
+                    put16(f"{k}.{i}.w2", torch.cat([w_rs[:Cn], eye], dim=1).contiguous(), flow, i)
+                    l32.view(flat32, f"{k}.{i}.res_b").copy_(b_rs[:Cn])
+                    flow.res_b[i] = l32.ptr(flat32, f"{k}.{i}.res_b")
+            l32.view(flat32, f"{k}.out_bias")[: 2 * n_half].copy_(bias8.float())
+            flow.out_bias = l32.ptr(flat32, f"{k}.out_bias")
+        self._tc = (flat16, flat32, table)
         return table
 
     @classmethod

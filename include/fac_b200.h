@@ -129,23 +129,35 @@ int fac_waveglow_infer_f32(const fac_wg_model* m, const float* mel_cl, float* au
                            const fac_wg_workspace* ws, int B, int F, void* stream);
 
 /* ---- WaveGlow WN layers on tcgen05 tensor cores -------------------------- */
-/* bf16 copies of the WN weights, [N][K] row-major (K contiguous): w1 = in_layer|cond_layer
- * (N = 2C gate-interleaved like in_cond_w, K = 3C + n_cond ordered tap0|tap1|tap2|cond),
- * w2 = res_skip (N = 2C or C, K = C).  *_hi = bf16(w), *_lo = bf16(w - hi) (split-bf16). */
+/* Weights of the tensor-core path, derived from the fp32 packed weights by packing.py.
+ * bf16 operand matrices are [N][K] row-major (K contiguous); *_hi = bf16(w), *_lo = bf16(w - hi).
+ *   w1 = in_layer|cond_layer: N = 2C gate-interleaved like in_cond_w, K = 3C + n_cond ordered
+ *        tap0|tap1|tap2|cond (glow.py:159-162)
+ *   w2 = [residual half of res_skip | identity]: N = C, K = 2C, so that the tensor core itself
+ *        performs x <- x + res (glow.py:164-166); lo has zeros in the identity half; unused for
+ *        the last layer, whose res_skip feeds the skip path only
+ *   wc = end.weight @ (skip half of res_skip): the skip path collapsed into an 8-channel update
+ *        per layer (glow.py:167-175: end() is linear in the skip sum); fp32 [8][C], rows >= 2*n_half zero
+ *   out_bias = end.bias + end.weight @ sum_i (skip half of res_skip bias_i); fp32 [8]
+ *   res_b = residual half of the res_skip bias; fp32 [C] */
 typedef struct fac_wg_tc_flow {
   const void* w1_hi[FAC_MAX_LAYERS]; const void* w1_lo[FAC_MAX_LAYERS];
   const void* w2_hi[FAC_MAX_LAYERS]; const void* w2_lo[FAC_MAX_LAYERS];
+  const float* wc[FAC_MAX_LAYERS];
+  const float* res_b[FAC_MAX_LAYERS];
+  const float* out_bias;
 } fac_wg_tc_flow;
 typedef struct fac_wg_tc_weights { fac_wg_tc_flow flows[FAC_MAX_FLOWS]; } fac_wg_tc_weights;
 
-/* Scratch of the tensor-core path for B utterances of T_g columns: fp32 masters (x, skip, the
- * upsampler output) and the bf16 hi/lo operand copies the TMA loads read ((B,T_g,channels)
- * channels-last).  The *_lo buffers may be NULL when nsplit == 1. */
+/* Scratch of the tensor-core path for B utterances of T_g columns: the fp32 upsampler output, the
+ * bf16 hi/lo operand copies the TMA loads read ((B,T_g,channels) channels-last; the residual
+ * stream x lives ONLY as its hi+lo pair) and out8 (B,T_g,8) fp32, the running end() pre-activation.
+ * The *_lo buffers may be NULL when nsplit == 1. */
 typedef struct fac_wg_tc_workspace {
   float* spect_f32; void* spect_hi; void* spect_lo;
-  float* x; void* x_hi; void* x_lo;
+  void* x_hi; void* x_lo;
   void* acts_hi; void* acts_lo;
-  float* skip;
+  float* out8;
 } fac_wg_tc_workspace;
 
 /* nsplit = 1: bf16 operands; nsplit = 2: split-bf16 (3 UMMAs per product, fp32-grade result). */
@@ -153,9 +165,16 @@ int fac_waveglow_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_workspa
                                   int B, int F, int nsplit, void* stream);
 int fac_wn_start_tc(const fac_wg_model* m, int flow, const float* audio, const fac_wg_tc_workspace* ws,
                     int B, int Tg, int nsplit, void* stream);
-/* glow.py:158-174 for one layer: TMA-fed tcgen05 GEMM + gate epilogue, then res/skip GEMM. */
+/* glow.py:158-174 for one layer: TMA-fed tcgen05 GEMM + gate epilogue (+ out8 update), then the
+ * residual GEMM (skipped for the last layer). */
 int fac_wn_layer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int layer,
                     const fac_wg_tc_workspace* ws, int B, int Tg, int nsplit, void* stream);
+/* glow.py:175 + 278-283 from out8: coupling inverse and invertible 1x1 (reverse), in place on audio. */
+int fac_wn_end_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, const float* out8, float* audio,
+                  int B, int Tg, void* stream);
+/* Optional cycle counters of the tensor-core kernel: device buffer of 2*256*8 int64 ([G1|G2][cta][8]:
+ * producer wait-empty, MMA wait-tmem, MMA wait-full, MMA total, epilogue wait, epilogue busy); NULL disables. */
+void fac_tc_set_profile_buffer(long long* device_buf);
 /* Same contract as fac_waveglow_infer_f32 (glow.py:252-293), WN layers on the tensor cores. */
 int fac_waveglow_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* mel_cl, float* audio,
                           const fac_wg_tc_workspace* ws, int B, int F, int nsplit, void* stream);

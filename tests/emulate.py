@@ -158,3 +158,49 @@ def tacotron_inference(packed, inputs, masks, n_steps, window, gate_threshold=2.
         hpost = conv_gemm([(hpost, 5, 1, 2)], v(f"post.conv{i}_w"), v(f"post.conv{i}_b"), width)
         hpost = torch.tanh(hpost) if i < n - 1 else hpost + mel
     return [mel.transpose(1, 2), hpost.transpose(1, 2), gate.unsqueeze(-1), align]
+
+
+# ===================================================================== tensor-core formulation (csrc/waveglow_tc.cu)
+def waveglow_infer_tc(packed, mel, audio):
+    """Mirror of the tensor-core path's ALGEBRA with torch fp32 on the CPU: bf16 hi+lo operand
+    matrices (summed), skip path collapsed into out8 += Wc acts, residual add through the
+    identity block of w2.  Checks packing.tc_weights() without a GPU."""
+    cfg, lay, flat = packed.cfg, packed.layout, packed.flat
+    packed.tc_weights()
+    flat16, flat32, _ = packed._tc
+    l16, l32 = packed.tc_layouts()
+    wn = cfg["WN_config"]
+    C, L, ks = wn["n_channels"], wn["n_layers"], wn["kernel_size"]
+    G, hop, n_mel = cfg["n_group"], cfg["hop_length"], cfg["n_mel_channels"]
+    n_cond, phases, taps = n_mel * G, hop // G, upsample_taps(cfg)
+    B, _, F = mel.shape
+    Tg = F * phases
+    mel_cl = mel.transpose(1, 2).contiguous()
+    spect = mel.new_zeros(B, F, phases, n_cond)
+    w_up, b_up = lay.view(flat, "upsample_w"), lay.view(flat, "upsample_b")
+    for p in range(phases):
+        spect[:, :, p] = conv_gemm([(mel_cl, taps, -1, 0)], w_up[p], b_up, n_cond)
+    spect = spect.view(B, Tg, n_cond)
+    audio = audio.clone()
+
+    def w16(name):
+        return l16.view(flat16, name + "_hi").float() + l16.view(flat16, name + "_lo").float()
+
+    for k in reversed(range(cfg["n_flows"])):
+        n_rem, n_half = flow_channels(cfg)[k]
+        off = G - n_rem
+        x = audio[:, :, off:off + n_half] @ lay.view(flat, f"{k}.start_w") + lay.view(flat, f"{k}.start_b")
+        out8 = audio.new_zeros(B, Tg, 8)
+        for i in range(L):
+            d = 2 ** i
+            a = torch.cat([gather_rows(x, ks, d, d * (ks - 1) // 2), spect], dim=-1)
+            pre = a @ w16(f"{k}.{i}.w1").t() + lay.view(flat, f"{k}.{i}.in_cond_b")[: 2 * C]
+            acts = torch.tanh(pre[..., 0::2]) * torch.sigmoid(pre[..., 1::2])
+            out8 = out8 + acts @ l32.view(flat32, f"{k}.{i}.wc").t()
+            if i < L - 1:
+                x = torch.cat([acts, x], dim=-1) @ w16(f"{k}.{i}.w2").t() + l32.view(flat32, f"{k}.{i}.res_b")
+        out = out8 + l32.view(flat32, f"{k}.out_bias")
+        a0 = audio[:, :, off:off + n_half]
+        a1 = (audio[:, :, off + n_half:] - out[..., :n_half]) / torch.exp(out[..., n_half:2 * n_half])
+        audio[:, :, off:] = torch.cat([a0, a1], dim=-1) @ lay.view(flat, f"{k}.w_inv").t()
+    return audio.reshape(B, Tg * G)

@@ -75,3 +75,16 @@ def test_window_only_attention_equals_dense_masked_attention():
     out = emulate.tacotron_inference(packed, ppg, masks, T, window=20)
     for a, b in zip(out, ref):
         assert (a - b).abs().max().item() <= 3e-4
+
+
+@pytest.mark.parametrize("name", ["waveglow_small_b2_f6.pt", "waveglow_full_b2_f5.pt"])
+def test_tensor_core_algebra_matches_golden(golden_dir, name):
+    """Skip-path collapse (end() folded into per-layer 8-channel updates), residual add through an
+    identity block and the bf16 hi+lo weight split reproduce the reference (torch fp32 on the CPU)."""
+    g = torch.load(os.path.join(golden_dir, name))
+    cfg = g["cfg"]
+    packed = PackedWaveGlow.from_state(synth.waveglow_state(cfg=cfg), cfg, "cpu")
+    mel = synth.synthetic_mel(g["batch"], g["frames"], seed=g["mel_seed"])
+    audio0 = emulate.fill_audio_slots(g["noise"], g["sigma"], cfg["n_group"])
+    out = emulate.waveglow_infer_tc(packed, mel, audio0)
+    assert (out - g["audio"]).pow(2).mean().sqrt().item() <= 2e-5

@@ -24,7 +24,7 @@ def build_model(cfg, seed=synth.SEED):
     model = WaveGlow(**cfg)
     model = WaveGlow.remove_weightnorm(model)
     model.load_state_dict(synth.waveglow_state(seed=seed, cfg=cfg), strict=True)
-    return model.to(DEV).eval()
+    return model.to(DEV).eval().set_precision("fp32")      # this file tests the exact-fp32 FFMA path
 
 
 # ---------------------------------------------------------------- kernel granularity
@@ -131,7 +131,7 @@ def test_infer_with_weightnorm_checkpoint_flavour():
     model = WaveGlow(**cfg)
     for wn in model.WN:                      # the constructor zero-inits `end`: make it matter
         torch.nn.init.normal_(wn.end.weight, std=0.05)
-    model = model.to(DEV).eval()
+    model = model.to(DEV).eval().set_precision("fp32")
     mel = synth.synthetic_mel(1, 3).to(DEV)
     noise = [torch.randn(1, 6, 60, device=DEV), torch.randn(1, 2, 60, device=DEV)]
     a = model.infer(mel, 0.5, noise=noise)
