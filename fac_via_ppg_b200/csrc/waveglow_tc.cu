@@ -17,8 +17,10 @@
 //   nsplit = 1  plain bf16 operands                                  (1 UMMA per product)
 //   nsplit = 2  split-bf16: v = hi + lo, a*w ~= ah*wh + al*wh + ah*wl (3 UMMAs per product),
 //               ~2^-16 relative operand error, fp32 accumulate: fp32-grade results.
-// Warp roles (192 threads, persistent over tiles, 1 CTA / SM): warp 0 = TMA producer,
-// warp 1 = UMMA issuer (one elected lane), warps 2-5 = epilogue (one TMEM lane quarter each).
+// Warp roles (320 threads, persistent over tiles, 1 CTA / SM): warp 0 = TMA producer, warp 1 = UMMA
+// issuer (one elected lane), warps 2-9 = epilogue (two per TMEM lane quarter, half of the columns each).
+// Every tile walks K from a tile-dependent rotation so that the 148 CTAs do not all request the
+// same weight lines from L2 at the same instant.
 #include "fac_common.cuh"
 #include "tc_common.cuh"
 
@@ -28,20 +30,23 @@ namespace {
 using namespace tc;
 
 constexpr int TC_BM = 128;       // time rows per tile (UMMA M)
-constexpr int TC_BK = 16;        // K per pipeline stage = one UMMA K step; 32-byte rows, SWIZZLE_32B
+constexpr int TC_BK = 32;        // K per pipeline stage = two UMMA K steps; 64-byte rows, SWIZZLE_64B
 constexpr int TC_ROWB = TC_BK * 2;
-constexpr int TC_STAGES = 5;
+constexpr int TC_STAGES = 4;
+constexpr int UMMA_K = 16;
 constexpr int TC_NMAX = 512;     // accumulator columns per tile (all of TMEM)
 constexpr int TC_NHALF = 256;    // N of one UMMA
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each owning half of the columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_NOUT = 8;       // channels of the collapsed skip path (= max 2*n_half)
 constexpr int TC_CMAX = 256;     // max WN channels (Wc staging)
-constexpr int A_BYTES = TC_BM * TC_ROWB;       // 4 KB
-constexpr int W_BYTES = TC_NMAX * TC_ROWB;     // 16 KB (two halves of 8 KB)
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;   // hi + lo of both operands = 40 KB
+constexpr int A_BYTES = TC_BM * TC_ROWB;       // 8 KB
+constexpr int W_BYTES = TC_NHALF * TC_ROWB;    // 16 KB: one 256-row block of the weight matrix
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;   // hi + lo of both operands = 48 KB
 constexpr int TC_BAR_BYTES = 256;
 constexpr int TC_WC_BYTES = TC_NOUT * TC_CMAX * 4;       // 8 KB
-constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + TC_BAR_BYTES + TC_WC_BYTES + 1024 /*alignment slack*/;
+constexpr int TC_X8_BYTES = TC_BM * TC_NOUT * 4;         // 4 KB: out8 partials handed between paired epilogue warps
+constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + TC_BAR_BYTES + TC_WC_BYTES + TC_X8_BYTES + 1024 /*alignment slack*/;
 
 enum { TC_GATE = 0, TC_RESIDUAL = 1 };
 
@@ -85,22 +90,27 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
   uint64_t* empty = full + TC_STAGES;
-  uint64_t* tmem_full = empty + TC_STAGES;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  uint64_t* tmem_full = empty + TC_STAGES;     // [2] one per accumulator region
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* wc_s = reinterpret_cast<float*>(smem + TC_STAGES * STAGE_BYTES + TC_BAR_BYTES);
+  float* x8_s = wc_s + TC_NOUT * TC_CMAX;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_halves = (p.n_total + TC_NHALF - 1) / TC_NHALF;
-  const int n_half_cols = p.n_total < TC_NHALF ? p.n_total : TC_NHALF;
+  // A work unit is (time tile, block of <= 256 output columns); its accumulator is one of the two
+  // 256-column TMEM regions, so the epilogue of unit u overlaps the UMMAs of unit u+1.
+  const int n_blocks = (p.n_total + TC_NHALF - 1) / TC_NHALF;
+  const int n_cols = p.n_total < TC_NHALF ? p.n_total : TC_NHALF;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 4);
+    for (int r = 0; r < 2; ++r) {
+      mbar_init(&tmem_full[r], 1);
+      mbar_init(&tmem_empty[r], TC_EPI_WARPS);
+    }
     fence_barrier_init();
     tma_prefetch_desc(&a0_hi);
     tma_prefetch_desc(&w_hi);
@@ -116,36 +126,35 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      const uint32_t w_bytes = (uint32_t)(n_halves * n_half_cols * TC_ROWB);
+      const uint32_t w_bytes = (uint32_t)(n_cols * TC_ROWB);
+      const int steps0 = p.src[0].taps * (p.src[0].channels / TC_BK);
       int stage = 0;
       uint32_t phase = 0;
       long long prod_wait = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_batch;
         const int t0 = (tile % p.tiles_per_batch) * TC_BM;
-        int ks = 0;
-        for (int s = 0; s < p.n_src; ++s) {
-          const CUtensorMap* mh = s == 0 ? &a0_hi : &a1_hi;
-          const CUtensorMap* ml = s == 0 ? &a0_lo : &a1_lo;
-          for (int tap = 0; tap < p.src[s].taps; ++tap) {
+        for (int nb = 0; nb < n_blocks; ++nb) {
+          for (int ks = 0; ks < p.k_steps; ++ks) {
+            // decode the K step into (source, tap, channel block)
+            int s = 0, rem = ks;
+            if (rem >= steps0) { s = 1; rem -= steps0; }
+            const int cps = p.src[s].channels / TC_BK;
+            const int tap = rem / cps, c0 = (rem - tap * cps) * TC_BK;
             const int row0 = t0 + tap * p.src[s].dilation - p.src[s].center;
-            for (int c0 = 0; c0 < p.src[s].channels; c0 += TC_BK, ++ks) {
-              const bool use_wlo = p.nsplit == 2 && ks < p.wlo_k_steps;
-              const long long w0 = clock64();
-              mbar_wait(&empty[stage], phase ^ 1);
-              prod_wait += clock64() - w0;
-              uint8_t* st = smem + stage * STAGE_BYTES;
-              mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.nsplit * A_BYTES) + w_bytes * (use_wlo ? 2u : 1u));
-              tma_load_3d(st, mh, &full[stage], c0, row0, b);
-              if (p.nsplit == 2) tma_load_3d(st + A_BYTES, ml, &full[stage], c0, row0, b);
-              for (int h = 0; h < n_halves; ++h) {
-                tma_load_2d(st + 2 * A_BYTES + h * (W_BYTES / 2), &w_hi, &full[stage], ks * TC_BK, h * TC_NHALF);
-                if (use_wlo)
-                  tma_load_2d(st + 2 * A_BYTES + W_BYTES + h * (W_BYTES / 2), &w_lo, &full[stage], ks * TC_BK,
-                              h * TC_NHALF);
-              }
-              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-            }
+            const CUtensorMap* mh = s == 0 ? &a0_hi : &a1_hi;
+            const CUtensorMap* ml = s == 0 ? &a0_lo : &a1_lo;
+            const bool use_wlo = p.nsplit == 2 && ks < p.wlo_k_steps;
+            const long long w0 = clock64();
+            mbar_wait(&empty[stage], phase ^ 1);
+            prod_wait += clock64() - w0;
+            uint8_t* st = smem + stage * STAGE_BYTES;
+            mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.nsplit * A_BYTES) + w_bytes * (use_wlo ? 2u : 1u));
+            tma_load_3d(st, mh, &full[stage], c0, row0, b);
+            if (p.nsplit == 2) tma_load_3d(st + A_BYTES, ml, &full[stage], c0, row0, b);
+            tma_load_2d(st + 2 * A_BYTES, &w_hi, &full[stage], ks * TC_BK, nb * TC_NHALF);
+            if (use_wlo) tma_load_2d(st + 2 * A_BYTES + W_BYTES, &w_lo, &full[stage], ks * TC_BK, nb * TC_NHALF);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -154,41 +163,46 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
   } else if (warp == 1) {
     // ===================================================== UMMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(TC_BM, n_half_cols);
+      const uint32_t idesc = make_idesc_bf16(TC_BM, n_cols);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
+      uint32_t u = 0;   // unit counter
       long long wait_tmem = 0, wait_full = 0;
       const long long k_start = clock64();
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        long long w0 = clock64();
-        mbar_wait(tmem_empty, (uint32_t)((it & 1) ^ 1));   // epilogue has drained the previous tile
-        wait_tmem += clock64() - w0;
-        tc_fence_after();
-        for (int ks = 0; ks < p.k_steps; ++ks) {
-          w0 = clock64();
-          mbar_wait(&full[stage], phase);
-          wait_full += clock64() - w0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int nb = 0; nb < n_blocks; ++nb, ++u) {
+          const uint32_t r = u & 1;
+          long long w0 = clock64();
+          mbar_wait(&tmem_empty[r], ((u >> 1) & 1) ^ 1);   // epilogue has drained this region
+          wait_tmem += clock64() - w0;
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_h = make_smem_desc(st, TC_ROWB);
-          const uint64_t a_l = make_smem_desc(st + A_BYTES, TC_ROWB);
-          for (int h = 0; h < n_halves; ++h) {
-            const uint32_t d = tmem_base + h * TC_NHALF;
-            const uint64_t w_h = make_smem_desc(st + 2 * A_BYTES + h * (W_BYTES / 2), TC_ROWB);
-            umma_bf16(d, a_h, w_h, idesc, ks > 0 ? 1u : 0u);
-            if (p.nsplit == 2) {
-              umma_bf16(d, a_l, w_h, idesc, 1u);
-              if (ks < p.wlo_k_steps) {
-                const uint64_t w_l = make_smem_desc(st + 2 * A_BYTES + W_BYTES + h * (W_BYTES / 2), TC_ROWB);
-                umma_bf16(d, a_h, w_l, idesc, 1u);
+          const uint32_t d = tmem_base + r * TC_NHALF;
+          for (int ks = 0; ks < p.k_steps; ++ks) {
+            w0 = clock64();
+            mbar_wait(&full[stage], phase);
+            wait_full += clock64() - w0;
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / UMMA_K; ++kk) {
+              const uint32_t koff = kk * UMMA_K * 2;   // bytes along K inside the swizzled row
+              const uint64_t a_h = make_smem_desc(st + koff, TC_ROWB);
+              const uint64_t w_h = make_smem_desc(st + 2 * A_BYTES + koff, TC_ROWB);
+              umma_bf16(d, a_h, w_h, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+              if (p.nsplit == 2) {
+                const uint64_t a_l = make_smem_desc(st + A_BYTES + koff, TC_ROWB);
+                umma_bf16(d, a_l, w_h, idesc, 1u);
+                if (ks < p.wlo_k_steps) {
+                  const uint64_t w_l = make_smem_desc(st + 2 * A_BYTES + W_BYTES + koff, TC_ROWB);
+                  umma_bf16(d, a_h, w_l, idesc, 1u);
+                }
               }
             }
+            umma_commit(&empty[stage]);   // frees the smem slot when these UMMAs have read it
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty[stage]);   // frees the smem slot when these UMMAs have read it
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(&tmem_full[r]);     // accumulator complete -> epilogue
         }
-        umma_commit(tmem_full);         // accumulator complete -> epilogue
       }
       if (p.prof) {
         p.prof[blockIdx.x * 8 + 1] = wait_tmem;
@@ -197,105 +211,125 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
       }
     }
   } else {
-    // ===================================================== epilogue (4 warps, one TMEM lane quarter each)
+    // ===================================================== epilogue (8 warps: lane quarter x column half)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int c_begin = half * (n_cols / 2), c_end = c_begin + n_cols / 2;
     const int row = q * 32 + lane;
-    int it = 0;
+    uint32_t u = 0;
     long long epi_wait = 0, epi_busy = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_batch;
       const int t = (tile % p.tiles_per_batch) * TC_BM + row;
       const bool valid = t < p.T;
       const long long col = (long long)b * p.T + t;
-      const long long e0 = clock64();
-      mbar_wait(tmem_full, (uint32_t)(it & 1));
-      const long long e1 = clock64();
-      epi_wait += e1 - e0;
-      tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-      float acc8[TC_NOUT];
+      for (int nb = 0; nb < n_blocks; ++nb, ++u) {
+        const uint32_t r = u & 1;
+        const long long e0 = clock64();
+        mbar_wait(&tmem_full[r], (u >> 1) & 1);
+        const long long e1 = clock64();
+        epi_wait += e1 - e0;
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + r * TC_NHALF;
+        float acc8[TC_NOUT];
 #pragma unroll
-      for (int o = 0; o < TC_NOUT; ++o) acc8[o] = 0.f;
-      for (int n0 = 0; n0 < p.n_total; n0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(trow + n0, r);
-        tmem_ld_wait();
-        if (!valid) continue;
-        float v[32];
+        for (int o = 0; o < TC_NOUT; ++o) acc8[o] = 0.f;
+        for (int c = c_begin; c < c_end; c += 32) {
+          uint32_t rr[32];
+          tmem_ld32(trow + c, rr);
+          tmem_ld_wait();
+          if (!valid) continue;
+          const int n0 = nb * TC_NHALF + c;     // global output column of this chunk
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-          v[j + 0] = __uint_as_float(r[j + 0]) + bv.x;
-          v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + bv.z;
-          v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
-        }
-        if (p.mode == TC_GATE) {
-          // columns (2c, 2c+1) hold the tanh / sigmoid pre-activations of channel c (glow.py:33-40)
-          float g[16];
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            v[j + 0] = __uint_as_float(rr[j + 0]) + bv.x;
+            v[j + 1] = __uint_as_float(rr[j + 1]) + bv.y;
+            v[j + 2] = __uint_as_float(rr[j + 2]) + bv.z;
+            v[j + 3] = __uint_as_float(rr[j + 3]) + bv.w;
+          }
+          if (p.mode == TC_GATE) {
+            // columns (2c, 2c+1) hold the tanh / sigmoid pre-activations of channel c (glow.py:33-40)
+            float g[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) g[j] = gate_act(v[2 * j], v[2 * j + 1]);
-          const int ch0 = n0 >> 1;
-          // collapsed skip path: out8 += Wc[:, ch0:ch0+16] g   (fp32, exact gate outputs)
+            for (int j = 0; j < 16; ++j) g[j] = gate_act(v[2 * j], v[2 * j + 1]);
+            const int ch0 = n0 >> 1;
+            // collapsed skip path: out8 += Wc[:, ch0:ch0+16] g   (fp32, exact gate outputs)
 #pragma unroll
-          for (int o = 0; o < TC_NOUT; ++o) {
-            const float4* wrow = reinterpret_cast<const float4*>(wc_s + o * p.C + ch0);
-            float a = acc8[o];
+            for (int o = 0; o < TC_NOUT; ++o) {
+              const float4* wrow = reinterpret_cast<const float4*>(wc_s + o * p.C + ch0);
+              float a = acc8[o];
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 w4 = wrow[j4];
-              a = fmaf(w4.x, g[4 * j4 + 0], a);
-              a = fmaf(w4.y, g[4 * j4 + 1], a);
-              a = fmaf(w4.z, g[4 * j4 + 2], a);
-              a = fmaf(w4.w, g[4 * j4 + 3], a);
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 w4 = wrow[j4];
+                a = fmaf(w4.x, g[4 * j4 + 0], a);
+                a = fmaf(w4.y, g[4 * j4 + 1], a);
+                a = fmaf(w4.z, g[4 * j4 + 2], a);
+                a = fmaf(w4.w, g[4 * j4 + 3], a);
+              }
+              acc8[o] = a;
             }
-            acc8[o] = a;
-          }
-          uint32_t hi[8], lo[8];
+            uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) split2(g[2 * j], g[2 * j + 1], hi[j], lo[j]);
-          const long long off = col * p.C + ch0;
-          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
-          dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          if (p.nsplit == 2) {
-            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
-            dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          }
-        } else {
-          // residual stream x_new = x + res (glow.py:166), already summed by the identity block:
-          // refresh the bf16 operand copies the next layer's TMA loads read
-          uint32_t hi[16], lo[16];
+            for (int j = 0; j < 8; ++j) split2(g[2 * j], g[2 * j + 1], hi[j], lo[j]);
+            const long long off = col * p.C + ch0;
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
+            dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            if (p.nsplit == 2) {
+              uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
+              dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+          } else {
+            // residual stream x_new = x + res (glow.py:166), already summed by the identity block:
+            // refresh the bf16 operand copies the next layer's TMA loads read
+            uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-          const long long off = col * p.C + n0;
-          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
+            for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+            const long long off = col * p.C + n0;
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          if (p.nsplit == 2) {
-            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
+            for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            if (p.nsplit == 2) {
+              uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
           }
         }
-      }
-      if (p.mode == TC_GATE && valid) {
-        float4* o8 = reinterpret_cast<float4*>(p.out8 + col * TC_NOUT);
-        float4 o0 = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
-        float4 o1 = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
-        if (p.accumulate_out8) {
-          const float4 p0 = o8[0], p1 = o8[1];
-          o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
-          o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+        // this warp is done reading the TMEM region: hand it back to the UMMA issuer early
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[r]);
+        if (p.mode == TC_GATE) {
+          // the warp owning the upper column half hands its partial sums to its partner (fixed
+          // order: deterministic rounding), which updates out8 (unit 0 of a tile starts or continues
+          // the layer sum, unit 1 always continues)
+          if (half == 1) {
+#pragma unroll
+            for (int o = 0; o < TC_NOUT; ++o) x8_s[row * TC_NOUT + o] = acc8[o];
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+          if (half == 0 && valid) {
+#pragma unroll
+            for (int o = 0; o < TC_NOUT; ++o) acc8[o] += x8_s[row * TC_NOUT + o];
+            float4* o8 = reinterpret_cast<float4*>(p.out8 + col * TC_NOUT);
+            float4 o0 = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
+            float4 o1 = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
+            if (p.accumulate_out8 || nb > 0) {
+              const float4 p0 = o8[0], p1 = o8[1];
+              o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+              o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+            }
+            o8[0] = o0;
+            o8[1] = o1;
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
         }
-        o8[0] = o0;
-        o8[1] = o1;
+        epi_busy += clock64() - e1;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty);
-      epi_busy += clock64() - e1;
     }
     if (p.prof && warp == 2 && lane == 0) {
       p.prof[blockIdx.x * 8 + 4] = epi_wait;
@@ -395,6 +429,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+constexpr CUtensorMapSwizzle TC_SWIZZLE = TC_ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                          : TC_ROWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+
 EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = [] {
     void* ptr = nullptr;
@@ -416,7 +453,7 @@ int make_act_map(CUtensorMap* m, const void* ptr, int B, int T, int C) {
   cuuint32_t box[3] = {TC_BK, TC_BM, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, TC_SWIZZLE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FAC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", B, T, C, (int)r);
   return 0;
@@ -430,7 +467,7 @@ int make_weight_map(CUtensorMap* m, const void* ptr, int N, int K) {
   cuuint32_t box[2] = {TC_BK, (cuuint32_t)(N < TC_NHALF ? N : TC_NHALF)};
   cuuint32_t es[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, TC_SWIZZLE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FAC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight %dx%d) failed: %d", N, K, (int)r);
   return 0;
@@ -476,7 +513,7 @@ static int tc_check(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac
   FAC_REQUIRE(w && ws, "tensor-core path: NULL weights/workspace");
   FAC_REQUIRE(nsplit == 1 || nsplit == 2, "tensor-core path: nsplit must be 1 (bf16) or 2 (split-bf16), got %d", nsplit);
   const int C = m->n_channels, n_cond = m->n_mel * m->n_group;
-  FAC_REQUIRE(C % 16 == 0 && n_cond % 16 == 0 && 2 * C <= TC_NMAX && C <= TC_CMAX,
+  FAC_REQUIRE(C % TC_BK == 0 && n_cond % TC_BK == 0 && 2 * C <= TC_NMAX && C <= TC_CMAX,
               "tensor-core path: needs n_channels %% 16 == 0 (<= %d) and n_cond %% 16 == 0", TC_CMAX);
   FAC_REQUIRE(m->n_group <= TC_NOUT, "tensor-core path: n_group %d > %d", m->n_group, TC_NOUT);
   FAC_REQUIRE(ws->spect_hi && ws->x_hi && ws->acts_hi && ws->out8, "tensor-core path: workspace incomplete");
