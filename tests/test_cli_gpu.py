@@ -1,0 +1,84 @@
+"""The CLI / glue surface on the GPU: generate_synthesis (reference src/script/generate_synthesis.py),
+checkpoint formats (pickled WaveGlow module, Tacotron2 state dict) and the Denoiser drop-in."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from scipy.io import wavfile
+
+import fac_via_ppg_b200
+from fac_via_ppg_b200 import synth
+from fac_via_ppg_b200.common.hparams import create_hparams_stage
+from fac_via_ppg_b200.common.utils import (get_inference, get_mask_from_lengths_window_and_time_step,
+                                           load_waveglow_model, waveglow_audio)
+from fac_via_ppg_b200.script import generate_synthesis
+from fac_via_ppg_b200.script.train_ppg2mel import load_model
+from fac_via_ppg_b200.waveglow.denoiser import Denoiser
+from fac_via_ppg_b200.waveglow.glow import WaveGlow
+from oracle import tacotron_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def small_waveglow():
+    cfg = synth.WAVEGLOW_CONFIG_SMALL
+    m = WaveGlow(**cfg)                                     # still weight-normed, like a training checkpoint
+    for wn in m.WN:
+        torch.nn.init.normal_(wn.end.weight, std=0.05)
+    return m
+
+
+def test_cli_synthetic_end_to_end(tmp_path):
+    out = tmp_path / "out"
+    rc = generate_synthesis.main(["--ppg2mel_model", "none", "--waveglow_model", "none", "--teacher_utterance_path",
+                                  "none", "--output_dir", str(out), "--synthetic", "0.4"])
+    assert rc == 0
+    fs, wav = wavfile.read(str(out / "ac.wav"))
+    assert fs == 16000 and wav.dtype == np.float32 and wav.ndim == 1
+    assert wav.shape[0] == 40 * 160 and np.isfinite(wav).all() and np.abs(wav).max() > 0
+    assert "Done!" in (out / "debug.log").read_text()
+
+
+def test_checkpoint_formats_and_glue(tmp_path):
+    fac_via_ppg_b200.install_aliases()
+    # WaveGlow: pickled module under key 'model' (reference train_waveglow.py:56-64)
+    wg_path = str(tmp_path / "waveglow.pt")
+    torch.save({"model": small_waveglow(), "iteration": 1}, wg_path)
+    wg = load_waveglow_model(wg_path)
+    assert not hasattr(wg.WN[0].start, "weight_g") and next(wg.parameters()).is_cuda
+    # Tacotron2: {'state_dict': ...} (reference train_ppg2mel.py:143-149)
+    taco_path = str(tmp_path / "taco.pt")
+    torch.save({"state_dict": synth.tacotron_state(), "iteration": 1}, taco_path)
+    taco = load_model(create_hparams_stage())
+    taco.load_state_dict(torch.load(taco_path, weights_only=False)["state_dict"])
+    taco.eval()
+    taco.decoder.gate_threshold, taco.decoder.max_decoder_steps = 2.0, 12
+    ppg = synth.synthetic_ppg(1, 12)[0].t().numpy()          # (T, D) like get_ppg returns
+    mel = get_inference(ppg, taco)
+    assert mel.shape == (1, 80, 12) and mel.is_cuda
+    audio = waveglow_audio(mel, wg, 0.6, True)
+    assert audio.shape == (1, 12 * 160) and torch.isfinite(audio).all()
+    pcm = waveglow_audio(mel, wg, 0.6, False)
+    assert pcm.dtype == np.int16 and pcm.shape == (12 * 160,)
+
+
+def test_denoiser_is_identity_at_zero_strength_and_removes_bias():
+    wg = WaveGlow.remove_weightnorm(small_waveglow()).cuda().eval()
+    den = Denoiser(wg, mode="zeros")
+    assert den.bias_spec.shape == (1, 513, 1)
+    t = torch.arange(16000, device="cuda") / 16000.0
+    audio = (0.3 * torch.sin(2 * np.pi * 220 * t) + 0.1 * torch.sin(2 * np.pi * 1330 * t))[None]
+    same = den(audio, strength=0.0)[:, 0]
+    assert same.shape == audio.shape
+    assert (same - audio)[:, 1024:-1024].abs().max().item() <= 1e-3     # STFT -> iSTFT reconstructs
+    less = den(audio, strength=1.0)[:, 0]
+    assert less.pow(2).mean() <= audio.pow(2).mean() + 1e-6            # magnitudes only shrink
+
+
+def test_window_mask_helper_matches_oracle():
+    lengths = torch.tensor([10, 7, 3], device="cuda")
+    for step in (0, 2, 5, 9, 30):
+        got = get_mask_from_lengths_window_and_time_step(lengths, 3, step).cpu()
+        ref = tacotron_oracle.window_mask([10, 7, 3], 3, step, 10)
+        assert torch.equal(got, ref), step
