@@ -106,6 +106,33 @@ def build_waveglow(device, precision):
     return model
 
 
+def measure_ppg2mel(dev, batch=8, frames=690):
+    """Side metric of BASELINE.json ('mel frames/sec'): Tacotron2.inference on synthetic PPGs
+    (batch x 5816 x frames, forced decode length), exact fp32 CUDA path, CUDA-event phase times."""
+    from fac_via_ppg_b200.common.hparams import create_hparams_stage
+    from fac_via_ppg_b200.common.model import Tacotron2
+    model = Tacotron2(create_hparams_stage())
+    model.load_state_dict(synth.tacotron_state())
+    model = model.to(dev).eval()
+    model.decoder.gate_threshold, model.decoder.max_decoder_steps = 2.0, frames
+    model.collect_timing, model.return_alignments = True, False
+    ppg = synth.synthetic_ppg(batch, frames).to(dev)
+    best = None
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.inference(ppg)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    tm = model.last_timing
+    return {"metric": "mel frames/sec (Tacotron2.inference PPG->Mel)", "value": batch * frames / best,
+            "unit": "frames/s", "batch": batch, "frames": frames, "dtype": "f32",
+            "decoder_us_per_step": tm["decoder_ms"] * 1e3 / frames, "encoder_ms": tm["encoder_ms"],
+            "decoder_ms": tm["decoder_ms"], "postnet_ms": tm["postnet_ms"],
+            "hbm_compulsory_gbs": batch * frames * 5816 * 4 / best / 1e9}
+
+
 def cpu_port_samples_per_s(frames, repeats, threads):
     """The reference's CPU implementation of the step (oracle restatement, torch CPU fp32)."""
     from oracle import waveglow_oracle   # the one place bench.py executes oracle/: the CPU baseline
@@ -175,6 +202,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ppg2mel", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -269,6 +297,11 @@ def main():
     peaks = measured_peaks()
     roof = model.profile_dominant_kernel(mel, peaks) if hasattr(model, "profile_dominant_kernel") else None
 
+    # ---- PPG -> Mel side metric (mel frames/s), short and outside the timed region ----------
+    ppg2mel = None
+    if world == 1 and not args.no_ppg2mel:
+        ppg2mel = measure_ppg2mel(dev)
+
     # ---- CPU baseline (bounded sample of the same workload, rank 0 only) ----------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -294,6 +327,7 @@ def main():
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "ppg2mel": ppg2mel,
         "tflops_algorithmic": value * WG_FLOP_PER_SAMPLE / 1e12,
         "hbm": {"compulsory_bytes_per_sample": WG_HBM_BYTES_PER_SAMPLE,
                 "achieved_gbs": value * WG_HBM_BYTES_PER_SAMPLE / 1e9 / world,

@@ -67,13 +67,13 @@ class WgTcWorkspace(C.Structure):
 
 
 class TacoDecoderWeights(C.Structure):
-    _fields_ = [(n, _fp) for n in ("w_att", "b_att", "w_dec", "b_dec", "wq_t", "w_loc", "w_ld_t", "v", "w_proj",
-                                   "b_proj", "w_pre1_t", "w_pre2_t")]
+    _fields_ = [(n, _fp) for n in ("w_att", "b_att", "w_dec", "b_dec", "wq", "w_loc", "w_ld_t", "v", "w_pp", "b_pp",
+                                   "w_pre2")]
 
 
 class TacoDecoderState(C.Structure):
-    _fields_ = [(n, _fp) for n in ("h_att", "c_att", "h_dec", "c_dec", "ctx", "pre", "w_prev", "w_cum", "done",
-                                   "out_len")]
+    _fields_ = [(n, _fp) for n in ("h_att", "c_att", "h_dec", "c_dec", "ctx", "pre", "p1", "pq", "w_prev", "w_cum",
+                                   "done", "out_len")]
 
 
 # name -> (restype, argtypes); every symbol include/fac_b200.h declares.
@@ -98,6 +98,7 @@ SIGNATURES = {
     "fac_waveglow_infer_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), _fp, _fp, _P(WgTcWorkspace), C.c_int, C.c_int,
                                         C.c_int, _fp]),
     "fac_tc_set_profile_buffer": (None, [_fp]),
+    "fac_selftest_grid_barrier": (C.c_int, [_fp, C.c_int, _fp]),
     "fac_lstm_bidir_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "fac_taco_decoder_run": (C.c_int, [_P(TacoDecoderWeights), _fp, _fp, _fp, _fp, _P(TacoDecoderState), _fp, _fp,
                                        _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),

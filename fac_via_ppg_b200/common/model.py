@@ -132,6 +132,7 @@ class Tacotron2(nn.Module):
     """Reference-compatible PPG->Mel model (reference model.py:538-610), CUDA-native inference."""
 
     rng_mode = "fast"            # 'fast' | 'reference'  (see module docstring)
+    collect_timing = False       # True: CUDA-event times of encoder / decoder / postnet in .last_timing (ms)
     return_alignments = True     # dense (B, T_out, T_in) like the reference; False saves memory on long inputs
 
     def __init__(self, hparams):
@@ -221,7 +222,8 @@ class Tacotron2(nn.Module):
                              torch.empty(B, T, A, device=dev), batch=B, rows=T)
         z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)  # noqa: E731
         st = {"h_att": z(2, B, R), "c_att": z(B, R), "h_dec": z(2, B, R), "c_dec": z(B, R), "ctx": z(B, E),
-              "pre": z(B, hp["prenet_dim"]), "w_prev": z(B, T), "w_cum": z(B, T),
+              "pre": z(B, hp["prenet_dim"]), "p1": z(B, hp["prenet_dim"]), "pq": z(B, A), "w_prev": z(B, T),
+              "w_cum": z(B, T),
               "done": torch.zeros(4, dtype=torch.int32, device=dev),
               "out_len": torch.zeros(B, dtype=torch.int32, device=dev)}
         cstate = _ext.TacoDecoderState(*[st[n].data_ptr() for n, _ in _ext.TacoDecoderState._fields_])
@@ -272,8 +274,15 @@ class Tacotron2(nn.Module):
         packed = self.packed()
         n_steps = int(self.decoder.max_decoder_steps)
         enc0, enc1, dec_masks = self._dropout_masks(B, T, n_steps, x.device, dropout_tape)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.collect_timing else None
+        if ev:
+            ev[0].record()
         memory = self._encode(packed, x, enc0, enc1)
+        if ev:
+            ev[1].record()
         mel_cl, gate, align, out_len, done = self._decode(packed, memory, dec_masks, n_steps)
+        if ev:
+            ev[2].record()
         lens = out_len.cpu()                                          # the one device->host sync of the call
         t_out = int(lens.max())
         if int(done.cpu()[1]) > 0:
@@ -284,6 +293,11 @@ class Tacotron2(nn.Module):
             mel_cl = mel_cl * keep
         self.last_output_lengths = lens
         post_cl = self._postnet(packed, mel_cl)
+        if ev:
+            ev[3].record()
+            torch.cuda.synchronize()
+            self.last_timing = {"encoder_ms": ev[0].elapsed_time(ev[1]), "decoder_ms": ev[1].elapsed_time(ev[2]),
+                                "postnet_ms": ev[2].elapsed_time(ev[3]), "decoder_steps": t_out}
         outputs = [mel_cl.transpose(1, 2), post_cl.transpose(1, 2), gate[:, :t_out].unsqueeze(-1),
                    align[:, :t_out] if align is not None else None]
         return self.parse_output(outputs)

@@ -3,19 +3,19 @@
 // :56-60 LocationLayer, :124-135 Prenet, src/common/utils.py:46-78 window mask).
 //
 // The reference spends ~40 kernel launches and >= 3 device->host syncs per output frame; here the
-// whole loop (up to max_steps frames, all B utterances in lock step) is a single launch:
-//   * the two LSTMCells (1200 x 1200 fp32 each, 11.5 MB together) are split by hidden unit across
-//     the shared memory of all CTAs (one CTA per SM) and stay resident for the whole sequence;
-//   * per step: [attention LSTM | all CTAs] -> grid barrier -> [location-sensitive attention over the
-//     +-window only | one CTA per utterance] -> barrier -> [decoder LSTM | all CTAs] -> barrier ->
-//     [mel projection + stop gate + prenet of the next step | one CTA per utterance] -> barrier;
-//   * the window mask of utils.py:46-78 sets every energy outside [t-w, t+w] to -inf, i.e. those
-//     softmax weights are exactly 0, so only the <= 2w+1 window positions are ever evaluated;
+// whole loop (up to max_steps frames, all B utterances in lock step) is a single launch.
+//   * EVERY weight matrix of the step is split by output row across the shared memory of all CTAs
+//     (one CTA per SM) and stays resident for the whole sequence: the two LSTMCells (11.5 MB fp32),
+//     the query layer, [mel projection | stop gate | prenet layer 0 composed with the projection]
+//     and prenet layer 1.  Per step the only global traffic is the small state vectors (L2 resident).
+//   * A step is six batched mat-vec phases separated by a lightweight grid barrier (one atomic +
+//     acquire spin): attention LSTM | query | location-sensitive attention (one CTA per utterance,
+//     only the <= 2w+1 window positions: everything outside [t-w, t+w] is masked to -inf by
+//     utils.py:46-78, i.e. has softmax weight exactly 0) | decoder LSTM | projection+gate+prenet0 |
+//     prenet1.  prenet0 has no bias or nonlinearity between it and the projection
+//     (model.py:132-135, 436-438), so W_pre0 (W_proj hc + b) is evaluated as one composed matrix.
 //   * the stop decision (sigmoid(gate) > threshold) is taken on the device.
 #include "fac_common.cuh"
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
 
 namespace fac {
 
@@ -44,28 +44,31 @@ constexpr int M = 80;     // n_acoustic_feat_dims
 constexpr int NF = 32;    // attention_location_n_filters
 constexpr int KF = 31;    // attention_location_kernel_size
 constexpr int KIN = R + E + R;  // 1200: LSTMCell input | hidden concatenation
+constexpr int KHC = R + E;      // 900: [h_dec | context]
+constexpr int NPP = M + 1 + R;  // 381 rows: mel projection, gate, composed prenet layer 0
 constexpr int MAXU = 3;         // hidden units per CTA (needs >= 100 CTAs)
-constexpr int CHUNK = 8;        // utterances staged per LSTM pass
+constexpr int MAXQ = 2;         // query rows per CTA
+constexpr int MAXPP = 4;        // projection rows per CTA
+constexpr int MAXP2 = 3;        // prenet-1 rows per CTA
+constexpr int CHUNK = 8;        // utterances staged per pass
 constexpr int MAXW = 64;        // max window positions (2*window+1 <= 64)
 
 struct Smem {
   float w_att[MAXU * 4][KIN];
   float w_dec[MAXU * 4][KIN];
+  float w_q[MAXQ][R];
+  float w_pp[MAXPP][KHC];
+  float w_p2[MAXP2][R];
   float w_loc[2 * KF][NF];   // [c*KF + k][f]
   float w_ld[NF][A];         // location_dense transposed
   float v[A];
   alignas(16) union {
-    float in[CHUNK][KIN];    // LSTM phases
-    struct {                 // attention / projection phases
-      float hq[R];
-      float part[DEC_WARPS][R];
+    float in[CHUNK][KIN];    // batched mat-vec phases
+    struct {                 // attention phase
       float pq[A];
       float cat[2][MAXW + KF - 1 + 2];
       float loc[MAXW][NF];
       float e[MAXW];
-      float hc[R + E];
-      float melv[M];
-      float p1[R];
     } a;
   } u;
 };
@@ -76,25 +79,53 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Grid-wide barrier: monotonically increasing arrival counter (zeroed by the host), release/acquire.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct Seg {           // one piece of a concatenated input vector: utterance b reads ptr[b*stride + k]
+  const float* ptr;
+  int len, stride;
+};
+
+// Stage the concatenated inputs of utterances [n0, n0+nb) into shared memory (read through L2:
+// they were written by other CTAs in the previous phase).
+__device__ __forceinline__ void stage_inputs(Smem& sm, const Seg* segs, int n_seg, int K, int n0, int nb) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb * K; i += DEC_THREADS) {
+    const int n = i / K;
+    int k = i - n * K;
+    const int b = n0 + n;
+    float v = 0.f;
+    int base = 0;
+    for (int s = 0; s < n_seg; ++s) {
+      if (k >= base && k < base + segs[s].len) v = __ldcg(segs[s].ptr + (long long)b * segs[s].stride + (k - base));
+      base += segs[s].len;
+    }
+    sm.u.in[n][k] = v;
+  }
+  __syncthreads();
+}
+
 // One LSTMCell for the units [u0, u0+nu) of this CTA and all B utterances.
-// in = [x0 (R) | ctx (E) | h_prev (R)]; writes h_next / c.
-__device__ void lstm_phase(Smem& sm, const float (*w_s)[KIN], const float* __restrict__ bias, const float* x0,
-                           const float* ctx, const float* h_prev, float* h_next, float* c, int B, int u0, int nu) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ void lstm_phase(Smem& sm, const float (*w_s)[KIN], const float* __restrict__ bias, const Seg* segs,
+                           float* h_next, float* c, int B, int u0, int nu) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int n0 = 0; n0 < B; n0 += CHUNK) {
     const int nb = min(CHUNK, B - n0);
-    __syncthreads();
-    for (int i = tid; i < nb * KIN; i += DEC_THREADS) {
-      const int n = i / KIN, k = i - n * KIN;
-      const int b = n0 + n;
-      float v;
-      // written by other CTAs in the previous phase: read through L2 (.cg), never a stale L1 line
-      if (k < R) v = __ldcg(x0 + b * R + k);
-      else if (k < R + E) v = __ldcg(ctx + b * E + (k - R));
-      else v = __ldcg(h_prev + b * R + (k - R - E));
-      sm.u.in[n][k] = v;
-    }
-    __syncthreads();
+    stage_inputs(sm, segs, 3, KIN, n0, nb);
     // warp tile: the 4 gate rows of one unit x 4 utterances
     const int n_tiles = nu * ((nb + 3) / 4);
     for (int tile = warp; tile < n_tiles; tile += DEC_WARPS) {
@@ -139,25 +170,37 @@ __device__ void lstm_phase(Smem& sm, const float (*w_s)[KIN], const float* __res
   }
 }
 
-// out[j] (j < n_out) = sum_k wt[k][j] * x[k], k < n_in; wt is (n_in, n_out) row-major in global memory.
-// K is split across the 8 warps, lanes run over j (coalesced), partials reduced through shared memory.
-__device__ void matvec_t(Smem& sm, const float* __restrict__ wt, const float* x_s, int n_in, int n_out, float* out_s) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int kper = (n_in + DEC_WARPS - 1) / DEC_WARPS;
-  const int k0 = warp * kper, k1 = min(n_in, k0 + kper);
-  for (int j = lane; j < n_out; j += 32) {
-    float acc = 0.f;
-    for (int k = k0; k < k1; ++k) acc = fmaf(__ldg(wt + (long long)k * n_out + j), x_s[k], acc);
-    sm.u.a.part[warp][j] = acc;
-  }
-  __syncthreads();
-  for (int j = tid; j < n_out; j += DEC_THREADS) {
-    float acc = 0.f;
+// Batched mat-vec over this CTA's resident rows: for every owned row r (global index row0 + r) and every
+// utterance b, epi(row0 + r, b, dot(w_s[r], in_b)).  K % 4 == 0.
+template <int KROW, typename Epi>
+__device__ void rows_phase(Smem& sm, const float (*w_s)[KROW], int row0, int nr, const Seg* segs, int n_seg, int B,
+                           Epi epi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int n0 = 0; n0 < B; n0 += CHUNK) {
+    const int nb = min(CHUNK, B - n0);
+    stage_inputs(sm, segs, n_seg, KROW, n0, nb);
+    const int n_tiles = nr * ((nb + 3) / 4);
+    for (int tile = warp; tile < n_tiles; tile += DEC_WARPS) {
+      const int r = tile % nr, ng = (tile / nr) * 4;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k4 = lane; k4 < KROW / 4; k4 += 32) {
+        const float4 wv = *reinterpret_cast<const float4*>(&w_s[r][k4 * 4]);
 #pragma unroll
-    for (int w = 0; w < DEC_WARPS; ++w) acc += sm.u.a.part[w][j];
-    out_s[j] = acc;
+        for (int n = 0; n < 4; ++n) {
+          if (ng + n < nb) {
+            const float4 xv = *reinterpret_cast<const float4*>(&sm.u.in[ng + n][k4 * 4]);
+            acc[n] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[n]))));
+          }
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) acc[n] = warp_sum(acc[n]);
+      if (lane < 4 && ng + lane < nb) {
+        const float a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        epi(row0 + r, n0 + ng + lane, a);
+      }
+    }
   }
-  __syncthreads();
 }
 
 __device__ __forceinline__ void window_bounds(int t, int window, int len, int& start, int& end) {
@@ -167,14 +210,14 @@ __device__ __forceinline__ void window_bounds(int t, int window, int len, int& s
   end = min(t + window, max_idx);
 }
 
-__device__ void attention_phase(Smem& sm, const DecParams& p, int b, int t, const float* h_att) {
+__device__ void attention_phase(Smem& sm, const DecParams& p, int b, int t) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int len = p.lengths[b];
   int start, end;
   window_bounds(t, p.window, len, start, end);
   const int nw = end - start + 1;
   __syncthreads();
-  for (int i = tid; i < R; i += DEC_THREADS) sm.u.a.hq[i] = __ldcg(h_att + b * R + i);
+  for (int i = tid; i < A; i += DEC_THREADS) sm.u.a.pq[i] = __ldcg(p.s.pq + b * A + i);   // query_layer (model.py:92)
   // previous / cumulative weights around the window (zero outside the sequence: conv padding)
   const int c0 = start - (KF - 1) / 2, ncat = nw + KF - 1;
   float* wprev = p.s.w_prev + (long long)b * p.T_in;
@@ -186,7 +229,6 @@ __device__ void attention_phase(Smem& sm, const DecParams& p, int b, int t, cons
     sm.u.a.cat[c][q] = v;
   }
   __syncthreads();
-  matvec_t(sm, p.w.wq_t, sm.u.a.hq, R, A, sm.u.a.pq);   // query_layer (model.py:92)
   // location_conv (model.py:57): loc[q][f] = sum_{c,k} w[f][c][k] * cat[c][q + k]
   for (int i = tid; i < nw * NF; i += DEC_THREADS) {
     const int q = i / NF, f = i - q * NF;
@@ -247,69 +289,33 @@ __device__ void attention_phase(Smem& sm, const DecParams& p, int b, int t, cons
   }
 }
 
-__device__ void output_phase(Smem& sm, const DecParams& p, int b, int t, const float* h_dec) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __syncthreads();
-  for (int i = tid; i < R + E; i += DEC_THREADS)
-    sm.u.a.hc[i] = i < R ? __ldcg(h_dec + b * R + i) : __ldcg(p.s.ctx + b * E + (i - R));
-  __syncthreads();
-  // linear_projection (rows 0..M-1) and gate_layer (row M), model.py:436-441
-  for (int r = warp; r <= M; r += DEC_WARPS) {
-    const float* wr = p.w.w_proj + (long long)r * (R + E);
-    float acc = 0.f;
-    for (int k = lane; k < R + E; k += 32) acc = fmaf(__ldg(wr + k), sm.u.a.hc[k], acc);
-    acc = warp_sum(acc) + __ldg(p.w.b_proj + r);
-    if (lane == 0) {
-      if (r < M) {
-        sm.u.a.melv[r] = acc;
-        p.mel[((long long)b * p.max_steps + t) * M + r] = acc;
-      } else {
-        p.gate[(long long)b * p.max_steps + t] = acc;
-        // stop test (model.py:524), per utterance
-        if (p.s.out_len[b] == 0) {
-          if (sigmoidf_exact(acc) > p.gate_threshold) {
-            p.s.out_len[b] = t + 1;
-            atomicAdd(p.s.done, 1);
-          } else if (t + 1 == p.max_steps) {
-            p.s.out_len[b] = p.max_steps;   // model.py:526-528 "Reached max decoder steps"
-            atomicAdd(p.s.done + 1, 1);
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (t + 1 >= p.max_steps) return;
-  // prenet of the next step (model.py:507, 132-135): dropout p=0.5 is always on -> mask * 2
-  const unsigned char* d1 = p.drop + (((long long)(t + 1) * 2 + 0) * p.B + b) * R;
-  const unsigned char* d2 = p.drop + (((long long)(t + 1) * 2 + 1) * p.B + b) * R;
-  for (int j = tid; j < R; j += DEC_THREADS) {
-    float acc = 0.f;
-    for (int k = 0; k < M; ++k) acc = fmaf(__ldg(p.w.w_pre1_t + k * R + j), sm.u.a.melv[k], acc);
-    sm.u.a.p1[j] = fmaxf(acc, 0.f) * (2.0f * (float)d1[j]);
-  }
-  __syncthreads();
-  matvec_t(sm, p.w.w_pre2_t, sm.u.a.p1, R, R, sm.u.a.hq);
-  for (int j = tid; j < R; j += DEC_THREADS) p.s.pre[b * R + j] = fmaxf(sm.u.a.hq[j], 0.f) * (2.0f * (float)d2[j]);
+__device__ __forceinline__ void row_range(int n_rows, int& r0, int& nr) {
+  r0 = (int)((long long)blockIdx.x * n_rows / gridDim.x);
+  nr = (int)((long long)(blockIdx.x + 1) * n_rows / gridDim.x) - r0;
 }
 
 __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int G = gridDim.x;
-  const int u0 = (int)((long long)blockIdx.x * R / G);
-  const int u1 = (int)((long long)(blockIdx.x + 1) * R / G);
-  const int nu = u1 - u0;
+  int u0, nu, q0, nq, pp0, npp, p20, np2;
+  row_range(R, u0, nu);
+  row_range(A, q0, nq);
+  row_range(NPP, pp0, npp);
+  row_range(R, p20, np2);
 
-  // resident weights: the LSTM rows of this CTA's hidden units + the small attention tensors
+  // ---- resident weights: this CTA's rows of every matrix of the step + the small attention tensors
   for (int i = tid; i < nu * 4 * KIN; i += DEC_THREADS) {
     const int q = i / KIN, k = i - q * KIN;
     const int g = q / nu, u = q - g * nu;
     sm.w_att[q][k] = __ldg(p.w.w_att + (long long)(g * R + u0 + u) * KIN + k);
     sm.w_dec[q][k] = __ldg(p.w.w_dec + (long long)(g * R + u0 + u) * KIN + k);
   }
+  for (int i = tid; i < nq * R; i += DEC_THREADS) sm.w_q[i / R][i % R] = __ldg(p.w.wq + (long long)q0 * R + i);
+  for (int i = tid; i < npp * KHC; i += DEC_THREADS)
+    sm.w_pp[i / KHC][i % KHC] = __ldg(p.w.w_pp + (long long)pp0 * KHC + i);
+  for (int i = tid; i < np2 * R; i += DEC_THREADS) sm.w_p2[i / R][i % R] = __ldg(p.w.w_pre2 + (long long)p20 * R + i);
   for (int i = tid; i < 2 * KF * NF; i += DEC_THREADS) {
     const int ck = i / NF, f = i - ck * NF;            // w_loc is (NF, 2, KF)
     sm.w_loc[ck][f] = __ldg(p.w.w_loc + f * 2 * KF + ck);
@@ -318,22 +324,79 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
   for (int i = tid; i < A; i += DEC_THREADS) sm.v[i] = __ldg(p.w.v + i);
   __syncthreads();
 
+  unsigned int* bar = reinterpret_cast<unsigned int*>(p.s.done + 3);
+  unsigned int bar_target = 0;
   int cur = 0;
   for (int t = 0; t < p.max_steps; ++t) {
     float* h_att_cur = p.s.h_att + cur * p.B * R;
     float* h_att_nxt = p.s.h_att + (cur ^ 1) * p.B * R;
     float* h_dec_cur = p.s.h_dec + cur * p.B * R;
     float* h_dec_nxt = p.s.h_dec + (cur ^ 1) * p.B * R;
-    // attention_rnn (model.py:400-402): input [prenet | context], hidden h_att
-    lstm_phase(sm, sm.w_att, p.w.b_att, p.s.pre, p.s.ctx, h_att_cur, h_att_nxt, p.s.c_att, p.B, u0, nu);
-    grid.sync();
-    for (int b = blockIdx.x; b < p.B; b += G) attention_phase(sm, p, b, t, h_att_nxt);
-    grid.sync();
-    // decoder_rnn (model.py:425-428): input [h_att | context], hidden h_dec
-    lstm_phase(sm, sm.w_dec, p.w.b_dec, h_att_nxt, p.s.ctx, h_dec_cur, h_dec_nxt, p.s.c_dec, p.B, u0, nu);
-    grid.sync();
-    for (int b = blockIdx.x; b < p.B; b += G) output_phase(sm, p, b, t, h_dec_nxt);
-    grid.sync();
+    // (1) attention_rnn (model.py:400-402): input [prenet | context], hidden h_att
+    {
+      const Seg segs[3] = {{p.s.pre, R, R}, {p.s.ctx, E, E}, {h_att_cur, R, R}};
+      lstm_phase(sm, sm.w_att, p.w.b_att, segs, h_att_nxt, p.s.c_att, p.B, u0, nu);
+    }
+    grid_barrier(bar, bar_target);
+    // (2) query_layer (model.py:92): pq = W_q h_att
+    {
+      const Seg segs[1] = {{h_att_nxt, R, R}};
+      float* pq = p.s.pq;
+      rows_phase<R>(sm, sm.w_q, q0, nq, segs, 1, p.B, [pq](int row, int b, float v) { pq[b * A + row] = v; });
+    }
+    grid_barrier(bar, bar_target);
+    // (3) location-sensitive attention, one CTA per utterance
+    for (int b = blockIdx.x; b < p.B; b += G) attention_phase(sm, p, b, t);
+    grid_barrier(bar, bar_target);
+    // (4) decoder_rnn (model.py:425-428): input [h_att | context], hidden h_dec
+    {
+      const Seg segs[3] = {{h_att_nxt, R, R}, {p.s.ctx, E, E}, {h_dec_cur, R, R}};
+      lstm_phase(sm, sm.w_dec, p.w.b_dec, segs, h_dec_nxt, p.s.c_dec, p.B, u0, nu);
+    }
+    grid_barrier(bar, bar_target);
+    // (5) [linear_projection | gate_layer | prenet layer 0 o projection] on hc = [h_dec | context]
+    //     (model.py:436-441, 507, 132-135)
+    {
+      const Seg segs[2] = {{h_dec_nxt, R, R}, {p.s.ctx, E, E}};
+      const DecParams* pp = &p;
+      const int tt = t;
+      rows_phase<KHC>(sm, sm.w_pp, pp0, npp, segs, 2, p.B, [pp, tt](int row, int b, float v) {
+        const DecParams& q = *pp;
+        v += __ldg(q.w.b_pp + row);
+        if (row < M) {
+          q.mel[((long long)b * q.max_steps + tt) * M + row] = v;
+        } else if (row == M) {
+          q.gate[(long long)b * q.max_steps + tt] = v;
+          if (q.s.out_len[b] == 0) {          // stop test (model.py:524), per utterance
+            if (sigmoidf_exact(v) > q.gate_threshold) {
+              q.s.out_len[b] = tt + 1;
+              atomicAdd(q.s.done, 1);
+            } else if (tt + 1 == q.max_steps) {
+              q.s.out_len[b] = q.max_steps;     // model.py:526-528 "Reached max decoder steps"
+              atomicAdd(q.s.done + 1, 1);
+            }
+          }
+        } else if (tt + 1 < q.max_steps) {
+          // prenet layer 0 of the NEXT step; dropout p = 0.5 is always on -> mask * 2
+          const int j = row - M - 1;
+          const unsigned char d = q.drop[(((long long)(tt + 1) * 2 + 0) * q.B + b) * R + j];
+          q.s.p1[b * R + j] = fmaxf(v, 0.f) * (2.0f * (float)d);
+        }
+      });
+    }
+    grid_barrier(bar, bar_target);
+    // (6) prenet layer 1 of the next step
+    if (t + 1 < p.max_steps) {
+      const Seg segs[1] = {{p.s.p1, R, R}};
+      const DecParams* pp = &p;
+      const int tt = t;
+      rows_phase<R>(sm, sm.w_p2, p20, np2, segs, 1, p.B, [pp, tt](int row, int b, float v) {
+        const DecParams& q = *pp;
+        const unsigned char d = q.drop[(((long long)(tt + 1) * 2 + 1) * q.B + b) * R + row];
+        q.s.pre[b * R + row] = fmaxf(v, 0.f) * (2.0f * (float)d);
+      });
+    }
+    grid_barrier(bar, bar_target);
     cur ^= 1;
     // every utterance has fired its stop gate (or hit max_steps): uniform exit
     const volatile int* done = p.s.done;
@@ -344,7 +407,29 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
   }
 }
 
+__global__ void __launch_bounds__(DEC_THREADS, 1) grid_barrier_selftest_kernel(unsigned int* counter, int iters) {
+  unsigned int target = 0;
+  for (int i = 0; i < iters; ++i) grid_barrier(counter, target);
+}
+
 }  // namespace
+
+// Diagnostic: `iters` back-to-back grid barriers on a full cooperative grid (1 CTA / SM); the caller
+// times the launch to get the per-barrier cost that bounds the decoder's step latency.
+int selftest_grid_barrier(unsigned int* counter, int iters, cudaStream_t st) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  void* args[] = {&counter, &iters};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)grid_barrier_selftest_kernel, dim3(sms), dim3(DEC_THREADS), args,
+                                              0, st);
+  count_launch();
+  if (e != cudaSuccess) {
+    set_error("selftest_grid_barrier: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
 
 int taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, const float* pmem, const int* lengths,
                      const unsigned char* drop, const fac_taco_decoder_state* s, float* mel, float* gate, float* align,
@@ -358,7 +443,8 @@ int taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, con
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   FAC_REQUIRE(coop, "taco_decoder: device lacks cooperative launch");
-  FAC_REQUIRE(sms * MAXU >= R, "taco_decoder: needs >= %d SMs, device has %d", (R + MAXU - 1) / MAXU, sms);
+  FAC_REQUIRE(sms * MAXU >= R && sms * MAXQ >= A && sms * (MAXPP - 1) >= NPP,
+              "taco_decoder: needs >= %d SMs, device has %d", (NPP + MAXPP - 2) / (MAXPP - 1), sms);
   const size_t smem = sizeof(Smem);
   cudaError_t e = cudaFuncSetAttribute(taco_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
@@ -372,6 +458,7 @@ int taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, con
   p.mel = mel; p.gate = gate; p.align = align;
   p.B = B; p.T_in = T_in; p.max_steps = max_steps; p.window = window; p.gate_threshold = gate_threshold;
   void* args[] = {&p};
+  // cooperative launch = co-residency guarantee for the grid barrier
   e = cudaLaunchCooperativeKernel((void*)taco_decoder_kernel, dim3(sms), dim3(DEC_THREADS), args, smem, st);
   count_launch();
   if (e != cudaSuccess) {

@@ -293,14 +293,13 @@ def tacotron_layout(hp) -> FlatLayout:
     lay.add("dec.b_att", (4 * R,))
     lay.add("dec.w_dec", (4 * R, kin))
     lay.add("dec.b_dec", (4 * R,))
-    lay.add("dec.wq_t", (R, A))
+    lay.add("dec.wq", (A, R))
     lay.add("dec.w_loc", (hp["attention_location_n_filters"], 2, hp["attention_location_kernel_size"]))
     lay.add("dec.w_ld_t", (hp["attention_location_n_filters"], A))
     lay.add("dec.v", (A,))
-    lay.add("dec.w_proj", (M + 1, R + E))
-    lay.add("dec.b_proj", (M + 1,))
-    lay.add("dec.w_pre1_t", (M, P))
-    lay.add("dec.w_pre2_t", (P, P))
+    lay.add("dec.w_pp", (M + 1 + P, R + E))
+    lay.add("dec.b_pp", (M + 1 + P,))
+    lay.add("dec.w_pre2", (P, P))
     n_post = hp["postnet_n_convolutions"]
     dims = [M] + [Pe] * (n_post - 1) + [M]
     for i in range(n_post):
@@ -334,8 +333,7 @@ class PackedTacotron:
         self.layout = tacotron_layout(hp)
         self.flat = torch.zeros(self.layout.size, dtype=torch.float32, device=device)
         w = _ext.TacoDecoderWeights()
-        for name in ("w_att", "b_att", "w_dec", "b_dec", "wq_t", "w_loc", "w_ld_t", "v", "w_proj", "b_proj",
-                     "w_pre1_t", "w_pre2_t"):
+        for name in ("w_att", "b_att", "w_dec", "b_dec", "wq", "w_loc", "w_ld_t", "v", "w_pp", "b_pp", "w_pre2"):
             setattr(w, name, self.layout.ptr(self.flat, "dec." + name))
         self.cdecoder = w
 
@@ -382,16 +380,19 @@ class PackedTacotron:
             p = f"decoder.{cell}."
             put(f"dec.w_{name}", torch.cat([get(p + "weight_ih"), get(p + "weight_hh")], dim=1))
             put(f"dec.b_{name}", get(p + "bias_ih") + get(p + "bias_hh"))
-        put("dec.wq_t", get(al + "query_layer.linear_layer.weight").t())
+        put("dec.wq", get(al + "query_layer.linear_layer.weight"))
         self.view("dec.w_loc").copy_(get(al + "location_layer.location_conv.conv.weight"))
         put("dec.w_ld_t", get(al + "location_layer.location_dense.linear_layer.weight").t())
         put("dec.v", get(al + "v.linear_layer.weight")[0])
-        put("dec.w_proj", torch.cat([get("decoder.linear_projection.linear_layer.weight"),
-                                     get("decoder.gate_layer.linear_layer.weight")], dim=0))
-        put("dec.b_proj", torch.cat([get("decoder.linear_projection.linear_layer.bias"),
-                                     get("decoder.gate_layer.linear_layer.bias")]))
-        put("dec.w_pre1_t", get("decoder.prenet.layers.0.linear_layer.weight").t())
-        put("dec.w_pre2_t", get("decoder.prenet.layers.1.linear_layer.weight").t())
+        # The next step's prenet layer 0 is applied straight to the projected frame (no bias, no
+        # nonlinearity in between): compose it with the projection in fp64 once.
+        w_proj, b_proj = get("decoder.linear_projection.linear_layer.weight"), get("decoder.linear_projection.linear_layer.bias")
+        w_pre0 = get("decoder.prenet.layers.0.linear_layer.weight").double()
+        put("dec.w_pp", torch.cat([w_proj, get("decoder.gate_layer.linear_layer.weight"),
+                                   (w_pre0 @ w_proj.double()).float()], dim=0))
+        put("dec.b_pp", torch.cat([b_proj, get("decoder.gate_layer.linear_layer.bias"),
+                                   (w_pre0 @ b_proj.double()).float()]))
+        put("dec.w_pre2", get("decoder.prenet.layers.1.linear_layer.weight"))
         for i in range(hp["postnet_n_convolutions"]):
             w, b = _fold_bn(sd, f"postnet.convolutions.{i}.", dev)
             put(f"post.conv{i}_w", w.permute(2, 1, 0).reshape(-1, w.shape[0]))

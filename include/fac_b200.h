@@ -194,14 +194,15 @@ typedef struct fac_taco_decoder_weights {
   const float* b_att;    /* [1200] bias_ih + bias_hh                                                            */
   const float* w_dec;    /* [1200][1200] decoder_rnn: cat(weight_ih (h_att 300 | context 600), weight_hh 300)   */
   const float* b_dec;    /* [1200]                                                                              */
-  const float* wq_t;     /* [300][150]  attention_layer.query_layer weight, transposed                          */
+  const float* wq;       /* [150][300]  attention_layer.query_layer weight                                      */
   const float* w_loc;    /* [32][2][31] attention_layer.location_layer.location_conv weight                     */
   const float* w_ld_t;   /* [32][150]   location_dense weight, transposed                                       */
   const float* v;        /* [150]       attention_layer.v weight                                                */
-  const float* w_proj;   /* [81][900]   rows 0..79 linear_projection, row 80 gate_layer                         */
-  const float* b_proj;   /* [81]                                                                                */
-  const float* w_pre1_t; /* [80][300]   decoder.prenet.layers.0 weight, transposed                              */
-  const float* w_pre2_t; /* [300][300]  decoder.prenet.layers.1 weight, transposed                              */
+  const float* w_pp;     /* [381][900]  rows 0..79 linear_projection, row 80 gate_layer, rows 81..380 =
+                                        prenet.layers.0 @ linear_projection (no bias / nonlinearity sits between
+                                        the projection and the first prenet layer, model.py:132-135, 436-438)   */
+  const float* b_pp;     /* [381]       projection bias, gate bias, prenet.layers.0 @ projection bias           */
+  const float* w_pre2;   /* [300][300]  decoder.prenet.layers.1 weight                                          */
 } fac_taco_decoder_weights;
 
 /* Decoder state the caller allocates ZERO-FILLED (reference model.py:304-335 initialises every
@@ -213,11 +214,17 @@ typedef struct fac_taco_decoder_state {
   float* c_dec;   /* [B][300]    decoder_cell                                */
   float* ctx;     /* [B][600]    attention_context                           */
   float* pre;     /* [B][300]    prenet output feeding the next step         */
+  float* p1;      /* [B][300]    prenet layer-0 output (scratch)             */
+  float* pq;      /* [B][150]    processed query (scratch)                   */
   float* w_prev;  /* [B][T_in]   attention_weights                           */
   float* w_cum;   /* [B][T_in]   attention_weights_cum                       */
-  int* done;      /* [4]: #utterances stopped by the gate, #stopped by max_steps, steps run, spare */
+  int* done;      /* [4]: #utterances stopped by the gate, #stopped by max_steps, steps run, grid-barrier counter */
   int* out_len;   /* [B] number of frames of each utterance (0 while running) */
 } fac_taco_decoder_state;
+
+/* Diagnostic: runs `iters` grid-wide barriers of the decoder kernel's kind on a full cooperative grid;
+ * time the launch to get the per-barrier latency.  `zeroed_counter` is one zero-initialised uint32. */
+int fac_selftest_grid_barrier(unsigned int* zeroed_counter, int iters, void* stream);
 
 /* The whole autoregressive loop of Decoder.inference (reference model.py:489-535 with decode
  * :387-442, Attention :100-121, window mask utils.py:46-78) in one persistent kernel.

@@ -131,7 +131,7 @@ def tacotron_inference(packed, inputs, masks, n_steps, window, gate_threshold=2.
         h_att, c_att = cell(v("dec.w_att"), v("dec.b_att"), torch.cat([pre, ctx, h_att], -1), c_att)
         start, end = min(max(0, t - window), T - 1), min(t + window, T - 1)
         nw = end - start + 1
-        pq = h_att @ v("dec.wq_t")
+        pq = h_att @ v("dec.wq").t()
         cat = torch.zeros(B, 2, nw + 30)
         for q in range(nw + 30):
             pos = start - 15 + q
@@ -146,11 +146,11 @@ def tacotron_inference(packed, inputs, masks, n_steps, window, gate_threshold=2.
         w_cum[:, start:end + 1] += w
         align[:, t, start:end + 1] = w
         h_dec, c_dec = cell(v("dec.w_dec"), v("dec.b_dec"), torch.cat([h_att, ctx, h_dec], -1), c_dec)
-        out = torch.cat([h_dec, ctx], -1) @ v("dec.w_proj").t() + v("dec.b_proj")
+        out = torch.cat([h_dec, ctx], -1) @ v("dec.w_pp").t() + v("dec.b_pp")
         mel[:, t], gate[:, t] = out[:, :M], out[:, M]
-        if t + 1 < n_steps:
-            p1 = torch.relu(out[:, :M] @ v("dec.w_pre1_t")) * masks[2 + 2 * (t + 1)]
-            pre = torch.relu(p1 @ v("dec.w_pre2_t")) * masks[3 + 2 * (t + 1)]
+        if t + 1 < n_steps:          # rows M+1.. = prenet layer 0 composed with the projection
+            p1 = torch.relu(out[:, M + 1:]) * masks[2 + 2 * (t + 1)]
+            pre = torch.relu(p1 @ v("dec.w_pre2").t()) * masks[3 + 2 * (t + 1)]
     hpost = mel
     n = hp["postnet_n_convolutions"]
     for i in range(n):
