@@ -58,11 +58,12 @@ class WgTcFlow(C.Structure):
 
 
 class WgTcWeights(C.Structure):
-    _fields_ = [("flows", WgTcFlow * FAC_MAX_FLOWS)]
+    _fields_ = [("up_hi", _fp), ("up_lo", _fp), ("mel_pad", C.c_int), ("_pad", C.c_int),
+                ("flows", WgTcFlow * FAC_MAX_FLOWS)]
 
 
 class WgTcWorkspace(C.Structure):
-    _fields_ = [(n, _fp) for n in ("spect_f32", "spect_hi", "spect_lo", "x_hi", "x_lo", "acts_hi", "acts_lo",
+    _fields_ = [(n, _fp) for n in ("mel_hi", "mel_lo", "spect_hi", "spect_lo", "x_hi", "x_lo", "acts_hi", "acts_lo",
                                    "out8")]
 
 
@@ -90,7 +91,8 @@ SIGNATURES = {
     "fac_wn_layer_f32": (C.c_int, [_P(WgModel), C.c_int, C.c_int, _P(WgWorkspace), C.c_int, C.c_int, _fp]),
     "fac_wn_end_coupling_f32": (C.c_int, [_P(WgModel), C.c_int, _fp, _fp, C.c_int, C.c_int, _fp]),
     "fac_waveglow_infer_f32": (C.c_int, [_P(WgModel), _fp, _fp, _P(WgWorkspace), C.c_int, C.c_int, _fp]),
-    "fac_waveglow_tc_prepare_spect": (C.c_int, [_P(WgModel), _P(WgTcWorkspace), _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    "fac_waveglow_tc_prepare_spect": (C.c_int, [_P(WgModel), _P(WgTcWeights), _P(WgTcWorkspace), _fp, C.c_int, C.c_int,
+                                                C.c_int, _fp]),
     "fac_wn_start_tc": (C.c_int, [_P(WgModel), C.c_int, _fp, _P(WgTcWorkspace), C.c_int, C.c_int, C.c_int, _fp]),
     "fac_wn_layer_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), C.c_int, C.c_int, _P(WgTcWorkspace), C.c_int,
                                   C.c_int, C.c_int, _fp]),

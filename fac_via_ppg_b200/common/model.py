@@ -24,6 +24,7 @@ The training direction (``forward`` / ``parse_batch``) is out of scope and raise
 from __future__ import annotations
 
 import ctypes as C
+import sys
 
 import torch
 from torch import nn
@@ -286,7 +287,7 @@ class Tacotron2(nn.Module):
         lens = out_len.cpu()                                          # the one device->host sync of the call
         t_out = int(lens.max())
         if int(done.cpu()[1]) > 0:
-            print("Warning! Reached max decoder steps")              # model.py:526-528
+            print("Warning! Reached max decoder steps", file=sys.stderr)   # model.py:526-528 (stderr: keeps stdout machine-readable)
         mel_cl = mel_cl[:, :t_out].contiguous()
         if B > 1 and int(lens.min()) < t_out:                        # per-utterance stop: zero the tail
             keep = (torch.arange(t_out, device=x.device)[None, :] < out_len[:, None]).unsqueeze(-1)

@@ -24,7 +24,8 @@ int wg_layer(const fac_wg_model*, int, int, const fac_wg_workspace*, int, int, c
 int wg_end(const fac_wg_model*, int, const float*, float*, int, int, cudaStream_t);
 int wg_infer(const fac_wg_model*, const float*, float*, const fac_wg_workspace*, int, int, cudaStream_t);
 
-int wg_tc_prepare_spect(const fac_wg_model*, const fac_wg_tc_workspace*, const float*, int, int, int, cudaStream_t);
+int wg_tc_prepare_spect(const fac_wg_model*, const fac_wg_tc_weights*, const fac_wg_tc_workspace*, const float*, int, int,
+                        int, cudaStream_t);
 int wg_tc_start(const fac_wg_model*, int, const float*, const fac_wg_tc_workspace*, int, int, int, cudaStream_t);
 int wg_tc_layer(const fac_wg_model*, const fac_wg_tc_weights*, int, int, const fac_wg_tc_workspace*, int, int, int,
                 cudaStream_t);
@@ -72,9 +73,9 @@ int fac_waveglow_infer_f32(const fac_wg_model* m, const float* mel_cl, float* au
   return fac::wg_infer(m, mel_cl, audio, ws, B, F, (cudaStream_t)stream);
 }
 
-int fac_waveglow_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_workspace* ws, const float* mel_cl, int B,
-                                  int F, int nsplit, void* stream) {
-  return fac::wg_tc_prepare_spect(m, ws, mel_cl, B, F, nsplit, (cudaStream_t)stream);
+int fac_waveglow_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac_wg_tc_workspace* ws,
+                                  const float* mel_cl, int B, int F, int nsplit, void* stream) {
+  return fac::wg_tc_prepare_spect(m, w, ws, mel_cl, B, F, nsplit, (cudaStream_t)stream);
 }
 int fac_wn_start_tc(const fac_wg_model* m, int flow, const float* audio, const fac_wg_tc_workspace* ws, int B, int Tg,
                     int nsplit, void* stream) {

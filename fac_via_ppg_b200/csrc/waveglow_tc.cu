@@ -65,6 +65,7 @@ struct TcParams {
   const float* wc;         // gate: [TC_NOUT][C] collapsed skip weights (fp32)
   float* out8;             // gate: (B, T, TC_NOUT) running end() pre-activation
   int accumulate_out8;
+  int out_row_mul, out_row_off;   // residual/linear epilogue: output row = column * mul + off (phase-strided upsampler)
   long long* prof;         // optional [grid][8] cycle counters
 };
 
@@ -238,8 +239,8 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
           uint32_t rr[32];
           tmem_ld32(trow + c, rr);
           tmem_ld_wait();
-          if (!valid) continue;
           const int n0 = nb * TC_NHALF + c;     // global output column of this chunk
+          if (!valid || n0 >= p.n_total) continue;
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -288,7 +289,7 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-            const long long off = col * p.C + n0;
+            const long long off = (col * p.out_row_mul + p.out_row_off) * p.C + n0;
             uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
 #pragma unroll
             for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
@@ -353,6 +354,19 @@ __global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* _
   split2(v.z, v.w, h1, l1);
   reinterpret_cast<uint2*>(hi)[i] = make_uint2(h0, h1);
   if (lo) reinterpret_cast<uint2*>(lo)[i] = make_uint2(l0, l1);
+}
+
+// mel (rows, n_mel) fp32 -> zero-padded (rows, pad) bf16 hi/lo operand copies of the upsampler GEMM.
+__global__ void mel_pad_split_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ hi,
+                                     __nv_bfloat16* __restrict__ lo, long long n_rows, int n_mel, int pad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * pad) return;
+  const long long r = i / pad;
+  const int c = (int)(i - r * pad);
+  const float v = c < n_mel ? __ldg(mel + r * n_mel + c) : 0.f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
 // x = start(audio_0) (glow.py:156), written as the bf16 operand copies of the first layer.
@@ -506,7 +520,6 @@ long long* g_tc_prof = nullptr;
 void tc_set_prof(long long* p) { g_tc_prof = p; }
 
 int wg_check_model(const fac_wg_model* m);
-int wg_upsample_squeeze(const fac_wg_model* m, const float* mel_cl, float* spect, int B, int F, cudaStream_t st);
 
 static int tc_check(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac_wg_tc_workspace* ws, int nsplit) {
   if (int rc = wg_check_model(m)) return rc;
@@ -521,16 +534,53 @@ static int tc_check(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac
   return 0;
 }
 
-int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_workspace* ws, const float* mel_cl, int B, int F,
-                        int nsplit, cudaStream_t st) {
-  FAC_REQUIRE(ws && ws->spect_f32 && ws->spect_hi, "tensor-core path: spect scratch missing");
-  if (int rc = wg_upsample_squeeze(m, mel_cl, ws->spect_f32, B, F, st)) return rc;
-  const long long n4 = (long long)B * F * (m->hop / m->n_group) * m->n_mel * m->n_group / 4;
-  split_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
-      ws->spect_f32, reinterpret_cast<__nv_bfloat16*>(ws->spect_hi),
-      nsplit == 2 ? reinterpret_cast<__nv_bfloat16*>(ws->spect_lo) : nullptr, n4);
+int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac_wg_tc_workspace* ws,
+                        const float* mel_cl, int B, int F, int nsplit, cudaStream_t st) {
+  // glow.py:253-259 on the tensor cores: the transposed conv is `phases` GEMMs over the mel frames
+  // (tap k of phase p reads frame f - k), written straight into the squeezed bf16 hi/lo layout.
+  if (int rc = wg_check_model(m)) return rc;
+  FAC_REQUIRE(w && w->up_hi && ws && ws->mel_hi && ws->spect_hi && mel_cl, "prepare_spect: NULL argument");
+  FAC_REQUIRE(nsplit == 1 || (w->up_lo && ws->mel_lo && ws->spect_lo), "prepare_spect: lo buffers missing");
+  const int n_cond = m->n_mel * m->n_group, phases = m->hop / m->n_group, pad = w->mel_pad;
+  FAC_REQUIRE(pad % TC_BK == 0 && pad >= m->n_mel, "prepare_spect: mel_pad %d must be a multiple of %d", pad, TC_BK);
+  const long long n_rows = (long long)B * F;
+  mel_pad_split_kernel<<<(unsigned)((n_rows * pad + 255) / 256), 256, 0, st>>>(
+      mel_cl, reinterpret_cast<__nv_bfloat16*>(ws->mel_hi),
+      nsplit == 2 ? reinterpret_cast<__nv_bfloat16*>(ws->mel_lo) : nullptr, n_rows, m->n_mel, pad);
   count_launch();
-  return check_launch("split_bf16_kernel");
+  if (int rc = check_launch("mel_pad_split_kernel")) return rc;
+  CUtensorMap maps[6];
+  if (int rc = make_act_map(&maps[0], ws->mel_hi, B, F, pad)) return rc;
+  if (int rc = make_act_map(&maps[1], nsplit == 2 ? ws->mel_lo : ws->mel_hi, B, F, pad)) return rc;
+  maps[2] = maps[0];
+  maps[3] = maps[1];
+  TcParams p{};
+  p.T = F;
+  p.B = B;
+  p.tiles_per_batch = ceil_div(F, TC_BM);
+  p.n_tiles = B * p.tiles_per_batch;
+  p.nsplit = nsplit;
+  p.C = n_cond;
+  p.n_src = 1;
+  p.src[0] = TcSrc{pad, m->upsample_taps, -1, 0};
+  p.n_total = n_cond;
+  p.k_steps = m->upsample_taps * pad / TC_BK;
+  p.wlo_k_steps = p.k_steps;
+  p.mode = TC_RESIDUAL;
+  p.bias = m->upsample_b;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(ws->spect_hi);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(ws->spect_lo);
+  p.out_row_mul = phases;
+  const long long w_phase = (long long)n_cond * m->upsample_taps * pad;   // elements per phase matrix
+  for (int ph = 0; ph < phases; ++ph) {
+    const __nv_bfloat16* wh = reinterpret_cast<const __nv_bfloat16*>(w->up_hi) + ph * w_phase;
+    const __nv_bfloat16* wl = nsplit == 2 ? reinterpret_cast<const __nv_bfloat16*>(w->up_lo) + ph * w_phase : wh;
+    if (int rc = make_weight_map(&maps[4], wh, n_cond, m->upsample_taps * pad)) return rc;
+    if (int rc = make_weight_map(&maps[5], wl, n_cond, m->upsample_taps * pad)) return rc;
+    p.out_row_off = ph;
+    if (int rc = launch_tc(maps, p, st)) return rc;
+  }
+  return 0;
 }
 
 int wg_tc_start(const fac_wg_model* m, int flow, const float* audio, const fac_wg_tc_workspace* ws, int B, int Tg,
@@ -578,6 +628,7 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
   p.nsplit = nsplit;
   p.C = C;
   p.prof = g_tc_prof;
+  p.out_row_mul = 1;
   // ---- G1: [x taps | spect] -> gate -> acts, out8 += Wc acts
   const int K1 = ks * C + n_cond;
   if (int rc = make_act_map(&maps[0], ws->x_hi, B, Tg, C)) return rc;
@@ -629,7 +680,7 @@ int wg_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* 
   if (int rc = tc_check(m, w, ws, nsplit)) return rc;
   FAC_REQUIRE(mel_cl && audio, "waveglow_infer_tc: NULL argument");
   const int Tg = F * (m->hop / m->n_group);
-  if (int rc = wg_tc_prepare_spect(m, ws, mel_cl, B, F, nsplit, st)) return rc;
+  if (int rc = wg_tc_prepare_spect(m, w, ws, mel_cl, B, F, nsplit, st)) return rc;
   for (int k = m->n_flows - 1; k >= 0; --k) {
     if (int rc = wg_tc_start(m, k, audio, ws, B, Tg, nsplit, st)) return rc;
     for (int i = 0; i < m->n_layers; ++i)

@@ -185,6 +185,11 @@ class PackedWaveGlow:
         return self
 
     # ------------------------------------------------------------------ tensor-core copies
+    @property
+    def mel_pad(self):
+        """mel channels rounded up to the tensor-core K block (32)."""
+        return _round_up(self.cfg["n_mel_channels"], 32)
+
     def tc_layouts(self):
         """Layouts of the derived tensor-core weights: (bf16 operand matrices, fp32 side tables)."""
         cfg = self.cfg
@@ -192,6 +197,9 @@ class PackedWaveGlow:
         Cn, L, ks = wn["n_channels"], wn["n_layers"], wn["kernel_size"]
         n_cond = cfg["n_mel_channels"] * cfg["n_group"]
         l16, l32 = FlatLayout(), FlatLayout()
+        phases, taps = cfg["hop_length"] // cfg["n_group"], upsample_taps(cfg)
+        for part in ("hi", "lo"):
+            l16.add(f"up_{part}", (phases, n_cond, taps * self.mel_pad))
         for k in range(cfg["n_flows"]):
             l32.add(f"{k}.out_bias", (8,))
             for i in range(L):
@@ -221,6 +229,18 @@ class PackedWaveGlow:
         flat32 = torch.zeros(l32.size, dtype=torch.float32, device=dev)
         table = _ext.WgTcWeights()
         eye = torch.eye(Cn, device=dev)
+        # upsampler phase matrices: fp32 [phases][taps*n_mel][n_cond] -> [phases][n_cond][taps*mel_pad]
+        n_mel, taps, pad = cfg["n_mel_channels"], upsample_taps(cfg), self.mel_pad
+        n_cond = n_mel * cfg["n_group"]
+        w_up = lay.view(self.flat, "upsample_w")[:, :, :n_cond]
+        w_up = w_up.reshape(w_up.shape[0], taps, n_mel, n_cond).permute(0, 3, 1, 2)          # p, n, tap, c
+        w_pad = w_up.new_zeros(w_up.shape[0], n_cond, taps, pad)
+        w_pad[..., :n_mel] = w_up
+        w_pad = w_pad.reshape(w_up.shape[0], n_cond, taps * pad)
+        up_hi = w_pad.to(torch.bfloat16)
+        l16.view(flat16, "up_hi").copy_(up_hi)
+        l16.view(flat16, "up_lo").copy_((w_pad - up_hi.float()).to(torch.bfloat16))
+        table.up_hi, table.up_lo, table.mel_pad = l16.ptr(flat16, "up_hi"), l16.ptr(flat16, "up_lo"), pad
 
         def put16(name, w, flow, i):
             hi = w.to(torch.bfloat16)

@@ -198,10 +198,10 @@ class WaveGlow(torch.nn.Module):
         Cn, n_cond = self.WN[0].n_channels, n_mel * G
         f32 = lambda c: torch.empty(B, Tg, c, device=dev, dtype=torch.float32)      # noqa: E731
         b16 = lambda c: torch.empty(B, Tg, c, device=dev, dtype=torch.bfloat16)     # noqa: E731
-        bufs = {"audio": audio, "mel_cl": mel_cl, "spect": f32(n_cond)}
+        bufs = {"audio": audio, "mel_cl": mel_cl}
         nsplit = self._nsplit()
         if nsplit == 0:
-            bufs["x"], bufs["skip"], bufs["acts"] = f32(Cn), f32(Cn), f32(Cn)
+            bufs["spect"], bufs["x"], bufs["skip"], bufs["acts"] = f32(n_cond), f32(Cn), f32(Cn), f32(Cn)
             bufs["ws"] = _ext.WgWorkspace(bufs["spect"].data_ptr(), bufs["x"].data_ptr(), bufs["acts"].data_ptr(),
                                           bufs["skip"].data_ptr())
         else:
@@ -209,8 +209,12 @@ class WaveGlow(torch.nn.Module):
                 bufs[name] = b16(c)
                 bufs[name[:-2] + "lo"] = b16(c) if nsplit == 2 else None
             bufs["out8"] = f32(8)
+            pad = self.packed().mel_pad
+            bufs["mel_hi"] = torch.empty(B, F, pad, device=dev, dtype=torch.bfloat16)
+            bufs["mel_lo"] = torch.empty_like(bufs["mel_hi"]) if nsplit == 2 else None
             bufs["ws"] = _ext.WgTcWorkspace(
-                bufs["spect"].data_ptr(), bufs["spect_hi"].data_ptr(), _ext.ptr(bufs["spect_lo"]),
+                bufs["mel_hi"].data_ptr(), _ext.ptr(bufs["mel_lo"]),
+                bufs["spect_hi"].data_ptr(), _ext.ptr(bufs["spect_lo"]),
                 bufs["x_hi"].data_ptr(), _ext.ptr(bufs["x_lo"]),
                 bufs["acts_hi"].data_ptr(), _ext.ptr(bufs["acts_lo"]), bufs["out8"].data_ptr())
         return bufs, B, F, Tg
@@ -262,7 +266,7 @@ class WaveGlow(torch.nn.Module):
                                                              B, F, st), "upsample")
         else:
             tcw = C.byref(packed.tc_weights())
-            _ext.check(lib.fac_waveglow_tc_prepare_spect(m, ws, bufs["mel_cl"].data_ptr(), B, F, nsplit, st),
+            _ext.check(lib.fac_waveglow_tc_prepare_spect(m, tcw, ws, bufs["mel_cl"].data_ptr(), B, F, nsplit, st),
                        "prepare_spect")
         cfg = self.config()
         Cn, L, ks = cfg["WN_config"]["n_channels"], cfg["WN_config"]["n_layers"], cfg["WN_config"]["kernel_size"]

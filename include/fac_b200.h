@@ -147,22 +147,30 @@ typedef struct fac_wg_tc_flow {
   const float* res_b[FAC_MAX_LAYERS];
   const float* out_bias;
 } fac_wg_tc_flow;
-typedef struct fac_wg_tc_weights { fac_wg_tc_flow flows[FAC_MAX_FLOWS]; } fac_wg_tc_weights;
+typedef struct fac_wg_tc_weights {
+  /* upsampler (glow.py:253) as hop/n_group phase GEMMs: [phases][n_mel*n_group][taps*mel_pad] bf16, K ordered
+   * tap-major with the mel channels zero-padded to mel_pad (a multiple of 32) */
+  const void* up_hi; const void* up_lo;
+  int mel_pad, _pad;
+  fac_wg_tc_flow flows[FAC_MAX_FLOWS];
+} fac_wg_tc_weights;
 
-/* Scratch of the tensor-core path for B utterances of T_g columns: the fp32 upsampler output, the
+/* Scratch of the tensor-core path for B utterances of T_g columns: the padded mel copies, the
  * bf16 hi/lo operand copies the TMA loads read ((B,T_g,channels) channels-last; the residual
  * stream x lives ONLY as its hi+lo pair) and out8 (B,T_g,8) fp32, the running end() pre-activation.
  * The *_lo buffers may be NULL when nsplit == 1. */
 typedef struct fac_wg_tc_workspace {
-  float* spect_f32; void* spect_hi; void* spect_lo;
+  void* mel_hi; void* mel_lo;          /* (B, F, mel_pad) bf16 */
+  void* spect_hi; void* spect_lo;
   void* x_hi; void* x_lo;
   void* acts_hi; void* acts_lo;
   float* out8;
 } fac_wg_tc_workspace;
 
 /* nsplit = 1: bf16 operands; nsplit = 2: split-bf16 (3 UMMAs per product, fp32-grade result). */
-int fac_waveglow_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_workspace* ws, const float* mel_cl,
-                                  int B, int F, int nsplit, void* stream);
+/* glow.py:253-259 (upsample + trim + squeeze) on the tensor cores, from mel_cl (B, F, n_mel) fp32. */
+int fac_waveglow_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac_wg_tc_workspace* ws,
+                                  const float* mel_cl, int B, int F, int nsplit, void* stream);
 int fac_wn_start_tc(const fac_wg_model* m, int flow, const float* audio, const fac_wg_tc_workspace* ws,
                     int B, int Tg, int nsplit, void* stream);
 /* glow.py:158-174 for one layer: TMA-fed tcgen05 GEMM + gate epilogue (+ out8 update), then the

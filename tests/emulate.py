@@ -177,9 +177,15 @@ def waveglow_infer_tc(packed, mel, audio):
     Tg = F * phases
     mel_cl = mel.transpose(1, 2).contiguous()
     spect = mel.new_zeros(B, F, phases, n_cond)
-    w_up, b_up = lay.view(flat, "upsample_w"), lay.view(flat, "upsample_b")
+    # upsampler from the tensor-core phase matrices [phases][n_cond][taps*mel_pad] (mel zero-padded)
+    pad = packed.mel_pad
+    mel_pad = mel_cl.new_zeros(B, F, pad)
+    mel_pad[..., :n_mel] = mel_cl
+    w_up = l16.view(flat16, "up_hi").float() + l16.view(flat16, "up_lo").float()
+    b_up = lay.view(flat, "upsample_b")[:n_cond]
+    a_up = gather_rows(mel_pad, taps, -1, 0)
     for p in range(phases):
-        spect[:, :, p] = conv_gemm([(mel_cl, taps, -1, 0)], w_up[p], b_up, n_cond)
+        spect[:, :, p] = a_up @ w_up[p].t() + b_up
     spect = spect.view(B, Tg, n_cond)
     audio = audio.clone()
 

@@ -69,7 +69,7 @@ def test_tc_layer_matches_fp32_layer(cfg_name, cols, precision):
         x_hi, x_lo, s_hi, s_lo = hi(x0), lo(x0), hi(spect), lo(spect)
         a_hi, a_lo = torch.zeros_like(x_hi), torch.zeros_like(x_hi)
         out8 = out8_0.clone()
-        wst = _ext.WgTcWorkspace(None, s_hi.data_ptr(), s_lo.data_ptr(), x_hi.data_ptr(), x_lo.data_ptr(),
+        wst = _ext.WgTcWorkspace(None, None, s_hi.data_ptr(), s_lo.data_ptr(), x_hi.data_ptr(), x_lo.data_ptr(),
                                  a_hi.data_ptr(), a_lo.data_ptr(), out8.data_ptr())
         rc = lib.fac_wn_layer_tc(C.byref(packed.cmodel), C.byref(packed.tc_weights()), 0, layer, C.byref(wst), B, cols,
                                  nsplit, st)

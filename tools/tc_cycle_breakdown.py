@@ -24,7 +24,7 @@ for prec in (sys.argv[1:] or ["bf16x3", "bf16"]):
     tcw = packed.tc_weights()
     bufs, B, F, Tg = m._alloc_io(mel, 0.6, None)
     st, mm, ws, ns = _ext.current_stream(), C.byref(packed.cmodel), C.byref(bufs["ws"]), m._nsplit()
-    lib.fac_waveglow_tc_prepare_spect(mm, ws, bufs["mel_cl"].data_ptr(), B, F, ns, st)
+    lib.fac_waveglow_tc_prepare_spect(mm, C.byref(tcw), ws, bufs["mel_cl"].data_ptr(), B, F, ns, st)
     lib.fac_wn_start_tc(mm, 5, bufs["audio"].data_ptr(), ws, B, Tg, ns, st)
     for i in range(3):
         lib.fac_wn_layer_tc(mm, C.byref(tcw), 5, i, ws, B, Tg, ns, st)
