@@ -35,7 +35,7 @@ struct DecParams {
 
 namespace {
 
-constexpr int DEC_THREADS = 256;
+constexpr int DEC_THREADS = 512;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr int R = 300;    // attention_rnn_dim == decoder_rnn_dim == prenet_dim
 constexpr int E = 600;    // encoder_embedding_dim
@@ -52,6 +52,8 @@ constexpr int MAXPP = 4;        // projection rows per CTA
 constexpr int MAXP2 = 3;        // prenet-1 rows per CTA
 constexpr int CHUNK = 8;        // utterances staged per pass
 constexpr int MAXW = 64;        // max window positions (2*window+1 <= 64)
+constexpr int KP = 2;           // K split of a mat-vec tile across warps (partials meet in shared memory)
+constexpr int MAXTILES = 16;    // (rows or units) x utterance groups of 4 per staged chunk
 
 struct Smem {
   float w_att[MAXU * 4][KIN];
@@ -62,6 +64,7 @@ struct Smem {
   float w_loc[2 * KF][NF];   // [c*KF + k][f]
   float w_ld[NF][A];         // location_dense transposed
   float v[A];
+  float part[KP][MAXTILES][16];   // per-tile partial sums of the K halves
   alignas(16) union {
     float in[CHUNK][KIN];    // batched mat-vec phases
     struct {                 // attention phase
@@ -97,45 +100,79 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 
 struct Seg {           // one piece of a concatenated input vector: utterance b reads ptr[b*stride + k]
   const float* ptr;
-  int len, stride;
+  int len, stride;     // multiples of 4 floats
 };
 
-// Stage the concatenated inputs of utterances [n0, n0+nb) into shared memory (read through L2:
-// they were written by other CTAs in the previous phase).
-__device__ __forceinline__ void stage_inputs(Smem& sm, const Seg* segs, int n_seg, int K, int n0, int nb) {
+// Stage the concatenated inputs of utterances [n0, n0+nb) into shared memory with 128-bit loads that
+// bypass L1 (.cg): the vectors were written by other CTAs in the previous phase.
+template <int NSEG>
+__device__ __forceinline__ void stage_inputs(Smem& sm, const Seg (&segs)[NSEG], int n0, int nb) {
   __syncthreads();
-  for (int i = threadIdx.x; i < nb * K; i += DEC_THREADS) {
-    const int n = i / K;
-    int k = i - n * K;
-    const int b = n0 + n;
-    float v = 0.f;
-    int base = 0;
-    for (int s = 0; s < n_seg; ++s) {
-      if (k >= base && k < base + segs[s].len) v = __ldcg(segs[s].ptr + (long long)b * segs[s].stride + (k - base));
-      base += segs[s].len;
+  int base = 0;
+#pragma unroll
+  for (int s = 0; s < NSEG; ++s) {
+    const int l4 = segs[s].len >> 2;
+    for (int i = threadIdx.x; i < nb * l4; i += DEC_THREADS) {
+      const int n = i / l4, k4 = i - n * l4;
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(segs[s].ptr + (long long)(n0 + n) * segs[s].stride) + k4);
+      *reinterpret_cast<float4*>(&sm.u.in[n][base + 4 * k4]) = v;
     }
-    sm.u.in[n][k] = v;
+    base += segs[s].len;
   }
   __syncthreads();
 }
 
-// One LSTMCell for the units [u0, u0+nu) of this CTA and all B utterances.
-__device__ void lstm_phase(Smem& sm, const float (*w_s)[KIN], const float* __restrict__ bias, const Seg* segs,
+// Sum 16 per-lane values across the warp with 16 shuffles (halving butterfly): afterwards lane l holds
+// the total of value index ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1) (lanes l and l^1 agree).
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 16;
+    const float send = up ? v[i] : v[i + 8];
+    const float keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? v[i] : v[i + 4];
+    const float keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? v[i] : v[i + 2];
+    const float keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// One LSTMCell for the units [u0, u0+nu) of this CTA and all B utterances.  Warp tile = the 4 gate rows
+// of one unit x 4 utterances x one K half; the halves meet in shared memory before the cell update.
+__device__ void lstm_phase(Smem& sm, const float (*w_s)[KIN], const float* __restrict__ bias, const Seg (&segs)[3],
                            float* h_next, float* c, int B, int u0, int nu) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int K4 = KIN / 4, K4H = (K4 + KP - 1) / KP;
   for (int n0 = 0; n0 < B; n0 += CHUNK) {
     const int nb = min(CHUNK, B - n0);
-    stage_inputs(sm, segs, 3, KIN, n0, nb);
-    // warp tile: the 4 gate rows of one unit x 4 utterances
-    const int n_tiles = nu * ((nb + 3) / 4);
-    for (int tile = warp; tile < n_tiles; tile += DEC_WARPS) {
+    stage_inputs(sm, segs, n0, nb);
+    const int n_groups = (nb + 3) / 4;
+    const int n_tiles = nu * n_groups;
+    for (int job = warp; job < n_tiles * KP; job += DEC_WARPS) {
+      const int tile = job % n_tiles, kp = job / n_tiles;
       const int u = tile % nu, ng = (tile / nu) * 4;
-      float acc[4][4];
+      float acc[16];
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-#pragma unroll
-        for (int n = 0; n < 4; ++n) acc[g][n] = 0.f;
-      for (int k4 = lane; k4 < KIN / 4; k4 += 32) {
+      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+      for (int k4 = kp * K4H + lane; k4 < min(K4, (kp + 1) * K4H); k4 += 32) {
         float4 wv[4], xv[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) wv[g] = *reinterpret_cast<const float4*>(&w_s[g * nu + u][k4 * 4]);
@@ -147,43 +184,50 @@ __device__ void lstm_phase(Smem& sm, const float (*w_s)[KIN], const float* __res
         for (int g = 0; g < 4; ++g)
 #pragma unroll
           for (int n = 0; n < 4; ++n)
-            acc[g][n] = fmaf(wv[g].x, xv[n].x,
-                             fmaf(wv[g].y, xv[n].y, fmaf(wv[g].z, xv[n].z, fmaf(wv[g].w, xv[n].w, acc[g][n]))));
+            acc[g * 4 + n] = fmaf(wv[g].x, xv[n].x, fmaf(wv[g].y, xv[n].y,
+                                  fmaf(wv[g].z, xv[n].z, fmaf(wv[g].w, xv[n].w, acc[g * 4 + n]))));
       }
+      const float total = warp_reduce16(acc, lane);
+      if ((lane & 1) == 0) sm.part[kp][tile][lane >> 1] = total;   // value index (gate*4 + utterance) = lane>>1
+    }
+    __syncthreads();
+    // cell update: one thread per (unit, utterance)
+    for (int i = tid; i < nu * nb; i += DEC_THREADS) {
+      const int u = i % nu, n = i / nu;
+      const int tile = (n >> 2) * nu + u, j = u0 + u, b = n0 + n;
+      float gv[4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+      for (int g = 0; g < 4; ++g) {
+        float a = __ldg(bias + g * R + j);
 #pragma unroll
-        for (int n = 0; n < 4; ++n) acc[g][n] = warp_sum(acc[g][n]);
-      if (lane < 4 && ng + lane < nb) {
-        const int b = n0 + ng + lane, j = u0 + u;
-        float gv[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float a = lane == 0 ? acc[g][0] : lane == 1 ? acc[g][1] : lane == 2 ? acc[g][2] : acc[g][3];
-          gv[g] = a + __ldg(bias + g * R + j);
-        }
-        const float cn = sigmoidf_exact(gv[1]) * c[b * R + j] + sigmoidf_exact(gv[0]) * tanhf(gv[2]);
-        c[b * R + j] = cn;
-        h_next[b * R + j] = sigmoidf_exact(gv[3]) * tanhf(cn);
+        for (int kp = 0; kp < KP; ++kp) a += sm.part[kp][tile][g * 4 + (n & 3)];
+        gv[g] = a;
       }
+      const float cn = sigmoidf_exact(gv[1]) * c[b * R + j] + sigmoidf_exact(gv[0]) * tanhf(gv[2]);
+      c[b * R + j] = cn;
+      h_next[b * R + j] = sigmoidf_exact(gv[3]) * tanhf(cn);
     }
   }
 }
 
 // Batched mat-vec over this CTA's resident rows: for every owned row r (global index row0 + r) and every
-// utterance b, epi(row0 + r, b, dot(w_s[r], in_b)).  K % 4 == 0.
-template <int KROW, typename Epi>
-__device__ void rows_phase(Smem& sm, const float (*w_s)[KROW], int row0, int nr, const Seg* segs, int n_seg, int B,
+// utterance b, epi(row0 + r, b, dot(w_s[r], in_b)).  KROW % (4*KP) == 0.  Warp tile = one row x 4
+// utterances x one K half.
+template <int KROW, int NSEG, typename Epi>
+__device__ void rows_phase(Smem& sm, const float (*w_s)[KROW], int row0, int nr, const Seg (&segs)[NSEG], int B,
                            Epi epi) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int K4 = KROW / 4, K4H = (K4 + KP - 1) / KP;
   for (int n0 = 0; n0 < B; n0 += CHUNK) {
     const int nb = min(CHUNK, B - n0);
-    stage_inputs(sm, segs, n_seg, KROW, n0, nb);
-    const int n_tiles = nr * ((nb + 3) / 4);
-    for (int tile = warp; tile < n_tiles; tile += DEC_WARPS) {
+    stage_inputs(sm, segs, n0, nb);
+    const int n_groups = (nb + 3) / 4;
+    const int n_tiles = nr * n_groups;
+    for (int job = warp; job < n_tiles * KP; job += DEC_WARPS) {
+      const int tile = job % n_tiles, kp = job / n_tiles;
       const int r = tile % nr, ng = (tile / nr) * 4;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int k4 = lane; k4 < KROW / 4; k4 += 32) {
+      for (int k4 = kp * K4H + lane; k4 < min(K4, (kp + 1) * K4H); k4 += 32) {
         const float4 wv = *reinterpret_cast<const float4*>(&w_s[r][k4 * 4]);
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
@@ -195,10 +239,16 @@ __device__ void rows_phase(Smem& sm, const float (*w_s)[KROW], int row0, int nr,
       }
 #pragma unroll
       for (int n = 0; n < 4; ++n) acc[n] = warp_sum(acc[n]);
-      if (lane < 4 && ng + lane < nb) {
-        const float a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-        epi(row0 + r, n0 + ng + lane, a);
-      }
+      if (lane < 4) sm.part[kp][tile][lane] = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+    }
+    __syncthreads();
+    for (int i = tid; i < nr * nb; i += DEC_THREADS) {
+      const int r = i % nr, n = i / nr;
+      const int tile = (n >> 2) * nr + r;
+      float a = 0.f;
+#pragma unroll
+      for (int kp = 0; kp < KP; ++kp) a += sm.part[kp][tile][n & 3];
+      epi(row0 + r, n0 + n, a);
     }
   }
 }
@@ -342,7 +392,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
     {
       const Seg segs[1] = {{h_att_nxt, R, R}};
       float* pq = p.s.pq;
-      rows_phase<R>(sm, sm.w_q, q0, nq, segs, 1, p.B, [pq](int row, int b, float v) { pq[b * A + row] = v; });
+      rows_phase<R>(sm, sm.w_q, q0, nq, segs, p.B, [pq](int row, int b, float v) { pq[b * A + row] = v; });
     }
     grid_barrier(bar, bar_target);
     // (3) location-sensitive attention, one CTA per utterance
@@ -360,7 +410,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
       const Seg segs[2] = {{h_dec_nxt, R, R}, {p.s.ctx, E, E}};
       const DecParams* pp = &p;
       const int tt = t;
-      rows_phase<KHC>(sm, sm.w_pp, pp0, npp, segs, 2, p.B, [pp, tt](int row, int b, float v) {
+      rows_phase<KHC>(sm, sm.w_pp, pp0, npp, segs, p.B, [pp, tt](int row, int b, float v) {
         const DecParams& q = *pp;
         v += __ldg(q.w.b_pp + row);
         if (row < M) {
@@ -390,7 +440,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
       const Seg segs[1] = {{p.s.p1, R, R}};
       const DecParams* pp = &p;
       const int tt = t;
-      rows_phase<R>(sm, sm.w_p2, p20, np2, segs, 1, p.B, [pp, tt](int row, int b, float v) {
+      rows_phase<R>(sm, sm.w_p2, p20, np2, segs, p.B, [pp, tt](int row, int b, float v) {
         const DecParams& q = *pp;
         const unsigned char d = q.drop[(((long long)(tt + 1) * 2 + 1) * q.B + b) * R + row];
         q.s.pre[b * R + row] = fmaxf(v, 0.f) * (2.0f * (float)d);
