@@ -29,6 +29,13 @@ inline int check_launch(const char* what) {
   } while (0)
 
 __device__ __forceinline__ float sigmoidf_exact(float v) { return 1.0f / (1.0f + expf(-v)); }
+// MUFU-based forms for the recurrent cells (ex2.approx + rcp.approx, ~2^-21 relative error): the cell
+// non-linearities are 40 % of the instructions of the LSTM step when evaluated with the libm versions.
+__device__ __forceinline__ float sigmoidf_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float tanhf_fast(float v) {
+  v = fminf(fmaxf(v, -15.f), 15.f);
+  return 1.0f - __fdividef(2.0f, __expf(2.0f * v) + 1.0f);
+}
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

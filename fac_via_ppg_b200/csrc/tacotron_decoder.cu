@@ -203,9 +203,9 @@ __device__ void lstm_phase(Smem& sm, const float (*w_s)[KIN], const float* __res
         for (int kp = 0; kp < KP; ++kp) a += sm.part[kp][tile][g * 4 + (n & 3)];
         gv[g] = a;
       }
-      const float cn = sigmoidf_exact(gv[1]) * c[b * R + j] + sigmoidf_exact(gv[0]) * tanhf(gv[2]);
+      const float cn = sigmoidf_fast(gv[1]) * c[b * R + j] + sigmoidf_fast(gv[0]) * tanhf_fast(gv[2]);
       c[b * R + j] = cn;
-      h_next[b * R + j] = sigmoidf_exact(gv[3]) * tanhf(cn);
+      h_next[b * R + j] = sigmoidf_fast(gv[3]) * tanhf_fast(cn);
     }
   }
 }
