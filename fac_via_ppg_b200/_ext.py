@@ -100,6 +100,7 @@ SIGNATURES = {
     "fac_waveglow_infer_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), _fp, _fp, _P(WgTcWorkspace), C.c_int, C.c_int,
                                         C.c_int, _fp]),
     "fac_tc_set_profile_buffer": (None, [_fp]),
+    "fac_tc_set_cta_group": (C.c_int, [C.c_int]),
     "fac_selftest_grid_barrier": (C.c_int, [_fp, C.c_int, _fp]),
     "fac_lstm_bidir_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "fac_taco_decoder_run": (C.c_int, [_P(TacoDecoderWeights), _fp, _fp, _fp, _fp, _P(TacoDecoderState), _fp, _fp,
@@ -133,6 +134,9 @@ def load(build_if_missing: bool = True):
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    cta_group = os.environ.get("FAC_TC_CTA_GROUP")
+    if cta_group:
+        check(lib.fac_tc_set_cta_group(int(cta_group)), "fac_tc_set_cta_group")
     return lib
 
 

@@ -32,7 +32,6 @@ using namespace tc;
 constexpr int TC_BM = 128;       // time rows per tile (UMMA M)
 constexpr int TC_BK = 32;        // K per pipeline stage = two UMMA K steps; 64-byte rows, SWIZZLE_64B
 constexpr int TC_ROWB = TC_BK * 2;
-constexpr int TC_STAGES = 4;
 constexpr int UMMA_K = 16;
 constexpr int TC_NMAX = 512;     // accumulator columns per tile (all of TMEM)
 constexpr int TC_NHALF = 256;    // N of one UMMA
@@ -41,12 +40,22 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_NOUT = 8;       // channels of the collapsed skip path (= max 2*n_half)
 constexpr int TC_CMAX = 256;     // max WN channels (Wc staging)
 constexpr int A_BYTES = TC_BM * TC_ROWB;       // 8 KB
-constexpr int W_BYTES = TC_NHALF * TC_ROWB;    // 16 KB: one 256-row block of the weight matrix
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;   // hi + lo of both operands = 48 KB
 constexpr int TC_BAR_BYTES = 256;
 constexpr int TC_WC_BYTES = TC_NOUT * TC_CMAX * 4;       // 8 KB
 constexpr int TC_X8_BYTES = TC_BM * TC_NOUT * 4;         // 4 KB: out8 partials handed between paired epilogue warps
-constexpr int TC_SMEM = TC_STAGES * STAGE_BYTES + TC_BAR_BYTES + TC_WC_BYTES + TC_X8_BYTES + 1024 /*alignment slack*/;
+constexpr int TC_MAX_STAGES = 12;
+constexpr int TC_RING_BYTES = 192 * 1024;   // operand ring; the stage count follows from the stage size
+
+// CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (thread-block cluster of 2, tcgen05 cta_group::2)
+// works on two adjacent tiles as ONE 256-row UMMA; each CTA stages only half of the weight rows, so
+// the per-SM operand traffic and shared-memory reads drop by a third and the ring gets 6 stages.
+template <int CG>
+struct TcCfg {
+  static constexpr int W_BYTES = (TC_NHALF / CG) * TC_ROWB;          // this CTA's share of a 256-row weight block
+  // a stage holds nsplit x (A tile + weight share): split-bf16 48 KB / 32 KB (4 / 6 stages), bf16 half of that
+  // (8 / 12 stages)
+  static constexpr int SMEM = TC_RING_BYTES + TC_BAR_BYTES + TC_WC_BYTES + TC_X8_BYTES + 1024 /*alignment*/;
+};
 
 enum { TC_GATE = 0, TC_RESIDUAL = 1 };
 
@@ -82,22 +91,29 @@ __device__ __forceinline__ float gate_act(float a, float b) {
   return __fdividef(ea - 1.f, (ea + 1.f) * (1.f + eb));
 }
 
+template <int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_constant__ CUtensorMap a0_lo,
                   const __grid_constant__ CUtensorMap a1_hi, const __grid_constant__ CUtensorMap a1_lo,
                   const __grid_constant__ CUtensorMap w_hi, const __grid_constant__ CUtensorMap w_lo,
                   const TcParams p) {
+  constexpr int W_BYTES = TcCfg<CG>::W_BYTES;
+  const int STAGE_BYTES = p.nsplit * (A_BYTES + W_BYTES);
+  const int TC_STAGES = min(TC_MAX_STAGES, TC_RING_BYTES / STAGE_BYTES);
+  const int W_OFF = p.nsplit * A_BYTES;      // stage layout: A_hi [A_lo] W_hi [W_lo]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
-  uint64_t* empty = full + TC_STAGES;
-  uint64_t* tmem_full = empty + TC_STAGES;     // [2] one per accumulator region
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_RING_BYTES);
+  uint64_t* empty = full + TC_MAX_STAGES;
+  uint64_t* tmem_full = empty + TC_MAX_STAGES;   // [2] one per accumulator region
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* wc_s = reinterpret_cast<float*>(smem + TC_STAGES * STAGE_BYTES + TC_BAR_BYTES);
+  float* wc_s = reinterpret_cast<float*>(smem + TC_RING_BYTES + TC_BAR_BYTES);
   float* x8_s = wc_s + TC_NOUT * TC_CMAX;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CG == 1 ? 0 : (int)cluster_ctarank();       // position inside the CTA pair
+  const int tile_first = (blockIdx.x / CG) * CG;               // pairs take adjacent tiles in lock step
   // A work unit is (time tile, block of <= 256 output columns); its accumulator is one of the two
   // 256-column TMEM regions, so the epilogue of unit u overlaps the UMMAs of unit u+1.
   const int n_blocks = (p.n_total + TC_NHALF - 1) / TC_NHALF;
@@ -110,7 +126,7 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
     }
     for (int r = 0; r < 2; ++r) {
       mbar_init(&tmem_full[r], 1);
-      mbar_init(&tmem_empty[r], TC_EPI_WARPS);
+      mbar_init(&tmem_empty[r], TC_EPI_WARPS * CG);           // CG = 2: both CTAs' epilogues release the leader
     }
     fence_barrier_init();
     tma_prefetch_desc(&a0_hi);
@@ -118,22 +134,28 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
   }
   if (p.mode == TC_GATE)
     for (int i = threadIdx.x; i < TC_NOUT * p.C; i += TC_THREADS) wc_s[i] = __ldg(p.wc + i);
-  if (warp == 1) tmem_alloc(tmem_slot, TC_NMAX);
+  if (warp == 1) {
+    if (CG == 1) tmem_alloc(tmem_slot, TC_NMAX);
+    else tmem_alloc_cg2(tmem_slot, TC_NMAX);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();     // the peer's barriers exist before anything is signalled remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      const uint32_t w_bytes = (uint32_t)(n_cols * TC_ROWB);
+      const int w_rows = n_cols / CG;                                   // weight rows staged by this CTA
+      const uint32_t w_bytes = (uint32_t)(w_rows * TC_ROWB);
       const int steps0 = p.src[0].taps * (p.src[0].channels / TC_BK);
       int stage = 0;
       uint32_t phase = 0;
       long long prod_wait = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int b = tile / p.tiles_per_batch;
+      for (int tb = tile_first; tb < p.n_tiles; tb += gridDim.x) {
+        const int tile = tb + rank;                    // may be one past the end for the pair's second CTA:
+        const int b = tile / p.tiles_per_batch;        // its loads are then fully out of bounds (zero fill)
         const int t0 = (tile % p.tiles_per_batch) * TC_BM;
         for (int nb = 0; nb < n_blocks; ++nb) {
           for (int ks = 0; ks < p.k_steps; ++ks) {
@@ -150,11 +172,23 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
             mbar_wait(&empty[stage], phase ^ 1);
             prod_wait += clock64() - w0;
             uint8_t* st = smem + stage * STAGE_BYTES;
-            mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.nsplit * A_BYTES) + w_bytes * (use_wlo ? 2u : 1u));
-            tma_load_3d(st, mh, &full[stage], c0, row0, b);
-            if (p.nsplit == 2) tma_load_3d(st + A_BYTES, ml, &full[stage], c0, row0, b);
-            tma_load_2d(st + 2 * A_BYTES, &w_hi, &full[stage], ks * TC_BK, nb * TC_NHALF);
-            if (use_wlo) tma_load_2d(st + 2 * A_BYTES + W_BYTES, &w_lo, &full[stage], ks * TC_BK, nb * TC_NHALF);
+            const uint32_t bytes = (uint32_t)(p.nsplit * A_BYTES) + w_bytes * (use_wlo ? 2u : 1u);
+            const int w_row = nb * TC_NHALF + rank * w_rows;
+            if (CG == 1) {
+              mbar_arrive_expect_tx(&full[stage], bytes);
+              tma_load_3d(st, mh, &full[stage], c0, row0, b);
+              if (p.nsplit == 2) tma_load_3d(st + A_BYTES, ml, &full[stage], c0, row0, b);
+              tma_load_2d(st + W_OFF, &w_hi, &full[stage], ks * TC_BK, w_row);
+              if (use_wlo) tma_load_2d(st + W_OFF + W_BYTES, &w_lo, &full[stage], ks * TC_BK, w_row);
+            } else {
+              // both CTAs' loads complete on the LEADER's barrier, which expects the pair's bytes
+              if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * bytes);
+              const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+              tma_load_3d_cg2(st, mh, lead_full, c0, row0, b);
+              if (p.nsplit == 2) tma_load_3d_cg2(st + A_BYTES, ml, lead_full, c0, row0, b);
+              tma_load_2d_cg2(st + W_OFF, &w_hi, lead_full, ks * TC_BK, w_row);
+              if (use_wlo) tma_load_2d_cg2(st + W_OFF + W_BYTES, &w_lo, lead_full, ks * TC_BK, w_row);
+            }
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -163,14 +197,22 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================================================== UMMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(TC_BM, n_cols);
+    if (lane == 0 && rank == 0) {                     // CG = 2: the leader issues for the pair
+      const uint32_t idesc = make_idesc_bf16(TC_BM * CG, n_cols);
+      auto mma = [](uint32_t d, uint64_t a, uint64_t w, uint32_t id, uint32_t acc) {
+        if (CG == 1) umma_bf16(d, a, w, id, acc);
+        else umma_bf16_cg2(d, a, w, id, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if (CG == 1) umma_commit(bar);
+        else umma_commit_cg2(bar, (uint16_t)0x3);
+      };
       int stage = 0;
       uint32_t phase = 0;
       uint32_t u = 0;   // unit counter
       long long wait_tmem = 0, wait_full = 0;
       const long long k_start = clock64();
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int tb = tile_first; tb < p.n_tiles; tb += gridDim.x) {
         for (int nb = 0; nb < n_blocks; ++nb, ++u) {
           const uint32_t r = u & 1;
           long long w0 = clock64();
@@ -188,21 +230,21 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
             for (int kk = 0; kk < TC_BK / UMMA_K; ++kk) {
               const uint32_t koff = kk * UMMA_K * 2;   // bytes along K inside the swizzled row
               const uint64_t a_h = make_smem_desc(st + koff, TC_ROWB);
-              const uint64_t w_h = make_smem_desc(st + 2 * A_BYTES + koff, TC_ROWB);
-              umma_bf16(d, a_h, w_h, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+              const uint64_t w_h = make_smem_desc(st + W_OFF + koff, TC_ROWB);
+              mma(d, a_h, w_h, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
               if (p.nsplit == 2) {
                 const uint64_t a_l = make_smem_desc(st + A_BYTES + koff, TC_ROWB);
-                umma_bf16(d, a_l, w_h, idesc, 1u);
+                mma(d, a_l, w_h, idesc, 1u);
                 if (ks < p.wlo_k_steps) {
-                  const uint64_t w_l = make_smem_desc(st + 2 * A_BYTES + W_BYTES + koff, TC_ROWB);
-                  umma_bf16(d, a_h, w_l, idesc, 1u);
+                  const uint64_t w_l = make_smem_desc(st + W_OFF + W_BYTES + koff, TC_ROWB);
+                  mma(d, a_h, w_l, idesc, 1u);
                 }
               }
             }
-            umma_commit(&empty[stage]);   // frees the smem slot when these UMMAs have read it
+            commit(&empty[stage]);        // frees the smem slot (in both CTAs) when these UMMAs have read it
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tmem_full[r]);     // accumulator complete -> epilogue
+          commit(&tmem_full[r]);          // accumulator complete -> epilogue (of both CTAs)
         }
       }
       if (p.prof) {
@@ -219,10 +261,11 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
     const int row = q * 32 + lane;
     uint32_t u = 0;
     long long epi_wait = 0, epi_busy = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (int tb = tile_first; tb < p.n_tiles; tb += gridDim.x) {
+      const int tile = tb + rank;
       const int b = tile / p.tiles_per_batch;
       const int t = (tile % p.tiles_per_batch) * TC_BM + row;
-      const bool valid = t < p.T;
+      const bool valid = tile < p.n_tiles && t < p.T;
       const long long col = (long long)b * p.T + t;
       for (int nb = 0; nb < n_blocks; ++nb, ++u) {
         const uint32_t r = u & 1;
@@ -303,7 +346,10 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
         // this warp is done reading the TMEM region: hand it back to the UMMA issuer early
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[r]);
+        if (lane == 0) {
+          if (CG == 1) mbar_arrive(&tmem_empty[r]);
+          else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[r]), 0));
+        }
         if (p.mode == TC_GATE) {
           // the warp owning the upper column half hands its partial sums to its partner (fixed
           // order: deterministic rounding), which updates out8 (unit 0 of a tile starts or continues
@@ -339,8 +385,12 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();     // nobody leaves while the peer may still signal / read this CTA
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, TC_NMAX);
+  if (warp == 1) {
+    if (CG == 1) tmem_dealloc(tmem_base, TC_NMAX);
+    else tmem_dealloc_cg2(tmem_base, TC_NMAX);
+  }
 }
 
 // fp32 -> bf16 (hi, lo) split of a flat array.
@@ -472,13 +522,19 @@ int make_act_map(CUtensorMap* m, const void* ptr, int B, int T, int C) {
   FAC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", B, T, C, (int)r);
   return 0;
 }
-// (N, K) row-major bf16 weight: box = 16 k x min(256, N) rows.
-int make_weight_map(CUtensorMap* m, const void* ptr, int N, int K) {
+int g_tc_cta_group = 0;   // 0 = automatic: CTA pairs for the split-bf16 mode, single CTAs for plain bf16
+
+// Measured on B200 (profiles/README.md): pairs win 9 % in split-bf16 (operand traffic and shared-memory reads
+// per UMMA drop by a third, 6-stage ring); plain bf16 is TMA-feed-bound either way and is 3 % faster unpaired.
+inline int tc_pick_cg(int nsplit) { return g_tc_cta_group ? g_tc_cta_group : (nsplit == 2 ? 2 : 1); }
+
+// (N, K) row-major bf16 weight: box = 32 k x (min(256, N) / cta_group) rows.
+int make_weight_map(CUtensorMap* m, const void* ptr, int N, int K, int cg) {
   EncodeTiledFn fn = encode_fn();
   FAC_REQUIRE(fn != nullptr, "tensor-core path: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {TC_BK, (cuuint32_t)(N < TC_NHALF ? N : TC_NHALF)};
+  cuuint32_t box[2] = {TC_BK, (cuuint32_t)((N < TC_NHALF ? N : TC_NHALF) / cg)};
   cuuint32_t es[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, TC_SWIZZLE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -497,20 +553,45 @@ int sm_count() {
   return sms;
 }
 
-int launch_tc(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st) {
+template <int CG>
+int launch_tc_cg(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st) {
   static bool attr_set = false;
+  constexpr int smem = TcCfg<CG>::SMEM;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wn_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(wn_gemm_tc_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
-      set_error("wn_gemm_tc: cannot reserve %d bytes of shared memory: %s", TC_SMEM, cudaGetErrorString(e));
+      set_error("wn_gemm_tc: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
       return 2;
     }
     attr_set = true;
   }
-  const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-  wn_gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  const int groups = ceil_div(p.n_tiles, CG);
+  const int max_groups = sm_count() / CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(CG * (groups < max_groups ? groups : max_groups)));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wn_gemm_tc_kernel<CG>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   count_launch();
+  if (e != cudaSuccess) {
+    set_error("wn_gemm_tc_kernel<%d>: launch failed: %s", CG, cudaGetErrorString(e));
+    return 2;
+  }
   return check_launch("wn_gemm_tc_kernel");
+}
+
+int launch_tc(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st, int cg) {
+  const int n_cols = p.n_total < TC_NHALF ? p.n_total : TC_NHALF;
+  FAC_REQUIRE(cg == 1 || (n_cols / 2) % 8 == 0, "wn_gemm_tc: %d columns cannot be split over a CTA pair", n_cols);
+  return cg == 2 ? launch_tc_cg<2>(maps, p, st) : launch_tc_cg<1>(maps, p, st);
 }
 
 long long* g_tc_prof = nullptr;
@@ -518,6 +599,11 @@ long long* g_tc_prof = nullptr;
 }  // namespace
 
 void tc_set_prof(long long* p) { g_tc_prof = p; }
+int tc_set_cta_group(int cg) {
+  FAC_REQUIRE(cg >= 0 && cg <= 2, "cta group must be 0 (auto), 1 or 2 (got %d)", cg);
+  g_tc_cta_group = cg;
+  return 0;
+}
 
 int wg_check_model(const fac_wg_model* m);
 
@@ -572,13 +658,14 @@ int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights* w, const
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(ws->spect_lo);
   p.out_row_mul = phases;
   const long long w_phase = (long long)n_cond * m->upsample_taps * pad;   // elements per phase matrix
+  const int cg = tc_pick_cg(nsplit);
   for (int ph = 0; ph < phases; ++ph) {
     const __nv_bfloat16* wh = reinterpret_cast<const __nv_bfloat16*>(w->up_hi) + ph * w_phase;
     const __nv_bfloat16* wl = nsplit == 2 ? reinterpret_cast<const __nv_bfloat16*>(w->up_lo) + ph * w_phase : wh;
-    if (int rc = make_weight_map(&maps[4], wh, n_cond, m->upsample_taps * pad)) return rc;
-    if (int rc = make_weight_map(&maps[5], wl, n_cond, m->upsample_taps * pad)) return rc;
+    if (int rc = make_weight_map(&maps[4], wh, n_cond, m->upsample_taps * pad, cg)) return rc;
+    if (int rc = make_weight_map(&maps[5], wl, n_cond, m->upsample_taps * pad, cg)) return rc;
     p.out_row_off = ph;
-    if (int rc = launch_tc(maps, p, st)) return rc;
+    if (int rc = launch_tc(maps, p, st, cg)) return rc;
   }
   return 0;
 }
@@ -635,8 +722,9 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
   if (int rc = make_act_map(&maps[1], nsplit == 2 ? ws->x_lo : ws->x_hi, B, Tg, C)) return rc;
   if (int rc = make_act_map(&maps[2], ws->spect_hi, B, Tg, n_cond)) return rc;
   if (int rc = make_act_map(&maps[3], nsplit == 2 ? ws->spect_lo : ws->spect_hi, B, Tg, n_cond)) return rc;
-  if (int rc = make_weight_map(&maps[4], wf.w1_hi[layer], 2 * C, K1)) return rc;
-  if (int rc = make_weight_map(&maps[5], nsplit == 2 ? wf.w1_lo[layer] : wf.w1_hi[layer], 2 * C, K1)) return rc;
+  const int cg = tc_pick_cg(nsplit);
+  if (int rc = make_weight_map(&maps[4], wf.w1_hi[layer], 2 * C, K1, cg)) return rc;
+  if (int rc = make_weight_map(&maps[5], nsplit == 2 ? wf.w1_lo[layer] : wf.w1_hi[layer], 2 * C, K1, cg)) return rc;
   p.n_src = 2;
   p.src[0] = TcSrc{C, ks, dil, dil * (ks - 1) / 2};
   p.src[1] = TcSrc{n_cond, 1, 0, 0};
@@ -650,15 +738,15 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
   p.wc = wf.wc[layer];
   p.out8 = ws->out8;
   p.accumulate_out8 = layer > 0;
-  if (int rc = launch_tc(maps, p, st)) return rc;
+  if (int rc = launch_tc(maps, p, st, cg)) return rc;
   if (last) return 0;   // the last layer feeds the skip path only (glow.py:168-169)
   // ---- G2: x <- [acts | x] [W_res | I]^T + b_res
   if (int rc = make_act_map(&maps[0], ws->acts_hi, B, Tg, C)) return rc;
   if (int rc = make_act_map(&maps[1], nsplit == 2 ? ws->acts_lo : ws->acts_hi, B, Tg, C)) return rc;
   if (int rc = make_act_map(&maps[2], ws->x_hi, B, Tg, C)) return rc;
   if (int rc = make_act_map(&maps[3], nsplit == 2 ? ws->x_lo : ws->x_hi, B, Tg, C)) return rc;
-  if (int rc = make_weight_map(&maps[4], wf.w2_hi[layer], C, 2 * C)) return rc;
-  if (int rc = make_weight_map(&maps[5], nsplit == 2 ? wf.w2_lo[layer] : wf.w2_hi[layer], C, 2 * C)) return rc;
+  if (int rc = make_weight_map(&maps[4], wf.w2_hi[layer], C, 2 * C, cg)) return rc;
+  if (int rc = make_weight_map(&maps[5], nsplit == 2 ? wf.w2_lo[layer] : wf.w2_hi[layer], C, 2 * C, cg)) return rc;
   p.n_src = 2;
   p.src[0] = TcSrc{C, 1, 0, 0};
   p.src[1] = TcSrc{C, 1, 0, 0};
@@ -672,7 +760,7 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
   p.wc = nullptr;
   p.out8 = nullptr;
   if (p.prof) p.prof += 8 * 256;   // G2 counters follow G1's
-  return launch_tc(maps, p, st);
+  return launch_tc(maps, p, st, cg);
 }
 
 int wg_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* mel_cl, float* audio,

@@ -183,6 +183,9 @@ int fac_wn_end_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, c
 /* Optional cycle counters of the tensor-core kernel: device buffer of 2*256*8 int64 ([G1|G2][cta][8]:
  * producer wait-empty, MMA wait-tmem, MMA wait-full, MMA total, epilogue wait, epilogue busy); NULL disables. */
 void fac_tc_set_profile_buffer(long long* device_buf);
+/* 0 (default): automatic; 1: one CTA per 128-column tile; 2: CTA pairs (thread-block cluster of 2,
+ * tcgen05 cta_group::2, UMMA M = 256, each CTA stages half of the weight rows). */
+int fac_tc_set_cta_group(int cta_group);
 /* Same contract as fac_waveglow_infer_f32 (glow.py:252-293), WN layers on the tensor cores. */
 int fac_waveglow_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* mel_cl, float* audio,
                           const fac_wg_tc_workspace* ws, int B, int F, int nsplit, void* stream);
