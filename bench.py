@@ -155,7 +155,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    frames = 200
+    frames = synth.frames_for_seconds(args.seconds)   # one full-length utterance of the config per step
     cfg = synth.WAVEGLOW_CONFIG
     from oracle import waveglow_oracle
     torch.set_num_threads(threads)
@@ -176,7 +176,7 @@ def run_reference(args, rank):
         "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "rtf": value / RATE,
-        "config": workload_config(args, 8, synth.frames_for_seconds(10.0)),
+        "config": dict(workload_config(args, args.batch, synth.frames_for_seconds(args.seconds)), precision="fp32 (torch CPU)"),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -296,6 +296,12 @@ def main():
     # ---- roofline of the dominant kernel (the WN layer GEMMs), timed live with CUDA events
     peaks = measured_peaks()
     roof = model.profile_dominant_kernel(mel, peaks) if hasattr(model, "profile_dominant_kernel") else None
+    traffic_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if roof is not None and precision == "bf16x3" and os.path.isfile(traffic_path):
+        with open(traffic_path) as fh:
+            t = json.load(fh)
+        roof["traffic"] = t["wn_gemm_tc_kernel"]["launch_weighted_mean_bytes"]     # DRAM bytes per launch (ncu)
+        roof["traffic_source"] = t["source"]
 
     # ---- PPG -> Mel side metric (mel frames/s), short and outside the timed region ----------
     ppg2mel = None
@@ -306,7 +312,7 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        frames = 200
+        frames = synth.frames_for_seconds(args.seconds)   # one full-length utterance of the config
         v, secs = cpu_port_samples_per_s(frames, repeats=2, threads=threads)
         cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
                "sample": "WaveGlow.infer on 1 x %d frames (%d samples), oracle port of reference glow.py, torch CPU "
