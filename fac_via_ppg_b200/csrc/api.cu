@@ -33,6 +33,7 @@ int wg_infer_tc(const fac_wg_model*, const fac_wg_tc_weights*, const float*, flo
                 int, int, cudaStream_t);
 int wg_tc_end(const fac_wg_model*, const fac_wg_tc_weights*, int, const float*, float*, int, int, cudaStream_t);
 void tc_set_prof(long long*);
+int denoise_spectrum(float*, const float*, float, long long, int, int, cudaStream_t);
 int tc_set_cta_group(int);
 int selftest_grid_barrier(unsigned int*, int, cudaStream_t);
 int lstm_bidir(const float*, const float*, float*, int, int, int, cudaStream_t);
@@ -98,6 +99,10 @@ void fac_tc_set_profile_buffer(long long* device_buf) { fac::tc_set_prof(device_
 int fac_tc_set_cta_group(int cta_group) { return fac::tc_set_cta_group(cta_group); }
 int fac_selftest_grid_barrier(unsigned int* zeroed_counter, int iters, void* stream) {
   return fac::selftest_grid_barrier(zeroed_counter, iters, (cudaStream_t)stream);
+}
+int fac_denoise_spectrum_f32(float* spec, const float* bias_mag, float strength, long long n_rows, int n_bins, int ld,
+                               void* stream) {
+  return fac::denoise_spectrum(spec, bias_mag, strength, n_rows, n_bins, ld, (cudaStream_t)stream);
 }
 int fac_lstm_bidir_f32(const float* xp, const float* w_hh, float* out, int B, int T, int H, void* stream) {
   return fac::lstm_bidir(xp, w_hh, out, B, T, H, (cudaStream_t)stream);

@@ -1,8 +1,14 @@
 """Drop-in for the reference ``src/waveglow/denoiser.py`` (the step right after ``infer`` on the CLI
-path, generate_synthesis.py:58-62, 94-95).  SURVEY.md section 8f ranks it "next": the bias audio comes
-from the CUDA-native ``WaveGlow.infer(zeros, sigma=0)``; the STFT / inverse STFT (reference
-src/common/stft.py:79-138, a dense-DFT conv) are still expressed with torch ops here -- plumbing
-around the hot path, not a hand-written kernel yet.
+path, generate_synthesis.py:58-62, 94-95), CUDA-native.
+
+The reference's STFT is a dense windowed-DFT Conv1d (stride = hop) and its inverse a
+ConvTranspose1d with the pseudo-inverse basis (src/common/stft.py:54-138).  With the signal reshaped
+into rows of ``hop`` samples both become 7-tap implicit GEMMs, so they run on the same
+``fac_conv_gemm_f32`` kernel as the rest of the path (forward: taps +1 over the sample rows; inverse:
+taps -1 over the frames, exactly like WaveGlow's upsampler); the window-sum-square normalisation
+(src/common/audio_processing.py:39-88) and the hop scaling are folded into the inverse GEMM's
+epilogue as a multiplicative mask, and the spectral subtraction (denoiser.py:63-68) is
+``fac_denoise_spectrum_f32``.  Only reflect-padding / cropping stay in torch.
 """
 from __future__ import annotations
 
@@ -10,51 +16,95 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from fac_via_ppg_b200 import _ext, ops
 
-def _hann(win_length):
-    n = np.arange(win_length)
-    return 0.5 - 0.5 * np.cos(2.0 * np.pi * n / win_length)       # scipy get_window('hann', fftbins=True)
+
+def _hann_periodic(n):
+    return 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n)       # scipy get_window('hann', n, fftbins=True)
 
 
 class STFT(torch.nn.Module):
-    """Windowed DFT as Conv1d / ConvTranspose1d, same bases as reference stft.py:54-77."""
+    """Windowed DFT bases of reference stft.py:54-77, packed for the hop-reshaped GEMM form."""
 
     def __init__(self, filter_length=800, hop_length=200, win_length=800):
         super().__init__()
+        if filter_length % 2 or hop_length % 8:
+            raise ValueError("filter_length must be even and hop_length a multiple of 8")
         self.filter_length, self.hop_length, self.win_length = filter_length, hop_length, win_length
+        self.taps = -(-filter_length // hop_length)
+        self.cutoff = filter_length // 2 + 1
+        self.n_out = 2 * self.cutoff
+        self.ld = (self.n_out + 7) // 8 * 8                          # leading dimension of a spectrum row
         basis = np.fft.fft(np.eye(filter_length))
-        cutoff = filter_length // 2 + 1
-        basis = np.vstack([np.real(basis[:cutoff]), np.imag(basis[:cutoff])])
+        basis = np.vstack([np.real(basis[:self.cutoff]), np.imag(basis[:self.cutoff])])
         window = np.zeros(filter_length)
         lpad = (filter_length - win_length) // 2
-        window[lpad:lpad + win_length] = _hann(win_length)
+        window[lpad:lpad + win_length] = _hann_periodic(win_length)
         scale = filter_length / hop_length
-        fwd = torch.tensor(basis[:, None, :] * window, dtype=torch.float32)
-        inv = torch.tensor(np.linalg.pinv(scale * basis).T[:, None, :] * window, dtype=torch.float32)
-        self.register_buffer("forward_basis", fwd)
-        self.register_buffer("inverse_basis", inv)
+        fwd = torch.tensor(basis * window, dtype=torch.float32)                               # (n_out, n_fft)
+        inv = torch.tensor(np.linalg.pinv(scale * basis).T * window, dtype=torch.float32)    # (n_out, n_fft)
+        k_pad = self.taps * hop_length
+        w_f = torch.zeros(k_pad, self.n_out)
+        w_f[:filter_length] = fwd.t()                                # rows = sample offset tap*hop + c
+        inv_pad = torch.zeros(self.n_out, k_pad)
+        inv_pad[:, :filter_length] = inv
+        w_i = torch.zeros(self.taps, self.ld, hop_length)            # rows = (tap, bin), cols = sample in hop
+        w_i[:, :self.n_out] = inv_pad.view(self.n_out, self.taps, hop_length).permute(1, 0, 2)
+        wf_p, _ = ops.pack_gemm_weight(w_f)
+        wi_p, _ = ops.pack_gemm_weight(w_i.reshape(self.taps * self.ld, hop_length))
+        self.register_buffer("w_forward", wf_p)
+        self.register_buffer("w_inverse", wi_p)
         self.register_buffer("window_sq", torch.tensor(window ** 2, dtype=torch.float32))
+        self._norm_cache = {}
+
+    def transform_raw(self, x):
+        """x (B, N) -> spectrum rows (B, frames, ld) = [real | imag | pad] (reference stft.py:79-97)."""
+        _ext.require_cuda(x, "audio")
+        B, N = x.shape
+        hop, pad = self.hop_length, self.filter_length // 2
+        xp = F.pad(x.float()[:, None, None, :], (pad, pad, 0, 0), mode="reflect").view(B, -1)
+        frames = (xp.shape[1] - self.filter_length) // hop + 1
+        rows = frames + self.taps - 1
+        if xp.shape[1] < rows * hop:
+            xp = F.pad(xp, (0, rows * hop - xp.shape[1]))
+        src = xp[:, : rows * hop].contiguous().view(B, rows, hop)
+        spec = torch.zeros(B, frames, self.ld, device=x.device, dtype=torch.float32)
+        ops.conv_gemm([ops.conv_src(src, self.taps, 1, 0)], self.w_forward, None, self.n_out, spec, batch=B,
+                      rows=frames, out_batch_stride=frames * self.ld, out_row_stride=self.ld)
+        return spec
 
     def transform(self, x):
-        pad = self.filter_length // 2
-        x = F.pad(x[:, None, None, :], (pad, pad, 0, 0), mode="reflect").squeeze(1)
-        ft = F.conv1d(x, self.forward_basis, stride=self.hop_length)
-        cutoff = self.filter_length // 2 + 1
-        re, im = ft[:, :cutoff], ft[:, cutoff:]
+        """reference STFT.transform: magnitude and phase (B, cutoff, frames)."""
+        spec = self.transform_raw(x)
+        re, im = spec[..., : self.cutoff].transpose(1, 2), spec[..., self.cutoff: self.n_out].transpose(1, 2)
         return torch.sqrt(re * re + im * im), torch.atan2(im, re)
 
-    def inverse(self, magnitude, phase):
-        spec = torch.cat([magnitude * torch.cos(phase), magnitude * torch.sin(phase)], dim=1)
-        out = F.conv_transpose1d(spec, self.inverse_basis, stride=self.hop_length)
-        n_frames = magnitude.size(-1)
-        # window sum-square envelope (reference audio_processing.py:39-88) as one transposed conv
-        ones = torch.ones(1, 1, n_frames, device=out.device)
-        wss = F.conv_transpose1d(ones, self.window_sq[None, None, :], stride=self.hop_length)[0, 0]
-        nz = wss > torch.finfo(torch.float32).tiny
-        out[:, :, nz] = out[:, :, nz] / wss[nz]
-        out = out * (float(self.filter_length) / self.hop_length)
+    def _normaliser(self, frames, batch, device):
+        """hop scaling / window-sum-square envelope of reference stft.py:119-132, as the epilogue mask."""
+        key = (frames, batch, str(device))
+        if key not in self._norm_cache:
+            hop, n_fft = self.hop_length, self.filter_length
+            rows = frames + self.taps - 1
+            ones = torch.ones(1, 1, frames, device=device)
+            wss = F.conv_transpose1d(ones, self.window_sq[None, None, :].to(device), stride=hop)[0, 0]
+            norm = torch.full_like(wss, float(n_fft) / hop)
+            nz = wss > torch.finfo(torch.float32).tiny
+            norm[nz] = norm[nz] / wss[nz]
+            full = torch.zeros(rows * hop, device=device)
+            full[: wss.numel()] = norm
+            self._norm_cache[key] = full.view(1, rows, hop).expand(batch, rows, hop).contiguous()
+        return self._norm_cache[key]
+
+    def inverse_raw(self, spec, n_samples):
+        """spectrum rows (B, frames, ld) -> audio (B, 1, n_samples) (reference stft.py:106-138)."""
+        B, frames, _ = spec.shape
+        hop = self.hop_length
+        rows = frames + self.taps - 1
+        out = torch.empty(B, rows, hop, device=spec.device, dtype=torch.float32)
+        ops.conv_gemm([ops.conv_src(spec, self.taps, -1, 0)], self.w_inverse, None, hop, out, batch=B, rows=rows,
+                      mask=self._normaliser(frames, B, spec.device))
         half = self.filter_length // 2
-        return out[:, :, half:-half]
+        return out.view(B, 1, rows * hop)[:, :, half: half + n_samples]
 
 
 class Denoiser(torch.nn.Module):
@@ -73,9 +123,14 @@ class Denoiser(torch.nn.Module):
         with torch.no_grad():
             bias_audio = waveglow.infer(mel_input, sigma=0.0).float()
             bias_spec, _ = self.stft.transform(bias_audio)
-        self.register_buffer("bias_spec", bias_spec[:, :, 0][:, :, None])
+        self.register_buffer("bias_spec", bias_spec[:, :, 0][:, :, None].contiguous())
 
+    @torch.no_grad()
     def forward(self, audio, strength=0.1):
-        spec, angles = self.stft.transform(audio.cuda().float())
-        spec = torch.clamp(spec - self.bias_spec * strength, 0.0)
-        return self.stft.inverse(spec, angles)
+        audio = audio.cuda().float()
+        spec = self.stft.transform_raw(audio)
+        B, frames, ld = spec.shape
+        rc = _ext.load().fac_denoise_spectrum_f32(spec.data_ptr(), self.bias_spec.data_ptr(), float(strength),
+                                                  B * frames, self.stft.cutoff, ld, _ext.current_stream())
+        _ext.check(rc, "fac_denoise_spectrum_f32")
+        return self.stft.inverse_raw(spec, audio.shape[1])

@@ -249,6 +249,14 @@ int fac_taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory,
                          float* mel, float* gate, float* align, int B, int T_in, int max_steps,
                          int window, float gate_threshold, void* stream);
 
+/* ---- Denoiser (the step after WaveGlow.infer on the CLI path) ------------- */
+/* reference src/waveglow/denoiser.py:63-68: in place on an STFT spectrum laid out as rows of
+ * [n_bins real | n_bins imaginary | padding] with leading dimension ld: magnitude <- max(magnitude -
+ * bias_mag[bin]*strength, 0), phase kept.  The STFT and its inverse (reference src/common/stft.py:79-138,
+ * a dense-DFT Conv1d / ConvTranspose1d) are fac_conv_gemm_f32 calls on the hop-reshaped signal. */
+int fac_denoise_spectrum_f32(float* spec, const float* bias_mag, float strength, long long n_rows, int n_bins,
+                             int ld, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

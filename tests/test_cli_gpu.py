@@ -82,3 +82,19 @@ def test_window_mask_helper_matches_oracle():
         got = get_mask_from_lengths_window_and_time_step(lengths, 3, step).cpu()
         ref = tacotron_oracle.window_mask([10, 7, 3], 3, step, 10)
         assert torch.equal(got, ref), step
+
+
+def test_denoiser_matches_reference_restatement():
+    """CUDA Denoiser (hop-reshaped STFT GEMMs + spectral kernel) vs the oracle restatement of
+    reference denoiser.py / stft.py on the same bias audio."""
+    from oracle import denoiser_oracle
+    wg = WaveGlow.remove_weightnorm(small_waveglow()).cuda().eval()
+    den = Denoiser(wg, mode="zeros")
+    bias_audio = wg.infer(torch.zeros(1, 80, 88, device="cuda"), sigma=0.0).float().cpu()
+    g = torch.Generator().manual_seed(1)
+    audio = torch.randn(2, 4800, generator=g) * 0.2
+    for strength in (0.005, 0.5):
+        ref = denoiser_oracle.denoise(audio, bias_audio, strength)
+        out = den(audio.cuda(), strength=strength)
+        assert out.shape == ref.shape == (2, 1, 4800)
+        assert (out.cpu() - ref).abs().max().item() <= 2e-4, strength

@@ -78,3 +78,19 @@ def test_tacotron_oracle_matches_live_reference():
     out = tacotron_oracle.tacotron_inference(sd, synth.TACOTRON_HPARAMS, ppg, None, 2.0, 12)
     for a, b in zip(ref, out):
         assert (a - b).abs().max().item() <= 1e-4
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+def test_denoiser_oracle_matches_live_reference_stft():
+    """oracle/denoiser_oracle.py vs the unmodified reference src/common/stft.py (transform and inverse)."""
+    from oracle import denoiser_oracle as do
+    ref_shim.install()
+    from common.stft import STFT  # type: ignore
+    torch.manual_seed(0)
+    x = torch.randn(2, 3200) * 0.3
+    ref = STFT(1024, 160, 1024)
+    fwd, inv, window = do.stft_bases()
+    mag_r, ph_r = ref.transform(x)
+    mag_o, ph_o = do.transform(x, fwd)
+    assert (mag_r - mag_o).abs().max().item() <= 1e-6 and (ph_r - ph_o).abs().max().item() <= 1e-6
+    assert (ref.inverse(mag_r, ph_r) - do.inverse(mag_o, ph_o, inv, window)).abs().max().item() <= 1e-5

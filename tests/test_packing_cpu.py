@@ -88,3 +88,34 @@ def test_tensor_core_algebra_matches_golden(golden_dir, name):
     audio0 = emulate.fill_audio_slots(g["noise"], g["sigma"], cfg["n_group"])
     out = emulate.waveglow_infer_tc(packed, mel, audio0)
     assert (out - g["audio"]).pow(2).mean().sqrt().item() <= 2e-5
+
+
+def test_hop_reshaped_stft_formulation_matches_oracle():
+    """The Denoiser's STFT / inverse STFT as 7-tap GEMMs over the hop-reshaped signal (forward taps +1,
+    inverse taps -1, window-sum-square folded into a mask) equal the reference's strided Conv1d /
+    ConvTranspose1d (oracle/denoiser_oracle.py, pinned to reference src/common/stft.py)."""
+    import torch.nn.functional as F
+    from fac_via_ppg_b200.waveglow.denoiser import STFT
+    from oracle import denoiser_oracle as do
+    stft = STFT(1024, 160, 1024)
+    torch.manual_seed(2)
+    x = torch.randn(2, 1600) * 0.3
+    fwd, inv, window = do.stft_bases()
+    mag, phase = do.transform(x, fwd)
+    # forward
+    xp = F.pad(x[:, None, None, :], (512, 512, 0, 0), mode="reflect").view(2, -1)
+    frames = (xp.shape[1] - 1024) // 160 + 1
+    rows = frames + stft.taps - 1
+    xp = F.pad(xp, (0, rows * 160 - xp.shape[1]))
+    spec = emulate.conv_gemm([(xp.view(2, rows, 160), stft.taps, 1, 0)], stft.w_forward, None, stft.n_out)[:, :frames]
+    re, im = spec[..., :513].transpose(1, 2), spec[..., 513:].transpose(1, 2)
+    assert (torch.sqrt(re * re + im * im) - mag).abs().max().item() <= 1e-4
+    # inverse (zero rows appended so that every output row exists in the emulation)
+    spec_ld = torch.zeros(2, rows, stft.ld)
+    spec_ld[:, :frames, : stft.n_out] = spec
+    out = emulate.conv_gemm([(spec_ld, stft.taps, -1, 0)], stft.w_inverse, None, 160)
+    out = out * stft._normaliser(frames, 2, "cpu")
+    rec = out.reshape(2, 1, rows * 160)[:, :, 512: 512 + 1600]
+    ref = do.inverse(mag, phase, inv, window)
+    assert (rec - ref).abs().max().item() <= 1e-4
+    assert (rec[:, 0] - x).abs().max().item() <= 1e-3          # and both reconstruct the signal
