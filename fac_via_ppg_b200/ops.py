@@ -15,6 +15,8 @@ def conv_src(t: torch.Tensor, taps: int = 1, dilation: int = 0, center: int = 0,
     _ext.require_cuda(t, "conv source")
     if t.dtype != torch.float32 or not t.is_contiguous():
         raise _ext.FacError("conv sources must be contiguous fp32 tensors")
+    if channel_major and t.shape[2] == 1:       # (B, C, 1) is the same memory as channels-last (B, 1, C)
+        t, channel_major = t.view(t.shape[0], 1, t.shape[1]), False
     if channel_major:
         B, Cc, T = t.shape
         src = _ext.ConvSrc(t.data_ptr(), Cc * T, 1, T, Cc, taps, dilation, center, T, 0)

@@ -113,3 +113,35 @@ def test_config4_shape_sixty_seconds_long_form(taco, waveglow):
     assert torch.equal(long[0][:, :, :300], short[0])
     wav = waveglow.infer(long[1][:1].clamp(-11.5, 2.0).contiguous(), 0.6)
     assert wav.shape == (1, T * 160) and torch.isfinite(wav).all()
+
+
+@pytest.mark.parametrize("t_in,steps", [(1, 4), (3, 9), (25, 40)])
+def test_tiny_and_ragged_tacotron_inputs(taco, t_in, steps):
+    """Inputs shorter than the attention window / the location kernel, and decodes that run past the end
+    of the input (the window then collapses onto the last frame, src/common/utils.py:65-69)."""
+    taco.decoder.gate_threshold, taco.decoder.max_decoder_steps = 2.0, steps
+    ppg = synth.synthetic_ppg(2, t_in, seed=t_in)
+    torch.manual_seed(t_in)
+    masks = tacotron_oracle.record_dropout_tape(2, t_in, steps)
+    ref = tacotron_oracle.tacotron_inference(synth.tacotron_state(), synth.TACOTRON_HPARAMS, ppg, masks, 2.0, steps)
+    out = taco.inference(ppg.to(DEV), dropout_tape=masks)
+    for name, a, b in zip(("mel", "mel_post", "gate", "align"), out, ref):
+        assert a.shape == b.shape, name
+        assert (a.cpu() - b).abs().max().item() <= 1e-3, name
+
+
+@pytest.mark.parametrize("batch,frames", [(1, 1), (3, 2), (5, 7)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_tiny_and_odd_waveglow_inputs(waveglow, batch, frames, precision):
+    """A single frame, odd batches, column counts far below one 128-row tile (and odd tile counts for
+    the CTA-pair kernel)."""
+    mel = synth.synthetic_mel(batch, frames, seed=frames)
+    torch.manual_seed(frames)
+    noise = waveglow_oracle.draw_noise(synth.WAVEGLOW_CONFIG, batch, frames * 20)
+    ref = waveglow_oracle.waveglow_infer(synth.waveglow_state(), synth.WAVEGLOW_CONFIG, mel, 0.6, noise)
+    try:
+        out = waveglow.set_precision(precision).infer(mel.to(DEV), 0.6, noise=[z.to(DEV) for z in noise])
+    finally:
+        waveglow.set_precision("bf16x3")
+    assert out.shape == ref.shape
+    assert rms(out, ref) <= (1e-5 if precision == "fp32" else 1e-4)
