@@ -101,6 +101,7 @@ SIGNATURES = {
                                         C.c_int, _fp]),
     "fac_tc_set_profile_buffer": (None, [_fp]),
     "fac_tc_set_cta_group": (C.c_int, [C.c_int]),
+    "fac_tc_set_k_block": (C.c_int, [C.c_int]),
     "fac_selftest_grid_barrier": (C.c_int, [_fp, C.c_int, _fp]),
     "fac_denoise_spectrum_f32": (C.c_int, [_fp, _fp, C.c_float, C.c_longlong, C.c_int, C.c_int, _fp]),
     "fac_lstm_bidir_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
@@ -135,9 +136,11 @@ def load(build_if_missing: bool = True):
         fn.restype = res
         fn.argtypes = args
     _lib = lib
-    cta_group = os.environ.get("FAC_TC_CTA_GROUP")
+    cta_group, k_block = os.environ.get("FAC_TC_CTA_GROUP"), os.environ.get("FAC_TC_K_BLOCK")
     if cta_group:
         check(lib.fac_tc_set_cta_group(int(cta_group)), "fac_tc_set_cta_group")
+    if k_block:
+        check(lib.fac_tc_set_k_block(int(k_block)), "fac_tc_set_k_block")
     return lib
 
 

@@ -35,6 +35,7 @@ int wg_tc_end(const fac_wg_model*, const fac_wg_tc_weights*, int, const float*, 
 void tc_set_prof(long long*);
 int denoise_spectrum(float*, const float*, float, long long, int, int, cudaStream_t);
 int tc_set_cta_group(int);
+int tc_set_k_block(int);
 int selftest_grid_barrier(unsigned int*, int, cudaStream_t);
 int lstm_bidir(const float*, const float*, float*, int, int, int, cudaStream_t);
 int taco_decoder_run(const fac_taco_decoder_weights*, const float*, const float*, const int*, const unsigned char*,
@@ -97,6 +98,7 @@ int fac_waveglow_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, con
 }
 void fac_tc_set_profile_buffer(long long* device_buf) { fac::tc_set_prof(device_buf); }
 int fac_tc_set_cta_group(int cta_group) { return fac::tc_set_cta_group(cta_group); }
+int fac_tc_set_k_block(int k_block) { return fac::tc_set_k_block(k_block); }
 int fac_selftest_grid_barrier(unsigned int* zeroed_counter, int iters, void* stream) {
   return fac::selftest_grid_barrier(zeroed_counter, iters, (cudaStream_t)stream);
 }

@@ -30,8 +30,9 @@ namespace {
 using namespace tc;
 
 constexpr int TC_BM = 128;       // time rows per tile (UMMA M)
-constexpr int TC_BK = 32;        // K per pipeline stage = two UMMA K steps; 64-byte rows, SWIZZLE_64B
-constexpr int TC_ROWB = TC_BK * 2;
+// K per pipeline stage (BK): 64 (128-byte rows, SWIZZLE_128B) by default, 32 (64-byte rows, SWIZZLE_64B) optional:
+// the TMA issue rate is per row request, so rows should be as wide as the stage budget allows.
+constexpr int TC_BK_MAX = 64;
 constexpr int UMMA_K = 16;
 constexpr int TC_NMAX = 512;     // accumulator columns per tile (all of TMEM)
 constexpr int TC_NHALF = 256;    // N of one UMMA
@@ -39,7 +40,6 @@ constexpr int TC_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each ownin
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_NOUT = 8;       // channels of the collapsed skip path (= max 2*n_half)
 constexpr int TC_CMAX = 256;     // max WN channels (Wc staging)
-constexpr int A_BYTES = TC_BM * TC_ROWB;       // 8 KB
 constexpr int TC_BAR_BYTES = 256;
 constexpr int TC_WC_BYTES = TC_NOUT * TC_CMAX * 4;       // 8 KB
 constexpr int TC_X8_BYTES = TC_BM * TC_NOUT * 4;         // 4 KB: out8 partials handed between paired epilogue warps
@@ -49,9 +49,11 @@ constexpr int TC_RING_BYTES = 192 * 1024;   // operand ring; the stage count fol
 // CG = 1: one CTA per 128-row tile.  CG = 2: a CTA pair (thread-block cluster of 2, tcgen05 cta_group::2)
 // works on two adjacent tiles as ONE 256-row UMMA; each CTA stages only half of the weight rows, so
 // the per-SM operand traffic and shared-memory reads drop by a third and the ring gets 6 stages.
-template <int CG>
+template <int CG, int BK>
 struct TcCfg {
-  static constexpr int W_BYTES = (TC_NHALF / CG) * TC_ROWB;          // this CTA's share of a 256-row weight block
+  static constexpr int ROWB = BK * 2;                                // bytes of one operand row
+  static constexpr int A_BYTES = TC_BM * ROWB;                       // 8 / 16 KB
+  static constexpr int W_BYTES = (TC_NHALF / CG) * ROWB;             // this CTA's share of a 256-row weight block
   // a stage holds nsplit x (A tile + weight share): split-bf16 48 KB / 32 KB (4 / 6 stages), bf16 half of that
   // (8 / 12 stages)
   static constexpr int SMEM = TC_RING_BYTES + TC_BAR_BYTES + TC_WC_BYTES + TC_X8_BYTES + 1024 /*alignment*/;
@@ -91,13 +93,13 @@ __device__ __forceinline__ float gate_act(float a, float b) {
   return __fdividef(ea - 1.f, (ea + 1.f) * (1.f + eb));
 }
 
-template <int CG>
+template <int CG, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_constant__ CUtensorMap a0_lo,
                   const __grid_constant__ CUtensorMap a1_hi, const __grid_constant__ CUtensorMap a1_lo,
                   const __grid_constant__ CUtensorMap w_hi, const __grid_constant__ CUtensorMap w_lo,
                   const TcParams p) {
-  constexpr int W_BYTES = TcCfg<CG>::W_BYTES;
+  constexpr int W_BYTES = TcCfg<CG, BK>::W_BYTES, A_BYTES = TcCfg<CG, BK>::A_BYTES, TC_ROWB = TcCfg<CG, BK>::ROWB, TC_BK = BK;
   const int STAGE_BYTES = p.nsplit * (A_BYTES + W_BYTES);
   const int TC_STAGES = min(TC_MAX_STAGES, TC_RING_BYTES / STAGE_BYTES);
   const int W_OFF = p.nsplit * A_BYTES;      // stage layout: A_hi [A_lo] W_hi [W_lo]
@@ -493,8 +495,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-constexpr CUtensorMapSwizzle TC_SWIZZLE = TC_ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                          : TC_ROWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+inline CUtensorMapSwizzle tc_swizzle(int bk) {
+  return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+int g_tc_bk = 0;   // 0 = automatic
+inline int tc_pick_bk(int) { return g_tc_bk ? g_tc_bk : 64; }   // measured: 64 wins in both modes (profiles/README.md)
 
 EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = [] {
@@ -509,15 +514,15 @@ EncodeTiledFn encode_fn() {
 }
 
 // (B, T, C) channels-last bf16 activation: box = 16 channels x 128 rows of one utterance.
-int make_act_map(CUtensorMap* m, const void* ptr, int B, int T, int C) {
+int make_act_map(CUtensorMap* m, const void* ptr, int B, int T, int C, int bk) {
   EncodeTiledFn fn = encode_fn();
   FAC_REQUIRE(fn != nullptr, "tensor-core path: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
-  cuuint32_t box[3] = {TC_BK, TC_BM, 1};
+  cuuint32_t box[3] = {(cuuint32_t)bk, TC_BM, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, TC_SWIZZLE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, tc_swizzle(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FAC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", B, T, C, (int)r);
   return 0;
@@ -529,15 +534,15 @@ int g_tc_cta_group = 0;   // 0 = automatic: CTA pairs for the split-bf16 mode, s
 inline int tc_pick_cg(int nsplit) { return g_tc_cta_group ? g_tc_cta_group : (nsplit == 2 ? 2 : 1); }
 
 // (N, K) row-major bf16 weight: box = 32 k x (min(256, N) / cta_group) rows.
-int make_weight_map(CUtensorMap* m, const void* ptr, int N, int K, int cg) {
+int make_weight_map(CUtensorMap* m, const void* ptr, int N, int K, int cg, int bk) {
   EncodeTiledFn fn = encode_fn();
   FAC_REQUIRE(fn != nullptr, "tensor-core path: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {TC_BK, (cuuint32_t)((N < TC_NHALF ? N : TC_NHALF) / cg)};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)((N < TC_NHALF ? N : TC_NHALF) / cg)};
   cuuint32_t es[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, TC_SWIZZLE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, tc_swizzle(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FAC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight %dx%d) failed: %d", N, K, (int)r);
   return 0;
@@ -553,12 +558,12 @@ int sm_count() {
   return sms;
 }
 
-template <int CG>
+template <int CG, int BK>
 int launch_tc_cg(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st) {
   static bool attr_set = false;
-  constexpr int smem = TcCfg<CG>::SMEM;
+  constexpr int smem = TcCfg<CG, BK>::SMEM;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wn_gemm_tc_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(wn_gemm_tc_kernel<CG, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("wn_gemm_tc: cannot reserve %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
       return 2;
@@ -579,7 +584,7 @@ int launch_tc_cg(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st) 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wn_gemm_tc_kernel<CG>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wn_gemm_tc_kernel<CG, BK>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   count_launch();
   if (e != cudaSuccess) {
     set_error("wn_gemm_tc_kernel<%d>: launch failed: %s", CG, cudaGetErrorString(e));
@@ -591,7 +596,9 @@ int launch_tc_cg(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st) 
 int launch_tc(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st, int cg) {
   const int n_cols = p.n_total < TC_NHALF ? p.n_total : TC_NHALF;
   FAC_REQUIRE(cg == 1 || (n_cols / 2) % 8 == 0, "wn_gemm_tc: %d columns cannot be split over a CTA pair", n_cols);
-  return cg == 2 ? launch_tc_cg<2>(maps, p, st) : launch_tc_cg<1>(maps, p, st);
+  const int bk = tc_pick_bk(p.nsplit);
+  if (bk == 64) return cg == 2 ? launch_tc_cg<2, 64>(maps, p, st) : launch_tc_cg<1, 64>(maps, p, st);
+  return cg == 2 ? launch_tc_cg<2, 32>(maps, p, st) : launch_tc_cg<1, 32>(maps, p, st);
 }
 
 long long* g_tc_prof = nullptr;
@@ -599,6 +606,11 @@ long long* g_tc_prof = nullptr;
 }  // namespace
 
 void tc_set_prof(long long* p) { g_tc_prof = p; }
+int tc_set_k_block(int bk) {
+  FAC_REQUIRE(bk == 0 || bk == 32 || bk == 64, "K block must be 0 (auto), 32 or 64 (got %d)", bk);
+  g_tc_bk = bk;
+  return 0;
+}
 int tc_set_cta_group(int cg) {
   FAC_REQUIRE(cg >= 0 && cg <= 2, "cta group must be 0 (auto), 1 or 2 (got %d)", cg);
   g_tc_cta_group = cg;
@@ -612,7 +624,7 @@ static int tc_check(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac
   FAC_REQUIRE(w && ws, "tensor-core path: NULL weights/workspace");
   FAC_REQUIRE(nsplit == 1 || nsplit == 2, "tensor-core path: nsplit must be 1 (bf16) or 2 (split-bf16), got %d", nsplit);
   const int C = m->n_channels, n_cond = m->n_mel * m->n_group;
-  FAC_REQUIRE(C % TC_BK == 0 && n_cond % TC_BK == 0 && 2 * C <= TC_NMAX && C <= TC_CMAX,
+  FAC_REQUIRE(C % TC_BK_MAX == 0 && n_cond % TC_BK_MAX == 0 && 2 * C <= TC_NMAX && C <= TC_CMAX,
               "tensor-core path: needs n_channels %% 16 == 0 (<= %d) and n_cond %% 16 == 0", TC_CMAX);
   FAC_REQUIRE(m->n_group <= TC_NOUT, "tensor-core path: n_group %d > %d", m->n_group, TC_NOUT);
   FAC_REQUIRE(ws->spect_hi && ws->x_hi && ws->acts_hi && ws->out8, "tensor-core path: workspace incomplete");
@@ -628,7 +640,9 @@ int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights* w, const
   FAC_REQUIRE(w && w->up_hi && ws && ws->mel_hi && ws->spect_hi && mel_cl, "prepare_spect: NULL argument");
   FAC_REQUIRE(nsplit == 1 || (w->up_lo && ws->mel_lo && ws->spect_lo), "prepare_spect: lo buffers missing");
   const int n_cond = m->n_mel * m->n_group, phases = m->hop / m->n_group, pad = w->mel_pad;
-  FAC_REQUIRE(pad % TC_BK == 0 && pad >= m->n_mel, "prepare_spect: mel_pad %d must be a multiple of %d", pad, TC_BK);
+  FAC_REQUIRE(pad % TC_BK_MAX == 0 && pad >= m->n_mel, "prepare_spect: mel_pad %d must be a multiple of %d", pad,
+              TC_BK_MAX);
+  const int bk = tc_pick_bk(nsplit);
   const long long n_rows = (long long)B * F;
   mel_pad_split_kernel<<<(unsigned)((n_rows * pad + 255) / 256), 256, 0, st>>>(
       mel_cl, reinterpret_cast<__nv_bfloat16*>(ws->mel_hi),
@@ -636,8 +650,8 @@ int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights* w, const
   count_launch();
   if (int rc = check_launch("mel_pad_split_kernel")) return rc;
   CUtensorMap maps[6];
-  if (int rc = make_act_map(&maps[0], ws->mel_hi, B, F, pad)) return rc;
-  if (int rc = make_act_map(&maps[1], nsplit == 2 ? ws->mel_lo : ws->mel_hi, B, F, pad)) return rc;
+  if (int rc = make_act_map(&maps[0], ws->mel_hi, B, F, pad, bk)) return rc;
+  if (int rc = make_act_map(&maps[1], nsplit == 2 ? ws->mel_lo : ws->mel_hi, B, F, pad, bk)) return rc;
   maps[2] = maps[0];
   maps[3] = maps[1];
   TcParams p{};
@@ -650,7 +664,7 @@ int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights* w, const
   p.n_src = 1;
   p.src[0] = TcSrc{pad, m->upsample_taps, -1, 0};
   p.n_total = n_cond;
-  p.k_steps = m->upsample_taps * pad / TC_BK;
+  p.k_steps = m->upsample_taps * pad / bk;
   p.wlo_k_steps = p.k_steps;
   p.mode = TC_RESIDUAL;
   p.bias = m->upsample_b;
@@ -662,8 +676,8 @@ int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights* w, const
   for (int ph = 0; ph < phases; ++ph) {
     const __nv_bfloat16* wh = reinterpret_cast<const __nv_bfloat16*>(w->up_hi) + ph * w_phase;
     const __nv_bfloat16* wl = nsplit == 2 ? reinterpret_cast<const __nv_bfloat16*>(w->up_lo) + ph * w_phase : wh;
-    if (int rc = make_weight_map(&maps[4], wh, n_cond, m->upsample_taps * pad, cg)) return rc;
-    if (int rc = make_weight_map(&maps[5], wl, n_cond, m->upsample_taps * pad, cg)) return rc;
+    if (int rc = make_weight_map(&maps[4], wh, n_cond, m->upsample_taps * pad, cg, bk)) return rc;
+    if (int rc = make_weight_map(&maps[5], wl, n_cond, m->upsample_taps * pad, cg, bk)) return rc;
     p.out_row_off = ph;
     if (int rc = launch_tc(maps, p, st, cg)) return rc;
   }
@@ -718,18 +732,18 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
   p.out_row_mul = 1;
   // ---- G1: [x taps | spect] -> gate -> acts, out8 += Wc acts
   const int K1 = ks * C + n_cond;
-  if (int rc = make_act_map(&maps[0], ws->x_hi, B, Tg, C)) return rc;
-  if (int rc = make_act_map(&maps[1], nsplit == 2 ? ws->x_lo : ws->x_hi, B, Tg, C)) return rc;
-  if (int rc = make_act_map(&maps[2], ws->spect_hi, B, Tg, n_cond)) return rc;
-  if (int rc = make_act_map(&maps[3], nsplit == 2 ? ws->spect_lo : ws->spect_hi, B, Tg, n_cond)) return rc;
-  const int cg = tc_pick_cg(nsplit);
-  if (int rc = make_weight_map(&maps[4], wf.w1_hi[layer], 2 * C, K1, cg)) return rc;
-  if (int rc = make_weight_map(&maps[5], nsplit == 2 ? wf.w1_lo[layer] : wf.w1_hi[layer], 2 * C, K1, cg)) return rc;
+  const int cg = tc_pick_cg(nsplit), bk = tc_pick_bk(nsplit);
+  if (int rc = make_act_map(&maps[0], ws->x_hi, B, Tg, C, bk)) return rc;
+  if (int rc = make_act_map(&maps[1], nsplit == 2 ? ws->x_lo : ws->x_hi, B, Tg, C, bk)) return rc;
+  if (int rc = make_act_map(&maps[2], ws->spect_hi, B, Tg, n_cond, bk)) return rc;
+  if (int rc = make_act_map(&maps[3], nsplit == 2 ? ws->spect_lo : ws->spect_hi, B, Tg, n_cond, bk)) return rc;
+  if (int rc = make_weight_map(&maps[4], wf.w1_hi[layer], 2 * C, K1, cg, bk)) return rc;
+  if (int rc = make_weight_map(&maps[5], nsplit == 2 ? wf.w1_lo[layer] : wf.w1_hi[layer], 2 * C, K1, cg, bk)) return rc;
   p.n_src = 2;
   p.src[0] = TcSrc{C, ks, dil, dil * (ks - 1) / 2};
   p.src[1] = TcSrc{n_cond, 1, 0, 0};
   p.n_total = 2 * C;
-  p.k_steps = K1 / TC_BK;
+  p.k_steps = K1 / bk;
   p.wlo_k_steps = p.k_steps;
   p.mode = TC_GATE;
   p.bias = f.in_cond_b[layer];
@@ -741,18 +755,18 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
   if (int rc = launch_tc(maps, p, st, cg)) return rc;
   if (last) return 0;   // the last layer feeds the skip path only (glow.py:168-169)
   // ---- G2: x <- [acts | x] [W_res | I]^T + b_res
-  if (int rc = make_act_map(&maps[0], ws->acts_hi, B, Tg, C)) return rc;
-  if (int rc = make_act_map(&maps[1], nsplit == 2 ? ws->acts_lo : ws->acts_hi, B, Tg, C)) return rc;
-  if (int rc = make_act_map(&maps[2], ws->x_hi, B, Tg, C)) return rc;
-  if (int rc = make_act_map(&maps[3], nsplit == 2 ? ws->x_lo : ws->x_hi, B, Tg, C)) return rc;
-  if (int rc = make_weight_map(&maps[4], wf.w2_hi[layer], C, 2 * C, cg)) return rc;
-  if (int rc = make_weight_map(&maps[5], nsplit == 2 ? wf.w2_lo[layer] : wf.w2_hi[layer], C, 2 * C, cg)) return rc;
+  if (int rc = make_act_map(&maps[0], ws->acts_hi, B, Tg, C, bk)) return rc;
+  if (int rc = make_act_map(&maps[1], nsplit == 2 ? ws->acts_lo : ws->acts_hi, B, Tg, C, bk)) return rc;
+  if (int rc = make_act_map(&maps[2], ws->x_hi, B, Tg, C, bk)) return rc;
+  if (int rc = make_act_map(&maps[3], nsplit == 2 ? ws->x_lo : ws->x_hi, B, Tg, C, bk)) return rc;
+  if (int rc = make_weight_map(&maps[4], wf.w2_hi[layer], C, 2 * C, cg, bk)) return rc;
+  if (int rc = make_weight_map(&maps[5], nsplit == 2 ? wf.w2_lo[layer] : wf.w2_hi[layer], C, 2 * C, cg, bk)) return rc;
   p.n_src = 2;
   p.src[0] = TcSrc{C, 1, 0, 0};
   p.src[1] = TcSrc{C, 1, 0, 0};
   p.n_total = C;
-  p.k_steps = 2 * C / TC_BK;
-  p.wlo_k_steps = C / TC_BK;        // the identity block has no lo part
+  p.k_steps = 2 * C / bk;
+  p.wlo_k_steps = C / bk;           // the identity block has no lo part
   p.mode = TC_RESIDUAL;
   p.bias = wf.res_b[layer];
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(ws->x_hi);

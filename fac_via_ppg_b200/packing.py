@@ -187,8 +187,8 @@ class PackedWaveGlow:
     # ------------------------------------------------------------------ tensor-core copies
     @property
     def mel_pad(self):
-        """mel channels rounded up to the tensor-core K block (32)."""
-        return _round_up(self.cfg["n_mel_channels"], 32)
+        """mel channels rounded up to the largest tensor-core K block (64)."""
+        return _round_up(self.cfg["n_mel_channels"], 64)
 
     def tc_layouts(self):
         """Layouts of the derived tensor-core weights: (bf16 operand matrices, fp32 side tables)."""
