@@ -100,6 +100,7 @@ SIGNATURES = {
     "fac_waveglow_infer_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), _fp, _fp, _P(WgTcWorkspace), C.c_int, C.c_int,
                                         C.c_int, _fp]),
     "fac_tc_set_profile_buffer": (None, [_fp]),
+    "fac_taco_set_profile_buffer": (None, [_fp]),
     "fac_tc_set_cta_group": (C.c_int, [C.c_int]),
     "fac_tc_set_k_block": (C.c_int, [C.c_int]),
     "fac_selftest_grid_barrier": (C.c_int, [_fp, C.c_int, _fp]),

@@ -33,6 +33,7 @@ int wg_infer_tc(const fac_wg_model*, const fac_wg_tc_weights*, const float*, flo
                 int, int, cudaStream_t);
 int wg_tc_end(const fac_wg_model*, const fac_wg_tc_weights*, int, const float*, float*, int, int, cudaStream_t);
 void tc_set_prof(long long*);
+void taco_set_prof(long long*);
 int denoise_spectrum(float*, const float*, float, long long, int, int, cudaStream_t);
 int tc_set_cta_group(int);
 int tc_set_k_block(int);
@@ -97,6 +98,7 @@ int fac_waveglow_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, con
   return fac::wg_infer_tc(m, w, mel_cl, audio, ws, B, F, nsplit, (cudaStream_t)stream);
 }
 void fac_tc_set_profile_buffer(long long* device_buf) { fac::tc_set_prof(device_buf); }
+void fac_taco_set_profile_buffer(long long* device_buf) { fac::taco_set_prof(device_buf); }
 int fac_tc_set_cta_group(int cta_group) { return fac::tc_set_cta_group(cta_group); }
 int fac_tc_set_k_block(int k_block) { return fac::tc_set_k_block(k_block); }
 int fac_selftest_grid_barrier(unsigned int* zeroed_counter, int iters, void* stream) {

@@ -314,7 +314,7 @@ def tacotron_layout(hp) -> FlatLayout:
     lay.add("dec.w_dec", (4 * R, kin))
     lay.add("dec.b_dec", (4 * R,))
     lay.add("dec.wq", (A, R))
-    lay.add("dec.w_loc", (hp["attention_location_n_filters"], 2, hp["attention_location_kernel_size"]))
+    lay.add("dec.w_loc", (2, hp["attention_location_kernel_size"], hp["attention_location_n_filters"]))
     lay.add("dec.w_ld_t", (hp["attention_location_n_filters"], A))
     lay.add("dec.v", (A,))
     lay.add("dec.w_pp", (M + 1 + P, R + E))
@@ -401,7 +401,7 @@ class PackedTacotron:
             put(f"dec.w_{name}", torch.cat([get(p + "weight_ih"), get(p + "weight_hh")], dim=1))
             put(f"dec.b_{name}", get(p + "bias_ih") + get(p + "bias_hh"))
         put("dec.wq", get(al + "query_layer.linear_layer.weight"))
-        self.view("dec.w_loc").copy_(get(al + "location_layer.location_conv.conv.weight"))
+        self.view("dec.w_loc").copy_(get(al + "location_layer.location_conv.conv.weight").permute(1, 2, 0))
         put("dec.w_ld_t", get(al + "location_layer.location_dense.linear_layer.weight").t())
         put("dec.v", get(al + "v.linear_layer.weight")[0])
         # The next step's prenet layer 0 is applied straight to the projected frame (no bias, no

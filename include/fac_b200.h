@@ -208,7 +208,7 @@ typedef struct fac_taco_decoder_weights {
   const float* w_dec;    /* [1200][1200] decoder_rnn: cat(weight_ih (h_att 300 | context 600), weight_hh 300)   */
   const float* b_dec;    /* [1200]                                                                              */
   const float* wq;       /* [150][300]  attention_layer.query_layer weight                                      */
-  const float* w_loc;    /* [32][2][31] attention_layer.location_layer.location_conv weight                     */
+  const float* w_loc;    /* [2][31][32] attention_layer.location_layer.location_conv weight, filter index last  */
   const float* w_ld_t;   /* [32][150]   location_dense weight, transposed                                       */
   const float* v;        /* [150]       attention_layer.v weight                                                */
   const float* w_pp;     /* [381][900]  rows 0..79 linear_projection, row 80 gate_layer, rows 81..380 =
@@ -238,6 +238,11 @@ typedef struct fac_taco_decoder_state {
 /* Diagnostic: runs `iters` grid-wide barriers of the decoder kernel's kind on a full cooperative grid;
  * time the launch to get the per-barrier latency.  `zeroed_counter` is one zero-initialised uint32. */
 int fac_selftest_grid_barrier(unsigned int* zeroed_counter, int iters, void* stream);
+
+/* Optional cycle counters of the decoder kernel: device buffer of grid*16 int64 per CTA
+ * ([2i] = cycles in phase i's body, [2i+1] = cycles waiting in the grid barrier after it, i = 0..4:
+ * attention LSTM, attention, decoder LSTM, projection, prenet; [10] = total); NULL disables. */
+void fac_taco_set_profile_buffer(long long* device_buf);
 
 /* The whole autoregressive loop of Decoder.inference (reference model.py:489-535 with decode
  * :387-442, Attention :100-121, window mask utils.py:46-78) in one persistent kernel.

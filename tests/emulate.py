@@ -126,7 +126,7 @@ def tacotron_inference(packed, inputs, masks, n_steps, window, gate_threshold=2.
     ctx, pre = torch.zeros(B, E), torch.zeros(B, R)
     w_prev, w_cum = torch.zeros(B, T), torch.zeros(B, T)
     mel, gate, align = torch.zeros(B, n_steps, M), torch.zeros(B, n_steps), torch.zeros(B, n_steps, T)
-    w_loc = v("dec.w_loc")                       # (32, 2, 31)
+    w_loc = v("dec.w_loc").permute(2, 0, 1)      # packed (2, 31, 32) -> (32, 2, 31)
     for t in range(n_steps):
         h_att, c_att = cell(v("dec.w_att"), v("dec.b_att"), torch.cat([pre, ctx, h_att], -1), c_att)
         start, end = min(max(0, t - window), T - 1), min(t + window, T - 1)
