@@ -214,7 +214,21 @@ class Tacotron2(nn.Module):
         return memory
 
     def _decode(self, packed, memory, dec_masks, n_steps):
-        """reference model.py:489-535 (Decoder.inference) -> mel_cl (B, n_steps, M), gate, align, lengths."""
+        """reference model.py:489-535 (Decoder.inference) -> mel_cl (B, n_steps, M), gate, align, lengths.
+        One launch decodes at most (SMs - 100) utterances (one attention CTA each next to >= 100 matrix
+        CTAs); larger batches run as consecutive groups."""
+        B = memory.shape[0]
+        limit = max(1, torch.cuda.get_device_properties(memory.device).multi_processor_count - 100)
+        group = min(limit, 32)
+        if B <= limit:
+            return self._decode_group(packed, memory, dec_masks, n_steps)
+        parts = [self._decode_group(packed, memory[i:i + group], dec_masks[:, :, i:i + group].contiguous(), n_steps)
+                 for i in range(0, B, group)]
+        mel, gate, align, out_len, done = zip(*parts)
+        return (torch.cat(mel), torch.cat(gate), torch.cat(align) if align[0] is not None else None,
+                torch.cat(out_len), torch.stack(done).sum(0))
+
+    def _decode_group(self, packed, memory, dec_masks, n_steps):
         hp = self.hp
         B, T, E = memory.shape
         dev = memory.device
@@ -225,7 +239,7 @@ class Tacotron2(nn.Module):
         st = {"h_att": z(2, B, R), "c_att": z(B, R), "h_dec": z(2, B, R), "c_dec": z(B, R), "ctx": z(B, E),
               "pre": z(B, hp["prenet_dim"]), "p1": z(B, hp["prenet_dim"]), "pq": z(B, A), "w_prev": z(B, T),
               "w_cum": z(B, T),
-              "done": torch.zeros(4, dtype=torch.int32, device=dev),
+              "done": torch.zeros(8, dtype=torch.int32, device=dev),
               "out_len": torch.zeros(B, dtype=torch.int32, device=dev)}
         cstate = _ext.TacoDecoderState(*[st[n].data_ptr() for n, _ in _ext.TacoDecoderState._fields_])
         lengths = torch.full((B,), T, dtype=torch.int32, device=dev)      # model.py:599

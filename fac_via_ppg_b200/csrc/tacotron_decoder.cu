@@ -3,17 +3,24 @@
 // :56-60 LocationLayer, :124-135 Prenet, src/common/utils.py:46-78 window mask).
 //
 // The reference spends ~40 kernel launches and >= 3 device->host syncs per output frame; here the
-// whole loop (up to max_steps frames, all B utterances in lock step) is a single launch.
-//   * EVERY weight matrix of the step is split by output row across the shared memory of all CTAs
-//     (one CTA per SM) and stays resident for the whole sequence: the two LSTMCells (11.5 MB fp32),
-//     the query layer, [mel projection | stop gate | prenet layer 0 composed with the projection]
-//     and prenet layer 1.  Per step the only global traffic is the small state vectors (L2 resident).
-//   * A step is six batched mat-vec phases separated by a lightweight grid barrier (one atomic +
-//     acquire spin): attention LSTM | query | location-sensitive attention (one CTA per utterance,
-//     only the <= 2w+1 window positions: everything outside [t-w, t+w] is masked to -inf by
-//     utils.py:46-78, i.e. has softmax weight exactly 0) | decoder LSTM | projection+gate+prenet0 |
-//     prenet1.  prenet0 has no bias or nonlinearity between it and the projection
-//     (model.py:132-135, 436-438), so W_pre0 (W_proj hc + b) is evaluated as one composed matrix.
+// whole loop (up to max_steps frames, all B utterances in lock step) is a single launch of one CTA per
+// SM, and the CTAs are specialised:
+//   * MATRIX CTAs (all but B of them) keep EVERY weight matrix of the step split by output row across
+//     their shared memory for the whole sequence: the two LSTMCells (11.5 MB fp32),
+//     [mel projection | stop gate | prenet layer 0 composed with the projection] and prenet layer 1.
+//     prenet0 has no bias or nonlinearity between it and the projection (model.py:132-135, 436-438),
+//     so W_pre0 (W_proj hc + b) is evaluated as one composed matrix.  A step is four batched mat-vec
+//     phases: attention LSTM | decoder LSTM | projection+gate+prenet0 | prenet1.
+//   * ATTENTION CTAs (one per utterance) own the location-sensitive attention of their utterance.
+//     The query matrix W_q (180 KB) is resident in their shared memory, and everything that does not
+//     depend on this step's attention-LSTM output -- location conv of the previous/cumulative weights,
+//     location_dense, processed_memory, the encoder rows of the window (held in registers) -- is
+//     prepared while the matrix CTAs run the other three phases.  On the critical path remain
+//     W_q h, 41 x 150 tanh, a 41-way softmax and the 41 x 600 context sum.  Only the <= 2w+1 window
+//     positions are evaluated: everything outside [t-w, t+w] is masked to -inf by utils.py:46-78,
+//     i.e. has softmax weight exactly 0.
+//   * phases hand over through lightweight grid barriers (one release-add + acquire spin); the two
+//     barriers between matrix-only phases do not involve the attention CTAs.
 //   * the stop decision (sigmoid(gate) > threshold) is taken on the device.
 #include "fac_common.cuh"
 
@@ -47,37 +54,42 @@ constexpr int KF = 31;    // attention_location_kernel_size
 constexpr int KIN = R + E + R;  // 1200: LSTMCell input | hidden concatenation
 constexpr int KHC = R + E;      // 900: [h_dec | context]
 constexpr int NPP = M + 1 + R;  // 381 rows: mel projection, gate, composed prenet layer 0
-constexpr int MAXU = 3;         // hidden units per CTA (needs >= 100 CTAs)
-constexpr int MAXPP = 3;        // projection rows per CTA (needs >= 127 CTAs)
-constexpr int MAXP2 = 3;        // prenet-1 rows per CTA
+constexpr int MIN_MATRIX_CTAS = 100;
+constexpr int MAXU = 3;         // hidden units per matrix CTA (>= 100 matrix CTAs)
+constexpr int MAXPP = 4;        // projection rows per matrix CTA
+constexpr int MAXP2 = 3;        // prenet-1 rows per matrix CTA
 constexpr int CHUNK = 8;        // utterances staged per pass (double-buffered)
-constexpr int MAXW = 64;        // max window positions (2*window+1 <= 64)
+constexpr int MAXW = 48;        // max window positions (2*window+1 <= 48)
 constexpr int CTXP = 3;         // q-range split of the context sum
+constexpr int QPP = MAXW / CTXP;  // window positions per part
 
-struct AttScratch {             // attention phase; shares storage with the staged inputs
-  float w_loc[2 * KF][NF];      // [c*KF + k][f]   (reloaded from L2 every step: 8 KB)
-  float w_ld[NF][A];            // location_dense transposed (19 KB)
-  float pq[A + 2];
-  float cat[2][MAXW + KF - 1 + 2];
-  float loc[MAXW][NF];
-  float e[MAXW];
-  alignas(16) float ctxp[CTXP][E];
-};
-
-struct Smem {
+struct MatSmem {                  // matrix CTAs
   float w_att[MAXU * 4][KIN];
   float w_dec[MAXU * 4][KIN];
   float w_pp[MAXPP][KHC];
   float w_p2[MAXP2][R];
-  float v[A + 2];
-  float b_att[MAXU * 4], b_dec[MAXU * 4], b_pp[4];
+  float b_att[MAXU * 4], b_dec[MAXU * 4], b_pp[MAXPP];
   float part[2][DEC_WARPS][16];   // per-job partial sums (one job per warp per chunk), double-buffered
-  alignas(16) union {
-    float in[2][CHUNK][KIN];      // staged input vectors of a chunk of utterances, double-buffered
-    AttScratch a;
-  } u;
+  int n_done;
+  unsigned int prof[16];
+  alignas(16) float in[2][CHUNK][KIN];   // staged input vectors of a chunk of utterances, double-buffered
 };
-static_assert(sizeof(Smem) <= 227 * 1024, "decoder shared memory");
+struct AttSmem {                  // attention CTAs
+  float wq[A][R];                 // query_layer weight, resident
+  float S[MAXW][A];               // location_dense(location_conv(.)) + processed_memory of the coming window
+  float v[A + 2];
+  float pq[A + 2];
+  float e[MAXW];
+  float wts[DEC_WARPS][MAXW];     // softmax weights, one copy per warp
+  float cat[2][MAXW + KF - 1 + 2];
+  int n_done;
+  unsigned int prof[16];
+  alignas(16) union {
+    float loc[MAXW][NF];          // preparation
+    float ctxp[CTXP][E];          // critical path
+  } x;
+};
+static_assert(sizeof(MatSmem) <= 227 * 1024 && sizeof(AttSmem) <= 227 * 1024, "decoder shared memory");
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -85,18 +97,18 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Grid-wide barrier: monotonically increasing arrival counter (zeroed by the host), release/acquire.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target) {
+// Barrier over `n` CTAs: monotonically increasing arrival counter (zeroed by the host).  The arrival is a
+// release (every write of this CTA that bar.sync ordered before it is visible to whoever acquires the
+// final count), the spin an acquire.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target, unsigned int n) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    target += gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
+    target += n;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     unsigned int seen;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
     } while (seen < target);
-    __threadfence();
   }
   __syncthreads();
 }
@@ -164,30 +176,69 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-// One batched mat-vec phase over this CTA's resident rows.  The rows are grouped in `n_rt` row tiles of
-// (up to) 4 rows -- the 4 gate rows of one LSTM unit, or the CTA's projection / prenet rows -- and the B
-// utterances in chunks of CHUNK whose input vectors are copied into shared memory asynchronously, one
+struct Prof {                 // thread 0's cycles between consecutive marks, per slot (accumulators in shared memory)
+  unsigned int* acc;          // [16]: slots 0..9, total, 11..13 = fetch wait / arithmetic / epilogue of the mat-vec phases
+  long long prev;
+  bool on;
+  __device__ __forceinline__ void init(bool enabled, unsigned int* smem_acc) {
+    on = enabled && threadIdx.x == 0;
+    acc = smem_acc;
+    if (on) {
+      for (int i = 0; i < 16; ++i) acc[i] = 0;
+      prev = clock64();
+    }
+  }
+  template <int SLOT>
+  __device__ __forceinline__ void mark() {
+    if (on) {
+      const long long now = clock64();
+      acc[SLOT] += (unsigned int)(now - prev);
+      if (SLOT < 10) acc[10] += (unsigned int)(now - prev);
+      prev = now;
+    }
+  }
+  // sub-interval: does not move `prev` (the enclosing phase slot still gets the whole interval)
+  template <int SLOT>
+  __device__ __forceinline__ void sub(long long& from) {
+    if (on) {
+      const long long now = clock64();
+      acc[SLOT] += (unsigned int)(now - from);
+      from = now;
+    }
+  }
+  __device__ __forceinline__ long long now() const { return on ? clock64() : 0; }
+  __device__ __forceinline__ void flush(long long* out) {
+    if (on)
+      for (int i = 0; i < 14; ++i) out[blockIdx.x * 16 + i] = acc[i];
+  }
+};
+
+// One batched mat-vec phase over a matrix CTA's resident rows.  The rows are grouped in `n_rt` row tiles
+// of (up to) 4 rows -- the 4 gate rows of one LSTM unit, or the CTA's projection / prenet rows -- and the
+// B utterances in chunks of CHUNK whose input vectors are copied into shared memory asynchronously, one
 // chunk ahead of the arithmetic.  Inside a chunk one warp owns one job = (row tile, 4 utterances, K part):
 // 16 accumulators per lane over its K slice, reduced across the lanes with a halving butterfly; the K
-// parts meet in shared memory and `epi(chunk buffer, first utterance, utterances, n_tiles, kparts)` finishes.
+// parts meet in shared memory and `epi(part buffer, first utterance, utterances, n_tiles, kparts)` finishes.
 //   row(rt, r): shared-memory pointer of row r of row tile rt (any valid row when r is past the end)
-//   pre(n0, nb): called right after the copies are in flight (loads the epilogue wants early)
+//   pre(n0, nb): called right after the copies are in flight (global loads the epilogue wants early)
 template <int NSEG, typename RowFn, typename PreFn, typename EpiFn>
-__device__ __forceinline__ void matvec_phase(Smem& sm, const Seg (&segs)[NSEG], int K4, int n_rt, int B, RowFn row,
-                                             PreFn pre, EpiFn epi) {
+__device__ __forceinline__ void matvec_phase(MatSmem& sm, Prof& prof, const Seg (&segs)[NSEG], int K4, int n_rt, int B,
+                                             RowFn row, PreFn pre, EpiFn epi) {
+  long long tp = prof.now();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_chunks = (B + CHUNK - 1) / CHUNK;
-  stage_async(sm.u.in[0], segs, 0, min(CHUNK, B));
+  stage_async(sm.in[0], segs, 0, min(CHUNK, B));
   for (int ci = 0; ci < n_chunks; ++ci) {
     const int n0 = ci * CHUNK, nb = min(CHUNK, B - n0), buf = ci & 1;
     pre(n0, nb);
     if (ci + 1 < n_chunks) {
-      stage_async(sm.u.in[buf ^ 1], segs, n0 + CHUNK, min(CHUNK, B - n0 - CHUNK));
+      stage_async(sm.in[buf ^ 1], segs, n0 + CHUNK, min(CHUNK, B - n0 - CHUNK));
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
+    prof.sub<11>(tp);
     const int n_groups = (nb + 3) >> 2;
     const int n_tiles = n_rt * n_groups;                 // <= 6
     const int kparts = DEC_WARPS / n_tiles;              // K split so that every warp has one job
@@ -198,7 +249,7 @@ __device__ __forceinline__ void matvec_phase(Smem& sm, const Seg (&segs)[NSEG], 
       const float4* w1 = reinterpret_cast<const float4*>(row(rt, 1));
       const float4* w2 = reinterpret_cast<const float4*>(row(rt, 2));
       const float4* w3 = reinterpret_cast<const float4*>(row(rt, 3));
-      const float (*xin)[KIN] = sm.u.in[buf];
+      const float (*xin)[KIN] = sm.in[buf];
       // utterances past the end of the chunk re-read the last valid one (results ignored)
       const float4* x0 = reinterpret_cast<const float4*>(xin[min(ng + 0, nb - 1)]);
       const float4* x1 = reinterpret_cast<const float4*>(xin[min(ng + 1, nb - 1)]);
@@ -222,12 +273,14 @@ __device__ __forceinline__ void matvec_phase(Smem& sm, const Seg (&segs)[NSEG], 
       if ((lane & 1) == 0) sm.part[buf][warp][lane >> 1] = total;   // value index (row*4 + utterance) = lane>>1
     }
     __syncthreads();
+    prof.sub<12>(tp);
     epi(buf, n0, nb, n_tiles, kparts);
+    prof.sub<13>(tp);
   }
 }
 
 // sum over the K parts of value (row r, utterance n of the chunk) of row tile rt
-__device__ __forceinline__ float part_sum(const Smem& sm, int buf, int n_rt, int n_tiles, int kparts, int rt, int r,
+__device__ __forceinline__ float part_sum(const MatSmem& sm, int buf, int n_rt, int n_tiles, int kparts, int rt, int r,
                                           int n) {
   const int tile = (n >> 2) * n_rt + rt;
   float a = 0.f;
@@ -236,12 +289,12 @@ __device__ __forceinline__ float part_sum(const Smem& sm, int buf, int n_rt, int
 }
 
 // One LSTMCell (model.py:400-402 / 425-428) for the units [u0, u0+nu) of this CTA and all B utterances.
-__device__ __forceinline__ void lstm_phase(Smem& sm, const float (*w_s)[KIN], const float* bias_s, const Seg (&segs)[3],
-                                           float* h_next, float* c, int B, int u0, int nu) {
+__device__ __forceinline__ void lstm_phase(MatSmem& sm, Prof& prof, const float (*w_s)[KIN], const float* bias_s,
+                                           const Seg (&segs)[3], float* h_next, float* c, int B, int u0, int nu) {
   const int tid = threadIdx.x;
   float c_old = 0.f;
   matvec_phase(
-      sm, segs, KIN / 4, nu, B, [&](int rt, int g) { return &w_s[g * nu + rt][0]; },
+      sm, prof, segs, KIN / 4, nu, B, [&](int rt, int g) { return &w_s[g * nu + rt][0]; },
       [&](int n0, int nb) {
         if (tid < nu * nb) c_old = c[(n0 + tid / nu) * R + u0 + tid % nu];   // only this thread ever touches it
       },
@@ -265,155 +318,19 @@ __device__ __forceinline__ void window_bounds(int t, int window, int len, int& s
   end = min(t + window, max_idx);
 }
 
-// Location-sensitive attention of utterance b at step t (model.py:100-121, 56-60, 78-98), including the
-// query projection W_q h_att (model.py:92), whose 180 KB matrix is streamed from L2 by this one CTA.
-__device__ void attention_phase(Smem& sm, const DecParams& p, const float* h_att, int b, int t) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  AttScratch& s = sm.u.a;
-  const int len = p.lengths[b];
-  int start, end;
-  window_bounds(t, p.window, len, start, end);
-  const int nw = end - start + 1;
-  // ---- everything that does not depend on this step's arithmetic is requested up front
-  for (int i = tid; i < 2 * KF * NF / 4; i += DEC_THREADS) cp_async16(&s.w_loc[0][0] + 4 * i, p.w.w_loc + 4 * i);
-  for (int i = tid; i < NF * A / 4; i += DEC_THREADS) cp_async16(&s.w_ld[0][0] + 4 * i, p.w.w_ld_t + 4 * i);
-  cp_async_commit();
-  // processed_memory of the window: warp q-strided positions, lane-strided channels (5 per lane)
-  float pm[4][5];
-#pragma unroll
-  for (int qi = 0; qi < 4; ++qi) {
-    const int q = warp + qi * DEC_WARPS;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const int a = lane + 32 * j;
-      pm[qi][j] = (q < nw && a < A) ? __ldg(p.pmem + ((long long)b * p.T_in + start + q) * A + a) : 0.f;
-    }
-  }
-  // previous / cumulative weights around the window (zero outside the sequence: conv padding)
-  const int c0 = start - (KF - 1) / 2, ncat = nw + KF - 1;
-  float* wprev = p.s.w_prev + (long long)b * p.T_in;
-  float* wcum = p.s.w_cum + (long long)b * p.T_in;
-  for (int i = tid; i < 2 * ncat; i += DEC_THREADS) {
-    const int c = i / ncat, q = i - c * ncat, pos = c0 + q;
-    float v = 0.f;
-    if (pos >= 0 && pos < p.T_in) v = c == 0 ? wprev[pos] : wcum[pos];
-    s.cat[c][q] = v;
-  }
-  // ---- query projection (model.py:92): pq = W_q h_att; warp per row, 75 float4 per row over the lanes
-  {
-    const float4* h4 = reinterpret_cast<const float4*>(h_att + b * R);
-    const float4 hz = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 hv0 = __ldcg(h4 + lane), hv1 = __ldcg(h4 + lane + 32), hv2 = lane < 11 ? __ldcg(h4 + lane + 64) : hz;
-    for (int r = warp; r < A; r += DEC_WARPS) {
-      const float4* w4 = reinterpret_cast<const float4*>(p.w.wq + (long long)r * R);
-      const float4 a0 = __ldg(w4 + lane), a1 = __ldg(w4 + lane + 32), a2 = lane < 11 ? __ldg(w4 + lane + 64) : hz;
-      float acc = a0.x * hv0.x + a0.y * hv0.y + a0.z * hv0.z + a0.w * hv0.w;
-      acc += a1.x * hv1.x + a1.y * hv1.y + a1.z * hv1.z + a1.w * hv1.w;
-      acc += a2.x * hv2.x + a2.y * hv2.y + a2.z * hv2.z + a2.w * hv2.w;
-      acc = warp_sum(acc);
-      if (lane == 0) s.pq[r] = acc;
-    }
-  }
-  cp_async_wait<0>();
-  __syncthreads();
-  // ---- location_conv (model.py:57): loc[q][f] = sum_{c,k} w[f][c][k] * cat[c][q + k]
-  for (int i = tid; i < nw * NF; i += DEC_THREADS) {
-    const int q = i / NF, f = i - q * NF;
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-    for (int k = 0; k < KF; ++k) {
-      acc0 = fmaf(s.w_loc[k][f], s.cat[0][q + k], acc0);
-      acc1 = fmaf(s.w_loc[KF + k][f], s.cat[1][q + k], acc1);
-    }
-    s.loc[q][f] = acc0 + acc1;
-  }
-  __syncthreads();
-  // ---- energies (model.py:94-97): e[q] = v . tanh(pq + location_dense(loc[q]) + processed_memory[q])
-#pragma unroll
-  for (int qi = 0; qi < 4; ++qi) {
-    const int q = warp + qi * DEC_WARPS;
-    if (q < nw) {
-      float part = 0.f;
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const int a = lane + 32 * j;
-        if (a < A) {
-          float pa = 0.f;
-#pragma unroll
-          for (int f = 0; f < NF; ++f) pa = fmaf(s.w_ld[f][a], s.loc[q][f], pa);
-          part = fmaf(sm.v[a], tanhf(s.pq[a] + pa + pm[qi][j]), part);
-        }
-      }
-      part = warp_sum(part);
-      if (lane == 0) s.e[q] = part;
-    }
-  }
-  __syncthreads();
-  // ---- softmax over the window (everything else is -inf -> weight 0, model.py:114-117); every warp
-  //      evaluates it redundantly so that no further block barrier is needed before the context sum
-  float mx, inv_sum;
-  {
-    const float e0 = lane < nw ? s.e[lane] : -INFINITY, e1 = lane + 32 < nw ? s.e[lane + 32] : -INFINITY;
-    mx = fmaxf(e0, e1);
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sft));
-    const float x0 = lane < nw ? expf(e0 - mx) : 0.f, x1 = lane + 32 < nw ? expf(e1 - mx) : 0.f;
-    inv_sum = 1.0f / warp_sum(x0 + x1);
-  }
-  // ---- context (model.py:118): ctx = sum_q w[q] * memory[start + q]; thread = (float4 column, q part)
-  {
-    const int c4 = tid % (E / 4), part = tid / (E / 4);
-    if (part < CTXP) {
-      const int per = (nw + CTXP - 1) / CTXP, q_lo = part * per, q_hi = min(nw, q_lo + per);
-      const float4* mrow = reinterpret_cast<const float4*>(p.memory + ((long long)b * p.T_in + start) * E) + c4;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-      for (int q = q_lo; q < q_hi; ++q) {
-        const float4 m = __ldg(mrow + (long long)q * (E / 4));
-        const float w = expf(s.e[q] - mx) * inv_sum;
-        acc.x = fmaf(w, m.x, acc.x);
-        acc.y = fmaf(w, m.y, acc.y);
-        acc.z = fmaf(w, m.z, acc.z);
-        acc.w = fmaf(w, m.w, acc.w);
-      }
-      *reinterpret_cast<float4*>(&s.ctxp[part][4 * c4]) = acc;
-    }
-  }
-  // new attention_weights (zero outside the window), cumulative weights (model.py:424), alignments
-  int ostart = 0, oend = -1;
-  if (t > 0) window_bounds(t - 1, p.window, len, ostart, oend);
-  for (int pos = ostart + tid; pos <= oend; pos += DEC_THREADS)
-    if (pos < start || pos > end) wprev[pos] = 0.f;
-  if (warp == 0) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int q = lane + 32 * h;
-      if (q < nw) {
-        const float wv = expf(s.e[q] - mx) * inv_sum;
-        wprev[start + q] = wv;
-        wcum[start + q] += wv;
-        if (p.align) p.align[((long long)b * p.max_steps + t) * p.T_in + start + q] = wv;
-      }
-    }
-  }
-  __syncthreads();
-  for (int c = tid; c < E; c += DEC_THREADS) p.s.ctx[b * E + c] = s.ctxp[0][c] + s.ctxp[1][c] + s.ctxp[2][c];
+__device__ __forceinline__ void row_range(int idx, int n_ctas, int n_rows, int& r0, int& nr) {
+  r0 = (int)((long long)idx * n_rows / n_ctas);
+  nr = (int)((long long)(idx + 1) * n_rows / n_ctas) - r0;
 }
 
-__device__ __forceinline__ void row_range(int n_rows, int& r0, int& nr) {
-  r0 = (int)((long long)blockIdx.x * n_rows / gridDim.x);
-  nr = (int)((long long)(blockIdx.x + 1) * n_rows / gridDim.x) - r0;
-}
-
-__global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+// ------------------------------------------------------------------------------------------ matrix CTAs
+__device__ void matrix_role(const DecParams& p, MatSmem& sm, int mi, int GM) {
   const int tid = threadIdx.x;
-  const int G = gridDim.x;
+  const unsigned int G = gridDim.x;
   int u0, nu, pp0, npp, p20, np2;
-  row_range(R, u0, nu);
-  row_range(NPP, pp0, npp);
-  row_range(R, p20, np2);
+  row_range(mi, GM, R, u0, nu);
+  row_range(mi, GM, NPP, pp0, npp);
+  row_range(mi, GM, R, p20, np2);
 
   // ---- resident weights: this CTA's rows of every matrix of the step
   for (int i = tid; i < nu * 4 * KIN; i += DEC_THREADS) {
@@ -431,22 +348,14 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
     sm.w_pp[i / KHC][i % KHC] = __ldg(p.w.w_pp + (long long)pp0 * KHC + i);
   for (int i = tid; i < npp; i += DEC_THREADS) sm.b_pp[i] = __ldg(p.w.b_pp + pp0 + i);
   for (int i = tid; i < np2 * R; i += DEC_THREADS) sm.w_p2[i / R][i % R] = __ldg(p.w.w_pre2 + (long long)p20 * R + i);
-  for (int i = tid; i < A; i += DEC_THREADS) sm.v[i] = __ldg(p.w.v + i);
   __syncthreads();
 
-  unsigned int* bar = reinterpret_cast<unsigned int*>(p.s.done + 3);
-  unsigned int bar_target = 0;
+  unsigned int* bar_all = reinterpret_cast<unsigned int*>(p.s.done + 3);
+  unsigned int* bar_mat = reinterpret_cast<unsigned int*>(p.s.done + 4);
+  unsigned int target_all = 0, target_mat = 0;
   int cur = 0;
-  long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const long long prof_t0 = clock64();
-  long long prof_prev = prof_t0;
-  auto mark = [&](int slot) {          // thread 0's cycles since the previous mark go to `slot`
-    if (p.prof != nullptr && tid == 0) {
-      const long long now = clock64();
-      prof_acc[slot] += now - prof_prev;
-      prof_prev = now;
-    }
-  };
+  Prof prof;
+  prof.init(p.prof != nullptr, sm.prof);
   for (int t = 0; t < p.max_steps; ++t) {
     float* h_att_cur = p.s.h_att + cur * p.B * R;
     float* h_att_nxt = p.s.h_att + (cur ^ 1) * p.B * R;
@@ -455,33 +364,37 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
     // (1) attention_rnn (model.py:400-402): input [prenet | context], hidden h_att
     {
       const Seg segs[3] = {{p.s.pre, R, R}, {p.s.ctx, E, E}, {h_att_cur, R, R}};
-      lstm_phase(sm, sm.w_att, sm.b_att, segs, h_att_nxt, p.s.c_att, p.B, u0, nu);
+      lstm_phase(sm, prof, sm.w_att, sm.b_att, segs, h_att_nxt, p.s.c_att, p.B, u0, nu);
     }
-    mark(0);
-    grid_barrier(bar, bar_target);
-    mark(1);
-    // (2) query projection + location-sensitive attention, one CTA per utterance
-    for (int b = blockIdx.x; b < p.B; b += G) {
-      attention_phase(sm, p, h_att_nxt, b, t);
-      __syncthreads();      // the scratch is reused (next utterance / staged inputs)
-    }
-    mark(2);
-    grid_barrier(bar, bar_target);
-    mark(3);
+    prof.mark<0>();
+    grid_barrier(bar_all, target_all, G);      // h_att(t) complete -> attention CTAs
+    prof.mark<1>();
+    // (2) attention CTAs at work
+    grid_barrier(bar_all, target_all, G);      // context(t) complete
+    prof.mark<3>();
     // (3) decoder_rnn (model.py:425-428): input [h_att | context], hidden h_dec
     {
       const Seg segs[3] = {{h_att_nxt, R, R}, {p.s.ctx, E, E}, {h_dec_cur, R, R}};
-      lstm_phase(sm, sm.w_dec, sm.b_dec, segs, h_dec_nxt, p.s.c_dec, p.B, u0, nu);
+      lstm_phase(sm, prof, sm.w_dec, sm.b_dec, segs, h_dec_nxt, p.s.c_dec, p.B, u0, nu);
     }
-    mark(4);
-    grid_barrier(bar, bar_target);
-    mark(5);
+    prof.mark<4>();
+    grid_barrier(bar_mat, target_mat, GM);
+    prof.mark<5>();
     // (4) [linear_projection | gate_layer | prenet layer 0 o projection] on hc = [h_dec | context]
     //     (model.py:436-441, 507, 132-135)
     {
       const Seg segs[2] = {{h_dec_nxt, R, R}, {p.s.ctx, E, E}};
+      const bool more = t + 1 < p.max_steps;
+      unsigned char drop0 = 0;
       matvec_phase(
-          sm, segs, KHC / 4, 1, p.B, [&](int, int r) { return &sm.w_pp[min(r, npp - 1)][0]; }, [](int, int) {},
+          sm, prof, segs, KHC / 4, 1, p.B, [&](int, int r) { return &sm.w_pp[min(r, npp - 1)][0]; },
+          [&](int n0, int nb) {     // the dropout mask byte comes from DRAM: ask for it before the arithmetic
+            if (tid < npp * nb) {
+              const int row = pp0 + tid % npp;
+              if (row > M && more)
+                drop0 = p.drop[(((long long)(t + 1) * 2 + 0) * p.B + n0 + tid / npp) * R + row - M - 1];
+            }
+          },
           [&](int buf, int n0, int nb, int n_tiles, int kparts) {
             if (tid < npp * nb) {
               const int r = tid % npp, n = tid / npp, row = pp0 + r, b = n0 + n;
@@ -494,58 +407,261 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
                   if (sigmoidf_exact(v) > p.gate_threshold) {
                     p.s.out_len[b] = t + 1;
                     atomicAdd(p.s.done, 1);
-                  } else if (t + 1 == p.max_steps) {
+                  } else if (!more) {
                     p.s.out_len[b] = p.max_steps;     // model.py:526-528 "Reached max decoder steps"
                     atomicAdd(p.s.done + 1, 1);
                   }
                 }
-              } else if (t + 1 < p.max_steps) {
+              } else if (more) {
                 // prenet layer 0 of the NEXT step; dropout p = 0.5 is always on -> mask * 2
-                const int j = row - M - 1;
-                const unsigned char d = p.drop[(((long long)(t + 1) * 2 + 0) * p.B + b) * R + j];
-                p.s.p1[b * R + j] = fmaxf(v, 0.f) * (2.0f * (float)d);
+                p.s.p1[b * R + row - M - 1] = fmaxf(v, 0.f) * (2.0f * (float)drop0);
               }
             }
           });
     }
-    mark(6);
-    grid_barrier(bar, bar_target);
-    mark(7);
-    // (5) prenet layer 1 of the next step
+    prof.mark<6>();
+    grid_barrier(bar_mat, target_mat, GM);
+    prof.mark<7>();
+    // (5) prenet layer 1 of the next step; the stop counters are final since the last barrier
+    if (tid == DEC_THREADS - 1) {
+      const volatile int* done = p.s.done;
+      sm.n_done = done[0] + done[1];
+    }
     if (t + 1 < p.max_steps) {
       const Seg segs[1] = {{p.s.p1, R, R}};
+      unsigned char drop1 = 0;
       matvec_phase(
-          sm, segs, R / 4, 1, p.B, [&](int, int r) { return &sm.w_p2[min(r, np2 - 1)][0]; }, [](int, int) {},
+          sm, prof, segs, R / 4, 1, p.B, [&](int, int r) { return &sm.w_p2[min(r, np2 - 1)][0]; },
+          [&](int n0, int nb) {
+            if (tid < np2 * nb)
+              drop1 = p.drop[(((long long)(t + 1) * 2 + 1) * p.B + n0 + tid / np2) * R + p20 + tid % np2];
+          },
           [&](int buf, int n0, int nb, int n_tiles, int kparts) {
             if (tid < np2 * nb) {
-              const int r = tid % np2, n = tid / np2, row = p20 + r, b = n0 + n;
+              const int r = tid % np2, n = tid / np2;
               const float v = part_sum(sm, buf, 1, n_tiles, kparts, 0, r, n);
-              const unsigned char d = p.drop[(((long long)(t + 1) * 2 + 1) * p.B + b) * R + row];
-              p.s.pre[b * R + row] = fmaxf(v, 0.f) * (2.0f * (float)d);
+              p.s.pre[(n0 + n) * R + p20 + r] = fmaxf(v, 0.f) * (2.0f * (float)drop1);
             }
           });
     }
-    mark(8);
-    grid_barrier(bar, bar_target);
-    mark(9);
+    prof.mark<8>();
+    grid_barrier(bar_all, target_all, G);
+    prof.mark<9>();
     cur ^= 1;
-    // every utterance has fired its stop gate (or hit max_steps): uniform exit
-    const volatile int* done = p.s.done;
-    if (done[0] + done[1] >= p.B) {
+    if (sm.n_done >= p.B) break;     // every utterance has fired its stop gate (or hit max_steps)
+  }
+  prof.flush(p.prof);
+}
+
+// --------------------------------------------------------------------------------------- attention CTAs
+// Location-sensitive attention of utterance b (model.py:100-121, 56-60, 78-98).
+//   prepare(t): everything of step t that only needs the attention weights of step t-1
+//   critical(t): the part that needs h_att(t)
+__device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned int G = gridDim.x;
+  const int len = p.lengths[b];
+  float* wprev = p.s.w_prev + (long long)b * p.T_in;
+  float* wcum = p.s.w_cum + (long long)b * p.T_in;
+  const float* pmem = p.pmem + (long long)b * p.T_in * A;
+  const float* memory = p.memory + (long long)b * p.T_in * E;
+  const int c4 = tid % (E / 4), cpart = tid / (E / 4);     // context sum: float4 column, q part (< CTXP active)
+
+  for (int i = tid; i < A * R / 4; i += DEC_THREADS)
+    reinterpret_cast<float4*>(&sm.wq[0][0])[i] = __ldg(reinterpret_cast<const float4*>(p.w.wq) + i);
+  for (int i = tid; i < A; i += DEC_THREADS) sm.v[i] = __ldg(p.w.v + i);
+  __syncthreads();
+
+  float4 mreg[QPP];      // encoder rows of this thread's share of the window
+  int start = 0, nw = 0;
+
+  auto prepare = [&](int t) {
+    int end;
+    window_bounds(t, p.window, len, start, end);
+    nw = end - start + 1;
+    // previous / cumulative weights around the window (zero outside the sequence: conv padding)
+    const int c0 = start - (KF - 1) / 2, ncat = nw + KF - 1;
+    for (int i = tid; i < 2 * ncat; i += DEC_THREADS) {
+      const int c = i / ncat, q = i - c * ncat, pos = c0 + q;
+      float v = 0.f;
+      if (pos >= 0 && pos < p.T_in) v = c == 0 ? wprev[pos] : wcum[pos];
+      sm.cat[c][q] = v;
+    }
+    __syncthreads();
+    // location_conv (model.py:57): loc[q][f] = sum_{c,k} w[c][k][f] * cat[c][q + k]
+    for (int i = tid; i < nw * NF; i += DEC_THREADS) {
+      const int q = i / NF, f = i - q * NF;
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < KF; ++k) {
+        acc0 = fmaf(__ldg(p.w.w_loc + k * NF + f), sm.cat[0][q + k], acc0);
+        acc1 = fmaf(__ldg(p.w.w_loc + (KF + k) * NF + f), sm.cat[1][q + k], acc1);
+      }
+      sm.x.loc[q][f] = acc0 + acc1;
+    }
+    __syncthreads();
+    // S[q][a] = location_dense(loc[q])[a] + processed_memory[q][a] (model.py:94-96): warp = 3 positions,
+    // lane = 5 channels
+    {
+      float acc[3][5];
+#pragma unroll
+      for (int qi = 0; qi < 3; ++qi)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int q = warp + qi * DEC_WARPS, a = lane + 32 * j;
+          acc[qi][j] = (q < nw && a < A) ? __ldg(pmem + (long long)(start + q) * A + a) : 0.f;
+        }
+#pragma unroll 4
+      for (int f = 0; f < NF; ++f) {
+        float wl[5], lq[3];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) wl[j] = lane + 32 * j < A ? __ldg(p.w.w_ld_t + f * A + lane + 32 * j) : 0.f;
+#pragma unroll
+        for (int qi = 0; qi < 3; ++qi) lq[qi] = sm.x.loc[min(warp + qi * DEC_WARPS, MAXW - 1)][f];
+#pragma unroll
+        for (int qi = 0; qi < 3; ++qi)
+#pragma unroll
+          for (int j = 0; j < 5; ++j) acc[qi][j] = fmaf(wl[j], lq[qi], acc[qi][j]);
+      }
+#pragma unroll
+      for (int qi = 0; qi < 3; ++qi)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int q = warp + qi * DEC_WARPS, a = lane + 32 * j;
+          if (q < nw && a < A) sm.S[q][a] = acc[qi][j];
+        }
+    }
+    // encoder outputs of the window -> registers (consumed by the context sum of step t)
+    {
+      const float4* mrow = reinterpret_cast<const float4*>(memory + (long long)start * E) + c4;
+#pragma unroll
+      for (int i = 0; i < QPP; ++i) {
+        const int q = cpart * QPP + i;
+        mreg[i] = (cpart < CTXP && q < nw) ? __ldg(mrow + (long long)q * (E / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();
+  };
+
+  auto critical = [&](int t, const float* h_att) {
+    // query projection (model.py:92): pq = W_q h_att; warp per row, 75 float4 per row over the lanes
+    {
+      const float4* h4 = reinterpret_cast<const float4*>(h_att + b * R);
+      const float4 hz = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 hv0 = __ldcg(h4 + lane), hv1 = __ldcg(h4 + lane + 32), hv2 = lane < 11 ? __ldcg(h4 + lane + 64) : hz;
+#pragma unroll 2
+      for (int r = warp; r < A; r += DEC_WARPS) {
+        const float4* w4 = reinterpret_cast<const float4*>(&sm.wq[r][0]);
+        const float4 a0 = w4[lane], a1 = w4[lane + 32], a2 = lane < 11 ? w4[lane + 64] : hz;
+        float acc = a0.x * hv0.x + a0.y * hv0.y + a0.z * hv0.z + a0.w * hv0.w;
+        acc += a1.x * hv1.x + a1.y * hv1.y + a1.z * hv1.z + a1.w * hv1.w;
+        acc += a2.x * hv2.x + a2.y * hv2.y + a2.z * hv2.z + a2.w * hv2.w;
+        acc = warp_sum(acc);
+        if (lane == 0) sm.pq[r] = acc;
+      }
+    }
+    __syncthreads();
+    // energies (model.py:94-97): e[q] = v . tanh(pq + S[q])
+#pragma unroll
+    for (int qi = 0; qi < 3; ++qi) {
+      const int q = warp + qi * DEC_WARPS;
+      if (q < nw) {
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int a = lane + 32 * j;
+          if (a < A) part = fmaf(sm.v[a], tanhf_fast(sm.pq[a] + sm.S[q][a]), part);
+        }
+        part = warp_sum(part);
+        if (lane == 0) sm.e[q] = part;
+      }
+    }
+    __syncthreads();
+    // softmax over the window (everything else is -inf -> weight 0, model.py:114-117), evaluated by every
+    // warp for itself
+    {
+      const float e0 = lane < nw ? sm.e[lane] : -INFINITY, e1 = lane + 32 < nw ? sm.e[lane + 32] : -INFINITY;
+      float mx = fmaxf(e0, e1);
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sft));
+      const float x0 = lane < nw ? expf(e0 - mx) : 0.f, x1 = lane + 32 < nw ? expf(e1 - mx) : 0.f;
+      const float inv_sum = 1.0f / warp_sum(x0 + x1);
+      sm.wts[warp][lane] = x0 * inv_sum;
+      if (lane + 32 < MAXW) sm.wts[warp][lane + 32] = x1 * inv_sum;
+      __syncwarp();
+    }
+    // context (model.py:118): ctx = sum_q w[q] * memory[start + q], encoder rows already in registers
+    if (cpart < CTXP) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < QPP; ++i) {
+        const float w = sm.wts[warp][cpart * QPP + i];      // 0 past the end of the window
+        acc.x = fmaf(w, mreg[i].x, acc.x);
+        acc.y = fmaf(w, mreg[i].y, acc.y);
+        acc.z = fmaf(w, mreg[i].z, acc.z);
+        acc.w = fmaf(w, mreg[i].w, acc.w);
+      }
+      *reinterpret_cast<float4*>(&sm.x.ctxp[cpart][4 * c4]) = acc;
+    }
+    __syncthreads();
+    for (int c = tid; c < E; c += DEC_THREADS) p.s.ctx[b * E + c] = sm.x.ctxp[0][c] + sm.x.ctxp[1][c] + sm.x.ctxp[2][c];
+    // new attention_weights (zero outside the window), cumulative weights (model.py:424), alignments
+    int ostart = 0, oend = -1;
+    if (t > 0) window_bounds(t - 1, p.window, len, ostart, oend);
+    for (int pos = ostart + tid; pos <= oend; pos += DEC_THREADS)
+      if (pos < start || pos >= start + nw) wprev[pos] = 0.f;
+    if (tid < nw) {
+      const float wv = sm.wts[0][tid];
+      wprev[start + tid] = wv;
+      wcum[start + tid] += wv;
+      if (p.align) p.align[((long long)b * p.max_steps + t) * p.T_in + start + tid] = wv;
+    }
+  };
+
+  unsigned int* bar_all = reinterpret_cast<unsigned int*>(p.s.done + 3);
+  unsigned int target_all = 0;
+  int cur = 0;
+  Prof prof;
+  prof.init(p.prof != nullptr, sm.prof);
+  prepare(0);
+  for (int t = 0; t < p.max_steps; ++t) {
+    const float* h_att_nxt = p.s.h_att + (cur ^ 1) * p.B * R;
+    prof.mark<0>();
+    grid_barrier(bar_all, target_all, G);      // h_att(t) complete
+    prof.mark<1>();
+    critical(t, h_att_nxt);
+    prof.mark<2>();
+    grid_barrier(bar_all, target_all, G);      // context(t) complete -> matrix CTAs
+    prof.mark<3>();
+    if (t + 1 < p.max_steps) prepare(t + 1);
+    prof.mark<4>();
+    grid_barrier(bar_all, target_all, G);      // end of step
+    prof.mark<9>();
+    cur ^= 1;
+    if (tid == 0) {
+      const volatile int* done = p.s.done;
+      sm.n_done = done[0] + done[1];
+    }
+    __syncthreads();
+    if (sm.n_done >= p.B) {
       if (blockIdx.x == 0 && tid == 0) p.s.done[2] = t + 1;
       break;
     }
   }
-  if (p.prof != nullptr && tid == 0) {
-#pragma unroll
-    for (int i = 0; i < 10; ++i) p.prof[blockIdx.x * 16 + i] = prof_acc[i];
-    p.prof[blockIdx.x * 16 + 10] = clock64() - prof_t0;
-  }
+  prof.flush(p.prof);
+}
+
+__global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  if ((int)blockIdx.x < p.B)
+    attention_role(p, *reinterpret_cast<AttSmem*>(smem_raw), blockIdx.x);
+  else
+    matrix_role(p, *reinterpret_cast<MatSmem*>(smem_raw), blockIdx.x - p.B, gridDim.x - p.B);
 }
 
 __global__ void __launch_bounds__(DEC_THREADS, 1) grid_barrier_selftest_kernel(unsigned int* counter, int iters) {
   unsigned int target = 0;
-  for (int i = 0; i < iters; ++i) grid_barrier(counter, target);
+  for (int i = 0; i < iters; ++i) grid_barrier(counter, target, gridDim.x);
 }
 
 }  // namespace
@@ -582,9 +698,11 @@ int taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, con
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   FAC_REQUIRE(coop, "taco_decoder: device lacks cooperative launch");
-  FAC_REQUIRE(sms * MAXU >= R && sms * MAXPP >= NPP && sms * MAXP2 >= R,
-              "taco_decoder: needs >= %d SMs, device has %d", (NPP + MAXPP - 1) / MAXPP, sms);
-  const size_t smem = sizeof(Smem);
+  FAC_REQUIRE(sms > MIN_MATRIX_CTAS, "taco_decoder: needs more than %d SMs, device has %d", MIN_MATRIX_CTAS, sms);
+  FAC_REQUIRE(B <= sms - MIN_MATRIX_CTAS,
+              "taco_decoder: at most %d utterances per launch on this device (one attention CTA each next to >= %d "
+              "matrix CTAs); split the batch", sms - MIN_MATRIX_CTAS, MIN_MATRIX_CTAS);
+  const size_t smem = sizeof(MatSmem) > sizeof(AttSmem) ? sizeof(MatSmem) : sizeof(AttSmem);
   cudaError_t e = cudaFuncSetAttribute(taco_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("taco_decoder: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));

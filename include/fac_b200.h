@@ -231,7 +231,8 @@ typedef struct fac_taco_decoder_state {
   float* pq;      /* [B][150]    processed query (scratch)                   */
   float* w_prev;  /* [B][T_in]   attention_weights                           */
   float* w_cum;   /* [B][T_in]   attention_weights_cum                       */
-  int* done;      /* [4]: #utterances stopped by the gate, #stopped by max_steps, steps run, grid-barrier counter */
+  int* done;      /* [8]: #utterances stopped by the gate, #stopped by max_steps, steps run, two grid-barrier
+                     counters, 3 spare */
   int* out_len;   /* [B] number of frames of each utterance (0 while running) */
 } fac_taco_decoder_state;
 
@@ -249,7 +250,8 @@ void fac_taco_set_profile_buffer(long long* device_buf);
  *   memory (B,T_in,600), pmem = memory_layer(memory) (B,T_in,150), lengths[B] (int32),
  *   drop (max_steps, 2, B, 300) uint8 in {0,1}: the always-on prenet dropout masks
  *   (model.py:132-135) of step t, layers 0/1;  outputs mel (B,max_steps,80), gate (B,max_steps),
- *   align (B,max_steps,T_in) pre-zeroed or NULL.  Stops when every utterance's
+ *   align (B,max_steps,T_in) pre-zeroed or NULL.  B <= (number of SMs - 100): one CTA per
+ *   utterance runs the attention, the others hold the matrices.  Stops when every utterance's
  *   sigmoid(gate) > gate_threshold has fired (model.py:524) or at max_steps (model.py:526-528). */
 int fac_taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, const float* pmem,
                          const int* lengths, const unsigned char* drop, const fac_taco_decoder_state* state,

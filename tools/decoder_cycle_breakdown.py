@@ -31,4 +31,5 @@ for B, T in zip(args[0::2], args[1::2]):
     print("B=%d T=%d: %.2f us/step, %.0f cycles/step (CTA 0)" % (B, T, us, p[0, 10]))
     for cta in (0, 147):
         print("  CTA %3d: " % cta + "  ".join("%s %d+%d" % (n, p[cta, 2 * i], p[cta, 2 * i + 1]) for i, n in enumerate(names)))
+    print("  CTA 147 mat-vec phases (all four): fetch wait %d, arithmetic %d, epilogue %d" % tuple(p[147, 11:14]))
     print("  mean   : " + "  ".join("%s %d+%d" % (n, p[:, 2 * i].mean(), p[:, 2 * i + 1].mean()) for i, n in enumerate(names)))
