@@ -32,6 +32,15 @@ class ConvEpilogue(C.Structure):
                 ("n_split", C.c_int), ("accumulate_out2", C.c_int)]
 
 
+class TcConv(C.Structure):
+    _fields_ = [("a_hi", _fp), ("a_lo", _fp), ("w_hi", _fp), ("w_lo", _fp), ("bias", _fp), ("mask", _fp),
+                ("residual", _fp), ("out", _fp), ("out_hi", _fp), ("out_lo", _fp),
+                ("mask_ld", C.c_longlong), ("res_ld", C.c_longlong), ("out_ld", C.c_longlong),
+                ("B", C.c_int), ("T", C.c_int), ("c_pad", C.c_int), ("taps", C.c_int), ("center", C.c_int),
+                ("n_pad", C.c_int), ("n_valid", C.c_int), ("act", C.c_int), ("nsplit", C.c_int), ("fp16", C.c_int),
+                ("k_chunk", C.c_int), ("_pad", C.c_int), ("scratch", _fp)]
+
+
 class WgFlow(C.Structure):
     _fields_ = [("n_half", C.c_int), ("n_rem", C.c_int),
                 ("start_w", _fp), ("start_b", _fp), ("end_w", _fp), ("end_b", _fp), ("w_inv", _fp),
@@ -99,6 +108,9 @@ SIGNATURES = {
     "fac_wn_end_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), C.c_int, _fp, _fp, C.c_int, C.c_int, _fp]),
     "fac_waveglow_infer_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), _fp, _fp, _P(WgTcWorkspace), C.c_int, C.c_int,
                                         C.c_int, _fp]),
+    "fac_conv_gemm_tc": (C.c_int, [_P(TcConv), _fp]),
+    "fac_transpose_split_16": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    "fac_pad_split_16": (C.c_int, [_fp, _fp, _fp, C.c_longlong, C.c_int, C.c_int, C.c_int, _fp]),
     "fac_tc_set_profile_buffer": (None, [_fp]),
     "fac_taco_set_profile_buffer": (None, [_fp]),
     "fac_tc_set_cta_group": (C.c_int, [C.c_int]),

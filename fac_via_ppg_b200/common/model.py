@@ -133,6 +133,8 @@ class Tacotron2(nn.Module):
     """Reference-compatible PPG->Mel model (reference model.py:538-610), CUDA-native inference."""
 
     rng_mode = "fast"            # 'fast' | 'reference'  (see module docstring)
+    precision = "fp16x3"         # encoder / postnet GEMMs: 'fp16x3' = split-fp16 (IEEE half hi + lo) on the tcgen05 tensor cores
+                                 # (fp32-grade, 3 UMMAs per product) | 'fp32' = exact FFMA implicit GEMM
     collect_timing = False       # True: CUDA-event times of encoder / decoder / postnet in .last_timing (ms)
     return_alignments = True     # dense (B, T_out, T_in) like the reference; False saves memory on long inputs
 
@@ -190,6 +192,28 @@ class Tacotron2(nn.Module):
         return enc[0], enc[1], dec
 
     # ------------------------------------------------------------------ stages
+    def set_precision(self, precision):
+        if precision not in ("fp16x3", "fp32"):
+            raise ValueError("precision must be 'fp16x3' or 'fp32', got %r" % (precision,))
+        self.precision = precision
+        return self
+
+    def _encode_tc(self, packed, inputs, enc0, enc1):
+        """Encoder.inference with every GEMM on the tensor cores (split-fp16): the PPG is transposed and split
+        once, each layer writes the fp16 hi/lo operand copies of the next one directly."""
+        hp = self.hp
+        B, D, T = inputs.shape
+        E = hp["encoder_embedding_dim"]
+        tw = packed.tc_weights()
+        a = ops.transpose_split(inputs, tw["enc.pre0"]["c_pad"])
+        _, a = ops.conv_gemm_tc(a, tw["enc.pre0"], act=_ext.ACT_RELU, mask=enc0)
+        _, a = ops.conv_gemm_tc(a, tw["enc.pre1"], act=_ext.ACT_RELU, mask=enc1)
+        for i in range(hp["encoder_n_convolutions"]):
+            _, a = ops.conv_gemm_tc(a, tw[f"enc.conv{i}"], act=_ext.ACT_RELU)
+        xp = torch.empty(B, T, 4 * E, device=inputs.device, dtype=torch.float32)
+        ops.conv_gemm_tc(a, tw["enc.lstm_ih"], out=xp, want_split=False)
+        return xp
+
     def _encode(self, packed, inputs, enc0, enc1):
         """reference model.py:237-249 (Encoder.inference): (B, D, T) -> memory (B, T, E)."""
         hp = self.hp
@@ -197,6 +221,13 @@ class Tacotron2(nn.Module):
         E, H = hp["encoder_embedding_dim"], hp["encoder_embedding_dim"] // 2
         dev = inputs.device
         new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        if self.precision == "fp16x3":
+            xp = self._encode_tc(packed, inputs, enc0, enc1)
+            memory = new(B, T, E)
+            rc = _ext.load().fac_lstm_bidir_f32(xp.data_ptr(), packed.view("enc.lstm_hh").data_ptr(),
+                                                memory.data_ptr(), B, T, H, _ext.current_stream())
+            _ext.check(rc, "fac_lstm_bidir_f32")
+            return memory
         h = ops.conv_gemm([ops.conv_src(inputs, channel_major=True)], packed.view("enc.pre0_w"), None, E,
                           new(B, T, E), batch=B, rows=T, act=_ext.ACT_RELU, mask=enc0)
         h = ops.conv_gemm([ops.conv_src(h)], packed.view("enc.pre1_w"), None, E, new(B, T, E), batch=B, rows=T,
@@ -258,6 +289,14 @@ class Tacotron2(nn.Module):
         hp = self.hp
         B, T, M = mel_cl.shape
         n, k, Pe = hp["postnet_n_convolutions"], hp["postnet_kernel_size"], hp["postnet_embedding_dim"]
+        if self.precision == "fp16x3":
+            tw = packed.tc_weights()
+            a = ops.pad_split(mel_cl, tw["post.conv0"]["c_pad"])
+            for i in range(n - 1):
+                _, a = ops.conv_gemm_tc(a, tw[f"post.conv{i}"], act=_ext.ACT_TANH)
+            out = torch.empty(B, T, M, device=mel_cl.device, dtype=torch.float32)
+            ops.conv_gemm_tc(a, tw[f"post.conv{n - 1}"], residual=mel_cl, out=out, want_split=False)
+            return out
         h = mel_cl
         for i in range(n):
             last = i == n - 1

@@ -34,6 +34,9 @@ int wg_infer_tc(const fac_wg_model*, const fac_wg_tc_weights*, const float*, flo
 int wg_tc_end(const fac_wg_model*, const fac_wg_tc_weights*, int, const float*, float*, int, int, cudaStream_t);
 void tc_set_prof(long long*);
 void taco_set_prof(long long*);
+int conv_gemm_tc(const fac_tc_conv*, cudaStream_t);
+int tc_transpose_split(const float*, void*, void*, int, int, int, int, int, cudaStream_t);
+int tc_pad_split(const float*, void*, void*, long long, int, int, int, cudaStream_t);
 int denoise_spectrum(float*, const float*, float, long long, int, int, cudaStream_t);
 int tc_set_cta_group(int);
 int tc_set_k_block(int);
@@ -98,6 +101,13 @@ int fac_waveglow_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, con
   return fac::wg_infer_tc(m, w, mel_cl, audio, ws, B, F, nsplit, (cudaStream_t)stream);
 }
 void fac_tc_set_profile_buffer(long long* device_buf) { fac::tc_set_prof(device_buf); }
+int fac_conv_gemm_tc(const fac_tc_conv* conv, void* stream) { return fac::conv_gemm_tc(conv, (cudaStream_t)stream); }
+int fac_transpose_split_16(const float* in, void* hi, void* lo, int B, int C, int T, int pad, int fp16, void* stream) {
+  return fac::tc_transpose_split(in, hi, lo, B, C, T, pad, fp16, (cudaStream_t)stream);
+}
+int fac_pad_split_16(const float* in, void* hi, void* lo, long long n_rows, int C, int pad, int fp16, void* stream) {
+  return fac::tc_pad_split(in, hi, lo, n_rows, C, pad, fp16, (cudaStream_t)stream);
+}
 void fac_taco_set_profile_buffer(long long* device_buf) { fac::taco_set_prof(device_buf); }
 int fac_tc_set_cta_group(int cta_group) { return fac::tc_set_cta_group(cta_group); }
 int fac_tc_set_k_block(int k_block) { return fac::tc_set_k_block(k_block); }

@@ -60,6 +60,7 @@ constexpr int MAXPP = 4;        // projection rows per matrix CTA
 constexpr int MAXP2 = 3;        // prenet-1 rows per matrix CTA
 constexpr int CHUNK = 8;        // utterances staged per pass (double-buffered)
 constexpr int MAXW = 48;        // max window positions (2*window+1 <= 48)
+constexpr int KPARTS = 4;       // fixed K split of every mat-vec (the summation order must not depend on B)
 constexpr int CTXP = 3;         // q-range split of the context sum
 constexpr int QPP = MAXW / CTXP;  // window positions per part
 
@@ -69,7 +70,7 @@ struct MatSmem {                  // matrix CTAs
   float w_pp[MAXPP][KHC];
   float w_p2[MAXP2][R];
   float b_att[MAXU * 4], b_dec[MAXU * 4], b_pp[MAXPP];
-  float part[2][DEC_WARPS][16];   // per-job partial sums (one job per warp per chunk), double-buffered
+  float part[2][6 * KPARTS][16];  // per-job partial sums of a chunk (<= 6 tiles x KPARTS), double-buffered
   int n_done;
   unsigned int prof[16];
   alignas(16) float in[2][CHUNK][KIN];   // staged input vectors of a chunk of utterances, double-buffered
@@ -216,9 +217,9 @@ struct Prof {                 // thread 0's cycles between consecutive marks, pe
 // One batched mat-vec phase over a matrix CTA's resident rows.  The rows are grouped in `n_rt` row tiles
 // of (up to) 4 rows -- the 4 gate rows of one LSTM unit, or the CTA's projection / prenet rows -- and the
 // B utterances in chunks of CHUNK whose input vectors are copied into shared memory asynchronously, one
-// chunk ahead of the arithmetic.  Inside a chunk one warp owns one job = (row tile, 4 utterances, K part):
+// chunk ahead of the arithmetic.  Inside a chunk a warp owns a job = (row tile, 4 utterances, K quarter):
 // 16 accumulators per lane over its K slice, reduced across the lanes with a halving butterfly; the K
-// parts meet in shared memory and `epi(part buffer, first utterance, utterances, n_tiles, kparts)` finishes.
+// quarters meet in shared memory (fixed split: the summation order of an output never depends on B) and `epi(part buffer, first utterance, utterances, n_tiles, kparts)` finishes.
 //   row(rt, r): shared-memory pointer of row r of row tile rt (any valid row when r is past the end)
 //   pre(n0, nb): called right after the copies are in flight (global loads the epilogue wants early)
 template <int NSEG, typename RowFn, typename PreFn, typename EpiFn>
@@ -241,9 +242,9 @@ __device__ __forceinline__ void matvec_phase(MatSmem& sm, Prof& prof, const Seg 
     prof.sub<11>(tp);
     const int n_groups = (nb + 3) >> 2;
     const int n_tiles = n_rt * n_groups;                 // <= 6
-    const int kparts = DEC_WARPS / n_tiles;              // K split so that every warp has one job
-    const int tile = warp % n_tiles, kp = warp / n_tiles;
-    if (kp < kparts) {
+    constexpr int kparts = KPARTS;
+    for (int job = warp; job < n_tiles * KPARTS; job += DEC_WARPS) {
+      const int tile = job % n_tiles, kp = job / n_tiles;
       const int rt = tile % n_rt, ng = (tile / n_rt) * 4;
       const float4* w0 = reinterpret_cast<const float4*>(row(rt, 0));
       const float4* w1 = reinterpret_cast<const float4*>(row(rt, 1));
@@ -270,7 +271,7 @@ __device__ __forceinline__ void matvec_phase(MatSmem& sm, Prof& prof, const Seg 
                                   fmaf(wv[g].z, xv[n].z, fmaf(wv[g].w, xv[n].w, acc[g * 4 + n]))));
       }
       const float total = warp_reduce16(acc, lane);
-      if ((lane & 1) == 0) sm.part[buf][warp][lane >> 1] = total;   // value index (row*4 + utterance) = lane>>1
+      if ((lane & 1) == 0) sm.part[buf][job][lane >> 1] = total;   // value index (row*4 + utterance) = lane>>1
     }
     __syncthreads();
     prof.sub<12>(tp);
@@ -284,7 +285,8 @@ __device__ __forceinline__ float part_sum(const MatSmem& sm, int buf, int n_rt, 
                                           int n) {
   const int tile = (n >> 2) * n_rt + rt;
   float a = 0.f;
-  for (int kp = 0; kp < kparts; ++kp) a += sm.part[buf][kp * n_tiles + tile][r * 4 + (n & 3)];
+#pragma unroll
+  for (int kp = 0; kp < KPARTS; ++kp) a += sm.part[buf][kp * n_tiles + tile][r * 4 + (n & 3)];
   return a;
 }
 

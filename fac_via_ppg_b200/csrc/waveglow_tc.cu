@@ -59,7 +59,7 @@ struct TcCfg {
   static constexpr int SMEM = TC_RING_BYTES + TC_BAR_BYTES + TC_WC_BYTES + TC_X8_BYTES + 1024 /*alignment*/;
 };
 
-enum { TC_GATE = 0, TC_RESIDUAL = 1 };
+enum { TC_GATE = 0, TC_RESIDUAL = 1, TC_LINEAR = 2 };
 
 struct TcSrc {
   int channels, taps, dilation, center;
@@ -76,7 +76,19 @@ struct TcParams {
   const float* wc;         // gate: [TC_NOUT][C] collapsed skip weights (fp32)
   float* out8;             // gate: (B, T, TC_NOUT) running end() pre-activation
   int accumulate_out8;
-  int out_row_mul, out_row_off;   // residual/linear epilogue: output row = column * mul + off (phase-strided upsampler)
+  int out_row_mul, out_row_off;   // residual epilogue: output row = column * mul + off (phase-strided upsampler)
+  // TC_LINEAR (generic Conv1d / Linear): v = act(acc + bias) [* mask] [+ residual] on the first n_valid columns,
+  // written as fp32 (out_f32, row stride out_ld) and/or as the bf16 hi/lo operand copies of the next layer
+  // (out_hi/out_lo, row stride C; columns >= n_valid are exact zeros because their weights and bias are)
+  int act, n_valid;
+  int fp16;                       // operands (and the hi/lo outputs of TC_LINEAR) are IEEE half instead of bf16
+  int k_step0;                    // first K step of this launch (K-chunked accumulation, see conv_gemm_tc)
+  const float* addend;            // fp32 partial sum of the earlier K chunks, added before the activation
+  long long addend_ld;
+  const float* mask;
+  const float* residual;
+  float* out_f32;
+  long long mask_ld, res_ld, out_ld;
   long long* prof;         // optional [grid][8] cycle counters
 };
 
@@ -162,7 +174,7 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
         for (int nb = 0; nb < n_blocks; ++nb) {
           for (int ks = 0; ks < p.k_steps; ++ks) {
             // decode the K step into (source, tap, channel block)
-            int s = 0, rem = ks;
+            int s = 0, rem = p.k_step0 + ks;
             if (rem >= steps0) { s = 1; rem -= steps0; }
             const int cps = p.src[s].channels / TC_BK;
             const int tap = rem / cps, c0 = (rem - tap * cps) * TC_BK;
@@ -180,16 +192,16 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
               mbar_arrive_expect_tx(&full[stage], bytes);
               tma_load_3d(st, mh, &full[stage], c0, row0, b);
               if (p.nsplit == 2) tma_load_3d(st + A_BYTES, ml, &full[stage], c0, row0, b);
-              tma_load_2d(st + W_OFF, &w_hi, &full[stage], ks * TC_BK, w_row);
-              if (use_wlo) tma_load_2d(st + W_OFF + W_BYTES, &w_lo, &full[stage], ks * TC_BK, w_row);
+              tma_load_2d(st + W_OFF, &w_hi, &full[stage], (p.k_step0 + ks) * TC_BK, w_row);
+              if (use_wlo) tma_load_2d(st + W_OFF + W_BYTES, &w_lo, &full[stage], (p.k_step0 + ks) * TC_BK, w_row);
             } else {
               // both CTAs' loads complete on the LEADER's barrier, which expects the pair's bytes
               if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * bytes);
               const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
               tma_load_3d_cg2(st, mh, lead_full, c0, row0, b);
               if (p.nsplit == 2) tma_load_3d_cg2(st + A_BYTES, ml, lead_full, c0, row0, b);
-              tma_load_2d_cg2(st + W_OFF, &w_hi, lead_full, ks * TC_BK, w_row);
-              if (use_wlo) tma_load_2d_cg2(st + W_OFF + W_BYTES, &w_lo, lead_full, ks * TC_BK, w_row);
+              tma_load_2d_cg2(st + W_OFF, &w_hi, lead_full, (p.k_step0 + ks) * TC_BK, w_row);
+              if (use_wlo) tma_load_2d_cg2(st + W_OFF + W_BYTES, &w_lo, lead_full, (p.k_step0 + ks) * TC_BK, w_row);
             }
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
@@ -200,7 +212,7 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
   } else if (warp == 1) {
     // ===================================================== UMMA issuer
     if (lane == 0 && rank == 0) {                     // CG = 2: the leader issues for the pair
-      const uint32_t idesc = make_idesc_bf16(TC_BM * CG, n_cols);
+      const uint32_t idesc = p.fp16 ? make_idesc_f16(TC_BM * CG, n_cols) : make_idesc_bf16(TC_BM * CG, n_cols);
       auto mma = [](uint32_t d, uint64_t a, uint64_t w, uint32_t id, uint32_t acc) {
         if (CG == 1) umma_bf16(d, a, w, id, acc);
         else umma_bf16_cg2(d, a, w, id, acc);
@@ -289,7 +301,8 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            const float4 bv = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
             v[j + 0] = __uint_as_float(rr[j + 0]) + bv.x;
             v[j + 1] = __uint_as_float(rr[j + 1]) + bv.y;
             v[j + 2] = __uint_as_float(rr[j + 2]) + bv.z;
@@ -327,6 +340,68 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
               uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
               dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
               dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+          } else if (p.mode == TC_LINEAR) {
+            // generic Conv1d / Linear epilogue (reference src/common/layers.py:40-71 users)
+            if (p.addend != nullptr) {
+              const float* arow = p.addend + col * p.addend_ld + n0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (n0 + j + 3 < p.n_valid) {
+                  const float4 m = *reinterpret_cast<const float4*>(arow + j);   // written by the previous launch
+                  v[j] += m.x; v[j + 1] += m.y; v[j + 2] += m.z; v[j + 3] += m.w;
+                }
+            }
+            if (p.act == FAC_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (p.act == FAC_ACT_TANH) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+            }
+            if (p.mask != nullptr) {
+              const float* mrow = p.mask + col * p.mask_ld + n0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (n0 + j + 3 < p.n_valid) {
+                  const float4 m = __ldg(reinterpret_cast<const float4*>(mrow + j));
+                  v[j] *= m.x; v[j + 1] *= m.y; v[j + 2] *= m.z; v[j + 3] *= m.w;
+                }
+            }
+            if (p.residual != nullptr) {
+              const float* rrow = p.residual + col * p.res_ld + n0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (n0 + j + 3 < p.n_valid) {
+                  const float4 m = __ldg(reinterpret_cast<const float4*>(rrow + j));
+                  v[j] += m.x; v[j + 1] += m.y; v[j + 2] += m.z; v[j + 3] += m.w;
+                }
+            }
+            if (p.out_f32 != nullptr) {
+              float* orow = p.out_f32 + col * p.out_ld + n0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (n0 + j + 3 < p.n_valid)
+                  *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (p.out_hi != nullptr) {
+              uint32_t hi[16], lo[16];
+              if (p.fp16) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) split2_f16(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+              }
+              const long long off = col * p.C + n0;
+              uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              if (p.nsplit == 2) {
+                uint4* dl = reinterpret_cast<uint4*>(p.out_lo + off);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
             }
           } else {
             // residual stream x_new = x + res (glow.py:166), already summed by the identity block:
@@ -602,6 +677,144 @@ int launch_tc(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st, int
 }
 
 long long* g_tc_prof = nullptr;
+
+// ---------------------------------------------------------------- generic Conv1d / Linear on the tensor cores
+// (B, C, T) channel-major fp32 -> (B, T, pad) channels-last bf16 hi/lo (the PPG input of the encoder prenet,
+// reference src/common/model.py:237-241): 32 x 32 tiles through shared memory.
+__device__ __forceinline__ void store_split(unsigned short* hi, unsigned short* lo, long long o, float v, bool fp16) {
+  if (fp16) {
+    const __half h = __float2half_rn(v);
+    hi[o] = __half_as_ushort(h);
+    if (lo) lo[o] = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[o] = __bfloat16_as_ushort(h);
+    if (lo) lo[o] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+  }
+}
+
+// (n_rows, C) fp32 -> zero-padded (n_rows, pad) 16-bit hi/lo operand copies.
+__global__ void pad_split_kernel(const float* __restrict__ in, unsigned short* __restrict__ hi,
+                                 unsigned short* __restrict__ lo, long long n_rows, int C, int pad, bool fp16) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * pad) return;
+  const long long r = i / pad;
+  const int c = (int)(i - r * pad);
+  store_split(hi, lo, i, c < C ? __ldg(in + r * C + c) : 0.f, fp16);
+}
+
+__global__ void transpose_split_kernel(const float* __restrict__ in, unsigned short* __restrict__ hi,
+                                       unsigned short* __restrict__ lo, int C, int T, int pad, bool fp16) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    tile[i][tx] = (c < C && t < T) ? __ldg(in + ((long long)b * C + c) * T + t) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    if (t < T && c < pad) store_split(hi, lo, ((long long)b * T + t) * pad + c, tile[tx][i], fp16);
+  }
+}
+
+}  // namespace
+
+int tc_transpose_split(const float* in, void* hi, void* lo, int B, int C, int T, int pad, int fp16, cudaStream_t st) {
+  FAC_REQUIRE(in && hi && B > 0 && C > 0 && T > 0 && pad >= C, "transpose_split: bad arguments");
+  dim3 grid((unsigned)ceil_div(T, 32), (unsigned)ceil_div(pad, 32), (unsigned)B);
+  transpose_split_kernel<<<grid, dim3(32, 8), 0, st>>>(in, reinterpret_cast<unsigned short*>(hi),
+                                                       reinterpret_cast<unsigned short*>(lo), C, T, pad, fp16 != 0);
+  count_launch();
+  return check_launch("transpose_split_kernel");
+}
+
+int tc_pad_split(const float* in, void* hi, void* lo, long long n_rows, int C, int pad, int fp16, cudaStream_t st) {
+  FAC_REQUIRE(in && hi && n_rows > 0 && C > 0 && pad >= C, "pad_split: bad arguments");
+  pad_split_kernel<<<(unsigned)((n_rows * pad + 255) / 256), 256, 0, st>>>(
+      in, reinterpret_cast<unsigned short*>(hi), reinterpret_cast<unsigned short*>(lo), n_rows, C, pad, fp16 != 0);
+  count_launch();
+  return check_launch("pad_split_kernel");
+}
+
+int conv_gemm_tc(const fac_tc_conv* c, cudaStream_t st) {
+  FAC_REQUIRE(c != nullptr, "conv_gemm_tc: NULL descriptor");
+  FAC_REQUIRE(c->nsplit == 1 || c->nsplit == 2, "conv_gemm_tc: nsplit must be 1 or 2 (got %d)", c->nsplit);
+  FAC_REQUIRE(c->a_hi && c->w_hi && (c->nsplit == 1 || (c->a_lo && c->w_lo)), "conv_gemm_tc: NULL operand");
+  FAC_REQUIRE(c->B > 0 && c->T > 0 && c->taps > 0, "conv_gemm_tc: empty problem");
+  FAC_REQUIRE(c->c_pad % TC_BK_MAX == 0, "conv_gemm_tc: input channels %d must be padded to a multiple of %d", c->c_pad,
+              TC_BK_MAX);
+  FAC_REQUIRE(c->n_pad % 64 == 0 && c->n_valid > 0 && c->n_valid <= c->n_pad && c->n_valid % 4 == 0,
+              "conv_gemm_tc: n_pad %d must be a multiple of 64 and n_valid %d a multiple of 4", c->n_pad, c->n_valid);
+  FAC_REQUIRE(c->out || c->out_hi, "conv_gemm_tc: no output");
+  FAC_REQUIRE(c->out_hi == nullptr || c->nsplit == 1 || c->out_lo, "conv_gemm_tc: out_lo missing");
+  const int cg = tc_pick_cg(c->nsplit), bk = tc_pick_bk(c->nsplit);
+  const int K = c->taps * c->c_pad;
+  CUtensorMap maps[6];
+  if (int rc = make_act_map(&maps[0], c->a_hi, c->B, c->T, c->c_pad, bk)) return rc;
+  if (int rc = make_act_map(&maps[1], c->nsplit == 2 ? c->a_lo : c->a_hi, c->B, c->T, c->c_pad, bk)) return rc;
+  maps[2] = maps[0];
+  maps[3] = maps[1];
+  if (int rc = make_weight_map(&maps[4], c->w_hi, c->n_pad, K, cg, bk)) return rc;
+  if (int rc = make_weight_map(&maps[5], c->nsplit == 2 ? c->w_lo : c->w_hi, c->n_pad, K, cg, bk)) return rc;
+  TcParams p{};
+  p.T = c->T;
+  p.B = c->B;
+  p.tiles_per_batch = ceil_div(c->T, TC_BM);
+  p.n_tiles = c->B * p.tiles_per_batch;
+  p.nsplit = c->nsplit;
+  p.C = c->n_pad;                 // row stride of the 16-bit outputs
+  p.n_src = 1;
+  p.src[0] = TcSrc{c->c_pad, c->taps, 1, c->center};
+  p.n_total = c->n_pad;
+  p.mode = TC_LINEAR;
+  p.out_row_mul = 1;
+  p.fp16 = c->fp16;
+  p.n_valid = c->n_valid;
+  // The tensor core's fp32 accumulator truncates on every accumulation, an error that grows with the number
+  // of UMMAs chained into one accumulator (measured: ~3e-5 relative at K = 5824).  With k_chunk > 0 the K
+  // range is cut into launches of at most k_chunk elements whose partial sums are added in fp32
+  // (round-to-nearest) by the epilogue through `scratch`; only the last launch applies the real epilogue.
+  const int total_steps = K / bk;
+  int steps_per_launch = total_steps;
+  if (c->k_chunk > 0) {
+    FAC_REQUIRE(c->k_chunk % bk == 0, "conv_gemm_tc: k_chunk %d must be a multiple of %d", c->k_chunk, bk);
+    steps_per_launch = c->k_chunk / bk;
+    FAC_REQUIRE(steps_per_launch >= total_steps || c->scratch != nullptr, "conv_gemm_tc: K-chunking needs scratch");
+  }
+  for (int k0 = 0; k0 < total_steps; k0 += steps_per_launch) {
+    const bool first = k0 == 0, last = k0 + steps_per_launch >= total_steps;
+    p.k_step0 = k0;
+    p.k_steps = last ? total_steps - k0 : steps_per_launch;
+    p.wlo_k_steps = p.k_steps;
+    p.addend = first ? nullptr : c->scratch;
+    p.addend_ld = c->n_valid;
+    if (last) {
+      p.bias = c->bias;
+      p.act = c->act;
+      p.mask = c->mask;
+      p.mask_ld = c->mask_ld;
+      p.residual = c->residual;
+      p.res_ld = c->res_ld;
+      p.out_f32 = c->out;
+      p.out_ld = c->out_ld;
+      p.out_hi = reinterpret_cast<__nv_bfloat16*>(c->out_hi);
+      p.out_lo = reinterpret_cast<__nv_bfloat16*>(c->out_lo);
+    } else {
+      p.bias = nullptr;
+      p.act = FAC_ACT_NONE;
+      p.mask = p.residual = nullptr;
+      p.out_f32 = c->scratch;
+      p.out_ld = c->n_valid;
+      p.out_hi = p.out_lo = nullptr;
+    }
+    if (int rc = launch_tc(maps, p, st, cg)) return rc;
+  }
+  return 0;
+}
+
+namespace {
 
 }  // namespace
 

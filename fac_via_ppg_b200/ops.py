@@ -55,3 +55,62 @@ def pack_gemm_weight(w_kn: torch.Tensor, bias=None):
         b = bias.new_zeros(n_pad)
         b[:N] = bias
     return w.contiguous(), b
+
+
+# ---------------------------------------------------------------------- tensor-core Conv1d / Linear
+def split_pair(shape, device, nsplit=2, dtype=torch.float16):
+    """Uninitialised 16-bit (hi, lo) operand buffers; lo is None in the single-operand mode."""
+    hi = torch.empty(*shape, dtype=dtype, device=device)
+    return hi, (torch.empty_like(hi) if nsplit == 2 else None)
+
+
+def transpose_split(x_cm: torch.Tensor, pad: int, nsplit=2, dtype=torch.float16):
+    """(B, C, T) channel-major fp32 -> (B, T, pad) channels-last 16-bit hi/lo (fac_transpose_split_16)."""
+    _ext.require_cuda(x_cm, "transpose_split input")
+    B, Cc, T = x_cm.shape
+    hi, lo = split_pair((B, T, pad), x_cm.device, nsplit, dtype)
+    rc = _ext.load().fac_transpose_split_16(x_cm.data_ptr(), hi.data_ptr(), _ext.ptr(lo), B, Cc, T, pad,
+                                            int(dtype == torch.float16), _ext.current_stream())
+    _ext.check(rc, "fac_transpose_split_16")
+    return hi, lo
+
+
+def pad_split(x_cl: torch.Tensor, pad: int, nsplit=2, dtype=torch.float16):
+    """(B, T, C) channels-last fp32 -> (B, T, pad) 16-bit hi/lo, padding channels zero (fac_pad_split_16)."""
+    _ext.require_cuda(x_cl, "pad_split input")
+    B, T, Cc = x_cl.shape
+    hi, lo = split_pair((B, T, pad), x_cl.device, nsplit, dtype)
+    rc = _ext.load().fac_pad_split_16(x_cl.data_ptr(), hi.data_ptr(), _ext.ptr(lo), B * T, Cc, pad,
+                                      int(dtype == torch.float16), _ext.current_stream())
+    _ext.check(rc, "fac_pad_split_16")
+    return hi, lo
+
+
+TC_K_CHUNK = 512   # contraction elements per tensor-core accumulation chain (see fac_tc_conv.k_chunk)
+
+
+def conv_gemm_tc(a, w, *, act=_ext.ACT_NONE, mask=None, residual=None, out=None, want_split=True, nsplit=2,
+                 k_chunk=None):
+    """Conv1d / Linear on the tensor cores (fac_conv_gemm_tc).  ``a`` = (hi, lo) 16-bit (B, T, c_pad) from
+    transpose_split/pad_split or a previous call; ``w`` = one entry of PackedTacotron.tc_weights() (same
+    16-bit type).  Returns (out_f32 or None, (hi, lo) or None)."""
+    a_hi, a_lo = a
+    B, T, c_pad = a_hi.shape
+    if c_pad != w["c_pad"]:
+        raise _ext.FacError("conv_gemm_tc: input has %d channels, weight expects %d" % (c_pad, w["c_pad"]))
+    if a_hi.dtype != w["hi"].dtype:
+        raise _ext.FacError("conv_gemm_tc: operand types differ (%s vs %s)" % (a_hi.dtype, w["hi"].dtype))
+    nxt = split_pair((B, T, w["n_pad"]), a_hi.device, nsplit, a_hi.dtype) if want_split else (None, None)
+    ld = lambda t: 0 if t is None else t.shape[-1]  # noqa: E731
+    k_chunk = TC_K_CHUNK if k_chunk is None else k_chunk
+    scratch = None
+    if k_chunk and w["taps"] * c_pad > k_chunk:
+        scratch = torch.empty(B * T, w["n_valid"], dtype=torch.float32, device=a_hi.device)
+    d = _ext.TcConv(a_hi.data_ptr(), _ext.ptr(a_lo), w["hi"].data_ptr(), w["lo"].data_ptr() if nsplit == 2 else None,
+                    _ext.ptr(w["bias"]), _ext.ptr(mask), _ext.ptr(residual), _ext.ptr(out), _ext.ptr(nxt[0]),
+                    _ext.ptr(nxt[1]), ld(mask), ld(residual), ld(out), B, T, c_pad, w["taps"],
+                    (w["taps"] - 1) // 2, w["n_pad"], w["n_valid"], act, nsplit, int(a_hi.dtype == torch.float16),
+                    k_chunk or 0, 0, _ext.ptr(scratch))
+    rc = _ext.load().fac_conv_gemm_tc(C.byref(d), _ext.current_stream())
+    _ext.check(rc, "fac_conv_gemm_tc")
+    return out, (nxt if want_split else None)

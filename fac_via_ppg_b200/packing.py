@@ -419,6 +419,43 @@ class PackedTacotron:
             put(f"post.conv{i}_b", b)
         return self
 
+    # ------------------------------------------------------------------ tensor-core copies
+    @torch.no_grad()
+    def tc_weights(self, dtype=torch.float16):
+        """16-bit hi/lo operand matrices (IEEE half: hi + lo carries 22 significand bits; the weights and
+        activations of this model are far inside its range) of the encoder / postnet GEMMs for fac_conv_gemm_tc, derived (once) from the
+        packed fp32 buffer: name -> dict(hi, lo, c_pad, taps, n_pad, n_valid, bias).  Layout [n_pad][taps*c_pad]
+        (K contiguous, tap-major), input channels zero-padded to a multiple of 64, rows to a multiple of 64."""
+        cached = getattr(self, "_tc", None)
+        if cached is not None:
+            return cached
+        hp = self.hp
+        E, D, M = hp["encoder_embedding_dim"], hp["n_symbols"], hp["n_acoustic_feat_dims"]
+        ke, kp, Pe = hp["encoder_kernel_size"], hp["postnet_kernel_size"], hp["postnet_embedding_dim"]
+        n_post = hp["postnet_n_convolutions"]
+        dims = [M] + [Pe] * (n_post - 1) + [M]
+        specs = [("enc.pre0", D, 1, E, False), ("enc.pre1", E, 1, E, False)]
+        specs += [(f"enc.conv{i}", E, ke, E, True) for i in range(hp["encoder_n_convolutions"])]
+        specs += [("enc.lstm_ih", E, 1, 4 * E, True)]
+        specs += [(f"post.conv{i}", dims[i], kp, dims[i + 1], True) for i in range(n_post)]
+        out = {}
+        for name, c_in, taps, n_out, has_bias in specs:
+            w = self.view(name + "_w")[:, :n_out]                              # (taps*c_in, n_out) fp32
+            c_pad, n_pad = _round_up(c_in, 64), _round_up(n_out, 64)
+            wp = w.new_zeros(n_pad, taps, c_pad)
+            wp[:n_out, :, :c_in] = w.reshape(taps, c_in, n_out).permute(2, 0, 1)
+            wp = wp.reshape(n_pad, taps * c_pad)
+            hi = wp.to(dtype)
+            lo = (wp - hi.float()).to(dtype)
+            bias = None
+            if has_bias:
+                bias = w.new_zeros(n_pad)
+                bias[:n_out] = self.view(name + "_b")[:n_out]
+            out[name] = dict(hi=hi.contiguous(), lo=lo.contiguous(), c_pad=c_pad, taps=taps, n_pad=n_pad,
+                             n_valid=n_out, bias=bias)
+        self._tc = out
+        return out
+
     @classmethod
     def from_state(cls, sd, hp, device):
         return cls(hp, device).load_state(sd)

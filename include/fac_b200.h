@@ -192,6 +192,40 @@ int fac_tc_set_k_block(int k_block);
 int fac_waveglow_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* mel_cl, float* audio,
                           const fac_wg_tc_workspace* ws, int B, int F, int nsplit, void* stream);
 
+/* ---- generic Conv1d / Linear on the tcgen05 tensor cores ------------------ */
+/* Same role as fac_conv_gemm_f32 (torch.nn.Conv1d / torch.nn.Linear behind ConvNorm / LinearNorm,
+ * reference src/common/layers.py:40-71; used by the encoder and the postnet, model.py:178-184, 237-249)
+ * with bf16 operands: the input is a channels-last (B, T, c_pad) bf16 tensor (a_hi [+ a_lo]), c_pad a
+ * multiple of 64 with zero padding channels; output row t reads input rows t + tap - center, rows outside
+ * [0, T) are zero (Conv1d padding).  Weights are [n_pad][taps*c_pad] bf16 (K contiguous, tap-major),
+ * n_pad a multiple of 64, rows >= n_valid zero.  nsplit = 1: single 16-bit operands; nsplit = 2: split
+ * operands (x = hi + lo, 3 UMMAs per product): ~2^-16 relative with bf16, ~2^-21 with IEEE half.  Epilogue: v = act(acc + bias) [* mask] [+ residual];
+ * bias is [n_pad] or NULL; mask / residual / out are fp32 with n_valid columns (n_valid % 4 == 0) and the
+ * given row strides; out_hi/out_lo (optional) receive the (B, T, n_pad) bf16 operand copies for the next
+ * layer (padding columns exact zeros). */
+typedef struct fac_tc_conv {
+  const void* a_hi; const void* a_lo;
+  const void* w_hi; const void* w_lo;
+  const float* bias;
+  const float* mask; const float* residual;
+  float* out;
+  void* out_hi; void* out_lo;
+  long long mask_ld, res_ld, out_ld;
+  int B, T, c_pad, taps, center, n_pad, n_valid, act, nsplit;
+  int fp16;   /* 0: operands are bf16; 1: IEEE half (hi + lo = 22 significand bits; needs |x| < 65504) */
+  /* K-chunked accumulation: the tensor core's fp32 accumulator truncates on every accumulation; with
+   * k_chunk > 0 (a multiple of 64) the contraction is cut into launches of <= k_chunk elements whose partial
+   * sums meet in fp32 round-to-nearest through scratch, a (B*T, n_valid) fp32 buffer.  0 = one launch. */
+  int k_chunk, _pad;
+  float* scratch;
+} fac_tc_conv;
+int fac_conv_gemm_tc(const fac_tc_conv* conv, void* stream);
+/* (B, C, T) channel-major fp32 -> (B, T, pad) channels-last 16-bit hi [+ lo] (bf16, or IEEE half when fp16 != 0),
+ * channels [C, pad) zero. */
+int fac_transpose_split_16(const float* in, void* hi, void* lo, int B, int C, int T, int pad, int fp16, void* stream);
+/* (n_rows, C) fp32 -> (n_rows, pad) 16-bit hi [+ lo], columns [C, pad) zero. */
+int fac_pad_split_16(const float* in, void* hi, void* lo, long long n_rows, int C, int pad, int fp16, void* stream);
+
 /* ---- PPG -> Mel (Tacotron2 variant) ------------------------------------- */
 /* Recurrent part of the encoder's bidirectional LSTM (reference src/common/model.py:211-213,
  * 246-247).  xp is (B, T, 2*4H): x W_ih^T + b_ih + b_hh of the forward direction in columns
