@@ -77,9 +77,9 @@ struct MatSmem {                  // matrix CTAs
 };
 struct AttSmem {                  // attention CTAs
   float wq[A][R];                 // query_layer weight, resident
-  float S[MAXW][A];               // location_dense(location_conv(.)) + processed_memory of the coming window
-  float v[A + 2];
-  float pq[A + 2];
+  float S[MAXW][A];               // exp(2 (location_dense(location_conv(.)) + processed_memory)) of the coming window
+  float v2[A + 2];                // -2 v
+  float upq[A + 2];               // exp(2 W_q h_att)
   float e[MAXW];
   float wts[DEC_WARPS][MAXW];     // softmax weights, one copy per warp
   float cat[2][MAXW + KF - 1 + 2];
@@ -471,11 +471,24 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
 
   for (int i = tid; i < A * R / 4; i += DEC_THREADS)
     reinterpret_cast<float4*>(&sm.wq[0][0])[i] = __ldg(reinterpret_cast<const float4*>(p.w.wq) + i);
-  for (int i = tid; i < A; i += DEC_THREADS) sm.v[i] = __ldg(p.w.v + i);
+  for (int i = tid; i < A; i += DEC_THREADS) sm.v2[i] = -2.0f * __ldg(p.w.v + i);
   __syncthreads();
+
+  // Energies (model.py:94-97) e[q] = sum_a v[a] tanh(pq[a] + s[q][a]).  With tanh(x) = 1 - 2 / (exp(2x) + 1) and
+  // exp(2 (pq + s)) = exp(2 pq) exp(2 s), the critical path keeps one multiply, one reciprocal and one FMA per
+  // (q, a): exp(2 s) is prepared ahead, exp(2 pq) costs 150 exponentials, and the constant sum_a v[a] drops
+  // out of the softmax.  Both exponents are clamped to +-20 (tanh is saturated to 1 ulp beyond +-9).
+  auto exp2x = [](float x) {
+    x = fminf(fmaxf(x, -20.f), 20.f);
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 2.8853900817779268f));
+    return r;
+  };
 
   float4 mreg[QPP];      // encoder rows of this thread's share of the window
   int start = 0, nw = 0;
+  Prof prof;
+  prof.init(p.prof != nullptr, sm.prof);
 
   auto prepare = [&](int t) {
     int end;
@@ -530,7 +543,7 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
           const int q = warp + qi * DEC_WARPS, a = lane + 32 * j;
-          if (q < nw && a < A) sm.S[q][a] = acc[qi][j];
+          if (q < nw && a < A) sm.S[q][a] = exp2x(acc[qi][j]);
         }
     }
     // encoder outputs of the window -> registers (consumed by the context sum of step t)
@@ -546,6 +559,7 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
   };
 
   auto critical = [&](int t, const float* h_att) {
+    long long tp = prof.now();
     // query projection (model.py:92): pq = W_q h_att; warp per row, 75 float4 per row over the lanes
     {
       const float4* h4 = reinterpret_cast<const float4*>(h_att + b * R);
@@ -559,26 +573,37 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
         acc += a1.x * hv1.x + a1.y * hv1.y + a1.z * hv1.z + a1.w * hv1.w;
         acc += a2.x * hv2.x + a2.y * hv2.y + a2.z * hv2.z + a2.w * hv2.w;
         acc = warp_sum(acc);
-        if (lane == 0) sm.pq[r] = acc;
+        if (lane == 0) sm.upq[r] = exp2x(acc);
       }
     }
     __syncthreads();
-    // energies (model.py:94-97): e[q] = v . tanh(pq + S[q])
+    prof.sub<11>(tp);
+    // energies up to a constant: e[q] = sum_a -2 v[a] / (exp(2 pq[a]) exp(2 s[q][a]) + 1)
+    {
+      float u[5], v2[5];
 #pragma unroll
-    for (int qi = 0; qi < 3; ++qi) {
-      const int q = warp + qi * DEC_WARPS;
-      if (q < nw) {
-        float part = 0.f;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const int a = lane + 32 * j;
-          if (a < A) part = fmaf(sm.v[a], tanhf_fast(sm.pq[a] + sm.S[q][a]), part);
-        }
-        part = warp_sum(part);
-        if (lane == 0) sm.e[q] = part;
+      for (int j = 0; j < 5; ++j) {
+        const int a = min(lane + 32 * j, A - 1);
+        u[j] = sm.upq[a];
+        v2[j] = lane + 32 * j < A ? sm.v2[a] : 0.f;
       }
+      float part[3];
+#pragma unroll
+      for (int qi = 0; qi < 3; ++qi) {
+        const int q = min(warp + qi * DEC_WARPS, MAXW - 1);
+        part[qi] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          part[qi] = fmaf(v2[j], __fdividef(1.0f, fmaf(u[j], sm.S[q][min(lane + 32 * j, A - 1)], 1.0f)), part[qi]);
+      }
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1)
+#pragma unroll
+        for (int qi = 0; qi < 3; ++qi) part[qi] += __shfl_xor_sync(0xffffffffu, part[qi], sft);
+      if (lane < 3 && warp + lane * DEC_WARPS < nw) sm.e[warp + lane * DEC_WARPS] = lane == 0 ? part[0] : lane == 1 ? part[1] : part[2];
     }
     __syncthreads();
+    prof.sub<12>(tp);
     // softmax over the window (everything else is -inf -> weight 0, model.py:114-117), evaluated by every
     // warp for itself
     {
@@ -606,6 +631,7 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
       *reinterpret_cast<float4*>(&sm.x.ctxp[cpart][4 * c4]) = acc;
     }
     __syncthreads();
+    prof.sub<13>(tp);
     for (int c = tid; c < E; c += DEC_THREADS) p.s.ctx[b * E + c] = sm.x.ctxp[0][c] + sm.x.ctxp[1][c] + sm.x.ctxp[2][c];
     // new attention_weights (zero outside the window), cumulative weights (model.py:424), alignments
     int ostart = 0, oend = -1;
@@ -623,8 +649,6 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
   unsigned int* bar_all = reinterpret_cast<unsigned int*>(p.s.done + 3);
   unsigned int target_all = 0;
   int cur = 0;
-  Prof prof;
-  prof.init(p.prof != nullptr, sm.prof);
   prepare(0);
   for (int t = 0; t < p.max_steps; ++t) {
     const float* h_att_nxt = p.s.h_att + (cur ^ 1) * p.B * R;
