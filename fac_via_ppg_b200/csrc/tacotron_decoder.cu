@@ -23,6 +23,8 @@
 //     barriers between matrix-only phases do not involve the attention CTAs.
 //   * the stop decision (sigmoid(gate) > threshold) is taken on the device.
 #include "fac_common.cuh"
+#include <cuda_fp16.h>
+#include <stdint.h>
 
 namespace fac {
 
@@ -58,22 +60,29 @@ constexpr int MIN_MATRIX_CTAS = 100;
 constexpr int MAXU = 3;         // hidden units per matrix CTA (>= 100 matrix CTAs)
 constexpr int MAXPP = 4;        // projection rows per matrix CTA
 constexpr int MAXP2 = 3;        // prenet-1 rows per matrix CTA
-constexpr int CHUNK = 8;        // utterances staged per pass (double-buffered)
+constexpr int CHUNK = 8;        // utterances per staging buffer = one mma n-tile
+constexpr int PASS = 2 * CHUNK; // utterances per arithmetic pass (both staging buffers)
 constexpr int MAXW = 48;        // max window positions (2*window+1 <= 48)
-constexpr int KPARTS = 4;       // fixed K split of every mat-vec (the summation order must not depend on B)
+constexpr int KS_LSTM = KIN + 8;        // halfs per resident LSTM weight row (+8: ldmatrix rows hit distinct banks)
+constexpr int KP_PP = 912, KS_PP = KP_PP + 8;   // projection K padded to whole k16 steps
+constexpr int KP_P2 = 304, KS_P2 = KP_P2 + 8;   // prenet-1 K padded
+constexpr int XS = KIN + 8;             // floats per staged input row
+constexpr float W_SCALE = 256.f;        // resident weights are stored times 2^8 so that their fp16 lo parts stay normal
 constexpr int CTXP = 3;         // q-range split of the context sum
 constexpr int QPP = MAXW / CTXP;  // window positions per part
 
 struct MatSmem {                  // matrix CTAs
-  float w_att[MAXU * 4][KIN];
-  float w_dec[MAXU * 4][KIN];
-  float w_pp[MAXPP][KHC];
-  float w_p2[MAXP2][R];
+  // resident weights as IEEE-half hi/lo pairs (w * 2^8 = hi + lo to ~2^-22): the operands of mma.sync
+  __half w_att[2][MAXU * 4][KS_LSTM];
+  __half w_dec[2][MAXU * 4][KS_LSTM];
+  __half w_pp[2][MAXPP][KS_PP];
+  __half w_p2[2][MAXP2][KS_P2];
   float b_att[MAXU * 4], b_dec[MAXU * 4], b_pp[MAXPP];
-  float part[2][6 * KPARTS][16];  // per-job partial sums of a chunk (<= 6 tiles x KPARTS), double-buffered
+  alignas(16) float part[DEC_WARPS][16][PASS];   // per-warp partial 16 x 16 tiles (K split over the warps)
+  float sums[16][PASS];
   int n_done;
   unsigned int prof[16];
-  alignas(16) float in[2][CHUNK][KIN];   // staged input vectors of a chunk of utterances, double-buffered
+  alignas(16) float in[2][CHUNK][XS];   // staged input vectors of a chunk of utterances, double-buffered
 };
 struct AttSmem {                  // attention CTAs
   float wq[A][R];                 // query_layer weight, resident
@@ -100,7 +109,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // Barrier over `n` CTAs: monotonically increasing arrival counter (zeroed by the host).  The arrival is a
 // release (every write of this CTA that bar.sync ordered before it is visible to whoever acquires the
-// final count), the spin an acquire.
+// final count), the spin an acquire.  (Measured: several staggered pollers per CTA are slower, not faster.)
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target, unsigned int n) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -127,54 +136,34 @@ struct Seg {           // one piece of a concatenated input vector: utterance b 
   int len, stride;     // multiples of 4 floats
 };
 
-// Start the asynchronous copy (L2 -> shared memory, bypassing L1: the vectors were written by other CTAs
-// in the previous phase) of the concatenated inputs of utterances [n0, n0+nb) into one staging buffer.
-template <int NSEG>
-__device__ __forceinline__ void stage_async(float (*buf)[KIN], const Seg (&segs)[NSEG], int n0, int nb) {
-  int base = 0;
-#pragma unroll
-  for (int s = 0; s < NSEG; ++s) {
-    const int l4 = segs[s].len >> 2;
-    for (int i = threadIdx.x; i < nb * l4; i += DEC_THREADS) {
-      const int n = i / l4, k4 = i - n * l4;
-      cp_async16(&buf[n][base + 4 * k4], segs[s].ptr + (long long)(n0 + n) * segs[s].stride + 4 * k4);
-    }
-    base += segs[s].len;
-  }
-  cp_async_commit();
+// Staging = asynchronous copies (L2 -> shared memory, bypassing L1: the vectors were written by other CTAs in
+// an earlier phase) of the concatenated input vectors; `mask` selects the segments (bit s = segment s).
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr)
+               : "memory");
 }
-
-// Sum 16 per-lane values across the warp with 16 shuffles (halving butterfly): afterwards lane l holds
-// the total of value index ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1) (lanes l and l^1 agree).
-__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool up = lane & 16;
-    const float send = up ? v[i] : v[i + 8];
-    const float keep = up ? v[i + 8] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool up = lane & 8;
-    const float send = up ? v[i] : v[i + 4];
-    const float keep = up ? v[i + 4] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool up = lane & 4;
-    const float send = up ? v[i] : v[i + 2];
-    const float keep = up ? v[i + 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  {
-    const bool up = lane & 2;
-    const float send = up ? v[0] : v[1];
-    const float keep = up ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+// D (16 x 8, fp32) += A (16 x 16, row-major halfs) * B (16 x 8, halfs; lane holds two k-pairs of one column)
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// fp32 pair -> IEEE-half hi/lo pairs (x = hi + lo to ~2^-22 relative)
+__device__ __forceinline__ void split_half2(float2 x, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x.x, x.y);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// resident weight element: w * 2^8 -> hi/lo halfs
+__device__ __forceinline__ void put_weight(__half* hi, __half* lo, float w) {
+  w *= W_SCALE;
+  const __half h = __float2half_rn(w);
+  *hi = h;
+  *lo = __float2half_rn(w - __half2float(h));
 }
 
 struct Prof {                 // thread 0's cycles between consecutive marks, per slot (accumulators in shared memory)
@@ -214,98 +203,139 @@ struct Prof {                 // thread 0's cycles between consecutive marks, pe
   }
 };
 
-// One batched mat-vec phase over a matrix CTA's resident rows.  The rows are grouped in `n_rt` row tiles
-// of (up to) 4 rows -- the 4 gate rows of one LSTM unit, or the CTA's projection / prenet rows -- and the
-// B utterances in chunks of CHUNK whose input vectors are copied into shared memory asynchronously, one
-// chunk ahead of the arithmetic.  Inside a chunk a warp owns a job = (row tile, 4 utterances, K quarter):
-// 16 accumulators per lane over its K slice, reduced across the lanes with a halving butterfly; the K
-// quarters meet in shared memory (fixed split: the summation order of an output never depends on B) and `epi(part buffer, first utterance, utterances, n_tiles, kparts)` finishes.
-//   row(rt, r): shared-memory pointer of row r of row tile rt (any valid row when r is past the end)
+// One batched mat-vec phase over a matrix CTA's resident rows (<= 16: the 4 gate rows of its LSTM units, or its
+// projection / prenet rows) on the tensor cores.  The B utterances go in passes of 16 (two mma n-tiles = the two
+// staging buffers); the fp32 input vectors of the next pass are copied into shared memory asynchronously behind
+// the reduction and the epilogue of the current one.
+// The K range is split over the 16 warps in whole k16 steps (a fixed split: the summation order of an output
+// never depends on B); per step a warp loads the hi and lo weight fragments with ldmatrix, splits its slice
+// of the inputs into half hi/lo pairs in registers and issues the three products hi*hi + lo*hi + hi*lo
+// (fp32-grade: ~2^-21 relative).  The 16 partial 16 x 8 tiles meet in shared memory in fp32.
 //   pre(n0, nb): called right after the copies are in flight (global loads the epilogue wants early)
-template <int NSEG, typename RowFn, typename PreFn, typename EpiFn>
-__device__ __forceinline__ void matvec_phase(MatSmem& sm, Prof& prof, const Seg (&segs)[NSEG], int K4, int n_rt, int B,
-                                             RowFn row, PreFn pre, EpiFn epi) {
-  long long tp = prof.now();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_chunks = (B + CHUNK - 1) / CHUNK;
-  stage_async(sm.in[0], segs, 0, min(CHUNK, B));
-  for (int ci = 0; ci < n_chunks; ++ci) {
-    const int n0 = ci * CHUNK, nb = min(CHUNK, B - n0), buf = ci & 1;
-    pre(n0, nb);
-    if (ci + 1 < n_chunks) {
-      stage_async(sm.in[buf ^ 1], segs, n0 + CHUNK, min(CHUNK, B - n0 - CHUNK));
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
+//   epi(n0, nb): reads sm.sums[row][utterance] (scaled by W_SCALE)
+//   early: segments of the first chunk that matvec_prefetch() already requested BEFORE the grid barrier
+//          (vectors that were complete one barrier earlier), so that only the fresh segment is fetched after it
+template <int NSEG>
+__device__ __forceinline__ void stage_pass(MatSmem& sm, const Seg (&segs)[NSEG], int n0, int B, unsigned int mask) {
+  // utterances [n0, n0 + 16) -> staging buffers 0 and 1, one cp.async group
+  int base = 0;
+  const int nb = min(PASS, B - n0);
+#pragma unroll
+  for (int s = 0; s < NSEG; ++s) {
+    if (mask >> s & 1) {
+      const int l4 = segs[s].len >> 2;
+      for (int i = threadIdx.x; i < nb * l4; i += DEC_THREADS) {
+        const int n = i / l4, k4 = i - n * l4;
+        cp_async16(&sm.in[n >> 3][n & 7][base + 4 * k4], segs[s].ptr + (long long)(n0 + n) * segs[s].stride + 4 * k4);
+      }
     }
+    base += segs[s].len;
+  }
+  cp_async_commit();
+}
+template <int NSEG>
+__device__ __forceinline__ void matvec_prefetch(MatSmem& sm, const Seg (&segs)[NSEG], int B, unsigned int early) {
+  stage_pass(sm, segs, 0, B, early);
+}
+template <int NSEG, typename PreFn, typename EpiFn>
+__device__ __forceinline__ void matvec_phase(MatSmem& sm, Prof& prof, const Seg (&segs)[NSEG], unsigned int early,
+                                             const __half* w_hi, const __half* w_lo, int ks, int n_rows, int k_steps,
+                                             int B, PreFn pre, EpiFn epi) {
+  long long tp = prof.now();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int base = k_steps / DEC_WARPS, extra = k_steps % DEC_WARPS;
+  const int my_steps = base + (warp < extra ? 1 : 0), my_first = warp * base + min(warp, extra);
+  // ldmatrix: lane l addresses row (l & 7) + 8 * ((l >> 3) & 1) of the 8 x 8 block at k offset 8 * (l >> 4)
+  int arow = (lane & 7) + ((lane >> 3) & 1) * 8;
+  if (arow >= n_rows) arow = 0;                       // rows past the end: any valid row, results ignored
+  const uint32_t a_off = (uint32_t)(arow * ks + (lane >> 4) * 8 + my_first * 16) * 2;
+  const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(w_hi) + a_off;
+  const uint32_t a_lo = (uint32_t)__cvta_generic_to_shared(w_lo) + a_off;
+  stage_pass(sm, segs, 0, B, ~early);
+  for (int n0 = 0; n0 < B; n0 += PASS) {
+    const int nb = min(PASS, B - n0);
+    pre(n0, nb);
+    cp_async_wait<0>();
     __syncthreads();
     prof.sub<11>(tp);
-    const int n_groups = (nb + 3) >> 2;
-    const int n_tiles = n_rt * n_groups;                 // <= 6
-    constexpr int kparts = KPARTS;
-    for (int job = warp; job < n_tiles * KPARTS; job += DEC_WARPS) {
-      const int tile = job % n_tiles, kp = job / n_tiles;
-      const int rt = tile % n_rt, ng = (tile / n_rt) * 4;
-      const float4* w0 = reinterpret_cast<const float4*>(row(rt, 0));
-      const float4* w1 = reinterpret_cast<const float4*>(row(rt, 1));
-      const float4* w2 = reinterpret_cast<const float4*>(row(rt, 2));
-      const float4* w3 = reinterpret_cast<const float4*>(row(rt, 3));
-      const float (*xin)[KIN] = sm.in[buf];
-      // utterances past the end of the chunk re-read the last valid one (results ignored)
-      const float4* x0 = reinterpret_cast<const float4*>(xin[min(ng + 0, nb - 1)]);
-      const float4* x1 = reinterpret_cast<const float4*>(xin[min(ng + 1, nb - 1)]);
-      const float4* x2 = reinterpret_cast<const float4*>(xin[min(ng + 2, nb - 1)]);
-      const float4* x3 = reinterpret_cast<const float4*>(xin[min(ng + 3, nb - 1)]);
-      float acc[16];
+    {
+      // B fragments: column (utterance) lane >> 2 of each n-tile, k pairs 2 * (lane & 3) and + 8
+      const int xo = my_first * 16 + 2 * (lane & 3);
+      const float* xrow0 = &sm.in[0][min(lane >> 2, nb - 1)][xo];
+      const float* xrow1 = &sm.in[1][min(lane >> 2, max(nb - 9, 0))][xo];
+      const bool two = nb > CHUNK;
+      // independent accumulation chains (hi*hi, lo*hi, hi*lo per n-tile), added in a fixed order at the end
+      float acc[2][3][4];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-      const int k_end = (kp + 1) * K4 / kparts;
-      for (int k4 = kp * K4 / kparts + lane; k4 < k_end; k4 += 32) {
-        const float4 wv[4] = {w0[k4], w1[k4], w2[k4], w3[k4]};
-        const float4 xv[4] = {x0[k4], x1[k4], x2[k4], x3[k4]};
+      for (int i = 0; i < 24; ++i) (&acc[0][0][0])[i] = 0.f;
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int n = 0; n < 4; ++n)
-            acc[g * 4 + n] = fmaf(wv[g].x, xv[n].x, fmaf(wv[g].y, xv[n].y,
-                                  fmaf(wv[g].z, xv[n].z, fmaf(wv[g].w, xv[n].w, acc[g * 4 + n]))));
+      for (int i = 0; i < 5; ++i) {
+        if (i < my_steps) {
+          uint32_t ah[4], al[4], bh[2], bl[2];
+          ldmatrix_x4(ah, a_hi + i * 32);
+          ldmatrix_x4(al, a_lo + i * 32);
+          split_half2(*reinterpret_cast<const float2*>(xrow0 + i * 16), bh[0], bl[0]);
+          split_half2(*reinterpret_cast<const float2*>(xrow0 + i * 16 + 8), bh[1], bl[1]);
+          mma_f16(acc[0][0], ah, bh);
+          mma_f16(acc[0][1], al, bh);
+          mma_f16(acc[0][2], ah, bl);
+          if (two) {
+            split_half2(*reinterpret_cast<const float2*>(xrow1 + i * 16), bh[0], bl[0]);
+            split_half2(*reinterpret_cast<const float2*>(xrow1 + i * 16 + 8), bh[1], bl[1]);
+            mma_f16(acc[1][0], ah, bh);
+            mma_f16(acc[1][1], al, bh);
+            mma_f16(acc[1][2], ah, bl);
+          }
+        }
       }
-      const float total = warp_reduce16(acc, lane);
-      if ((lane & 1) == 0) sm.part[buf][job][lane >> 1] = total;   // value index (row*4 + utterance) = lane>>1
+      // accumulator layout: rows lane >> 2 and + 8, columns 2 * (lane & 3) + {0, 1} of the n-tile
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        if (nt == 0 || two) {
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = acc[nt][0][j] + (acc[nt][1][j] + acc[nt][2][j]);
+          *reinterpret_cast<float2*>(&sm.part[warp][lane >> 2][nt * 8 + 2 * (lane & 3)]) = make_float2(v[0], v[1]);
+          *reinterpret_cast<float2*>(&sm.part[warp][(lane >> 2) + 8][nt * 8 + 2 * (lane & 3)]) = make_float2(v[2], v[3]);
+        }
+      }
+    }
+    __syncthreads();
+    // the staging buffers are free again: fetch the next pass behind the reduction and the epilogue
+    if (n0 + PASS < B) stage_pass(sm, segs, n0 + PASS, B, ~0u);
+    if (tid < 16 * PASS) {
+      const int r = tid >> 4, c = tid & 15;
+      if (c < nb) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < DEC_WARPS; ++w) a += sm.part[w][r][c];
+        sm.sums[r][c] = a * (1.0f / W_SCALE);
+      }
     }
     __syncthreads();
     prof.sub<12>(tp);
-    epi(buf, n0, nb, n_tiles, kparts);
+    epi(n0, nb);
     prof.sub<13>(tp);
   }
 }
 
-// sum over the K parts of value (row r, utterance n of the chunk) of row tile rt
-__device__ __forceinline__ float part_sum(const MatSmem& sm, int buf, int n_rt, int n_tiles, int kparts, int rt, int r,
-                                          int n) {
-  const int tile = (n >> 2) * n_rt + rt;
-  float a = 0.f;
-#pragma unroll
-  for (int kp = 0; kp < KPARTS; ++kp) a += sm.part[buf][kp * n_tiles + tile][r * 4 + (n & 3)];
-  return a;
-}
-
 // One LSTMCell (model.py:400-402 / 425-428) for the units [u0, u0+nu) of this CTA and all B utterances.
-__device__ __forceinline__ void lstm_phase(MatSmem& sm, Prof& prof, const float (*w_s)[KIN], const float* bias_s,
-                                           const Seg (&segs)[3], float* h_next, float* c, int B, int u0, int nu) {
+__device__ __forceinline__ void lstm_phase(MatSmem& sm, Prof& prof, const __half (*w_s)[MAXU * 4][KS_LSTM],
+                                           const float* bias_s, const Seg (&segs)[3], unsigned int early,
+                                           float* h_next, float* c, int B, int u0, int nu) {
   const int tid = threadIdx.x;
   float c_old = 0.f;
   matvec_phase(
-      sm, prof, segs, KIN / 4, nu, B, [&](int rt, int g) { return &w_s[g * nu + rt][0]; },
+      sm, prof, segs, early, &w_s[0][0][0], &w_s[1][0][0], KS_LSTM, 4 * nu, KIN / 16, B,
       [&](int n0, int nb) {
         if (tid < nu * nb) c_old = c[(n0 + tid / nu) * R + u0 + tid % nu];   // only this thread ever touches it
       },
-      [&](int buf, int n0, int nb, int n_tiles, int kparts) {
+      [&](int n0, int nb) {
         if (tid < nu * nb) {                        // cell update: one thread per (unit, utterance)
           const int u = tid % nu, n = tid / nu, j = u0 + u, b = n0 + n;
           float gv[4];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) gv[g] = bias_s[g * nu + u] + part_sum(sm, buf, nu, n_tiles, kparts, u, g, n);
+          for (int g = 0; g < 4; ++g) gv[g] = bias_s[g * nu + u] + sm.sums[g * nu + u][n];
           const float cn = sigmoidf_fast(gv[1]) * c_old + sigmoidf_fast(gv[0]) * tanhf_fast(gv[2]);
           c[b * R + j] = cn;
           h_next[b * R + j] = sigmoidf_fast(gv[3]) * tanhf_fast(cn);
@@ -334,22 +364,30 @@ __device__ void matrix_role(const DecParams& p, MatSmem& sm, int mi, int GM) {
   row_range(mi, GM, NPP, pp0, npp);
   row_range(mi, GM, R, p20, np2);
 
-  // ---- resident weights: this CTA's rows of every matrix of the step
-  for (int i = tid; i < nu * 4 * KIN; i += DEC_THREADS) {
-    const int q = i / KIN, k = i - q * KIN;
+  // ---- resident weights: this CTA's rows of every matrix of the step, as half hi/lo pairs; zero K padding
+  for (int i = tid; i < nu * 4 * KS_LSTM; i += DEC_THREADS) {
+    const int q = i / KS_LSTM, k = i - q * KS_LSTM;
     const int g = q / nu, u = q - g * nu;
-    sm.w_att[q][k] = __ldg(p.w.w_att + (long long)(g * R + u0 + u) * KIN + k);
-    sm.w_dec[q][k] = __ldg(p.w.w_dec + (long long)(g * R + u0 + u) * KIN + k);
+    const long long src = (long long)(g * R + u0 + u) * KIN + k;
+    put_weight(&sm.w_att[0][q][k], &sm.w_att[1][q][k], k < KIN ? __ldg(p.w.w_att + src) : 0.f);
+    put_weight(&sm.w_dec[0][q][k], &sm.w_dec[1][q][k], k < KIN ? __ldg(p.w.w_dec + src) : 0.f);
   }
   for (int i = tid; i < nu * 4; i += DEC_THREADS) {
     const int g = i / nu, u = i - g * nu;
     sm.b_att[i] = __ldg(p.w.b_att + g * R + u0 + u);
     sm.b_dec[i] = __ldg(p.w.b_dec + g * R + u0 + u);
   }
-  for (int i = tid; i < npp * KHC; i += DEC_THREADS)
-    sm.w_pp[i / KHC][i % KHC] = __ldg(p.w.w_pp + (long long)pp0 * KHC + i);
+  for (int i = tid; i < npp * KS_PP; i += DEC_THREADS) {
+    const int q = i / KS_PP, k = i - q * KS_PP;
+    put_weight(&sm.w_pp[0][q][k], &sm.w_pp[1][q][k], k < KHC ? __ldg(p.w.w_pp + (long long)(pp0 + q) * KHC + k) : 0.f);
+  }
   for (int i = tid; i < npp; i += DEC_THREADS) sm.b_pp[i] = __ldg(p.w.b_pp + pp0 + i);
-  for (int i = tid; i < np2 * R; i += DEC_THREADS) sm.w_p2[i / R][i % R] = __ldg(p.w.w_pre2 + (long long)p20 * R + i);
+  for (int i = tid; i < np2 * KS_P2; i += DEC_THREADS) {
+    const int q = i / KS_P2, k = i - q * KS_P2;
+    put_weight(&sm.w_p2[0][q][k], &sm.w_p2[1][q][k], k < R ? __ldg(p.w.w_pre2 + (long long)(p20 + q) * R + k) : 0.f);
+  }
+  // the K padding of the staged inputs must hold finite values (it meets zero weights)
+  for (int i = tid; i < 2 * CHUNK * XS; i += DEC_THREADS) (&sm.in[0][0][0])[i] = 0.f;
   __syncthreads();
 
   unsigned int* bar_all = reinterpret_cast<unsigned int*>(p.s.done + 3);
@@ -363,33 +401,35 @@ __device__ void matrix_role(const DecParams& p, MatSmem& sm, int mi, int GM) {
     float* h_att_nxt = p.s.h_att + (cur ^ 1) * p.B * R;
     float* h_dec_cur = p.s.h_dec + cur * p.B * R;
     float* h_dec_nxt = p.s.h_dec + (cur ^ 1) * p.B * R;
-    // (1) attention_rnn (model.py:400-402): input [prenet | context], hidden h_att
+    // (1) attention_rnn (model.py:400-402): input [prenet | context], hidden h_att.  The context and the
+    //     hidden state were requested before the barrier that ended the previous step (see below).
     {
       const Seg segs[3] = {{p.s.pre, R, R}, {p.s.ctx, E, E}, {h_att_cur, R, R}};
-      lstm_phase(sm, prof, sm.w_att, sm.b_att, segs, h_att_nxt, p.s.c_att, p.B, u0, nu);
+      lstm_phase(sm, prof, sm.w_att, sm.b_att, segs, t > 0 ? 6u : 0u, h_att_nxt, p.s.c_att, p.B, u0, nu);
     }
     prof.mark<0>();
     grid_barrier(bar_all, target_all, G);      // h_att(t) complete -> attention CTAs
     prof.mark<1>();
-    // (2) attention CTAs at work
+    // (2) attention CTAs at work; meanwhile fetch the two decoder_rnn inputs that are already complete
+    const Seg segs_dec[3] = {{h_att_nxt, R, R}, {p.s.ctx, E, E}, {h_dec_cur, R, R}};
+    matvec_prefetch(sm, segs_dec, p.B, 5u);
     grid_barrier(bar_all, target_all, G);      // context(t) complete
     prof.mark<3>();
     // (3) decoder_rnn (model.py:425-428): input [h_att | context], hidden h_dec
-    {
-      const Seg segs[3] = {{h_att_nxt, R, R}, {p.s.ctx, E, E}, {h_dec_cur, R, R}};
-      lstm_phase(sm, prof, sm.w_dec, sm.b_dec, segs, h_dec_nxt, p.s.c_dec, p.B, u0, nu);
-    }
+    lstm_phase(sm, prof, sm.w_dec, sm.b_dec, segs_dec, 5u, h_dec_nxt, p.s.c_dec, p.B, u0, nu);
+    const Seg segs_pp[2] = {{h_dec_nxt, R, R}, {p.s.ctx, E, E}};
+    matvec_prefetch(sm, segs_pp, p.B, 2u);     // the context, ahead of the barrier
     prof.mark<4>();
     grid_barrier(bar_mat, target_mat, GM);
     prof.mark<5>();
     // (4) [linear_projection | gate_layer | prenet layer 0 o projection] on hc = [h_dec | context]
     //     (model.py:436-441, 507, 132-135)
     {
-      const Seg segs[2] = {{h_dec_nxt, R, R}, {p.s.ctx, E, E}};
+      const Seg (&segs)[2] = segs_pp;
       const bool more = t + 1 < p.max_steps;
       unsigned char drop0 = 0;
       matvec_phase(
-          sm, prof, segs, KHC / 4, 1, p.B, [&](int, int r) { return &sm.w_pp[min(r, npp - 1)][0]; },
+          sm, prof, segs, 2u, &sm.w_pp[0][0][0], &sm.w_pp[1][0][0], KS_PP, npp, KP_PP / 16, p.B,
           [&](int n0, int nb) {     // the dropout mask byte comes from DRAM: ask for it before the arithmetic
             if (tid < npp * nb) {
               const int row = pp0 + tid % npp;
@@ -397,10 +437,10 @@ __device__ void matrix_role(const DecParams& p, MatSmem& sm, int mi, int GM) {
                 drop0 = p.drop[(((long long)(t + 1) * 2 + 0) * p.B + n0 + tid / npp) * R + row - M - 1];
             }
           },
-          [&](int buf, int n0, int nb, int n_tiles, int kparts) {
+          [&](int n0, int nb) {
             if (tid < npp * nb) {
               const int r = tid % npp, n = tid / npp, row = pp0 + r, b = n0 + n;
-              const float v = sm.b_pp[r] + part_sum(sm, buf, 1, n_tiles, kparts, 0, r, n);
+              const float v = sm.b_pp[r] + sm.sums[r][n];
               if (row < M) {
                 p.mel[((long long)b * p.max_steps + t) * M + row] = v;
               } else if (row == M) {
@@ -433,25 +473,32 @@ __device__ void matrix_role(const DecParams& p, MatSmem& sm, int mi, int GM) {
       const Seg segs[1] = {{p.s.p1, R, R}};
       unsigned char drop1 = 0;
       matvec_phase(
-          sm, prof, segs, R / 4, 1, p.B, [&](int, int r) { return &sm.w_p2[min(r, np2 - 1)][0]; },
+          sm, prof, segs, 0u, &sm.w_p2[0][0][0], &sm.w_p2[1][0][0], KS_P2, np2, KP_P2 / 16, p.B,
           [&](int n0, int nb) {
             if (tid < np2 * nb)
               drop1 = p.drop[(((long long)(t + 1) * 2 + 1) * p.B + n0 + tid / np2) * R + p20 + tid % np2];
           },
-          [&](int buf, int n0, int nb, int n_tiles, int kparts) {
+          [&](int n0, int nb) {
             if (tid < np2 * nb) {
               const int r = tid % np2, n = tid / np2;
-              const float v = part_sum(sm, buf, 1, n_tiles, kparts, 0, r, n);
+              const float v = sm.sums[r][n];
               p.s.pre[(n0 + n) * R + p20 + r] = fmaxf(v, 0.f) * (2.0f * (float)drop1);
             }
           });
     }
     prof.mark<8>();
+    {
+      // the next attention_rnn's context and hidden state are complete: request them ahead of the barrier
+      // (a group left in flight by the last step is drained by the exit of the kernel)
+      const Seg segs[3] = {{p.s.pre, R, R}, {p.s.ctx, E, E}, {h_att_nxt, R, R}};
+      matvec_prefetch(sm, segs, p.B, 6u);
+    }
     grid_barrier(bar_all, target_all, G);
     prof.mark<9>();
     cur ^= 1;
     if (sm.n_done >= p.B) break;     // every utterance has fired its stop gate (or hit max_steps)
   }
+  cp_async_wait<0>();                // the last prefetch
   prof.flush(p.prof);
 }
 
