@@ -268,7 +268,7 @@ class Tacotron2(nn.Module):
                              torch.empty(B, T, A, device=dev), batch=B, rows=T)
         z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)  # noqa: E731
         st = {"h_att": z(2, B, R), "c_att": z(B, R), "h_dec": z(2, B, R), "c_dec": z(B, R), "ctx": z(B, E),
-              "pre": z(B, hp["prenet_dim"]), "p1": z(B, hp["prenet_dim"]), "pq": z(B, A), "w_prev": z(B, T),
+              "pre": z(B, hp["prenet_dim"]), "p1": z(B, hp["prenet_dim"]), "h_tag": z(B, R, 2), "w_prev": z(B, T),
               "w_cum": z(B, T),
               "done": torch.zeros(8, dtype=torch.int32, device=dev),
               "out_len": torch.zeros(B, dtype=torch.int32, device=dev)}

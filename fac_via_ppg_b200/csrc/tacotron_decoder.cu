@@ -89,6 +89,7 @@ struct AttSmem {                  // attention CTAs
   float S[MAXW][A];               // exp(2 (location_dense(location_conv(.)) + processed_memory)) of the coming window
   float v2[A + 2];                // -2 v
   float upq[A + 2];               // exp(2 W_q h_att)
+  alignas(16) float h[R];         // attention_hidden of this step
   float e[MAXW];
   float wts[DEC_WARPS][MAXW];     // softmax weights, one copy per warp
   float cat[2][MAXW + KF - 1 + 2];
@@ -322,7 +323,8 @@ __device__ __forceinline__ void matvec_phase(MatSmem& sm, Prof& prof, const Seg 
 // One LSTMCell (model.py:400-402 / 425-428) for the units [u0, u0+nu) of this CTA and all B utterances.
 __device__ __forceinline__ void lstm_phase(MatSmem& sm, Prof& prof, const __half (*w_s)[MAXU * 4][KS_LSTM],
                                            const float* bias_s, const Seg (&segs)[3], unsigned int early,
-                                           float* h_next, float* c, int B, int u0, int nu) {
+                                           float* h_next, float* c, int B, int u0, int nu,
+                                           unsigned long long* h_tag = nullptr, unsigned int tag = 0) {
   const int tid = threadIdx.x;
   float c_old = 0.f;
   matvec_phase(
@@ -338,7 +340,11 @@ __device__ __forceinline__ void lstm_phase(MatSmem& sm, Prof& prof, const __half
           for (int g = 0; g < 4; ++g) gv[g] = bias_s[g * nu + u] + sm.sums[g * nu + u][n];
           const float cn = sigmoidf_fast(gv[1]) * c_old + sigmoidf_fast(gv[0]) * tanhf_fast(gv[2]);
           c[b * R + j] = cn;
-          h_next[b * R + j] = sigmoidf_fast(gv[3]) * tanhf_fast(cn);
+          const float h = sigmoidf_fast(gv[3]) * tanhf_fast(cn);
+          h_next[b * R + j] = h;
+          if (h_tag != nullptr)      // (value, tag) in ONE 8-byte store: whoever reads the tag has the value
+            *reinterpret_cast<volatile unsigned long long*>(h_tag + b * R + j) =
+                ((unsigned long long)tag << 32) | __float_as_uint(h);
         }
       });
 }
@@ -405,10 +411,13 @@ __device__ void matrix_role(const DecParams& p, MatSmem& sm, int mi, int GM) {
     //     hidden state were requested before the barrier that ended the previous step (see below).
     {
       const Seg segs[3] = {{p.s.pre, R, R}, {p.s.ctx, E, E}, {h_att_cur, R, R}};
-      lstm_phase(sm, prof, sm.w_att, sm.b_att, segs, t > 0 ? 6u : 0u, h_att_nxt, p.s.c_att, p.B, u0, nu);
+      lstm_phase(sm, prof, sm.w_att, sm.b_att, segs, t > 0 ? 6u : 0u, h_att_nxt, p.s.c_att, p.B, u0, nu,
+                 reinterpret_cast<unsigned long long*>(p.s.h_tag), (unsigned int)(t + 1));
     }
     prof.mark<0>();
-    grid_barrier(bar_all, target_all, G);      // h_att(t) complete -> attention CTAs
+    // the attention CTAs pick h_att(t) up from the tagged copy without a barrier; this one (matrix CTAs only,
+    // hidden behind the attention) orders the plain copy for the prefetch below
+    grid_barrier(bar_mat, target_mat, GM);
     prof.mark<1>();
     // (2) attention CTAs at work; meanwhile fetch the two decoder_rnn inputs that are already complete
     const Seg segs_dec[3] = {{h_att_nxt, R, R}, {p.s.ctx, E, E}, {h_dec_cur, R, R}};
@@ -605,13 +614,23 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
     __syncthreads();
   };
 
-  auto critical = [&](int t, const float* h_att) {
+  auto critical = [&](int t) {
     long long tp = prof.now();
     // query projection (model.py:92): pq = W_q h_att; warp per row, 75 float4 per row over the lanes
     {
-      const float4* h4 = reinterpret_cast<const float4*>(h_att + b * R);
+      // h_att(t): spin on the (value, tag) pairs the matrix CTAs publish -- one-way latency, no barrier
+      if (tid < R) {
+        const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(p.s.h_tag) + b * R + tid;
+        unsigned long long v;
+        do {
+          v = *src;
+        } while ((unsigned int)(v >> 32) != (unsigned int)(t + 1));
+        sm.h[tid] = __uint_as_float((unsigned int)v);
+      }
+      __syncthreads();
+      const float4* h4 = reinterpret_cast<const float4*>(sm.h);
       const float4 hz = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 hv0 = __ldcg(h4 + lane), hv1 = __ldcg(h4 + lane + 32), hv2 = lane < 11 ? __ldcg(h4 + lane + 64) : hz;
+      const float4 hv0 = h4[lane], hv1 = h4[lane + 32], hv2 = lane < 11 ? h4[lane + 64] : hz;
 #pragma unroll 2
       for (int r = warp; r < A; r += DEC_WARPS) {
         const float4* w4 = reinterpret_cast<const float4*>(&sm.wq[r][0]);
@@ -698,11 +717,8 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
   int cur = 0;
   prepare(0);
   for (int t = 0; t < p.max_steps; ++t) {
-    const float* h_att_nxt = p.s.h_att + (cur ^ 1) * p.B * R;
     prof.mark<0>();
-    grid_barrier(bar_all, target_all, G);      // h_att(t) complete
-    prof.mark<1>();
-    critical(t, h_att_nxt);
+    critical(t);
     prof.mark<2>();
     grid_barrier(bar_all, target_all, G);      // context(t) complete -> matrix CTAs
     prof.mark<3>();

@@ -262,7 +262,8 @@ typedef struct fac_taco_decoder_state {
   float* ctx;     /* [B][600]    attention_context                           */
   float* pre;     /* [B][300]    prenet output feeding the next step         */
   float* p1;      /* [B][300]    prenet layer-0 output (scratch)             */
-  float* pq;      /* [B][150]    processed query (scratch)                   */
+  float* h_tag;   /* [B][300][2] attention_hidden of the current step as (value, step tag) 8-byte pairs: the
+                     matrix CTAs publish it, the utterance's attention CTA polls it (no barrier in between) */
   float* w_prev;  /* [B][T_in]   attention_weights                           */
   float* w_cum;   /* [B][T_in]   attention_weights_cum                       */
   int* done;      /* [8]: #utterances stopped by the gate, #stopped by max_steps, steps run, two grid-barrier
