@@ -36,3 +36,5 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_ext.WgWorkspace) == 4 * 8
     assert C.sizeof(_ext.WgFlow) == 8 + 5 * 8 + 4 * 16 * 8
     assert C.sizeof(_ext.WgModel) == 10 * 4 + 2 * 8 + 16 * C.sizeof(_ext.WgFlow)
+    assert C.sizeof(_ext.TcConv) == 10 * 8 + 3 * 8 + 12 * 4 + 8
+    assert C.sizeof(_ext.TacoDecoderState) == 12 * 8

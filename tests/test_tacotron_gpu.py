@@ -70,6 +70,42 @@ def test_inference_matches_oracle_batched_forced_length(model, batch, t_in):
         assert (a.cpu() - b).abs().max().item() <= MEL_TOL, name
 
 
+def test_exact_fp32_precision_mode_matches_oracle(model):
+    """precision='fp32' keeps the encoder / postnet GEMMs on the exact FFMA implicit-GEMM path."""
+    batch, t_in = 2, 40
+    force_length(model, t_in)
+    sd = synth.tacotron_state()
+    ppg = synth.synthetic_ppg(batch, t_in, seed=21)
+    torch.manual_seed(21)
+    masks = tacotron_oracle.record_dropout_tape(batch, t_in, t_in)
+    ref = tacotron_oracle.tacotron_inference(sd, synth.TACOTRON_HPARAMS, ppg, masks, 2.0, t_in)
+    model.set_precision("fp32")
+    try:
+        out = model.inference(ppg.to(DEV), dropout_tape=masks)
+    finally:
+        model.set_precision("fp16x3")
+    for name, a, b in zip(("mel", "mel_post", "gate", "align"), out, ref):
+        assert (a.cpu() - b).abs().max().item() <= MEL_TOL, name
+    with pytest.raises(ValueError):
+        model.set_precision("int8")
+
+
+def test_batches_beyond_one_launch_are_split_into_groups(model):
+    """One decoder launch holds (SMs - 100) utterances; a larger batch runs as consecutive groups and every
+    utterance still equals the same utterance processed alone, bit for bit."""
+    batch, t_in = 50, 14
+    force_length(model, t_in)
+    ppg = synth.synthetic_ppg(batch, t_in, seed=4).to(DEV)
+    torch.manual_seed(4)
+    masks = tacotron_oracle.record_dropout_tape(batch, t_in, t_in)
+    out = model.inference(ppg, dropout_tape=masks)
+    assert out[1].shape == (batch, 80, t_in) and out[3].shape == (batch, t_in, t_in)
+    for k in (0, 31, 32, 49):
+        alone = model.inference(ppg[k:k + 1].contiguous(), dropout_tape=[m[k:k + 1] for m in masks])
+        assert torch.equal(out[1][k], alone[1][0]), k
+        assert torch.equal(out[3][k], alone[3][0]), k
+
+
 def test_gate_stops_decoding_like_reference(model):
     """Natural stop: the reference (B == 1) breaks after the first frame whose sigmoid(gate) > threshold."""
     sd = synth.tacotron_state()
