@@ -108,7 +108,8 @@ def build_waveglow(device, precision):
 
 def measure_ppg2mel(dev, batch=8, frames=690):
     """Side metric of BASELINE.json ('mel frames/sec'): Tacotron2.inference on synthetic PPGs
-    (batch x 5816 x frames, forced decode length), exact fp32 CUDA path, CUDA-event phase times."""
+    (batch x 5816 x frames, forced decode length), fp32-grade CUDA path (split-fp16 tensor-core GEMMs with
+    fp32 accumulation, fp32 recurrences), CUDA-event phase times."""
     from fac_via_ppg_b200.common.hparams import create_hparams_stage
     from fac_via_ppg_b200.common.model import Tacotron2
     model = Tacotron2(create_hparams_stage())
@@ -127,10 +128,58 @@ def measure_ppg2mel(dev, batch=8, frames=690):
         best = dt if best is None else min(best, dt)
     tm = model.last_timing
     return {"metric": "mel frames/sec (Tacotron2.inference PPG->Mel)", "value": batch * frames / best,
-            "unit": "frames/s", "batch": batch, "frames": frames, "dtype": "f32",
+            "unit": "frames/s", "batch": batch, "frames": frames,
+            "dtype": "f32 results; GEMM operands split into fp16 hi/lo pairs (3 tensor-core products each)",
             "decoder_us_per_step": tm["decoder_ms"] * 1e3 / frames, "encoder_ms": tm["encoder_ms"],
             "decoder_ms": tm["decoder_ms"], "postnet_ms": tm["postnet_ms"],
             "hbm_compulsory_gbs": batch * frames * 5816 * 4 / best / 1e9}
+
+
+def measure_pipeline(dev, wg, batch=32, seconds=5.0):
+    """Side metric: BASELINE.json configs[2], the full PPG -> Mel -> WaveGlow pipeline of generate_synthesis.py on
+    32 x 5 s with the bf16 vocoder.  Resident = PPG already in HBM; e2e = pinned host PPG in, host waveform out."""
+    from fac_via_ppg_b200.common.hparams import create_hparams_stage
+    from fac_via_ppg_b200.common.model import Tacotron2
+    taco = Tacotron2(create_hparams_stage())
+    taco.load_state_dict(synth.tacotron_state())
+    taco = taco.to(dev).eval()
+    frames = synth.frames_for_seconds(seconds)
+    taco.decoder.gate_threshold, taco.decoder.max_decoder_steps, taco.return_alignments = 2.0, frames, False
+    old = wg.precision
+    wg.set_precision("bf16")
+    ppg_host = synth.synthetic_ppg(batch, frames).pin_memory()
+    ppg = ppg_host.to(dev)
+    out_host = torch.empty(batch, frames * 160).pin_memory()
+
+    def run(host):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x = ppg_host.to(dev, non_blocking=True) if host else ppg
+        mel = taco.inference(x)[1]
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        wav = wg.infer(mel.clamp(-11.5, 2.0).contiguous(), 0.6)
+        if host:
+            out_host.copy_(wav, non_blocking=True)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, t1 - t0
+
+    try:
+        import contextlib
+        import io
+        with contextlib.redirect_stderr(io.StringIO()):      # "Reached max decoder steps" (forced length)
+            run(False)
+            res = min(run(False) for _ in range(3))
+            e2e = min(run(True) for _ in range(3))
+    finally:
+        wg.set_precision(old)
+    n = batch * frames * 160
+    return {"workload": "PPG->Mel->WaveGlow, batch=%dx%.0f s, bf16 vocoder, fp32-grade acoustic model (BASELINE configs[2])"
+                        % (batch, seconds),
+            "value": n / res[0], "unit": "samples/s", "rtf": n / res[0] / RATE, "ms": res[0] * 1e3,
+            "ppg2mel_ms": res[1] * 1e3, "mel2wav_ms": (res[0] - res[1]) * 1e3,
+            "e2e": {"value": n / e2e[0], "unit": "samples/s", "ms": e2e[0] * 1e3,
+                    "h2d_bytes_per_step": ppg_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4}}
 
 
 def cpu_port_samples_per_s(frames, repeats, threads):
@@ -304,9 +353,10 @@ def main():
         roof["traffic_source"] = t["source"]
 
     # ---- PPG -> Mel side metric (mel frames/s), short and outside the timed region ----------
-    ppg2mel = None
+    ppg2mel = pipeline = None
     if world == 1 and not args.no_ppg2mel:
         ppg2mel = measure_ppg2mel(dev)
+        pipeline = measure_pipeline(dev, model)
 
     # ---- CPU baseline (bounded sample of the same workload, rank 0 only) ----------------
     cpu = None
@@ -334,6 +384,7 @@ def main():
         "roofline": roof,
         "cpu_baseline": cpu,
         "ppg2mel": ppg2mel,
+        "pipeline": pipeline,
         "tflops_algorithmic": value * WG_FLOP_PER_SAMPLE / 1e12,
         "hbm": {"compulsory_bytes_per_sample": WG_HBM_BYTES_PER_SAMPLE,
                 "achieved_gbs": value * WG_HBM_BYTES_PER_SAMPLE / 1e9 / world,

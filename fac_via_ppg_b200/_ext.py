@@ -114,6 +114,7 @@ SIGNATURES = {
     "fac_tc_set_profile_buffer": (None, [_fp]),
     "fac_taco_set_profile_buffer": (None, [_fp]),
     "fac_tc_set_cta_group": (C.c_int, [C.c_int]),
+    "fac_tc_set_batch_group": (C.c_int, [C.c_int]),
     "fac_tc_set_k_block": (C.c_int, [C.c_int]),
     "fac_selftest_grid_barrier": (C.c_int, [_fp, C.c_int, _fp]),
     "fac_denoise_spectrum_f32": (C.c_int, [_fp, _fp, C.c_float, C.c_longlong, C.c_int, C.c_int, _fp]),
@@ -150,6 +151,8 @@ def load(build_if_missing: bool = True):
         fn.argtypes = args
     _lib = lib
     cta_group, k_block = os.environ.get("FAC_TC_CTA_GROUP"), os.environ.get("FAC_TC_K_BLOCK")
+    if os.environ.get("FAC_TC_BATCH_GROUP"):
+        check(lib.fac_tc_set_batch_group(int(os.environ["FAC_TC_BATCH_GROUP"])), "fac_tc_set_batch_group")
     if cta_group:
         check(lib.fac_tc_set_cta_group(int(cta_group)), "fac_tc_set_cta_group")
     if k_block:

@@ -32,6 +32,7 @@ int wg_tc_layer(const fac_wg_model*, const fac_wg_tc_weights*, int, int, const f
 int wg_infer_tc(const fac_wg_model*, const fac_wg_tc_weights*, const float*, float*, const fac_wg_tc_workspace*, int,
                 int, int, cudaStream_t);
 int wg_tc_end(const fac_wg_model*, const fac_wg_tc_weights*, int, const float*, float*, int, int, cudaStream_t);
+int tc_set_batch_group(int);
 void tc_set_prof(long long*);
 void taco_set_prof(long long*);
 int conv_gemm_tc(const fac_tc_conv*, cudaStream_t);
@@ -109,6 +110,7 @@ int fac_pad_split_16(const float* in, void* hi, void* lo, long long n_rows, int 
   return fac::tc_pad_split(in, hi, lo, n_rows, C, pad, fp16, (cudaStream_t)stream);
 }
 void fac_taco_set_profile_buffer(long long* device_buf) { fac::taco_set_prof(device_buf); }
+int fac_tc_set_batch_group(int utterances) { return fac::tc_set_batch_group(utterances); }
 int fac_tc_set_cta_group(int cta_group) { return fac::tc_set_cta_group(cta_group); }
 int fac_tc_set_k_block(int k_block) { return fac::tc_set_k_block(k_block); }
 int fac_selftest_grid_barrier(unsigned int* zeroed_counter, int iters, void* stream) {

@@ -602,6 +602,7 @@ int make_act_map(CUtensorMap* m, const void* ptr, int B, int T, int C, int bk) {
   FAC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", B, T, C, (int)r);
   return 0;
 }
+int g_tc_batch_group = 0; // utterances per pass of fac_waveglow_infer_tc over a flow; 0 = the whole batch
 int g_tc_cta_group = 0;   // 0 = automatic: CTA pairs for the split-bf16 mode, single CTAs for plain bf16
 
 // Measured on B200 (profiles/README.md): pairs win 9 % in split-bf16 (operand traffic and shared-memory reads
@@ -824,6 +825,11 @@ int tc_set_k_block(int bk) {
   g_tc_bk = bk;
   return 0;
 }
+int tc_set_batch_group(int n) {
+  FAC_REQUIRE(n >= 0, "batch group must be >= 0 (got %d)", n);
+  g_tc_batch_group = n;
+  return 0;
+}
 int tc_set_cta_group(int cg) {
   FAC_REQUIRE(cg >= 0 && cg <= 2, "cta group must be 0 (auto), 1 or 2 (got %d)", cg);
   g_tc_cta_group = cg;
@@ -996,11 +1002,32 @@ int wg_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* 
   FAC_REQUIRE(mel_cl && audio, "waveglow_infer_tc: NULL argument");
   const int Tg = F * (m->hop / m->n_group);
   if (int rc = wg_tc_prepare_spect(m, w, ws, mel_cl, B, F, nsplit, st)) return rc;
+  // Utterances are independent, so a flow can run group by group: with a group whose residual stream and
+  // gated activations (2 KB per column in split mode) fit the L2, the second GEMM of a layer and the next
+  // layer's first GEMM find them there instead of in HBM.
+  const int group = g_tc_batch_group > 0 ? (g_tc_batch_group < B ? g_tc_batch_group : B) : B;
+  const int C = m->n_channels, n_cond = m->n_mel * m->n_group;
   for (int k = m->n_flows - 1; k >= 0; --k) {
-    if (int rc = wg_tc_start(m, k, audio, ws, B, Tg, nsplit, st)) return rc;
-    for (int i = 0; i < m->n_layers; ++i)
-      if (int rc = wg_tc_layer(m, w, k, i, ws, B, Tg, nsplit, st)) return rc;
-    if (int rc = wg_tc_end(m, w, k, ws->out8, audio, B, Tg, st)) return rc;
+    for (int b0 = 0; b0 < B; b0 += group) {
+      const int nb = b0 + group <= B ? group : B - b0;
+      const long long col0 = (long long)b0 * Tg;
+      fac_wg_tc_workspace g = *ws;
+      auto shift = [&](void* base, long long elems) -> void* {
+        return base ? static_cast<void*>(static_cast<__nv_bfloat16*>(base) + elems) : nullptr;
+      };
+      g.spect_hi = shift(ws->spect_hi, col0 * n_cond);
+      g.spect_lo = shift(ws->spect_lo, col0 * n_cond);
+      g.x_hi = shift(ws->x_hi, col0 * C);
+      g.x_lo = shift(ws->x_lo, col0 * C);
+      g.acts_hi = shift(ws->acts_hi, col0 * C);
+      g.acts_lo = shift(ws->acts_lo, col0 * C);
+      g.out8 = ws->out8 + col0 * TC_NOUT;
+      float* audio_g = audio + col0 * m->n_group;
+      if (int rc = wg_tc_start(m, k, audio_g, &g, nb, Tg, nsplit, st)) return rc;
+      for (int i = 0; i < m->n_layers; ++i)
+        if (int rc = wg_tc_layer(m, w, k, i, &g, nb, Tg, nsplit, st)) return rc;
+      if (int rc = wg_tc_end(m, w, k, g.out8, audio_g, nb, Tg, st)) return rc;
+    }
   }
   return 0;
 }

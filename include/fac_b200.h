@@ -186,6 +186,10 @@ void fac_tc_set_profile_buffer(long long* device_buf);
 /* 0 (default): automatic; 1: one CTA per 128-column tile; 2: CTA pairs (thread-block cluster of 2,
  * tcgen05 cta_group::2, UMMA M = 256, each CTA stages half of the weight rows). */
 int fac_tc_set_cta_group(int cta_group);
+/* Utterances per pass of fac_waveglow_infer_tc over a flow (they are independent): 0 (default) = the whole
+ * batch; a group whose residual stream and gated activations fit the L2 keeps them out of HBM between the
+ * GEMMs of a layer. */
+int fac_tc_set_batch_group(int utterances);
 /* K elements per TMA/UMMA pipeline stage: 0 (default) automatic, 32 (SWIZZLE_64B rows) or 64 (SWIZZLE_128B rows). */
 int fac_tc_set_k_block(int k_block);
 /* Same contract as fac_waveglow_infer_f32 (glow.py:252-293), WN layers on the tensor cores. */
