@@ -113,6 +113,7 @@ SIGNATURES = {
     "fac_pad_split_16": (C.c_int, [_fp, _fp, _fp, C.c_longlong, C.c_int, C.c_int, C.c_int, _fp]),
     "fac_tc_set_profile_buffer": (None, [_fp]),
     "fac_taco_set_profile_buffer": (None, [_fp]),
+    "fac_lstm_set_profile_buffer": (None, [_fp]),
     "fac_tc_set_cta_group": (C.c_int, [C.c_int]),
     "fac_tc_set_batch_group": (C.c_int, [C.c_int]),
     "fac_tc_set_k_block": (C.c_int, [C.c_int]),

@@ -35,6 +35,7 @@ int wg_tc_end(const fac_wg_model*, const fac_wg_tc_weights*, int, const float*, 
 int tc_set_batch_group(int);
 void tc_set_prof(long long*);
 void taco_set_prof(long long*);
+void lstm_set_prof(long long*);
 int conv_gemm_tc(const fac_tc_conv*, cudaStream_t);
 int tc_transpose_split(const float*, void*, void*, int, int, int, int, int, cudaStream_t);
 int tc_pad_split(const float*, void*, void*, long long, int, int, int, cudaStream_t);
@@ -109,6 +110,7 @@ int fac_transpose_split_16(const float* in, void* hi, void* lo, int B, int C, in
 int fac_pad_split_16(const float* in, void* hi, void* lo, long long n_rows, int C, int pad, int fp16, void* stream) {
   return fac::tc_pad_split(in, hi, lo, n_rows, C, pad, fp16, (cudaStream_t)stream);
 }
+void fac_lstm_set_profile_buffer(long long* device_buf) { fac::lstm_set_prof(device_buf); }
 void fac_taco_set_profile_buffer(long long* device_buf) { fac::taco_set_prof(device_buf); }
 int fac_tc_set_batch_group(int utterances) { return fac::tc_set_batch_group(utterances); }
 int fac_tc_set_cta_group(int cta_group) { return fac::tc_set_cta_group(cta_group); }

@@ -60,7 +60,7 @@ constexpr int LSTM_MAXK4 = 3;   // ceil((H/4) / 32) for H <= 384
 template <int NB>
 __global__ void __cluster_dims__(LSTM_CLUSTER, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
     bilstm_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh, float* __restrict__ out,
-                          int B, int T, int H, int upc) {
+                          int B, int T, int H, int upc, long long* prof) {
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -106,6 +106,14 @@ __global__ void __cluster_dims__(LSTM_CLUSTER, 1, 1) __launch_bounds__(LSTM_THRE
   load_xp(0, xv_cur);
 
   int cur = 0;
+  long long pa[4] = {0, 0, 0, 0}, pt = clock64();
+  auto pmark = [&](int i) {
+    if (prof != nullptr && tid == 0) {
+      const long long now = clock64();
+      pa[i] += now - pt;
+      pt = now;
+    }
+  };
   for (int step = 0; step < T; ++step) {
     load_xp(step + 1, xv_nxt);
     // write h_{t-1} (complete in h_buf[cur] after the previous cluster barrier) to global now: the
@@ -129,6 +137,7 @@ __global__ void __cluster_dims__(LSTM_CLUSTER, 1, 1) __launch_bounds__(LSTM_THRE
         hreg[n][i] = (n < NB && k4 < H4) ? *reinterpret_cast<const float4*>(hcur + n * H + 4 * k4)
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    pmark(0);
 #pragma unroll
     for (int j = 0; j < UPW; ++j) {
       const int u = warp + j * (LSTM_THREADS / 32);
@@ -174,11 +183,15 @@ __global__ void __cluster_dims__(LSTM_CLUSTER, 1, 1) __launch_bounds__(LSTM_THRE
       }
       __syncwarp();
     }
+    pmark(1);
     cluster.sync();  // release/acquire: every CTA sees the complete h_t before step t+1
+    pmark(2);
     cur ^= 1;
 #pragma unroll
     for (int j = 0; j < UPW; ++j) xv_cur[j] = xv_nxt[j];
   }
+  if (prof != nullptr && tid == 0)
+    for (int i = 0; i < 3; ++i) prof[blockIdx.x * 4 + i] = pa[i];
   // the last step's h
   {
     const int tp = dir == 0 ? T - 1 : 0;
@@ -188,6 +201,35 @@ __global__ void __cluster_dims__(LSTM_CLUSTER, 1, 1) __launch_bounds__(LSTM_THRE
         out[((long long)(n0 + n) * T + tp) * (2 * H) + dir * H + u0 + u] = h_buf[cur * 4 * H + n * H + u0 + u];
     }
   }
+}
+
+long long* g_lstm_prof = nullptr;
+
+// Clusters of 8 CTAs (1 CTA per SM) that can be resident at once: the GPC boundaries leave fewer than
+// SMs / 8 (measured on B200: 16 clusters requested -> a second wave, 2x the time).
+template <int NB>
+int max_resident_clusters(size_t smem) {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cudaFuncSetAttribute(bilstm_cluster_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(LSTM_CLUSTER * 32);
+  cfg.blockDim = dim3(LSTM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = LSTM_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, bilstm_cluster_kernel<NB>, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = 1;
+  }
+  cached = n;
+  return n;
 }
 
 template <int NB>
@@ -201,12 +243,15 @@ int launch_bilstm(const float* xp, const float* w_hh, float* out, int B, int T, 
     return 2;
   }
   const int groups = ceil_div(B, NB);
-  bilstm_cluster_kernel<NB><<<2 * groups * LSTM_CLUSTER, LSTM_THREADS, smem, st>>>(xp, w_hh, out, B, T, H, upc);
+  bilstm_cluster_kernel<NB><<<2 * groups * LSTM_CLUSTER, LSTM_THREADS, smem, st>>>(xp, w_hh, out, B, T, H, upc,
+                                                                                   g_lstm_prof);
   count_launch();
   return check_launch("bilstm_cluster_kernel");
 }
 
 }  // namespace
+
+void lstm_set_prof(long long* p) { g_lstm_prof = p; }
 
 int lstm_bidir(const float* xp, const float* w_hh, float* out, int B, int T, int H, cudaStream_t st) {
   FAC_REQUIRE(xp && w_hh && out, "bilstm: NULL argument");
@@ -214,9 +259,10 @@ int lstm_bidir(const float* xp, const float* w_hh, float* out, int B, int T, int
   FAC_REQUIRE(ceil_div(ceil_div(H, LSTM_CLUSTER), LSTM_THREADS / 32) <= 3, "bilstm: hidden size %d needs more than 3 units per warp", H);
   FAC_REQUIRE(H > 0 && H % 4 == 0 && H <= 128 * LSTM_MAXK4, "bilstm: hidden size %d unsupported (multiple of 4, max %d)",
               H, 128 * LSTM_MAXK4);
-  // fill the machine: 18 clusters of 8 CTAs fit 148 SMs; more utterances per cluster beyond that
-  if (2 * B <= 18) return launch_bilstm<1>(xp, w_hh, out, B, T, H, st);
-  if (B <= 18) return launch_bilstm<2>(xp, w_hh, out, B, T, H, st);
+  // one wave: the fewest utterances per cluster whose cluster count is resident at once
+  const size_t smem = (size_t)(4 * ceil_div(H, LSTM_CLUSTER) * H + 2 * 4 * H + 4 * ceil_div(H, LSTM_CLUSTER)) * sizeof(float);
+  if (2 * B <= max_resident_clusters<1>(smem)) return launch_bilstm<1>(xp, w_hh, out, B, T, H, st);
+  if (2 * ceil_div(B, 2) <= max_resident_clusters<2>(smem)) return launch_bilstm<2>(xp, w_hh, out, B, T, H, st);
   return launch_bilstm<4>(xp, w_hh, out, B, T, H, st);
 }
 
