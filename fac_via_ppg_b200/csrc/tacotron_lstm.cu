@@ -1,15 +1,20 @@
 // Encoder BiLSTM recurrence (reference src/common/model.py:211-213, 246-247: nn.LSTM, 1 layer,
 // bidirectional, batch_first) as a thread-block-cluster kernel.
 //
-// The input projection x W_ih^T + b_ih + b_hh of both directions is one fac_conv_gemm_f32 call
-// (xp, (B, T, 2*4H)); this kernel runs the sequential part h_t = f(xp_t + W_hh h_{t-1}).
-// One cluster of 8 CTAs owns one direction and up to NB utterances: W_hh (4H x H fp32 = 1.44 MB
-// for H = 300) is split by hidden unit across the 8 CTAs' shared memory and stays resident for
-// all T steps; each step every CTA computes the 4 gates of its units, updates c/h, and pushes
-// its slice of h into all 8 CTAs' next-step buffer through distributed shared memory, followed
-// by one cluster barrier.  No HBM traffic per step besides reading xp and writing h.
+// The input projection x W_ih^T + b_ih + b_hh of both directions is one GEMM (xp, (B, T, 2*4H)); this
+// kernel runs the sequential part h_t = f(xp_t + W_hh h_{t-1}).  One cluster of 8 CTAs owns one
+// direction and up to 8 utterances: W_hh (4H x H = 1.44 MB fp32 for H = 300) is split by hidden unit
+// across the 8 CTAs' shared memory and stays resident for all T steps as IEEE-half hi/lo pairs
+// (w * 2^8 = hi + lo to ~2^-22).  Each step a CTA computes the 4 gates of its units for the cluster's
+// utterances on the tensor cores (mma.sync m16n8k16, split-fp16: hi*hi + lo*hi + hi*lo, fp32
+// accumulate; warp = (K quarter, group of m-tiles), the quarters meet in shared memory in fp32),
+// updates c (registers) and h, and pushes its slice of h into all 8 CTAs' next-step buffer through
+// distributed shared memory, followed by one cluster barrier.  No HBM traffic per step besides
+// reading xp (prefetched one step ahead) and writing h.
 #include "fac_common.cuh"
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
 
 namespace cg = cooperative_groups;
 
@@ -18,91 +23,118 @@ namespace {
 
 constexpr int LSTM_CLUSTER = 8;
 constexpr int LSTM_THREADS = 512;
+constexpr int LSTM_NB = 8;            // utterance slots per cluster = one mma n-tile
+constexpr int LSTM_KQ = 4;            // K quarters (warp & 3)
+constexpr int LSTM_MG = 4;            // groups of m-tiles (warp >> 2), <= 3 m-tiles each
+constexpr float LSTM_W_SCALE = 256.f;
 
-// Sum 16 per-lane values across the warp with 16 shuffles (halving butterfly): afterwards lane l holds
-// the total of value index (l >> 1) & 15 (lanes l and l^1 agree).
-__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool up = lane & 16;
-    const float send = up ? v[i] : v[i + 8];
-    const float keep = up ? v[i + 8] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool up = lane & 8;
-    const float send = up ? v[i] : v[i + 4];
-    const float keep = up ? v[i + 4] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool up = lane & 4;
-    const float send = up ? v[i] : v[i + 2];
-    const float keep = up ? v[i + 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  {
-    const bool up = lane & 2;
-    const float send = up ? v[0] : v[1];
-    const float keep = up ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_half2(float2 x, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x.x, x.y);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-constexpr int LSTM_MAXK4 = 3;   // ceil((H/4) / 32) for H <= 384
+struct LstmGeom {
+  int upc;        // hidden units per CTA
+  int rows;       // 4 * upc gate rows (unit-major: row = unit * 4 + gate)
+  int m_tiles;    // ceil(rows / 16)
+  int k_steps;    // ceil(H / 16)
+  int ks;         // halfs per weight row  (16 * k_steps + 8: ldmatrix rows hit distinct banks)
+  int hs;         // floats per h row      (16 * k_steps + 8)
+  size_t off_wlo, off_part, off_h, bytes;
+};
+inline LstmGeom lstm_geom(int H) {
+  LstmGeom g;
+  g.upc = ceil_div(H, LSTM_CLUSTER);
+  g.rows = 4 * g.upc;
+  g.m_tiles = ceil_div(g.rows, 16);
+  g.k_steps = ceil_div(H, 16);
+  g.ks = 16 * g.k_steps + 8;
+  g.hs = 16 * g.k_steps + 8;
+  const size_t w_bytes = (size_t)g.rows * g.ks * sizeof(__half);
+  g.off_wlo = w_bytes;
+  g.off_part = 2 * w_bytes;
+  g.off_h = g.off_part + (size_t)LSTM_KQ * g.m_tiles * 16 * LSTM_NB * sizeof(float);
+  g.bytes = g.off_h + (size_t)2 * LSTM_NB * g.hs * sizeof(float);
+  return g;
+}
 
-// NB is 1, 2 or 4 utterances per cluster.  Each warp owns whole hidden units: for a unit it computes the
-// 4 gate rows x NB utterances with h_{t-1} held in registers (loaded once per step), reduces the 16
-// partial sums with a halving butterfly, updates c/h in-warp and pushes h to all 8 CTAs of the cluster.
-template <int NB>
 __global__ void __cluster_dims__(LSTM_CLUSTER, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
     bilstm_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh, float* __restrict__ out,
-                          int B, int T, int H, int upc, long long* prof) {
-  extern __shared__ __align__(16) float smem[];
+                          int B, int T, int H, int nb_per_cluster, const LstmGeom geo, long long* prof) {
+  extern __shared__ __align__(16) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cluster_id = blockIdx.x / LSTM_CLUSTER;
   const int dir = cluster_id & 1;
-  const int n0 = (cluster_id >> 1) * NB;  // first utterance of this cluster
+  const int n0 = (cluster_id >> 1) * nb_per_cluster;   // first utterance of this cluster
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int u0 = rank * upc;
-  const int nu = max(0, min(H, u0 + upc) - u0);  // hidden units owned by this CTA
-  const int H4 = H >> 2;
+  const int upc = geo.upc, u0 = rank * upc;
+  const int nu = max(0, min(H, u0 + upc) - u0);          // hidden units owned by this CTA
+  const int ks = geo.ks, hs = geo.hs;
 
-  float* w_s = smem;                        // [upc][4][H]  unit-major: the 4 gate rows of a unit are adjacent
-  float* h_buf = w_s + 4 * upc * H;         // [2][4][H]    (utterance slots beyond NB stay zero)
-  float* c_s = h_buf + 2 * 4 * H;           // [upc][4]     cell state
+  __half* w_hi = reinterpret_cast<__half*>(smem);
+  __half* w_lo = reinterpret_cast<__half*>(smem + geo.off_wlo);
+  float* part = reinterpret_cast<float*>(smem + geo.off_part);   // [KQ][m_tiles*16][NB]
+  float* h_buf = reinterpret_cast<float*>(smem + geo.off_h);     // [2][NB][hs]
+  const int prow = geo.m_tiles * 16;
 
+  // resident weights: row = unit * 4 + gate, zero K padding and zero rows for units past the end
   const float* w_dir = w_hh + (long long)dir * 4 * H * H;
-  for (int i = tid; i < nu * 4 * H; i += LSTM_THREADS) {
-    const int u = i / (4 * H), rem = i - u * 4 * H;
-    const int g = rem / H, k = rem - g * H;
-    w_s[i] = __ldg(w_dir + (long long)(g * H + u0 + u) * H + k);
+  for (int i = tid; i < geo.rows * ks; i += LSTM_THREADS) {
+    const int r = i / ks, k = i - r * ks;
+    const int u = r >> 2, g = r & 3;
+    float w = 0.f;
+    if (u < nu && k < H) w = __ldg(w_dir + (long long)(g * H + u0 + u) * H + k) * LSTM_W_SCALE;
+    const __half h = __float2half_rn(w);
+    w_hi[i] = h;
+    w_lo[i] = __float2half_rn(w - __half2float(h));
   }
-  for (int i = tid; i < 2 * 4 * H; i += LSTM_THREADS) h_buf[i] = 0.f;
-  for (int i = tid; i < upc * 4; i += LSTM_THREADS) c_s[i] = 0.f;
+  for (int i = tid; i < 2 * LSTM_NB * hs; i += LSTM_THREADS) h_buf[i] = 0.f;
   cluster.sync();
 
+  // ---- warp job: K quarter kq, m-tiles [mt0, mt0 + nmt)
+  const int kq = warp & (LSTM_KQ - 1), mg = warp >> 2;
+  const int kbase = geo.k_steps / LSTM_KQ, kextra = geo.k_steps % LSTM_KQ;
+  const int my_steps = kbase + (kq < kextra ? 1 : 0), k_first = kq * kbase + min(kq, kextra);
+  const int mbase = geo.m_tiles / LSTM_MG, mextra = geo.m_tiles % LSTM_MG;
+  const int nmt = mbase + (mg < mextra ? 1 : 0), mt0 = mg * mbase + min(mg, mextra);
+  // ldmatrix: lane l addresses row (l & 7) + 8 * ((l >> 3) & 1) of the 8 x 8 block at k offset 8 * (l >> 4)
+  uint32_t a_off[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    int r = (mt0 + j) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    if (j >= nmt || r >= geo.rows) r = 0;
+    a_off[j] = (uint32_t)(r * ks + (lane >> 4) * 8 + k_first * 16) * 2;
+  }
+  const uint32_t whi_s = (uint32_t)__cvta_generic_to_shared(w_hi), wlo_s = (uint32_t)__cvta_generic_to_shared(w_lo);
+
+  // ---- epilogue thread = (unit eu, utterance slot en); c lives in a register for the whole sequence
+  const int eu = tid % upc, en = tid / upc;
+  const bool e_act = tid < upc * LSTM_NB && eu < nu && en < nb_per_cluster && n0 + en < B;
   const long long xp_row = 2LL * 4 * H;
-  constexpr int UPW = 3;                         // units per warp: ceil(38 / 16)
-  // lane -> (gate, utterance) of the input projection it fetches; software-pipelined one step ahead so
-  // the global-load latency never sits on the recurrence's critical path
-  const int xn = lane & 3, xg = (lane >> 2) & 3;
-  const bool x_lane = lane < 16 && xn < NB && n0 + xn < B;
-  auto load_xp = [&](int step, float (&dst)[UPW]) {
+  auto load_xp = [&](int step, float (&dst)[4]) {
     const int tt = dir == 0 ? step : T - 1 - step;
 #pragma unroll
-    for (int j = 0; j < UPW; ++j) {
-      const int u = warp + j * (LSTM_THREADS / 32);
-      dst[j] = (x_lane && u < nu && step < T)
-                   ? __ldg(xp + ((long long)(n0 + xn) * T + tt) * xp_row + (long long)dir * 4 * H + xg * H + u0 + u)
+    for (int g = 0; g < 4; ++g)
+      dst[g] = (e_act && step < T)
+                   ? __ldg(xp + ((long long)(n0 + en) * T + tt) * xp_row + (long long)dir * 4 * H + g * H + u0 + eu)
                    : 0.f;
-    }
   };
-  float xv_cur[UPW], xv_nxt[UPW];
+  float xv_cur[4], xv_nxt[4], c_reg = 0.f;
   load_xp(0, xv_cur);
 
   int cur = 0;
@@ -116,102 +148,85 @@ __global__ void __cluster_dims__(LSTM_CLUSTER, 1, 1) __launch_bounds__(LSTM_THRE
   };
   for (int step = 0; step < T; ++step) {
     load_xp(step + 1, xv_nxt);
-    // write h_{t-1} (complete in h_buf[cur] after the previous cluster barrier) to global now: the
-    // stores drain during this step instead of stalling the next barrier's release
-    if (step > 0) {
-      const int tp = dir == 0 ? step - 1 : T - step;
-      for (int i = tid; i < nu * NB; i += LSTM_THREADS) {
-        const int n = i / nu, u = i - n * nu;
-        if (n0 + n < B)
-          out[((long long)(n0 + n) * T + tp) * (2 * H) + dir * H + u0 + u] = h_buf[cur * 4 * H + n * H + u0 + u];
-      }
-    }
-    // h_{t-1} of the 4 utterance slots into registers: float4 index k4 = lane + 32*i
-    float4 hreg[4][LSTM_MAXK4];
-    const float* hcur = h_buf + cur * 4 * H;
+    // ---- gate pre-activations of this CTA's units: [rows x K] x [K x NB] on the tensor cores
+    {
+      const float* xrow = h_buf + (cur * LSTM_NB + (lane >> 2)) * hs + k_first * 16 + 2 * (lane & 3);
+      float acc[3][3][4];
 #pragma unroll
-    for (int n = 0; n < 4; ++n)
+      for (int i = 0; i < 36; ++i) (&acc[0][0][0])[i] = 0.f;
 #pragma unroll
-      for (int i = 0; i < LSTM_MAXK4; ++i) {
-        const int k4 = lane + 32 * i;
-        hreg[n][i] = (n < NB && k4 < H4) ? *reinterpret_cast<const float4*>(hcur + n * H + 4 * k4)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    pmark(0);
+      for (int i = 0; i < 5; ++i) {
+        if (i < my_steps) {
+          uint32_t bh[2], bl[2];
+          split_half2(*reinterpret_cast<const float2*>(xrow + i * 16), bh[0], bl[0]);
+          split_half2(*reinterpret_cast<const float2*>(xrow + i * 16 + 8), bh[1], bl[1]);
 #pragma unroll
-    for (int j = 0; j < UPW; ++j) {
-      const int u = warp + j * (LSTM_THREADS / 32);
-      if (u >= nu) break;
-      const float xv = xv_cur[j];
-      float acc[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-      const float* wu = w_s + (long long)u * 4 * H;
-#pragma unroll
-      for (int i = 0; i < LSTM_MAXK4; ++i) {
-        const int k4 = lane + 32 * i;
-        if (k4 < H4) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 wv = *reinterpret_cast<const float4*>(wu + g * H + 4 * k4);
-#pragma unroll
-            for (int n = 0; n < NB; ++n)
-              acc[g * 4 + n] = fmaf(wv.x, hreg[n][i].x, fmaf(wv.y, hreg[n][i].y,
-                                    fmaf(wv.z, hreg[n][i].z, fmaf(wv.w, hreg[n][i].w, acc[g * 4 + n]))));
+          for (int j = 0; j < 3; ++j) {
+            if (j < nmt) {
+              uint32_t ah[4], al[4];
+              ldmatrix_x4(ah, whi_s + a_off[j] + i * 32);
+              ldmatrix_x4(al, wlo_s + a_off[j] + i * 32);
+              mma_f16(acc[j][0], ah, bh);
+              mma_f16(acc[j][1], al, bh);
+              mma_f16(acc[j][2], ah, bl);
+            }
           }
         }
       }
-      const float tot = warp_reduce16(acc, lane);     // lane 2*(g*4+n) (and +1) holds gate g of utterance n
-      // gather the 4 gates of utterance n = lane & 3 (every lane participates in the shuffles)
-      const int n = lane & 3;
-      const float gi = __shfl_sync(0xffffffffu, tot, 2 * (0 * 4 + n)) + __shfl_sync(0xffffffffu, xv, 0 * 4 + n);
-      const float gf = __shfl_sync(0xffffffffu, tot, 2 * (1 * 4 + n)) + __shfl_sync(0xffffffffu, xv, 1 * 4 + n);
-      const float gg = __shfl_sync(0xffffffffu, tot, 2 * (2 * 4 + n)) + __shfl_sync(0xffffffffu, xv, 2 * 4 + n);
-      const float go = __shfl_sync(0xffffffffu, tot, 2 * (3 * 4 + n)) + __shfl_sync(0xffffffffu, xv, 3 * 4 + n);
-      // every group of 4 lanes now holds the same (n-indexed) gates: lane = r*4 + n serves cluster rank r
-      float hval = 0.f;
-      if (n < NB && n0 + n < B) {
-        const float c_old = c_s[u * 4 + n];
-        const float c_new = sigmoidf_fast(gf) * c_old + sigmoidf_fast(gi) * tanhf_fast(gg);
-        hval = sigmoidf_fast(go) * tanhf_fast(c_new);
-        __syncwarp(__activemask());
-        if (lane < 4) c_s[u * 4 + n] = c_new;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (j < nmt) {
+          float v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = acc[j][0][q] + (acc[j][1][q] + acc[j][2][q]);
+          float* dst = part + ((long long)kq * prow + (mt0 + j) * 16 + (lane >> 2)) * LSTM_NB + 2 * (lane & 3);
+          *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+          *reinterpret_cast<float2*>(dst + 8 * LSTM_NB) = make_float2(v[2], v[3]);
+        }
       }
-      if (n < NB) {
-        float* slot = h_buf + (cur ^ 1) * 4 * H + n * H + u0 + u;
-        *cluster.map_shared_rank(slot, lane >> 2) = hval;     // 8 ranks x 4 utterance slots = 32 lanes
+    }
+    __syncthreads();
+    pmark(0);
+    // ---- cell update (gate order i, f, g, o) and hand-over of h_t
+    float hval = 0.f;
+    if (e_act) {
+      float gv[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < LSTM_KQ; ++q) a += part[((long long)q * prow + eu * 4 + g) * LSTM_NB + en];
+        gv[g] = a * (1.0f / LSTM_W_SCALE) + xv_cur[g];
       }
-      __syncwarp();
+      c_reg = sigmoidf_fast(gv[1]) * c_reg + sigmoidf_fast(gv[0]) * tanhf_fast(gv[2]);
+      hval = sigmoidf_fast(gv[3]) * tanhf_fast(c_reg);
+      const int tt = dir == 0 ? step : T - 1 - step;
+      out[((long long)(n0 + en) * T + tt) * (2 * H) + dir * H + u0 + eu] = hval;
+    }
+    if (tid < upc * LSTM_NB && eu < nu && en < nb_per_cluster) {
+      float* slot = h_buf + ((cur ^ 1) * LSTM_NB + en) * hs + u0 + eu;
+#pragma unroll
+      for (int r = 0; r < LSTM_CLUSTER; ++r) *cluster.map_shared_rank(slot, r) = hval;
     }
     pmark(1);
     cluster.sync();  // release/acquire: every CTA sees the complete h_t before step t+1
     pmark(2);
     cur ^= 1;
 #pragma unroll
-    for (int j = 0; j < UPW; ++j) xv_cur[j] = xv_nxt[j];
+    for (int g = 0; g < 4; ++g) xv_cur[g] = xv_nxt[g];
   }
   if (prof != nullptr && tid == 0)
     for (int i = 0; i < 3; ++i) prof[blockIdx.x * 4 + i] = pa[i];
-  // the last step's h
-  {
-    const int tp = dir == 0 ? T - 1 : 0;
-    for (int i = tid; i < nu * NB; i += LSTM_THREADS) {
-      const int n = i / nu, u = i - n * nu;
-      if (n0 + n < B)
-        out[((long long)(n0 + n) * T + tp) * (2 * H) + dir * H + u0 + u] = h_buf[cur * 4 * H + n * H + u0 + u];
-    }
-  }
 }
 
 long long* g_lstm_prof = nullptr;
 
 // Clusters of 8 CTAs (1 CTA per SM) that can be resident at once: the GPC boundaries leave fewer than
 // SMs / 8 (measured on B200: 16 clusters requested -> a second wave, 2x the time).
-template <int NB>
 int max_resident_clusters(size_t smem) {
   static int cached = -1;
-  if (cached >= 0) return cached;
-  cudaFuncSetAttribute(bilstm_cluster_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t cached_smem = 0;
+  if (cached >= 0 && cached_smem == smem) return cached;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(LSTM_CLUSTER * 32);
   cfg.blockDim = dim3(LSTM_THREADS);
@@ -224,29 +239,13 @@ int max_resident_clusters(size_t smem) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, bilstm_cluster_kernel<NB>, &cfg) != cudaSuccess || n <= 0) {
+  if (cudaOccupancyMaxActiveClusters(&n, bilstm_cluster_kernel, &cfg) != cudaSuccess || n <= 0) {
     cudaGetLastError();
     n = 1;
   }
   cached = n;
+  cached_smem = smem;
   return n;
-}
-
-template <int NB>
-int launch_bilstm(const float* xp, const float* w_hh, float* out, int B, int T, int H, cudaStream_t st) {
-  const int upc = ceil_div(H, LSTM_CLUSTER);
-  const size_t smem = (size_t)(4 * upc * H + 2 * 4 * H + 4 * upc) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(bilstm_cluster_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
-  if (e != cudaSuccess) {
-    set_error("bilstm: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
-    return 2;
-  }
-  const int groups = ceil_div(B, NB);
-  bilstm_cluster_kernel<NB><<<2 * groups * LSTM_CLUSTER, LSTM_THREADS, smem, st>>>(xp, w_hh, out, B, T, H, upc,
-                                                                                   g_lstm_prof);
-  count_launch();
-  return check_launch("bilstm_cluster_kernel");
 }
 
 }  // namespace
@@ -256,14 +255,26 @@ void lstm_set_prof(long long* p) { g_lstm_prof = p; }
 int lstm_bidir(const float* xp, const float* w_hh, float* out, int B, int T, int H, cudaStream_t st) {
   FAC_REQUIRE(xp && w_hh && out, "bilstm: NULL argument");
   FAC_REQUIRE(B > 0 && T > 0, "bilstm: empty problem B=%d T=%d", B, T);
-  FAC_REQUIRE(ceil_div(ceil_div(H, LSTM_CLUSTER), LSTM_THREADS / 32) <= 3, "bilstm: hidden size %d needs more than 3 units per warp", H);
-  FAC_REQUIRE(H > 0 && H % 4 == 0 && H <= 128 * LSTM_MAXK4, "bilstm: hidden size %d unsupported (multiple of 4, max %d)",
-              H, 128 * LSTM_MAXK4);
-  // one wave: the fewest utterances per cluster whose cluster count is resident at once
-  const size_t smem = (size_t)(4 * ceil_div(H, LSTM_CLUSTER) * H + 2 * 4 * H + 4 * ceil_div(H, LSTM_CLUSTER)) * sizeof(float);
-  if (2 * B <= max_resident_clusters<1>(smem)) return launch_bilstm<1>(xp, w_hh, out, B, T, H, st);
-  if (2 * ceil_div(B, 2) <= max_resident_clusters<2>(smem)) return launch_bilstm<2>(xp, w_hh, out, B, T, H, st);
-  return launch_bilstm<4>(xp, w_hh, out, B, T, H, st);
+  FAC_REQUIRE(H > 0 && H % 4 == 0, "bilstm: hidden size %d must be a positive multiple of 4", H);
+  const LstmGeom geo = lstm_geom(H);
+  FAC_REQUIRE(geo.m_tiles <= 3 * LSTM_MG && geo.k_steps <= 5 * LSTM_KQ && geo.upc * LSTM_NB <= LSTM_THREADS &&
+                  geo.bytes <= 227 * 1024,
+              "bilstm: hidden size %d unsupported (needs %zu bytes of shared memory per CTA)", H, geo.bytes);
+  cudaError_t e = cudaFuncSetAttribute(bilstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)geo.bytes);
+  if (e != cudaSuccess) {
+    set_error("bilstm: cannot reserve %zu bytes of shared memory: %s", geo.bytes, cudaGetErrorString(e));
+    return 2;
+  }
+  // one wave: the fewest utterances per cluster (<= 8) whose cluster count is resident at once
+  const int resident = max_resident_clusters(geo.bytes);
+  int nb = 1;
+  while (nb < LSTM_NB && 2 * ceil_div(B, nb) > resident) ++nb;
+  const int groups = ceil_div(B, nb);
+  bilstm_cluster_kernel<<<2 * groups * LSTM_CLUSTER, LSTM_THREADS, geo.bytes, st>>>(xp, w_hh, out, B, T, H, nb, geo,
+                                                                                    g_lstm_prof);
+  count_launch();
+  return check_launch("bilstm_cluster_kernel");
 }
 
 }  // namespace fac

@@ -238,8 +238,8 @@ int fac_pad_split_16(const float* in, void* hi, void* lo, long long n_rows, int 
  * (B, T, 2H) = [forward h | reverse h], i.e. the encoder `memory`. */
 int fac_lstm_bidir_f32(const float* xp, const float* w_hh, float* out, int B, int T, int H, void* stream);
 
-/* Optional cycle counters of the BiLSTM kernel: device buffer of grid*4 int64 per CTA (operand loads, unit
- * arithmetic + DSMEM stores, cluster barrier); NULL disables. */
+/* Optional cycle counters of the BiLSTM kernel: device buffer of grid*4 int64 per CTA (tensor-core gate mat-vec, cell
+ * update + DSMEM hand-over, cluster barrier); NULL disables. */
 void fac_lstm_set_profile_buffer(long long* device_buf);
 
 /* Decoder weights (fp32 device pointers), packed by fac_via_ppg_b200/packing.py from the
