@@ -82,6 +82,8 @@ struct TcParams {
   // (out_hi/out_lo, row stride C; columns >= n_valid are exact zeros because their weights and bias are)
   int act, n_valid;
   int fp16;                       // operands (and the hi/lo outputs of TC_LINEAR) are IEEE half instead of bf16
+  int flat_units;                 // 1: (tile, column block) units are dealt round-robin to the CTA groups (TC_LINEAR);
+                                  // 0: a CTA group owns whole tiles (the gate epilogue's out8 update needs that)
   int k_step0;                    // first K step of this launch (K-chunked accumulation, see conv_gemm_tc)
   const float* addend;            // fp32 partial sum of the earlier K chunks, added before the activation
   long long addend_ld;
@@ -132,6 +134,21 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
   // 256-column TMEM regions, so the epilogue of unit u overlaps the UMMAs of unit u+1.
   const int n_blocks = (p.n_total + TC_NHALF - 1) / TC_NHALF;
   const int n_cols = p.n_total < TC_NHALF ? p.n_total : TC_NHALF;
+  // unit schedule, identical in the three roles: the it-th unit of this CTA group is (first tile tb, block nb)
+  const int n_groups = (int)gridDim.x / CG, group_id = (int)blockIdx.x / CG;
+  const int total_units = ((p.n_tiles + CG - 1) / CG) * n_blocks;
+  auto unit_at = [&](int it, int& tb, int& nb) -> bool {
+    if (p.flat_units) {
+      const int uidx = group_id + it * n_groups;
+      if (uidx >= total_units) return false;
+      tb = (uidx / n_blocks) * CG;
+      nb = uidx % n_blocks;
+      return true;
+    }
+    tb = tile_first + (it / n_blocks) * (int)gridDim.x;
+    nb = it % n_blocks;
+    return tb < p.n_tiles;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -167,11 +184,13 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       long long prod_wait = 0;
-      for (int tb = tile_first; tb < p.n_tiles; tb += gridDim.x) {
+      for (int it = 0;; ++it) {
+        int tb, nb;
+        if (!unit_at(it, tb, nb)) break;
         const int tile = tb + rank;                    // may be one past the end for the pair's second CTA:
         const int b = tile / p.tiles_per_batch;        // its loads are then fully out of bounds (zero fill)
         const int t0 = (tile % p.tiles_per_batch) * TC_BM;
-        for (int nb = 0; nb < n_blocks; ++nb) {
+        {
           for (int ks = 0; ks < p.k_steps; ++ks) {
             // decode the K step into (source, tap, channel block)
             int s = 0, rem = p.k_step0 + ks;
@@ -226,8 +245,10 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
       uint32_t u = 0;   // unit counter
       long long wait_tmem = 0, wait_full = 0;
       const long long k_start = clock64();
-      for (int tb = tile_first; tb < p.n_tiles; tb += gridDim.x) {
-        for (int nb = 0; nb < n_blocks; ++nb, ++u) {
+      for (int it = 0;; ++it) {
+        int tb, nb;
+        if (!unit_at(it, tb, nb)) break;
+        for (int once = 0; once < 1; ++once, ++u) {
           const uint32_t r = u & 1;
           long long w0 = clock64();
           mbar_wait(&tmem_empty[r], ((u >> 1) & 1) ^ 1);   // epilogue has drained this region
@@ -275,13 +296,15 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
     const int row = q * 32 + lane;
     uint32_t u = 0;
     long long epi_wait = 0, epi_busy = 0;
-    for (int tb = tile_first; tb < p.n_tiles; tb += gridDim.x) {
+    for (int it = 0;; ++it) {
+      int tb, nb;
+      if (!unit_at(it, tb, nb)) break;
       const int tile = tb + rank;
       const int b = tile / p.tiles_per_batch;
       const int t = (tile % p.tiles_per_batch) * TC_BM + row;
       const bool valid = tile < p.n_tiles && t < p.T;
       const long long col = (long long)b * p.T + t;
-      for (int nb = 0; nb < n_blocks; ++nb, ++u) {
+      for (int once = 0; once < 1; ++once, ++u) {
         const uint32_t r = u & 1;
         const long long e0 = clock64();
         mbar_wait(&tmem_full[r], (u >> 1) & 1);
@@ -646,7 +669,8 @@ int launch_tc_cg(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st) 
     }
     attr_set = true;
   }
-  const int groups = ceil_div(p.n_tiles, CG);
+  const int n_blocks = ceil_div(p.n_total, TC_NHALF);
+  const int groups = ceil_div(p.n_tiles, CG) * (p.flat_units ? n_blocks : 1);
   const int max_groups = sm_count() / CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(CG * (groups < max_groups ? groups : max_groups)));
@@ -770,6 +794,7 @@ int conv_gemm_tc(const fac_tc_conv* c, cudaStream_t st) {
   p.src[0] = TcSrc{c->c_pad, c->taps, 1, c->center};
   p.n_total = c->n_pad;
   p.mode = TC_LINEAR;
+  p.flat_units = 1;
   p.out_row_mul = 1;
   p.fp16 = c->fp16;
   p.n_valid = c->n_valid;
