@@ -493,19 +493,6 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
   }
 }
 
-// fp32 -> bf16 (hi, lo) split of a flat array.
-__global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, long long n4) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
-  uint32_t h0, l0, h1, l1;
-  split2(v.x, v.y, h0, l0);
-  split2(v.z, v.w, h1, l1);
-  reinterpret_cast<uint2*>(hi)[i] = make_uint2(h0, h1);
-  if (lo) reinterpret_cast<uint2*>(lo)[i] = make_uint2(l0, l1);
-}
-
 // mel (rows, n_mel) fp32 -> zero-padded (rows, pad) bf16 hi/lo operand copies of the upsampler GEMM.
 __global__ void mel_pad_split_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ hi,
                                      __nv_bfloat16* __restrict__ lo, long long n_rows, int n_mel, int pad) {

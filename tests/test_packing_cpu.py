@@ -119,3 +119,27 @@ def test_hop_reshaped_stft_formulation_matches_oracle():
     ref = do.inverse(mag, phase, inv, window)
     assert (rec - ref).abs().max().item() <= 1e-4
     assert (rec[:, 0] - x).abs().max().item() <= 1e-3          # and both reconstruct the signal
+
+
+def test_tacotron_tensor_core_weights_layout_cpu():
+    """PackedTacotron.tc_weights(): [n_pad][taps * c_pad] half hi/lo pairs reproduce the packed fp32 weights
+    (22 significand bits), padding rows / channels are exact zeros, biases are padded with zeros."""
+    from fac_via_ppg_b200.packing import PackedTacotron
+    packed = PackedTacotron.from_state(synth.tacotron_state(), synth.TACOTRON_HPARAMS, "cpu")
+    tw = packed.tc_weights()
+    assert set(tw) == {"enc.pre0", "enc.pre1", "enc.conv0", "enc.conv1", "enc.conv2", "enc.lstm_ih",
+                       "post.conv0", "post.conv1", "post.conv2", "post.conv3", "post.conv4"}
+    for name, (c_in, taps, n_out) in {"enc.pre0": (5816, 1, 600), "enc.conv1": (600, 5, 600),
+                                      "enc.lstm_ih": (600, 1, 2400), "post.conv0": (80, 5, 512),
+                                      "post.conv4": (512, 5, 80)}.items():
+        w = tw[name]
+        assert w["c_pad"] % 64 == 0 and w["n_pad"] % 64 == 0 and w["c_pad"] >= c_in and w["n_pad"] >= n_out
+        assert w["hi"].shape == (w["n_pad"], taps * w["c_pad"]) and w["hi"].dtype == torch.float16
+        both = (w["hi"].float() + w["lo"].float()).view(w["n_pad"], taps, w["c_pad"])
+        ref = packed.view(name + "_w")[:, :n_out].reshape(taps, c_in, n_out).permute(2, 0, 1)
+        assert (both[:n_out, :, :c_in] - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
+        assert both[n_out:].abs().max().item() == 0.0 if w["n_pad"] > n_out else True
+        assert both[:, :, c_in:].abs().max().item() == 0.0 if w["c_pad"] > c_in else True
+        if w["bias"] is not None:
+            assert w["bias"].shape == (w["n_pad"],) and w["bias"][n_out:].abs().sum().item() == 0.0
+    assert tw["enc.pre0"]["bias"] is None and packed.tc_weights() is tw        # cached
