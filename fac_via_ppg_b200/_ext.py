@@ -93,6 +93,7 @@ SIGNATURES = {
     "fac_last_error": (C.c_char_p, []),
     "fac_launch_count": (C.c_longlong, []),
     "fac_reset_launch_count": (None, []),
+    "fac_add_launch_count": (None, [C.c_longlong]),
     "fac_conv_gemm_f32": (C.c_int, [_P(ConvSrc), C.c_int, _fp, _fp, C.c_int, C.c_int, C.c_int, _P(ConvEpilogue),
                                     C.c_int, C.c_longlong, C.c_longlong, _fp]),
     "fac_waveglow_upsample_squeeze_f32": (C.c_int, [_P(WgModel), _fp, _fp, C.c_int, C.c_int, _fp]),

@@ -55,6 +55,7 @@ int fac_version(void) { return 100; }
 const char* fac_last_error(void) { return fac::g_error; }
 long long fac_launch_count(void) { return fac::g_launches.load(); }
 void fac_reset_launch_count(void) { fac::g_launches.store(0); }
+void fac_add_launch_count(long long n) { fac::g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int fac_conv_gemm_f32(const fac_conv_src* srcs, int n_srcs, const float* w_packed, const float* bias, int B, int T_out,
                       int N, const fac_conv_epilogue* epi, int n_phases, long long w_phase_stride,

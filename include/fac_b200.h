@@ -33,6 +33,9 @@ const char* fac_last_error(void);
  * (bench.py reports it as gpu_launches). */
 long long fac_launch_count(void);
 void fac_reset_launch_count(void);
+/* Launches replayed from a CUDA graph captured around the entry points do not pass through the library:
+ * the caller adds them here (the count taken while capturing, once per replay). */
+void fac_add_launch_count(long long n);
 
 /* ---- generic implicit-GEMM Conv1d / Linear (fp32 FFMA) ----------------- */
 /* One input of a K-concatenated implicit GEMM.  Output row m (time step) reads

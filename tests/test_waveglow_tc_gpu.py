@@ -113,3 +113,27 @@ def test_tc_full_size_prefix_locality_and_independence():
                                          [z[:1, :, :Fp * 20].cpu() for z in noise])
     safe_cols = Fp * 20 - 12 * 255 - 8 * 20
     assert rms(full[0, :safe_cols * 8], ref[0, :safe_cols * 8]) <= 1e-4
+
+
+def test_small_inputs_replay_a_cuda_graph():
+    """Launch-bound sizes are captured once per shape in a CUDA graph: same bits as the eager path (sigma = 0
+    removes the noise), fresh noise on every replay, launches still accounted for."""
+    cfg = synth.WAVEGLOW_CONFIG
+    model = WaveGlow.remove_weightnorm(WaveGlow(**cfg))
+    model.load_state_dict(synth.waveglow_state(cfg=cfg))
+    model = model.to(DEV).eval()
+    mel = synth.synthetic_mel(2, 9, seed=4).to(DEV)
+    model.graph_max_frames = 0
+    eager = model.infer(mel, sigma=0.0)
+    model.graph_max_frames = 4096
+    lib = _ext.load()
+    first = model.infer(mel, sigma=0.0)            # captures
+    lib.fac_reset_launch_count()
+    again = model.infer(mel, sigma=0.0)            # replays
+    assert lib.fac_launch_count() > 200
+    assert torch.equal(first, eager) and torch.equal(again, eager)
+    mel2 = synth.synthetic_mel(2, 9, seed=5).to(DEV)
+    assert torch.equal(model.infer(mel2, sigma=0.0), model._infer_eager(mel2, 0.0, None))   # new input, same graph
+    a, b = model.infer(mel, sigma=0.6), model.infer(mel, sigma=0.6)
+    assert torch.isfinite(a).all() and not torch.equal(a, b)                                 # new draws per replay
+    assert len(model._fac_graphs) == 2
