@@ -417,6 +417,12 @@ class PackedTacotron:
             w, b = _fold_bn(sd, f"postnet.convolutions.{i}.", dev)
             put(f"post.conv{i}_w", w.permute(2, 1, 0).reshape(-1, w.shape[0]))
             put(f"post.conv{i}_b", b)
+        # the recurrent kernels keep these matrices in shared memory as half hi/lo pairs of w * 2^8
+        for name in ("enc.lstm_hh", "dec.w_att", "dec.w_dec", "dec.w_pp", "dec.w_pre2"):
+            peak = float(self.view(name).abs().max())
+            if not peak < 200.0:
+                raise _ext.FacError("%s: |weight| up to %.3g is outside the range (< 200) the resident half-precision "
+                                    "operand pairs of the recurrent kernels support" % (name, peak))
         return self
 
     # ------------------------------------------------------------------ tensor-core copies
@@ -445,6 +451,9 @@ class PackedTacotron:
             wp = w.new_zeros(n_pad, taps, c_pad)
             wp[:n_out, :, :c_in] = w.reshape(taps, c_in, n_out).permute(2, 0, 1)
             wp = wp.reshape(n_pad, taps * c_pad)
+            if dtype == torch.float16 and float(wp.abs().max()) > 3.0e4:
+                raise _ext.FacError("%s: |weight| up to %.3g does not fit the half-precision operand range of the "
+                                    "tensor-core path; use Tacotron2.set_precision('fp32')" % (name, float(wp.abs().max())))
             hi = wp.to(dtype)
             lo = (wp - hi.float()).to(dtype)
             bias = None

@@ -143,3 +143,14 @@ def test_tacotron_tensor_core_weights_layout_cpu():
         if w["bias"] is not None:
             assert w["bias"].shape == (w["n_pad"],) and w["bias"][n_out:].abs().sum().item() == 0.0
     assert tw["enc.pre0"]["bias"] is None and packed.tc_weights() is tw        # cached
+
+
+def test_out_of_range_weights_fail_loudly():
+    """The half-precision operand pairs of the recurrent kernels hold w * 2^8: a checkpoint whose weights do not
+    fit is refused at packing time instead of producing infinities on the GPU."""
+    from fac_via_ppg_b200 import _ext
+    from fac_via_ppg_b200.packing import PackedTacotron
+    sd = dict(synth.tacotron_state())
+    sd["decoder.attention_rnn.weight_hh"] = sd["decoder.attention_rnn.weight_hh"] * 1e4
+    with pytest.raises(_ext.FacError):
+        PackedTacotron.from_state(sd, synth.TACOTRON_HPARAMS, "cpu")
