@@ -38,3 +38,15 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_ext.WgModel) == 10 * 4 + 2 * 8 + 16 * C.sizeof(_ext.WgFlow)
     assert C.sizeof(_ext.TcConv) == 10 * 8 + 3 * 8 + 12 * 4 + 8
     assert C.sizeof(_ext.TacoDecoderState) == 12 * 8
+
+
+def test_build_digest_does_not_depend_on_the_checkout_path(monkeypatch):
+    """The library built here must be accepted as up to date in a copy of the repository elsewhere (the GPU box):
+    otherwise every rank of a torchrun launch rebuilds it at import time, concurrently."""
+    from fac_via_ppg_b200 import build
+    here = build._digest()
+    link = os.path.join(ROOT, "fac-via-ppg_b200")              # the same package through its symlinked name
+    assert os.path.isdir(link)
+    monkeypatch.setattr(build, "CSRC", os.path.join(link, "csrc"))
+    assert build._digest() == here
+    assert build.build() == build.LIB_PATH                      # up to date: no compiler involved
