@@ -153,9 +153,13 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], c
 }
 // fp32 pair -> IEEE-half hi/lo pairs (x = hi + lo to ~2^-22 relative)
 __device__ __forceinline__ void split_half2(float2 x, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(x.x, x.y);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
+  // hi = x with the low 13 mantissa bits cleared (exactly representable in half: 11 significant bits), lo = the
+  // exact remainder rounded to half.  Type conversions run at 16 lanes per cycle per SM, an eighth of the FP32
+  // rate: this form needs two of them per pair of values instead of six (round, convert back, round again).
+  const float hx = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+  const float hy = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+  const __half2 h = __floats2half2_rn(hx, hy);
+  const __half2 l = __floats2half2_rn(x.x - hx, x.y - hy);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -200,7 +204,7 @@ struct Prof {                 // thread 0's cycles between consecutive marks, pe
   __device__ __forceinline__ long long now() const { return on ? clock64() : 0; }
   __device__ __forceinline__ void flush(long long* out) {
     if (on)
-      for (int i = 0; i < 14; ++i) out[blockIdx.x * 16 + i] = acc[i];
+      for (int i = 0; i < 16; ++i) out[blockIdx.x * 16 + i] = acc[i];
   }
 };
 
@@ -301,7 +305,10 @@ __device__ __forceinline__ void matvec_phase(MatSmem& sm, Prof& prof, const Seg 
         }
       }
     }
+    long long tq = tp;
+    prof.sub<14>(tq);
     __syncthreads();
+    prof.sub<15>(tq);
     // the staging buffers are free again: fetch the next pass behind the reduction and the epilogue
     if (n0 + PASS < B) stage_pass(sm, segs, n0 + PASS, B, ~0u);
     if (tid < 16 * PASS) {

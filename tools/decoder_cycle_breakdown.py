@@ -32,5 +32,6 @@ for B, T in zip(args[0::2], args[1::2]):
     for cta in (0, 147):
         print("  CTA %3d: " % cta + "  ".join("%s %d+%d" % (n, p[cta, 2 * i], p[cta, 2 * i + 1]) for i, n in enumerate(names)))
     print("  CTA 147 mat-vec phases (all four): fetch wait %d, arithmetic %d, epilogue %d" % tuple(p[147, 11:14]))
+    print("  CTA 147 arithmetic detail: mma section (warp 0) %d, wait for the other warps %d" % tuple(p[147, 14:16]))
     print("  CTA 0 attention critical path: h load + query projection %d, energies %d, softmax + context %d" % tuple(p[0, 11:14]))
     print("  mean   : " + "  ".join("%s %d+%d" % (n, p[:, 2 * i].mean(), p[:, 2 * i + 1].mean()) for i, n in enumerate(names)))
