@@ -6,10 +6,13 @@ unchanged; ``Tacotron2.inference(inputs)`` keeps its signature and return list
 ``[mel, mel_postnet, gate, alignments]`` (reference model.py:597-610).  The modules hold
 parameters only.  All arithmetic runs in libfacb200.so:
 
-  encoder prenet / convs+BN / LSTM input projection / memory layer / postnet
-      -> fac_conv_gemm_f32 (implicit-GEMM Conv1d/Linear, BN folded, fused ReLU/tanh/dropout mask)
-  encoder BiLSTM recurrence -> fac_lstm_bidir_f32 (8-CTA clusters, W_hh resident in DSMEM)
-  decoder loop              -> fac_taco_decoder_run (one persistent cooperative kernel)
+  encoder prenet / convs+BN / LSTM input projection / postnet
+      -> fac_conv_gemm_tc (tcgen05 tensor cores, split-fp16 operands, K-chunked fp32 accumulation; BN folded,
+         fused ReLU/tanh/dropout mask), or fac_conv_gemm_f32 (exact FFMA) with set_precision('fp32')
+  memory layer              -> fac_conv_gemm_f32
+  encoder BiLSTM recurrence -> fac_lstm_bidir_f32 (8-CTA clusters, W_hh resident in DSMEM, mma.sync)
+  decoder loop              -> fac_taco_decoder_run (one persistent cooperative kernel: matrix CTAs + one
+                               attention CTA per utterance)
 
 Differences from the reference that a caller can observe:
   * B > 1 works (the reference's stop test only supports B == 1, model.py:524): every

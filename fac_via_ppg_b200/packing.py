@@ -340,8 +340,9 @@ def validate_tacotron_hparams(hp):
     if hp["n_symbols"] % 8 or hp["postnet_embedding_dim"] % 8:
         raise _ext.FacError("n_symbols and postnet_embedding_dim must be multiples of 8")
     w = hp["attention_window_size"]
-    if w is None or 2 * w + 1 > 64:
-        raise _ext.FacError("attention_window_size must be set and <= 31 (windowed attention kernel)")
+    if w is None or 2 * w + 1 > 48:
+        raise _ext.FacError("attention_window_size must be set and <= 23 (the attention CTA keeps the window's "
+                            "encoder rows in registers and its location terms in shared memory)")
 
 
 class PackedTacotron:
