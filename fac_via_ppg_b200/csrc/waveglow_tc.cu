@@ -84,9 +84,9 @@ struct TcParams {
   int fp16;                       // operands (and the hi/lo outputs of TC_LINEAR) are IEEE half instead of bf16
   int flat_units;                 // 1: (tile, column block) units are dealt round-robin to the CTA groups (TC_LINEAR);
                                   // 0: a CTA group owns whole tiles (the gate epilogue's out8 update needs that)
-  int k_step0;                    // first K step of this launch (K-chunked accumulation, see conv_gemm_tc)
-  const float* addend;            // fp32 partial sum of the earlier K chunks, added before the activation
-  long long addend_ld;
+  int chunk_steps;                // K steps per accumulation chain (K-chunked accumulation, see conv_gemm_tc); 0 = all
+  float* scratch;                 // fp32 partial sums of the earlier K chunks of a unit, (rows, n_valid)
+  long long scratch_ld;
   const float* mask;
   const float* residual;
   float* out_f32;
@@ -137,16 +137,22 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
   // unit schedule, identical in the three roles: the it-th unit of this CTA group is (first tile tb, block nb)
   const int n_groups = (int)gridDim.x / CG, group_id = (int)blockIdx.x / CG;
   const int total_units = ((p.n_tiles + CG - 1) / CG) * n_blocks;
-  auto unit_at = [&](int it, int& tb, int& nb) -> bool {
+  // K chunks (flat schedule only): a unit's contraction is walked in chains of chunk_steps K steps, each with its
+  // own accumulator; the chains of a unit are consecutive entries of the schedule of the same CTA group
+  const int chunk_steps = (p.flat_units && p.chunk_steps > 0) ? p.chunk_steps : p.k_steps;
+  const int n_chunks = (p.k_steps + chunk_steps - 1) / chunk_steps;
+  auto unit_at = [&](int it, int& tb, int& nb, int& ck) -> bool {
     if (p.flat_units) {
-      const int uidx = group_id + it * n_groups;
+      const int uidx = group_id + (it / n_chunks) * n_groups;
       if (uidx >= total_units) return false;
       tb = (uidx / n_blocks) * CG;
       nb = uidx % n_blocks;
+      ck = it % n_chunks;
       return true;
     }
     tb = tile_first + (it / n_blocks) * (int)gridDim.x;
     nb = it % n_blocks;
+    ck = 0;
     return tb < p.n_tiles;
   };
 
@@ -185,15 +191,16 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
       uint32_t phase = 0;
       long long prod_wait = 0;
       for (int it = 0;; ++it) {
-        int tb, nb;
-        if (!unit_at(it, tb, nb)) break;
+        int tb, nb, ck;
+        if (!unit_at(it, tb, nb, ck)) break;
         const int tile = tb + rank;                    // may be one past the end for the pair's second CTA:
         const int b = tile / p.tiles_per_batch;        // its loads are then fully out of bounds (zero fill)
         const int t0 = (tile % p.tiles_per_batch) * TC_BM;
         {
-          for (int ks = 0; ks < p.k_steps; ++ks) {
+          const int ks_end = min(p.k_steps, (ck + 1) * chunk_steps);
+          for (int ks = ck * chunk_steps; ks < ks_end; ++ks) {
             // decode the K step into (source, tap, channel block)
-            int s = 0, rem = p.k_step0 + ks;
+            int s = 0, rem = ks;
             if (rem >= steps0) { s = 1; rem -= steps0; }
             const int cps = p.src[s].channels / TC_BK;
             const int tap = rem / cps, c0 = (rem - tap * cps) * TC_BK;
@@ -211,16 +218,16 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
               mbar_arrive_expect_tx(&full[stage], bytes);
               tma_load_3d(st, mh, &full[stage], c0, row0, b);
               if (p.nsplit == 2) tma_load_3d(st + A_BYTES, ml, &full[stage], c0, row0, b);
-              tma_load_2d(st + W_OFF, &w_hi, &full[stage], (p.k_step0 + ks) * TC_BK, w_row);
-              if (use_wlo) tma_load_2d(st + W_OFF + W_BYTES, &w_lo, &full[stage], (p.k_step0 + ks) * TC_BK, w_row);
+              tma_load_2d(st + W_OFF, &w_hi, &full[stage], ks * TC_BK, w_row);
+              if (use_wlo) tma_load_2d(st + W_OFF + W_BYTES, &w_lo, &full[stage], ks * TC_BK, w_row);
             } else {
               // both CTAs' loads complete on the LEADER's barrier, which expects the pair's bytes
               if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * bytes);
               const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
               tma_load_3d_cg2(st, mh, lead_full, c0, row0, b);
               if (p.nsplit == 2) tma_load_3d_cg2(st + A_BYTES, ml, lead_full, c0, row0, b);
-              tma_load_2d_cg2(st + W_OFF, &w_hi, lead_full, (p.k_step0 + ks) * TC_BK, w_row);
-              if (use_wlo) tma_load_2d_cg2(st + W_OFF + W_BYTES, &w_lo, lead_full, (p.k_step0 + ks) * TC_BK, w_row);
+              tma_load_2d_cg2(st + W_OFF, &w_hi, lead_full, ks * TC_BK, w_row);
+              if (use_wlo) tma_load_2d_cg2(st + W_OFF + W_BYTES, &w_lo, lead_full, ks * TC_BK, w_row);
             }
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
@@ -246,8 +253,9 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
       long long wait_tmem = 0, wait_full = 0;
       const long long k_start = clock64();
       for (int it = 0;; ++it) {
-        int tb, nb;
-        if (!unit_at(it, tb, nb)) break;
+        int tb, nb, ck;
+        if (!unit_at(it, tb, nb, ck)) break;
+        const int ks_begin = ck * chunk_steps, ks_end = min(p.k_steps, ks_begin + chunk_steps);
         for (int once = 0; once < 1; ++once, ++u) {
           const uint32_t r = u & 1;
           long long w0 = clock64();
@@ -255,7 +263,7 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
           wait_tmem += clock64() - w0;
           tc_fence_after();
           const uint32_t d = tmem_base + r * TC_NHALF;
-          for (int ks = 0; ks < p.k_steps; ++ks) {
+          for (int ks = ks_begin; ks < ks_end; ++ks) {
             w0 = clock64();
             mbar_wait(&full[stage], phase);
             wait_full += clock64() - w0;
@@ -266,7 +274,7 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
               const uint32_t koff = kk * UMMA_K * 2;   // bytes along K inside the swizzled row
               const uint64_t a_h = make_smem_desc(st + koff, TC_ROWB);
               const uint64_t w_h = make_smem_desc(st + W_OFF + koff, TC_ROWB);
-              mma(d, a_h, w_h, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+              mma(d, a_h, w_h, idesc, (ks > ks_begin || kk > 0) ? 1u : 0u);
               if (p.nsplit == 2) {
                 const uint64_t a_l = make_smem_desc(st + A_BYTES + koff, TC_ROWB);
                 mma(d, a_l, w_h, idesc, 1u);
@@ -297,8 +305,9 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
     uint32_t u = 0;
     long long epi_wait = 0, epi_busy = 0;
     for (int it = 0;; ++it) {
-      int tb, nb;
-      if (!unit_at(it, tb, nb)) break;
+      int tb, nb, ck;
+      if (!unit_at(it, tb, nb, ck)) break;
+      const bool first_chunk = ck == 0, last_chunk = ck == n_chunks - 1;
       const int tile = tb + rank;
       const int b = tile / p.tiles_per_batch;
       const int t = (tile % p.tiles_per_batch) * TC_BM + row;
@@ -324,8 +333,8 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 bv = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 bv = (p.bias != nullptr && last_chunk) ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
             v[j + 0] = __uint_as_float(rr[j + 0]) + bv.x;
             v[j + 1] = __uint_as_float(rr[j + 1]) + bv.y;
             v[j + 2] = __uint_as_float(rr[j + 2]) + bv.z;
@@ -366,14 +375,25 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
             }
           } else if (p.mode == TC_LINEAR) {
             // generic Conv1d / Linear epilogue (reference src/common/layers.py:40-71 users)
-            if (p.addend != nullptr) {
-              const float* arow = p.addend + col * p.addend_ld + n0;
+            if (n_chunks > 1) {
+              // K-chunked accumulation: the partial sums of a unit's chains meet in fp32 (round to nearest) in
+              // `scratch`; this thread wrote what it reads (same row, same columns, previous chain)
+              float* srow = p.scratch + col * p.scratch_ld + n0;
+              if (!first_chunk) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (n0 + j + 3 < p.n_valid) {
-                  const float4 m = *reinterpret_cast<const float4*>(arow + j);   // written by the previous launch
-                  v[j] += m.x; v[j + 1] += m.y; v[j + 2] += m.z; v[j + 3] += m.w;
-                }
+                for (int j = 0; j < 32; j += 4)
+                  if (n0 + j + 3 < p.n_valid) {
+                    const float4 m = *reinterpret_cast<const float4*>(srow + j);
+                    v[j] += m.x; v[j + 1] += m.y; v[j + 2] += m.z; v[j + 3] += m.w;
+                  }
+              }
+              if (!last_chunk) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  if (n0 + j + 3 < p.n_valid)
+                    *reinterpret_cast<float4*>(srow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                continue;
+              }
             }
             if (p.act == FAC_ACT_RELU) {
 #pragma unroll
@@ -786,45 +806,34 @@ int conv_gemm_tc(const fac_tc_conv* c, cudaStream_t st) {
   p.fp16 = c->fp16;
   p.n_valid = c->n_valid;
   // The tensor core's fp32 accumulator truncates on every accumulation, an error that grows with the number
-  // of UMMAs chained into one accumulator (measured: ~3e-5 relative at K = 5824).  With k_chunk > 0 the K
-  // range is cut into launches of at most k_chunk elements whose partial sums are added in fp32
-  // (round-to-nearest) by the epilogue through `scratch`; only the last launch applies the real epilogue.
+  // of UMMAs chained into one accumulator (measured: ~3e-5 relative at K = 5824).  With k_chunk > 0 every unit
+  // walks its K range in chains of at most k_chunk elements, each in its own TMEM accumulator, whose partial
+  // sums are added in fp32 (round-to-nearest) by the epilogue through `scratch`; the last chain applies the
+  // real epilogue.
   const int total_steps = K / bk;
-  int steps_per_launch = total_steps;
+  p.k_steps = total_steps;
+  p.wlo_k_steps = total_steps;
+  p.chunk_steps = 0;
   if (c->k_chunk > 0) {
     FAC_REQUIRE(c->k_chunk % bk == 0, "conv_gemm_tc: k_chunk %d must be a multiple of %d", c->k_chunk, bk);
-    steps_per_launch = c->k_chunk / bk;
-    FAC_REQUIRE(steps_per_launch >= total_steps || c->scratch != nullptr, "conv_gemm_tc: K-chunking needs scratch");
-  }
-  for (int k0 = 0; k0 < total_steps; k0 += steps_per_launch) {
-    const bool first = k0 == 0, last = k0 + steps_per_launch >= total_steps;
-    p.k_step0 = k0;
-    p.k_steps = last ? total_steps - k0 : steps_per_launch;
-    p.wlo_k_steps = p.k_steps;
-    p.addend = first ? nullptr : c->scratch;
-    p.addend_ld = c->n_valid;
-    if (last) {
-      p.bias = c->bias;
-      p.act = c->act;
-      p.mask = c->mask;
-      p.mask_ld = c->mask_ld;
-      p.residual = c->residual;
-      p.res_ld = c->res_ld;
-      p.out_f32 = c->out;
-      p.out_ld = c->out_ld;
-      p.out_hi = reinterpret_cast<__nv_bfloat16*>(c->out_hi);
-      p.out_lo = reinterpret_cast<__nv_bfloat16*>(c->out_lo);
-    } else {
-      p.bias = nullptr;
-      p.act = FAC_ACT_NONE;
-      p.mask = p.residual = nullptr;
-      p.out_f32 = c->scratch;
-      p.out_ld = c->n_valid;
-      p.out_hi = p.out_lo = nullptr;
+    if (c->k_chunk / bk < total_steps) {
+      FAC_REQUIRE(c->scratch != nullptr, "conv_gemm_tc: K-chunking needs scratch");
+      p.chunk_steps = c->k_chunk / bk;
+      p.scratch = c->scratch;
+      p.scratch_ld = c->n_valid;
     }
-    if (int rc = launch_tc(maps, p, st, cg)) return rc;
   }
-  return 0;
+  p.bias = c->bias;
+  p.act = c->act;
+  p.mask = c->mask;
+  p.mask_ld = c->mask_ld;
+  p.residual = c->residual;
+  p.res_ld = c->res_ld;
+  p.out_f32 = c->out;
+  p.out_ld = c->out_ld;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(c->out_hi);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(c->out_lo);
+  return launch_tc(maps, p, st, cg);
 }
 
 namespace {

@@ -221,8 +221,9 @@ typedef struct fac_tc_conv {
   int B, T, c_pad, taps, center, n_pad, n_valid, act, nsplit;
   int fp16;   /* 0: operands are bf16; 1: IEEE half (hi + lo = 22 significand bits; needs |x| < 65504) */
   /* K-chunked accumulation: the tensor core's fp32 accumulator truncates on every accumulation; with
-   * k_chunk > 0 (a multiple of 64) the contraction is cut into launches of <= k_chunk elements whose partial
-   * sums meet in fp32 round-to-nearest through scratch, a (B*T, n_valid) fp32 buffer.  0 = one launch. */
+   * k_chunk > 0 (a multiple of 64) every output tile walks the contraction in chains of <= k_chunk elements,
+   * each in its own TMEM accumulator, whose partial sums meet in fp32 round-to-nearest through scratch, a
+   * (B*T, n_valid) fp32 buffer.  0 = one chain. */
   int k_chunk, _pad;
   float* scratch;
 } fac_tc_conv;
