@@ -19,8 +19,9 @@
 //               ~2^-16 relative operand error, fp32 accumulate: fp32-grade results.
 // Warp roles (320 threads, persistent over tiles, 1 CTA / SM): warp 0 = TMA producer, warp 1 = UMMA
 // issuer (one elected lane), warps 2-9 = epilogue (two per TMEM lane quarter, half of the columns each).
-// Every tile walks K from a tile-dependent rotation so that the 148 CTAs do not all request the
-// same weight lines from L2 at the same instant.
+// The same kernel serves the acoustic model's Conv1d / Linear layers (TC_LINEAR epilogue, IEEE-half operand
+// pairs): there the (tile, column block) units are dealt round-robin to the CTA pairs and every unit walks its
+// contraction in chains of <= k_chunk elements that alternate the two TMEM accumulators (see conv_gemm_tc).
 #include "fac_common.cuh"
 #include "tc_common.cuh"
 
