@@ -12,6 +12,7 @@ _ALIASES = {
     "waveglow": "fac_via_ppg_b200.waveglow",
     "waveglow.glow": "fac_via_ppg_b200.waveglow.glow",
     "waveglow.denoiser": "fac_via_ppg_b200.waveglow.denoiser",
+    "waveglow.convert_model": "fac_via_ppg_b200.waveglow.convert_model",
     "common": "fac_via_ppg_b200.common",
     "common.model": "fac_via_ppg_b200.common.model",
     "common.layers": "fac_via_ppg_b200.common.layers",

@@ -29,7 +29,7 @@ class ConvEpilogue(C.Structure):
     _fields_ = [("kind", C.c_int), ("act", C.c_int), ("out", _fp),
                 ("out_batch_stride", C.c_longlong), ("out_row_stride", C.c_longlong),
                 ("mask", _fp), ("residual", _fp), ("out2", _fp),
-                ("n_split", C.c_int), ("accumulate_out2", C.c_int)]
+                ("n_split", C.c_int), ("accumulate_out2", C.c_int), ("row_lengths", _fp)]
 
 
 class TcConv(C.Structure):
@@ -38,7 +38,7 @@ class TcConv(C.Structure):
                 ("mask_ld", C.c_longlong), ("res_ld", C.c_longlong), ("out_ld", C.c_longlong),
                 ("B", C.c_int), ("T", C.c_int), ("c_pad", C.c_int), ("taps", C.c_int), ("center", C.c_int),
                 ("n_pad", C.c_int), ("n_valid", C.c_int), ("act", C.c_int), ("nsplit", C.c_int), ("fp16", C.c_int),
-                ("k_chunk", C.c_int), ("_pad", C.c_int), ("scratch", _fp)]
+                ("k_chunk", C.c_int), ("_pad", C.c_int), ("scratch", _fp), ("row_lengths", _fp)]
 
 
 class WgFlow(C.Structure):
@@ -121,6 +121,7 @@ SIGNATURES = {
     "fac_selftest_grid_barrier": (C.c_int, [_fp, C.c_int, _fp]),
     "fac_denoise_spectrum_f32": (C.c_int, [_fp, _fp, C.c_float, C.c_longlong, C.c_int, C.c_int, _fp]),
     "fac_lstm_bidir_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
+    "fac_lstm_bidir_var_f32": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "fac_taco_decoder_run": (C.c_int, [_P(TacoDecoderWeights), _fp, _fp, _fp, _fp, _P(TacoDecoderState), _fp, _fp,
                                        _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),
 }
@@ -179,5 +180,11 @@ def current_stream():
 
 
 def require_cuda(t, name: str):
+    """Every entry point launches on the CURRENT device's current stream (one process per GPU): a CPU tensor or a
+    tensor of another device is refused instead of launching with foreign pointers."""
     if not t.is_cuda:
         raise FacError("%s must live on a CUDA device: this package has no CPU path (got %s)" % (name, t.device))
+    import torch
+    if t.device.index != torch.cuda.current_device():
+        raise FacError("%s lives on %s but the current device is cuda:%d; wrap the call in "
+                       "torch.cuda.device(...) (one process per GPU)" % (name, t.device, torch.cuda.current_device()))

@@ -17,7 +17,12 @@ parameters only.  All arithmetic runs in libfacb200.so:
 Differences from the reference that a caller can observe:
   * B > 1 works (the reference's stop test only supports B == 1, model.py:524): every
     utterance stops on its own gate; frames after an utterance's stop are zeroed and the
-    per-utterance lengths are left in ``model.last_output_lengths``.
+    per-utterance lengths are left in ``model.last_output_lengths``.  A batch is defined as B
+    independent B == 1 runs: ``inference(inputs, input_lengths=...)`` accepts a ragged batch
+    (zero-padded to the longest input; the reference builds ``input_lengths`` at model.py:599 and
+    masks per utterance in utils.py:46-78): convolutions see each utterance's own zero padding, the
+    reverse LSTM direction starts at each utterance's own last frame, the attention window is
+    clamped to each utterance's length, and the postnet stops at each utterance's own last frame.
   * the always-on prenet dropout (model.py:132-135) draws its masks from torch's generator
     on the input's device.  ``rng_mode='reference'`` replays the reference's draw order
     call by call (seed-exact); the default ``'fast'`` makes one draw per tensor kind.
@@ -201,68 +206,80 @@ class Tacotron2(nn.Module):
         self.precision = precision
         return self
 
-    def _encode_tc(self, packed, inputs, enc0, enc1):
+    def _encode_tc(self, packed, inputs, enc0, enc1, lens):
         """Encoder.inference with every GEMM on the tensor cores (split-fp16): the PPG is transposed and split
-        once, each layer writes the fp16 hi/lo operand copies of the next one directly."""
+        once, each layer writes the fp16 hi/lo operand copies of the next one directly.  ``lens`` (int32 [B] or
+        None): rows beyond an utterance's length are written as zeros by every layer, which is the zero padding
+        the next Conv1d would see if the utterance were processed alone."""
         hp = self.hp
         B, D, T = inputs.shape
         E = hp["encoder_embedding_dim"]
         tw = packed.tc_weights()
         a = ops.transpose_split(inputs, tw["enc.pre0"]["c_pad"])
-        _, a = ops.conv_gemm_tc(a, tw["enc.pre0"], act=_ext.ACT_RELU, mask=enc0)
-        _, a = ops.conv_gemm_tc(a, tw["enc.pre1"], act=_ext.ACT_RELU, mask=enc1)
+        _, a = ops.conv_gemm_tc(a, tw["enc.pre0"], act=_ext.ACT_RELU, mask=enc0, row_lengths=lens)
+        _, a = ops.conv_gemm_tc(a, tw["enc.pre1"], act=_ext.ACT_RELU, mask=enc1, row_lengths=lens)
         for i in range(hp["encoder_n_convolutions"]):
-            _, a = ops.conv_gemm_tc(a, tw[f"enc.conv{i}"], act=_ext.ACT_RELU)
+            _, a = ops.conv_gemm_tc(a, tw[f"enc.conv{i}"], act=_ext.ACT_RELU, row_lengths=lens)
         xp = torch.empty(B, T, 4 * E, device=inputs.device, dtype=torch.float32)
         ops.conv_gemm_tc(a, tw["enc.lstm_ih"], out=xp, want_split=False)
         return xp
 
-    def _encode(self, packed, inputs, enc0, enc1):
-        """reference model.py:237-249 (Encoder.inference): (B, D, T) -> memory (B, T, E)."""
+    def _encode(self, packed, inputs, enc0, enc1, lens=None):
+        """reference model.py:237-249 (Encoder.inference): (B, D, T) -> memory (B, T, E); rows beyond an
+        utterance's length (ragged batch) are zero."""
         hp = self.hp
         B, D, T = inputs.shape
         E, H = hp["encoder_embedding_dim"], hp["encoder_embedding_dim"] // 2
         dev = inputs.device
         new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         if self.precision == "fp16x3":
-            xp = self._encode_tc(packed, inputs, enc0, enc1)
-            memory = new(B, T, E)
-            rc = _ext.load().fac_lstm_bidir_f32(xp.data_ptr(), packed.view("enc.lstm_hh").data_ptr(),
-                                                memory.data_ptr(), B, T, H, _ext.current_stream())
-            _ext.check(rc, "fac_lstm_bidir_f32")
-            return memory
-        h = ops.conv_gemm([ops.conv_src(inputs, channel_major=True)], packed.view("enc.pre0_w"), None, E,
-                          new(B, T, E), batch=B, rows=T, act=_ext.ACT_RELU, mask=enc0)
-        h = ops.conv_gemm([ops.conv_src(h)], packed.view("enc.pre1_w"), None, E, new(B, T, E), batch=B, rows=T,
-                          act=_ext.ACT_RELU, mask=enc1)
-        k = hp["encoder_kernel_size"]
-        for i in range(hp["encoder_n_convolutions"]):
-            h = ops.conv_gemm([ops.conv_src(h, k, 1, (k - 1) // 2)], packed.view(f"enc.conv{i}_w"),
-                              packed.view(f"enc.conv{i}_b"), E, new(B, T, E), batch=B, rows=T, act=_ext.ACT_RELU)
-        xp = ops.conv_gemm([ops.conv_src(h)], packed.view("enc.lstm_ih_w"), packed.view("enc.lstm_ih_b"), 8 * H,
-                           new(B, T, 8 * H), batch=B, rows=T)
-        memory = new(B, T, E)
-        rc = _ext.load().fac_lstm_bidir_f32(xp.data_ptr(), packed.view("enc.lstm_hh").data_ptr(), memory.data_ptr(),
-                                            B, T, H, _ext.current_stream())
-        _ext.check(rc, "fac_lstm_bidir_f32")
+            xp = self._encode_tc(packed, inputs, enc0, enc1, lens)
+        else:
+            h = ops.conv_gemm([ops.conv_src(inputs, channel_major=True)], packed.view("enc.pre0_w"), None, E,
+                              new(B, T, E), batch=B, rows=T, act=_ext.ACT_RELU, mask=enc0, row_lengths=lens)
+            h = ops.conv_gemm([ops.conv_src(h)], packed.view("enc.pre1_w"), None, E, new(B, T, E), batch=B, rows=T,
+                              act=_ext.ACT_RELU, mask=enc1, row_lengths=lens)
+            k = hp["encoder_kernel_size"]
+            for i in range(hp["encoder_n_convolutions"]):
+                h = ops.conv_gemm([ops.conv_src(h, k, 1, (k - 1) // 2)], packed.view(f"enc.conv{i}_w"),
+                                  packed.view(f"enc.conv{i}_b"), E, new(B, T, E), batch=B, rows=T, act=_ext.ACT_RELU,
+                                  row_lengths=lens)
+            xp = ops.conv_gemm([ops.conv_src(h)], packed.view("enc.lstm_ih_w"), packed.view("enc.lstm_ih_b"), 8 * H,
+                               new(B, T, 8 * H), batch=B, rows=T)
+        memory = new(B, T, E) if lens is None else torch.zeros(B, T, E, device=dev, dtype=torch.float32)
+        rc = _ext.load().fac_lstm_bidir_var_f32(xp.data_ptr(), packed.view("enc.lstm_hh").data_ptr(),
+                                                memory.data_ptr(), _ext.ptr(lens), B, T, H, _ext.current_stream())
+        _ext.check(rc, "fac_lstm_bidir_var_f32")
         return memory
 
-    def _decode(self, packed, memory, dec_masks, n_steps):
+    def _decode(self, packed, memory, dec_masks, n_steps, lens=None):
         """reference model.py:489-535 (Decoder.inference) -> mel_cl (B, n_steps, M), gate, align, lengths.
         One launch decodes at most (SMs - 100) utterances (one attention CTA each next to >= 100 matrix
-        CTAs); larger batches run as consecutive groups."""
+        CTAs); larger batches run as consecutive groups.  A ragged batch is length-sorted into the groups
+        (src/common/data_utils.py sorts training batches the same way), so that a group of short utterances
+        retires as soon as its own longest member has fired its stop gate; an utterance's result does not
+        depend on the group it runs in (the decoder's arithmetic is batch-invariant)."""
         B = memory.shape[0]
         limit = max(1, torch.cuda.get_device_properties(memory.device).multi_processor_count - 100)
         group = min(limit, 32)
         if B <= limit:
-            return self._decode_group(packed, memory, dec_masks, n_steps)
-        parts = [self._decode_group(packed, memory[i:i + group], dec_masks[:, :, i:i + group].contiguous(), n_steps)
+            return self._decode_group(packed, memory, dec_masks, n_steps, lens)
+        order = torch.argsort(lens, descending=True, stable=True) if lens is not None else None
+        if order is not None:
+            memory, dec_masks, lens = memory[order], dec_masks[:, :, order], lens[order]
+        parts = [self._decode_group(packed, memory[i:i + group].contiguous(),
+                                    dec_masks[:, :, i:i + group].contiguous(), n_steps,
+                                    None if lens is None else lens[i:i + group].contiguous())
                  for i in range(0, B, group)]
         mel, gate, align, out_len, done = zip(*parts)
-        return (torch.cat(mel), torch.cat(gate), torch.cat(align) if align[0] is not None else None,
-                torch.cat(out_len), torch.stack(done).sum(0))
+        out = [torch.cat(mel), torch.cat(gate), torch.cat(align) if align[0] is not None else None, torch.cat(out_len)]
+        if order is not None:
+            inv = torch.empty_like(order)
+            inv[order] = torch.arange(B, device=order.device)
+            out = [None if t is None else t[inv] for t in out]
+        return (*out, torch.stack(done).sum(0))
 
-    def _decode_group(self, packed, memory, dec_masks, n_steps):
+    def _decode_group(self, packed, memory, dec_masks, n_steps, lens=None):
         hp = self.hp
         B, T, E = memory.shape
         dev = memory.device
@@ -276,7 +293,7 @@ class Tacotron2(nn.Module):
               "done": torch.zeros(8, dtype=torch.int32, device=dev),
               "out_len": torch.zeros(B, dtype=torch.int32, device=dev)}
         cstate = _ext.TacoDecoderState(*[st[n].data_ptr() for n, _ in _ext.TacoDecoderState._fields_])
-        lengths = torch.full((B,), T, dtype=torch.int32, device=dev)      # model.py:599
+        lengths = lens if lens is not None else torch.full((B,), T, dtype=torch.int32, device=dev)   # model.py:599
         mel = z(B, n_steps, M)
         gate = z(B, n_steps)
         align = z(B, n_steps, T) if self.return_alignments else None
@@ -287,8 +304,10 @@ class Tacotron2(nn.Module):
         _ext.check(rc, "fac_taco_decoder_run")
         return mel, gate, align, st["out_len"], st["done"]
 
-    def _postnet(self, packed, mel_cl):
-        """reference model.py:178-184 + 604-605: mel_post = mel + postnet(mel), channels-last in/out."""
+    def _postnet(self, packed, mel_cl, out_len=None):
+        """reference model.py:178-184 + 604-605: mel_post = mel + postnet(mel), channels-last in/out.  ``out_len``
+        (int32 [B] or None): every layer writes zeros beyond an utterance's own last frame, so an utterance that
+        stopped early sees the Conv1d zero padding it would see alone."""
         hp = self.hp
         B, T, M = mel_cl.shape
         n, k, Pe = hp["postnet_n_convolutions"], hp["postnet_kernel_size"], hp["postnet_embedding_dim"]
@@ -296,9 +315,10 @@ class Tacotron2(nn.Module):
             tw = packed.tc_weights()
             a = ops.pad_split(mel_cl, tw["post.conv0"]["c_pad"])
             for i in range(n - 1):
-                _, a = ops.conv_gemm_tc(a, tw[f"post.conv{i}"], act=_ext.ACT_TANH)
+                _, a = ops.conv_gemm_tc(a, tw[f"post.conv{i}"], act=_ext.ACT_TANH, row_lengths=out_len)
             out = torch.empty(B, T, M, device=mel_cl.device, dtype=torch.float32)
-            ops.conv_gemm_tc(a, tw[f"post.conv{n - 1}"], residual=mel_cl, out=out, want_split=False)
+            ops.conv_gemm_tc(a, tw[f"post.conv{n - 1}"], residual=mel_cl, out=out, want_split=False,
+                             row_lengths=out_len)
             return out
         h = mel_cl
         for i in range(n):
@@ -307,7 +327,8 @@ class Tacotron2(nn.Module):
             h = ops.conv_gemm([ops.conv_src(h, k, 1, (k - 1) // 2)], packed.view(f"post.conv{i}_w"),
                               packed.view(f"post.conv{i}_b"), width,
                               torch.empty(B, T, width, device=mel_cl.device), batch=B, rows=T,
-                              act=_ext.ACT_NONE if last else _ext.ACT_TANH, residual=mel_cl if last else None)
+                              act=_ext.ACT_NONE if last else _ext.ACT_TANH, residual=mel_cl if last else None,
+                              row_lengths=out_len)
         return h
 
     # ------------------------------------------------------------------ public API
@@ -318,8 +339,12 @@ class Tacotron2(nn.Module):
         return [o if o is None else o.float() for o in outputs] if self.fp16_run else outputs   # model.py:566-578 (no masking at inference)
 
     @torch.no_grad()
-    def inference(self, inputs, dropout_tape=None):
-        """inputs (B, n_symbols, T_in) -> [mel (B,M,T_out), mel_postnet, gate (B,T_out,1), alignments (B,T_out,T_in)]."""
+    def inference(self, inputs, dropout_tape=None, input_lengths=None):
+        """inputs (B, n_symbols, T_in) -> [mel (B,M,T_out), mel_postnet, gate (B,T_out,1), alignments (B,T_out,T_in)].
+
+        ``input_lengths`` (optional, B ints <= T_in) makes the batch ragged: utterance b only has its first
+        input_lengths[b] frames (the rest is padding and is ignored), and its outputs equal those of a B == 1
+        call on inputs[b:b+1, :, :input_lengths[b]] with the same dropout masks."""
         _ext.require_cuda(inputs, "inputs")
         inputs = self.parse_input(inputs)
         x = inputs.float().contiguous()
@@ -328,28 +353,39 @@ class Tacotron2(nn.Module):
             raise ValueError("inputs have %d symbols, model expects %d" % (D, self.hp["n_symbols"]))
         if B == 0 or T == 0:
             raise ValueError("empty input batch")
+        lens = None
+        if input_lengths is not None:
+            lens_host = torch.as_tensor(input_lengths).to("cpu", torch.int64).flatten()
+            if lens_host.numel() != B or int(lens_host.min()) < 1 or int(lens_host.max()) > T:
+                raise ValueError("input_lengths must hold %d values in [1, %d]" % (B, T))
+            if int(lens_host.min()) < T:                     # all full length: the plain path
+                lens = lens_host.to(device=x.device, dtype=torch.int32)
         packed = self.packed()
         n_steps = int(self.decoder.max_decoder_steps)
         enc0, enc1, dec_masks = self._dropout_masks(B, T, n_steps, x.device, dropout_tape)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.collect_timing else None
         if ev:
             ev[0].record()
-        memory = self._encode(packed, x, enc0, enc1)
+        memory = self._encode(packed, x, enc0, enc1, lens)
         if ev:
             ev[1].record()
-        mel_cl, gate, align, out_len, done = self._decode(packed, memory, dec_masks, n_steps)
+        mel_cl, gate, align, out_len, done = self._decode(packed, memory, dec_masks, n_steps, lens)
         if ev:
             ev[2].record()
-        lens = out_len.cpu()                                          # the one device->host sync of the call
-        t_out = int(lens.max())
+        out_lens = out_len.cpu()                                      # the one device->host sync of the call
+        t_out = int(out_lens.max())
         if int(done.cpu()[1]) > 0:
             print("Warning! Reached max decoder steps", file=sys.stderr)   # model.py:526-528 (stderr: keeps stdout machine-readable)
         mel_cl = mel_cl[:, :t_out].contiguous()
-        if B > 1 and int(lens.min()) < t_out:                        # per-utterance stop: zero the tail
+        ragged_out = B > 1 and int(out_lens.min()) < t_out
+        if ragged_out:                                               # per-utterance stop: zero the tail
             keep = (torch.arange(t_out, device=x.device)[None, :] < out_len[:, None]).unsqueeze(-1)
             mel_cl = mel_cl * keep
-        self.last_output_lengths = lens
-        post_cl = self._postnet(packed, mel_cl)
+            gate = gate[:, :t_out] * keep[..., 0]
+            if align is not None:
+                align = align[:, :t_out] * keep
+        self.last_output_lengths = out_lens
+        post_cl = self._postnet(packed, mel_cl, out_len.contiguous() if ragged_out else None)
         if ev:
             ev[3].record()
             torch.cuda.synchronize()

@@ -59,10 +59,13 @@ def get_inference(seq, model, is_clip=False):
 def load_waveglow_model(path):
     """reference utils.py:177-181: a pickled ``{'model': WaveGlow}`` checkpoint -> eval model on the GPU.
     The pickle refers to ``waveglow.glow.WaveGlow``; ``fac_via_ppg_b200.install_aliases()`` (called here)
-    makes that name resolve to the drop-in class."""
+    makes that name resolve to the drop-in class.  Checkpoints in the old res_layers / skip_layers format are
+    converted on the fly; with FAC_PACK_CACHE set the packed weight buffer is cached on disk (packing.py)."""
     import fac_via_ppg_b200
+    from fac_via_ppg_b200.waveglow.convert_model import update_model
     fac_via_ppg_b200.install_aliases()
     model = torch.load(path, weights_only=False)["model"]
+    model = update_model(model)              # old res_layers/skip_layers format (reference convert_model.py:43-70)
     model = model.remove_weightnorm(model)
     model.cuda().eval()
     return model

@@ -43,7 +43,7 @@ int denoise_spectrum(float*, const float*, float, long long, int, int, cudaStrea
 int tc_set_cta_group(int);
 int tc_set_k_block(int);
 int selftest_grid_barrier(unsigned int*, int, cudaStream_t);
-int lstm_bidir(const float*, const float*, float*, int, int, int, cudaStream_t);
+int lstm_bidir(const float*, const float*, float*, const int*, int, int, int, cudaStream_t);
 int taco_decoder_run(const fac_taco_decoder_weights*, const float*, const float*, const int*, const unsigned char*,
                      const fac_taco_decoder_state*, float*, float*, float*, int, int, int, int, float, cudaStream_t);
 
@@ -51,7 +51,7 @@ int taco_decoder_run(const fac_taco_decoder_weights*, const float*, const float*
 
 extern "C" {
 
-int fac_version(void) { return 100; }
+int fac_version(void) { return 200; }
 const char* fac_last_error(void) { return fac::g_error; }
 long long fac_launch_count(void) { return fac::g_launches.load(); }
 void fac_reset_launch_count(void) { fac::g_launches.store(0); }
@@ -124,7 +124,11 @@ int fac_denoise_spectrum_f32(float* spec, const float* bias_mag, float strength,
   return fac::denoise_spectrum(spec, bias_mag, strength, n_rows, n_bins, ld, (cudaStream_t)stream);
 }
 int fac_lstm_bidir_f32(const float* xp, const float* w_hh, float* out, int B, int T, int H, void* stream) {
-  return fac::lstm_bidir(xp, w_hh, out, B, T, H, (cudaStream_t)stream);
+  return fac::lstm_bidir(xp, w_hh, out, nullptr, B, T, H, (cudaStream_t)stream);
+}
+int fac_lstm_bidir_var_f32(const float* xp, const float* w_hh, float* out, const int* lengths, int B, int T, int H,
+                           void* stream) {
+  return fac::lstm_bidir(xp, w_hh, out, lengths, B, T, H, (cudaStream_t)stream);
 }
 int fac_taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, const float* pmem, const int* lengths,
                          const unsigned char* drop, const fac_taco_decoder_state* state, float* mel, float* gate,

@@ -37,6 +37,15 @@ __device__ __forceinline__ float tanhf_fast(float v) {
   return 1.0f - __fdividef(2.0f, __expf(2.0f * v) + 1.0f);
 }
 
+// Per-process caches of device properties / function attributes are keyed by the CURRENT device: a process
+// that drives several GPUs must not reuse what it learnt (or set) on another one.
+constexpr int FAC_MAX_DEVICES = 64;
+inline int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < FAC_MAX_DEVICES ? dev : 0;
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

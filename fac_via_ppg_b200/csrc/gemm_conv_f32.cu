@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_gemm_f32_kernel(const GemmPa
     const int m = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4));
     const int t = t0 + m;
     if (t >= p.T) continue;
+    const bool dead_row = e.kind == FAC_EPI_LINEAR && e.row_lengths != nullptr && t >= __ldg(e.row_lengths + b);
     const long long row = zoff + b * e.out_batch_stride + (long long)t * e.out_row_stride;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_gemm_f32_kernel(const GemmPa
             float o = apply_act(v[j], e.act);
             if (e.mask) o *= __ldg(e.mask + row + n + j);
             if (e.residual) o += __ldg(e.residual + row + n + j);
-            e.out[row + n + j] = o;
+            e.out[row + n + j] = dead_row ? 0.f : o;
           }
         }
       }

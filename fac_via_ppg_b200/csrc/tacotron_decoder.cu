@@ -540,9 +540,11 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
   // Energies (model.py:94-97) e[q] = sum_a v[a] tanh(pq[a] + s[q][a]).  With tanh(x) = 1 - 2 / (exp(2x) + 1) and
   // exp(2 (pq + s)) = exp(2 pq) exp(2 s), the critical path keeps one multiply, one reciprocal and one FMA per
   // (q, a): exp(2 s) is prepared ahead, exp(2 pq) costs 150 exponentials, and the constant sum_a v[a] drops
-  // out of the softmax.  Both exponents are clamped to +-20 (tanh is saturated to 1 ulp beyond +-9).
+  // out of the softmax.  Each exponent is clamped to +-43: exp(+-86) = 2^+-124 is still a normal fp32 (no 0 * inf),
+  // a product that overflows saturates tanh correctly through the reciprocal (1 / inf = 0), and terms that
+  // partly cancel (pq = 25, s = -24 -> tanh(1)) keep their sum, unlike a clamp at the saturation point of tanh.
   auto exp2x = [](float x) {
-    x = fminf(fmaxf(x, -20.f), 20.f);
+    x = fminf(fmaxf(x, -43.f), 43.f);
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 2.8853900817779268f));
     return r;

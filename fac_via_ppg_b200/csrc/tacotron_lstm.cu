@@ -78,7 +78,8 @@ inline LstmGeom lstm_geom(int H) {
 
 __global__ void __cluster_dims__(LSTM_CLUSTER, 1, 1) __launch_bounds__(LSTM_THREADS, 1)
     bilstm_cluster_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh, float* __restrict__ out,
-                          int B, int T, int H, int nb_per_cluster, const LstmGeom geo, long long* prof) {
+                          const int* __restrict__ lengths, int B, int T, int H, int nb_per_cluster, const LstmGeom geo,
+                          long long* prof) {
   extern __shared__ __align__(16) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -129,12 +130,15 @@ __global__ void __cluster_dims__(LSTM_CLUSTER, 1, 1) __launch_bounds__(LSTM_THRE
   // ---- epilogue thread = (unit eu, utterance slot en); c lives in a register for the whole sequence
   const int eu = tid % upc, en = tid / upc;
   const bool e_act = tid < upc * LSTM_NB && eu < nu && en < nb_per_cluster && n0 + en < B;
+  // ragged batch: this utterance has my_len valid rows; its reverse direction starts at row my_len - 1 and the
+  // steps beyond its length neither read xp nor write out (their state is never consumed)
+  const int my_len = e_act ? (lengths != nullptr ? min(max(__ldg(lengths + n0 + en), 0), T) : T) : 0;
   const long long xp_row = 2LL * 4 * H;
   auto load_xp = [&](int step, float (&dst)[4]) {
-    const int tt = dir == 0 ? step : T - 1 - step;
+    const int tt = dir == 0 ? step : my_len - 1 - step;
 #pragma unroll
     for (int g = 0; g < 4; ++g)
-      dst[g] = (e_act && step < T)
+      dst[g] = (e_act && step < my_len)
                    ? __ldg(xp + ((long long)(n0 + en) * T + tt) * xp_row + (long long)dir * 4 * H + g * H + u0 + eu)
                    : 0.f;
   };
@@ -204,8 +208,8 @@ __global__ void __cluster_dims__(LSTM_CLUSTER, 1, 1) __launch_bounds__(LSTM_THRE
       }
       c_reg = sigmoidf_fast(gv[1]) * c_reg + sigmoidf_fast(gv[0]) * tanhf_fast(gv[2]);
       hval = sigmoidf_fast(gv[3]) * tanhf_fast(c_reg);
-      const int tt = dir == 0 ? step : T - 1 - step;
-      out[((long long)(n0 + en) * T + tt) * (2 * H) + dir * H + u0 + eu] = hval;
+      const int tt = dir == 0 ? step : my_len - 1 - step;
+      if (step < my_len) out[((long long)(n0 + en) * T + tt) * (2 * H) + dir * H + u0 + eu] = hval;
     }
     if (tid < upc * LSTM_NB && eu < nu && en < nb_per_cluster) {
       float* slot = h_buf + ((cur ^ 1) * LSTM_NB + en) * hs + u0 + eu;
@@ -228,9 +232,12 @@ long long* g_lstm_prof = nullptr;
 // Clusters of 8 CTAs (1 CTA per SM) that can be resident at once: the GPC boundaries leave fewer than
 // SMs / 8 (measured on B200: 16 clusters requested -> a second wave, 2x the time).
 int max_resident_clusters(size_t smem) {
-  static int cached = -1;
-  static size_t cached_smem = 0;
-  if (cached >= 0 && cached_smem == smem) return cached;
+  static int cached_on[FAC_MAX_DEVICES];
+  static size_t cached_smem_on[FAC_MAX_DEVICES] = {};
+  const int slot = current_device_slot();
+  int& cached = cached_on[slot];
+  size_t& cached_smem = cached_smem_on[slot];
+  if (cached > 0 && cached_smem == smem) return cached;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(LSTM_CLUSTER * 32);
   cfg.blockDim = dim3(LSTM_THREADS);
@@ -256,7 +263,8 @@ int max_resident_clusters(size_t smem) {
 
 void lstm_set_prof(long long* p) { g_lstm_prof = p; }
 
-int lstm_bidir(const float* xp, const float* w_hh, float* out, int B, int T, int H, cudaStream_t st) {
+int lstm_bidir(const float* xp, const float* w_hh, float* out, const int* lengths, int B, int T, int H,
+               cudaStream_t st) {
   FAC_REQUIRE(xp && w_hh && out, "bilstm: NULL argument");
   FAC_REQUIRE(B > 0 && T > 0, "bilstm: empty problem B=%d T=%d", B, T);
   FAC_REQUIRE(H > 0 && H % 4 == 0, "bilstm: hidden size %d must be a positive multiple of 4", H);
@@ -275,8 +283,8 @@ int lstm_bidir(const float* xp, const float* w_hh, float* out, int B, int T, int
   int nb = 1;
   while (nb < LSTM_NB && 2 * ceil_div(B, nb) > resident) ++nb;
   const int groups = ceil_div(B, nb);
-  bilstm_cluster_kernel<<<2 * groups * LSTM_CLUSTER, LSTM_THREADS, geo.bytes, st>>>(xp, w_hh, out, B, T, H, nb, geo,
-                                                                                    g_lstm_prof);
+  bilstm_cluster_kernel<<<2 * groups * LSTM_CLUSTER, LSTM_THREADS, geo.bytes, st>>>(xp, w_hh, out, lengths, B, T, H,
+                                                                                    nb, geo, g_lstm_prof);
   count_launch();
   return check_launch("bilstm_cluster_kernel");
 }

@@ -128,7 +128,10 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // fp32 -> (hi, lo) fp16 split of two values, packed as half2 words (element 0 in the low half).
+// Values beyond the half range saturate to +-65504 (instead of hi = inf, lo = NaN poisoning the whole utterance).
 __device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
   const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);

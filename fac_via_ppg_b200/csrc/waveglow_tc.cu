@@ -92,6 +92,7 @@ struct TcParams {
   const float* residual;
   float* out_f32;
   long long mask_ld, res_ld, out_ld;
+  const int* row_lengths;  // TC_LINEAR, optional [B]: rows t >= row_lengths[b] are written as zeros (ragged batches)
   long long* prof;         // optional [grid][8] cycle counters
 };
 
@@ -313,6 +314,7 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
       const int b = tile / p.tiles_per_batch;
       const int t = (tile % p.tiles_per_batch) * TC_BM + row;
       const bool valid = tile < p.n_tiles && t < p.T;
+      const bool dead_row = valid && p.row_lengths != nullptr && t >= __ldg(p.row_lengths + b);
       const long long col = (long long)b * p.T + t;
       for (int once = 0; once < 1; ++once, ++u) {
         const uint32_t r = u & 1;
@@ -420,6 +422,10 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
                   const float4 m = __ldg(reinterpret_cast<const float4*>(rrow + j));
                   v[j] += m.x; v[j + 1] += m.y; v[j + 2] += m.z; v[j + 3] += m.w;
                 }
+            }
+            if (dead_row) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
             if (p.out_f32 != nullptr) {
               float* orow = p.out_f32 + col * p.out_ld + n0;
@@ -656,18 +662,16 @@ int make_weight_map(CUtensorMap* m, const void* ptr, int N, int K, int cg, int b
 }
 
 int sm_count() {
-  static int sms = [] {
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
-  return sms;
+  static int sms[FAC_MAX_DEVICES] = {};
+  const int dev = current_device_slot();
+  if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
 }
 
 template <int CG, int BK>
 int launch_tc_cg(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_on[FAC_MAX_DEVICES] = {};      // function attributes are per device
+  bool& attr_set = attr_set_on[current_device_slot()];
   constexpr int smem = TcCfg<CG, BK>::SMEM;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wn_gemm_tc_kernel<CG, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -716,6 +720,7 @@ long long* g_tc_prof = nullptr;
 // reference src/common/model.py:237-241): 32 x 32 tiles through shared memory.
 __device__ __forceinline__ void store_split(unsigned short* hi, unsigned short* lo, long long o, float v, bool fp16) {
   if (fp16) {
+    v = fminf(fmaxf(v, -65504.f), 65504.f);          // saturate instead of inf / NaN (see split2_f16)
     const __half h = __float2half_rn(v);
     hi[o] = __half_as_ushort(h);
     if (lo) lo[o] = __half_as_ushort(__float2half_rn(v - __half2float(h)));
@@ -834,6 +839,7 @@ int conv_gemm_tc(const fac_tc_conv* c, cudaStream_t st) {
   p.out_ld = c->out_ld;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(c->out_hi);
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(c->out_lo);
+  p.row_lengths = c->row_lengths;
   return launch_tc(maps, p, st, cg);
 }
 

@@ -29,7 +29,7 @@ def conv_src(t: torch.Tensor, taps: int = 1, dilation: int = 0, center: int = 0,
 
 def conv_gemm(srcs, w_packed, bias, n_out, out, *, batch, rows, kind=_ext.EPI_LINEAR, act=_ext.ACT_NONE,
               mask=None, residual=None, out2=None, n_split=0, accumulate_out2=False, out_batch_stride=None,
-              out_row_stride=None, phases=1, w_phase_stride=0, out_phase_stride=0):
+              out_row_stride=None, phases=1, w_phase_stride=0, out_phase_stride=0, row_lengths=None):
     """out[b, t, :n_out] = epilogue(sum over sources/taps/channels ... ) -- fac_conv_gemm_f32."""
     lib = _ext.load()
     arr = (_ext.ConvSrc * len(srcs))(*srcs)
@@ -37,7 +37,8 @@ def conv_gemm(srcs, w_packed, bias, n_out, out, *, batch, rows, kind=_ext.EPI_LI
     epi = _ext.ConvEpilogue(kind, act, out.data_ptr(),
                             out_batch_stride if out_batch_stride is not None else rows * width,
                             out_row_stride if out_row_stride is not None else width,
-                            _ext.ptr(mask), _ext.ptr(residual), _ext.ptr(out2), n_split, int(accumulate_out2))
+                            _ext.ptr(mask), _ext.ptr(residual), _ext.ptr(out2), n_split, int(accumulate_out2),
+                            _ext.ptr(row_lengths))
     rc = lib.fac_conv_gemm_f32(arr, len(srcs), w_packed.data_ptr(), _ext.ptr(bias), batch, rows, n_out,
                                C.byref(epi), phases, w_phase_stride, out_phase_stride, _ext.current_stream())
     _ext.check(rc, "fac_conv_gemm_f32")
@@ -90,10 +91,11 @@ TC_K_CHUNK = 512   # contraction elements per tensor-core accumulation chain (se
 
 
 def conv_gemm_tc(a, w, *, act=_ext.ACT_NONE, mask=None, residual=None, out=None, want_split=True, nsplit=2,
-                 k_chunk=None):
+                 k_chunk=None, row_lengths=None):
     """Conv1d / Linear on the tensor cores (fac_conv_gemm_tc).  ``a`` = (hi, lo) 16-bit (B, T, c_pad) from
     transpose_split/pad_split or a previous call; ``w`` = one entry of PackedTacotron.tc_weights() (same
-    16-bit type).  Returns (out_f32 or None, (hi, lo) or None)."""
+    16-bit type).  ``row_lengths`` (int32 [B], optional): rows beyond an utterance's length are written as
+    zeros.  Returns (out_f32 or None, (hi, lo) or None)."""
     a_hi, a_lo = a
     B, T, c_pad = a_hi.shape
     if c_pad != w["c_pad"]:
@@ -110,7 +112,7 @@ def conv_gemm_tc(a, w, *, act=_ext.ACT_NONE, mask=None, residual=None, out=None,
                     _ext.ptr(w["bias"]), _ext.ptr(mask), _ext.ptr(residual), _ext.ptr(out), _ext.ptr(nxt[0]),
                     _ext.ptr(nxt[1]), ld(mask), ld(residual), ld(out), B, T, c_pad, w["taps"],
                     (w["taps"] - 1) // 2, w["n_pad"], w["n_valid"], act, nsplit, int(a_hi.dtype == torch.float16),
-                    k_chunk or 0, 0, _ext.ptr(scratch))
+                    k_chunk or 0, 0, _ext.ptr(scratch), _ext.ptr(row_lengths))
     rc = _ext.load().fac_conv_gemm_tc(C.byref(d), _ext.current_stream())
     _ext.check(rc, "fac_conv_gemm_tc")
     return out, (nxt if want_split else None)

@@ -12,6 +12,9 @@ WaveGlow input format: the state dict of a ``WaveGlow`` after
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
+import json
+import os
 from collections import OrderedDict
 
 import torch
@@ -276,8 +279,46 @@ class PackedWaveGlow:
         return table
 
     @classmethod
-    def from_state(cls, sd, cfg, device):
-        return cls(cfg, device).load_state(sd)
+    def from_state(cls, sd, cfg, device, cache_dir=None):
+        """Packs ``sd``.  With ``cache_dir`` (default: the FAC_PACK_CACHE environment variable; unset = no cache)
+        the flat buffer is kept on disk under a key derived from the configuration, the pack format and a hash of
+        every weight, so a checkpoint is repacked (transposes, gate interleaving, W^-1 through cuSOLVER ...) once
+        per machine instead of once per process (reference load path: src/common/utils.py:177-181)."""
+        cache_dir = os.environ.get("FAC_PACK_CACHE") if cache_dir is None else cache_dir
+        if not cache_dir:
+            return cls(cfg, device).load_state(sd)
+        path = os.path.join(cache_dir, "waveglow-%s.pack" % state_fingerprint(sd, cfg))
+        packed = cls(cfg, device)
+        if os.path.isfile(path):
+            try:
+                blob = torch.load(path, map_location="cpu", weights_only=True)
+                if blob["format"] == PACK_FORMAT and blob["flat"].numel() == packed.flat.numel():
+                    packed.flat.copy_(blob["flat"])
+                    packed.from_cache = path
+                    return packed
+            except Exception:          # unreadable / truncated cache entry: repack and overwrite
+                pass
+        packed.load_state(sd)
+        os.makedirs(cache_dir, exist_ok=True)
+        tmp = "%s.tmp.%d" % (path, os.getpid())
+        torch.save({"format": PACK_FORMAT, "flat": packed.flat.detach().cpu()}, tmp)
+        os.replace(tmp, path)          # atomic: concurrent ranks see the old or the new file
+        return packed
+
+
+PACK_FORMAT = 2        # bump when waveglow_layout() or load_state() change what the flat buffer holds
+
+
+def state_fingerprint(sd, cfg) -> str:
+    """sha256 over the pack format, the configuration and every tensor (name, shape, bytes) of a state dict."""
+    h = hashlib.sha256()
+    h.update(("fac-pack-%d|" % PACK_FORMAT).encode())
+    h.update(json.dumps(cfg, sort_keys=True).encode())
+    for name in sorted(sd):
+        t = sd[name].detach().to("cpu", torch.float32).contiguous()
+        h.update(("|%s|%s|" % (name, tuple(t.shape))).encode())
+        h.update(t.numpy().tobytes())
+    return h.hexdigest()[:32]
 
 
 # ===================================================================== Tacotron2 (PPG -> Mel)

@@ -4,8 +4,10 @@ constants (sigma 0.6, denoiser strength 0.005, 16 kHz float32 WAV) and outputs
 
 PPG extraction (Kaldi nnet3 via pykaldi, reference src/ppg/) is out of scope, so
 ``--teacher_utterance_path`` accepts a precomputed PPG: a ``.npy`` file holding a (T, 5816) float
-array.  A ``.wav`` path is accepted only when the reference's ``ppg``/``common.data_utils`` modules are
-importable (then the original ``get_ppg`` runs unchanged).  Two extras help on boxes without
+array (what the reference's ``get_ppg`` returns, src/common/data_utils.py:55-59).  A recording (``.wav``)
+is accepted only when ``FAC_REFERENCE_SRC`` points at a reference ``src/`` tree whose Kaldi front-end
+imports: the original ``get_ppg`` then runs unchanged, with the reference's own ``common`` / ``ppg``
+packages imported in isolation from this package's drop-in aliases.  Two extras help on boxes without
 checkpoints: ``--synthetic SECONDS`` ignores the model/utterance paths and runs seeded random-init
 models on a synthetic PPG, and ``--no_denoiser`` skips the post-filter.
 """
@@ -38,13 +40,33 @@ def load_teacher_ppg(path):
         if ppg.ndim != 2:
             raise ValueError("expected a (T, n_symbols) PPG array in %s" % path)
         return ppg.astype(np.float32)
-    try:                                   # the reference's own front-end, when available
+    return _reference_get_ppg(path)
+
+
+def _reference_get_ppg(path):
+    """The reference's own front-end (src/common/data_utils.py:55-59 get_ppg + src/ppg DependenciesPPG) from the
+    tree FAC_REFERENCE_SRC names.  install_aliases() binds ``common`` to this package's drop-ins, which have no
+    ``data_utils``: the reference packages are therefore imported with those names temporarily un-aliased and
+    are removed again afterwards, so both worlds keep resolving to their own modules."""
+    src = os.environ.get("FAC_REFERENCE_SRC")
+    if not src or not os.path.isdir(os.path.join(src, "common")):
+        raise SystemExit("PPG extraction from a recording needs the reference's Kaldi front-end: set "
+                         "FAC_REFERENCE_SRC to the reference's src/ directory (with pykaldi installed), or pass a "
+                         "precomputed (T, 5816) .npy PPG as --teacher_utterance_path")
+    mine = lambda name: name.split(".")[0] in ("common", "ppg")                       # noqa: E731
+    saved = {name: sys.modules.pop(name) for name in list(sys.modules) if mine(name)}
+    sys.path.insert(0, src)
+    try:
         import ppg as ppg_module
         from common.data_utils import get_ppg
+        return np.asarray(get_ppg(path, ppg_module.DependenciesPPG()), dtype=np.float32)
     except ImportError as exc:
-        raise SystemExit("PPG extraction needs the reference's Kaldi front-end (pykaldi); pass a .npy PPG "
-                         "instead (%s)" % exc)
-    return get_ppg(path, ppg_module.DependenciesPPG())
+        raise SystemExit("the reference front-end under %s does not import (%s); pass a .npy PPG instead" % (src, exc))
+    finally:
+        sys.path.remove(src)
+        for name in [n for n in sys.modules if mine(n)]:
+            del sys.modules[name]
+        sys.modules.update(saved)
 
 
 def main(argv=None):

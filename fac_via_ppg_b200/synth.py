@@ -66,8 +66,13 @@ def flow_channels(cfg):
     return out
 
 
-def waveglow_state(seed: int = SEED, cfg=None, end_std: float = 0.02):
+def waveglow_state(seed: int = SEED, cfg=None, end_std: float = 0.02, convinv: str = "orthonormal"):
     """State dict of a weight-norm-free WaveGlow with non-degenerate weights.
+
+    ``convinv='orthonormal'`` keeps the reference's initialisation of the invertible 1x1
+    convolutions (a rotation, glow.py:74-80), for which W^-1 == W^T; ``convinv='general'``
+    draws W = Q1 diag(s) Q2^T with singular values s in [0.5, 2], what a trained checkpoint
+    looks like: only there is the inverse of glow.py:89-95 distinguishable from a transpose.
 
     ``WN.end`` is zero-initialised by the reference constructor
     (src/waveglow/glow.py:126-130), which would turn every coupling into the
@@ -102,6 +107,12 @@ def waveglow_state(seed: int = SEED, cfg=None, end_std: float = 0.02):
         q, _ = torch.linalg.qr(_normal(gen, (n_rem, n_rem), 1.0))
         if torch.det(q) < 0:
             q[:, 0] = -q[:, 0]
+        if convinv == "general":
+            q2, _ = torch.linalg.qr(_normal(gen, (n_rem, n_rem), 1.0))
+            s = torch.exp2(torch.rand((n_rem,), generator=gen) * 2.0 - 1.0)      # log-uniform in [0.5, 2]
+            q = (q * s[None, :]) @ q2.t()
+        elif convinv != "orthonormal":
+            raise ValueError("convinv must be 'orthonormal' or 'general'")
         sd[f"convinv.{k}.conv.weight"] = q.contiguous().view(n_rem, n_rem, 1)
     return sd
 

@@ -119,7 +119,7 @@ class Denoiser(torch.nn.Module):
         elif mode == "normal":
             mel_input = torch.randn((1, 80, 88), dtype=w.dtype, device=w.device)
         else:
-            raise Exception("Mode {} if not supported".format(mode))
+            raise Exception("Denoiser mode %r is unknown: use 'zeros' or 'normal'" % (mode,))
         with torch.no_grad():
             bias_audio = waveglow.infer(mel_input, sigma=0.0).float()
             bias_spec, _ = self.stft.transform(bias_audio)

@@ -249,8 +249,10 @@ class WaveGlow(torch.nn.Module):
         # the N(0,1) draws stay OUTSIDE the graph: same generator calls, shapes and order as the eager path (and as
         # the reference), so seeding behaves identically; the graph reads them from static buffers
         noise = self.noise_like_reference(B, F * self.upsample.stride[0] // self.n_group, spect.device, spect.dtype)
-        key = (tuple(spect.shape), spect.dtype, spect.device, self.precision, float(sigma), id(packed))
-        cache = self.__dict__.setdefault("_fac_graphs", {})
+        # the graphs live ON the packed weights they captured pointers of: a rebuilt (or adopted) pack starts with
+        # an empty cache and the old graphs die with the old buffers -- never keyed by id(), which CPython reuses
+        key = (tuple(spect.shape), spect.dtype, spect.device, self.precision, float(sigma))
+        cache = packed.__dict__.setdefault("_graphs", {})
         entry = cache.pop(key, None)
         if entry is None:
             static_in, static_noise = spect.clone(), [z.clone() for z in noise]

@@ -68,6 +68,9 @@ typedef struct fac_conv_epilogue {
   float* out2;           /* FAC_EPI_RES_SKIP: skip accumulator (same strides)       */
   int n_split;           /* FAC_EPI_RES_SKIP: width of the residual part            */
   int accumulate_out2;   /* 0: out2 = v, 1: out2 += v                               */
+  const int* row_lengths; /* FAC_EPI_LINEAR, optional [B]: utterance b has row_lengths[b] valid rows; rows beyond
+                             are written as exact zeros, so the next Conv1d sees the zero padding a shorter
+                             utterance processed alone would see (variable-length batches)                   */
 } fac_conv_epilogue;
 
 /* Replaces torch.nn.Conv1d / torch.nn.Linear as used through ConvNorm / LinearNorm
@@ -226,6 +229,8 @@ typedef struct fac_tc_conv {
    * (B*T, n_valid) fp32 buffer.  0 = one chain. */
   int k_chunk, _pad;
   float* scratch;
+  const int* row_lengths;  /* optional [B]: rows t >= row_lengths[b] of utterance b are written as exact zeros
+                              (fp32 and 16-bit outputs): per-utterance Conv1d zero padding in a ragged batch */
 } fac_tc_conv;
 int fac_conv_gemm_tc(const fac_tc_conv* conv, void* stream);
 /* (B, C, T) channel-major fp32 -> (B, T, pad) channels-last 16-bit hi [+ lo] (bf16, or IEEE half when fp16 != 0),
@@ -241,6 +246,12 @@ int fac_pad_split_16(const float* in, void* hi, void* lo, long long n_rows, int 
  * fac_conv_gemm_f32.  w_hh is [2][4H][H] (weight_hh_l0, weight_hh_l0_reverse).  out is
  * (B, T, 2H) = [forward h | reverse h], i.e. the encoder `memory`. */
 int fac_lstm_bidir_f32(const float* xp, const float* w_hh, float* out, int B, int T, int H, void* stream);
+/* Same for a ragged batch (the batched form of Tacotron2.inference; the reference builds input_lengths at
+ * src/common/model.py:599 and packs the sequences for nn.LSTM in Encoder.forward :225-233): utterance b has
+ * lengths[b] <= T valid rows, its reverse direction starts at row lengths[b]-1, and rows >= lengths[b] of `out`
+ * are left untouched (the caller zero-fills them).  lengths == NULL means T for everybody. */
+int fac_lstm_bidir_var_f32(const float* xp, const float* w_hh, float* out, const int* lengths, int B, int T, int H,
+                           void* stream);
 
 /* Optional cycle counters of the BiLSTM kernel: device buffer of grid*4 int64 per CTA (tensor-core gate mat-vec, cell
  * update + DSMEM hand-over, cluster barrier); NULL disables. */

@@ -34,8 +34,8 @@ def _replay_normal(noise):
     return orig, fake
 
 
-def waveglow_case(name, cfg, batch, frames, sigma, seed):
-    sd = synth.waveglow_state(cfg=cfg)
+def waveglow_case(name, cfg, batch, frames, sigma, seed, **state_kwargs):
+    sd = synth.waveglow_state(cfg=cfg, **state_kwargs)
     model = ref_shim.reference_waveglow(sd, cfg)
     mel = synth.synthetic_mel(batch, frames, seed=seed)
     torch.manual_seed(seed)
@@ -48,7 +48,7 @@ def waveglow_case(name, cfg, batch, frames, sigma, seed):
     finally:
         torch.Tensor.normal_ = orig
     torch.save({"cfg": cfg, "batch": batch, "frames": frames, "sigma": sigma, "mel_seed": seed,
-                "noise": noise, "audio": audio.clone(), "generator": "reference src/waveglow/glow.py WaveGlow.infer"},
+                "state_kwargs": state_kwargs, "noise": noise, "audio": audio.clone(), "generator": "reference src/waveglow/glow.py WaveGlow.infer"},
                os.path.join(GOLDEN, name))
     print(name, tuple(audio.shape), float(audio.std()))
 
@@ -78,6 +78,10 @@ def main():
     waveglow_case("waveglow_small_b2_f6.pt", synth.WAVEGLOW_CONFIG_SMALL, 2, 6, 0.6, 11)
     waveglow_case("waveglow_full_b2_f5.pt", synth.WAVEGLOW_CONFIG, 2, 5, 0.6, 12)
     waveglow_case("waveglow_full_b1_f88_sigma0.pt", synth.WAVEGLOW_CONFIG, 1, 88, 0.0, 13)  # the Denoiser call
+    # trained-checkpoint-like invertible 1x1 convs: W^-1 != W^T (glow.py:82-97)
+    waveglow_case("waveglow_small_b2_f6_general_convinv.pt", synth.WAVEGLOW_CONFIG_SMALL, 2, 6, 0.6, 14,
+                  convinv="general")
+    waveglow_case("waveglow_full_b2_f5_general_convinv.pt", synth.WAVEGLOW_CONFIG, 2, 5, 0.6, 15, convinv="general")
     tacotron_case("tacotron_b1_t24.pt", 24, 21)
 
 

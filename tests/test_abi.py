@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _ext.load()
-    assert lib.fac_version() >= 100
+    assert lib.fac_version() >= 200
     assert isinstance(lib.fac_last_error(), bytes)
 
 
@@ -36,7 +36,8 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_ext.WgWorkspace) == 4 * 8
     assert C.sizeof(_ext.WgFlow) == 8 + 5 * 8 + 4 * 16 * 8
     assert C.sizeof(_ext.WgModel) == 10 * 4 + 2 * 8 + 16 * C.sizeof(_ext.WgFlow)
-    assert C.sizeof(_ext.TcConv) == 10 * 8 + 3 * 8 + 12 * 4 + 8
+    assert C.sizeof(_ext.TcConv) == 10 * 8 + 3 * 8 + 12 * 4 + 8 + 8
+    assert C.sizeof(_ext.ConvEpilogue) == 2 * 4 + 8 + 2 * 8 + 3 * 8 + 2 * 4 + 8
     assert C.sizeof(_ext.TacoDecoderState) == 12 * 8
 
 

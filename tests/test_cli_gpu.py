@@ -98,3 +98,67 @@ def test_denoiser_matches_reference_restatement():
         out = den(audio.cuda(), strength=strength)
         assert out.shape == ref.shape == (2, 1, 4800)
         assert (out.cpu() - ref).abs().max().item() <= 2e-4, strength
+
+
+def test_cli_with_checkpoints_and_npy_ppg(tmp_path, monkeypatch):
+    """f4: the non-synthetic branch of the CLI -- Tacotron2 state-dict checkpoint, pickled WaveGlow module, a
+    precomputed (T, 5816) .npy PPG as --teacher_utterance_path (what get_ppg returns,
+    reference src/common/data_utils.py:55-59) -- with the on-disk pack cache enabled (f3)."""
+    fac_via_ppg_b200.install_aliases()
+    monkeypatch.setenv("FAC_PACK_CACHE", str(tmp_path / "packs"))
+    taco_path, wg_path, ppg_path = (str(tmp_path / n) for n in ("taco.pt", "waveglow.pt", "teacher.npy"))
+    state = synth.tacotron_state()
+    state["decoder.gate_layer.linear_layer.bias"] = torch.tensor([-10.0])        # never fires: 1000 frames
+    torch.save({"state_dict": state, "iteration": 1}, taco_path)
+    torch.save({"model": small_waveglow(), "iteration": 1}, wg_path)
+    np.save(ppg_path, synth.synthetic_ppg(1, 30, seed=3)[0].t().numpy())          # (T, 5816)
+    out = tmp_path / "out"
+    torch.manual_seed(0)
+    rc = generate_synthesis.main(["--ppg2mel_model", taco_path, "--waveglow_model", wg_path,
+                                  "--teacher_utterance_path", ppg_path, "--output_dir", str(out)])
+    assert rc == 0
+    fs, wav = wavfile.read(str(out / "ac.wav"))
+    # the gate never fires: the decoder runs to max_decoder_steps = 1000 (hparams.py:216) like the reference
+    assert fs == 16000 and wav.dtype == np.float32 and wav.shape == (1000 * 160,) and np.isfinite(wav).all()
+    assert os.listdir(tmp_path / "packs")                                        # the WaveGlow pack was cached
+    # a missing utterance is reported like the reference does (generate_synthesis.py:99-100), not raised
+    rc = generate_synthesis.main(["--ppg2mel_model", taco_path, "--waveglow_model", wg_path,
+                                  "--teacher_utterance_path", str(tmp_path / "nope.npy"), "--output_dir", str(out)])
+    assert rc == 1
+
+
+def test_old_format_waveglow_checkpoint_loads_and_matches(tmp_path):
+    """f3: a pickled WaveGlow in the res_layers / skip_layers format (reference convert_model.py:43-70) goes
+    through load_waveglow_model and produces the same audio as the same weights in the current format."""
+    fac_via_ppg_b200.install_aliases()
+    new = small_waveglow()
+    old = small_waveglow()
+    old.load_state_dict(new.state_dict())
+    C = synth.WAVEGLOW_CONFIG_SMALL["WN_config"]["n_channels"]
+    wnorm = torch.nn.utils.weight_norm
+    for wn in old.WN:
+        wn.res_layers, wn.skip_layers = torch.nn.ModuleList(), torch.nn.ModuleList()
+        for i, src in enumerate(wn.res_skip_layers):
+            last = i == wn.n_layers - 1
+            v, g = src.weight_v.detach(), src.weight_g.detach()
+            w = v * (g / v.flatten(1).norm(dim=1).view(-1, 1, 1))
+            b = src.bias.detach()
+            if not last:
+                res = torch.nn.Conv1d(C, C, 1)
+                res.weight.data, res.bias.data = w[:C].clone(), b[:C].clone()
+                wn.res_layers.append(wnorm(res, name="weight"))
+            skip = torch.nn.Conv1d(C, C, 1)
+            skip.weight.data, skip.bias.data = (w if last else w[C:]).clone(), (b if last else b[C:]).clone()
+            wn.skip_layers.append(wnorm(skip, name="weight"))
+        del wn.res_skip_layers
+    old_path, new_path = str(tmp_path / "old.pt"), str(tmp_path / "new.pt")
+    torch.save({"model": old}, old_path)
+    torch.save({"model": new}, new_path)
+    a, b = load_waveglow_model(old_path), load_waveglow_model(new_path)
+    assert hasattr(a.WN[0], "res_skip_layers") and not hasattr(a.WN[0], "res_layers")
+    mel = synth.synthetic_mel(1, 6, seed=2).cuda()
+    noise = [torch.randn(1, 6, 120, device="cuda"), torch.randn(1, 2, 120, device="cuda")]
+    for precision in ("fp32", "bf16x3"):
+        xa = a.set_precision(precision).infer(mel, 0.6, noise=noise)
+        xb = b.set_precision(precision).infer(mel, 0.6, noise=noise)
+        assert (xa - xb).abs().max().item() <= 1e-5, precision

@@ -9,16 +9,25 @@ import torch
 from fac_via_ppg_b200 import synth
 from oracle import ref_shim, tacotron_oracle, waveglow_oracle
 
-WG_CASES = ["waveglow_small_b2_f6.pt", "waveglow_full_b2_f5.pt", "waveglow_full_b1_f88_sigma0.pt"]
+WG_CASES = ["waveglow_small_b2_f6.pt", "waveglow_full_b2_f5.pt", "waveglow_full_b1_f88_sigma0.pt",
+            "waveglow_small_b2_f6_general_convinv.pt", "waveglow_full_b2_f5_general_convinv.pt"]
 
 
 @pytest.mark.parametrize("name", WG_CASES)
 def test_waveglow_oracle_matches_golden(golden_dir, name):
     g = torch.load(os.path.join(golden_dir, name))
-    sd = synth.waveglow_state(cfg=g["cfg"])
+    sd = synth.waveglow_state(cfg=g["cfg"], **g.get("state_kwargs", {}))
     mel = synth.synthetic_mel(g["batch"], g["frames"], seed=g["mel_seed"])
     out = waveglow_oracle.waveglow_infer(sd, g["cfg"], mel, g["sigma"], g["noise"])
     assert out.shape == g["audio"].shape
+    if g.get("state_kwargs", {}).get("convinv") == "general":
+        # the case exists to tell W^-1 from W^T (glow.py:82-97): the transpose must NOT reproduce the golden
+        wrong = dict(sd)
+        for k in range(g["cfg"]["n_flows"]):
+            w = sd[f"convinv.{k}.conv.weight"][:, :, 0]
+            wrong[f"convinv.{k}.conv.weight"] = w.t().inverse().contiguous()[:, :, None]
+        bad = waveglow_oracle.waveglow_infer(wrong, g["cfg"], mel, g["sigma"], g["noise"])
+        assert (bad - g["audio"]).abs().max().item() > 1e-2
     # same arithmetic, same library: tolerance only covers thread-count dependent summation order
     assert (out - g["audio"]).abs().max().item() <= 2e-5
 

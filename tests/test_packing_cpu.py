@@ -154,3 +154,79 @@ def test_out_of_range_weights_fail_loudly():
     sd["decoder.attention_rnn.weight_hh"] = sd["decoder.attention_rnn.weight_hh"] * 1e4
     with pytest.raises(_ext.FacError):
         PackedTacotron.from_state(sd, synth.TACOTRON_HPARAMS, "cpu")
+
+
+def test_pack_cache_round_trip_and_invalidation(tmp_path, monkeypatch):
+    """f3: the packed buffer is cached on disk under a hash of the weights; a hit skips the repacking, a changed
+    weight misses."""
+    cfg = synth.WAVEGLOW_CONFIG_SMALL
+    sd = synth.waveglow_state(cfg=cfg, seed=5)
+    first = PackedWaveGlow.from_state(sd, cfg, "cpu", cache_dir=str(tmp_path))
+    files = os.listdir(tmp_path)
+    assert len(files) == 1 and files[0].startswith("waveglow-") and not hasattr(first, "from_cache")
+    monkeypatch.setattr(PackedWaveGlow, "load_state", lambda self, sd: (_ for _ in ()).throw(AssertionError("repacked")))
+    again = PackedWaveGlow.from_state(sd, cfg, "cpu", cache_dir=str(tmp_path))
+    assert again.from_cache.endswith(files[0]) and torch.equal(again.flat, first.flat)
+    monkeypatch.setenv("FAC_PACK_CACHE", str(tmp_path))                 # the environment default
+    assert torch.equal(PackedWaveGlow.from_state(sd, cfg, "cpu").flat, first.flat)
+    monkeypatch.undo()
+    changed = dict(sd)
+    changed["WN.1.end.bias"] = sd["WN.1.end.bias"] + 1e-3
+    other = PackedWaveGlow.from_state(changed, cfg, "cpu", cache_dir=str(tmp_path))
+    assert len(os.listdir(tmp_path)) == 2 and not torch.equal(other.flat, first.flat)
+    # a truncated entry is repacked, not trusted
+    path = os.path.join(tmp_path, files[0])
+    open(path, "wb").write(b"garbage")
+    assert torch.equal(PackedWaveGlow.from_state(sd, cfg, "cpu", cache_dir=str(tmp_path)).flat, first.flat)
+
+
+def test_old_format_checkpoint_is_converted_like_the_reference():
+    """f3: res_layers / skip_layers checkpoints (reference src/waveglow/convert_model.py:43-70) are merged into
+    res_skip_layers; the converted model's plain weights equal a directly built current-format model."""
+    from fac_via_ppg_b200.waveglow.convert_model import _check_model_old_version, update_model
+    from fac_via_ppg_b200.waveglow.glow import WaveGlow
+    cfg = synth.WAVEGLOW_CONFIG_SMALL
+    sd = synth.waveglow_state(cfg=cfg, seed=6)
+    new = WaveGlow.remove_weightnorm(WaveGlow(**cfg))
+    new.load_state_dict(sd)
+    # synthesize the old format from the same weights: split every res_skip conv into weight-normed res / skip convs
+    old = WaveGlow(**cfg)
+    old.load_state_dict(WaveGlow(**cfg).state_dict())
+    old.upsample.load_state_dict(new.upsample.state_dict())
+    C = cfg["WN_config"]["n_channels"]
+    wnorm = torch.nn.utils.weight_norm
+    for k, wn in enumerate(old.WN):
+        ref = new.WN[k]
+        old.convinv[k].load_state_dict(new.convinv[k].state_dict())
+        wn.end.load_state_dict(ref.end.state_dict())
+        for name in ("start",):
+            conv = torch.nn.Conv1d(ref.start.in_channels, C, 1)
+            conv.load_state_dict(ref.start.state_dict())
+            wn.start = wnorm(conv, name="weight")
+        for lst in ("in_layers", "cond_layers"):
+            for i, src in enumerate(getattr(ref, lst)):
+                conv = torch.nn.Conv1d(src.in_channels, src.out_channels, src.kernel_size[0], dilation=src.dilation[0],
+                                       padding=src.padding[0])
+                conv.load_state_dict(src.state_dict())
+                getattr(wn, lst)[i] = wnorm(conv, name="weight")
+        wn.res_layers, wn.skip_layers = torch.nn.ModuleList(), torch.nn.ModuleList()
+        for i, src in enumerate(ref.res_skip_layers):
+            last = i == wn.n_layers - 1
+            w, b = src.weight.detach(), src.bias.detach()
+            if not last:
+                res = torch.nn.Conv1d(C, C, 1)
+                res.weight.data, res.bias.data = w[:C].clone(), b[:C].clone()
+                wn.res_layers.append(wnorm(res, name="weight"))
+            skip = torch.nn.Conv1d(C, C, 1)
+            skip.weight.data, skip.bias.data = (w if last else w[C:]).clone(), (b if last else b[C:]).clone()
+            wn.skip_layers.append(wnorm(skip, name="weight"))
+        del wn.res_skip_layers
+    assert _check_model_old_version(old) and not _check_model_old_version(new)
+    assert update_model(new) is new
+    conv = update_model(old)
+    assert _check_model_old_version(old) and not _check_model_old_version(conv)       # the input is left alone
+    conv = WaveGlow.remove_weightnorm(conv)
+    got, want = conv.plain_state(), new.plain_state()
+    assert set(got) == set(want)
+    for name in want:
+        assert (got[name] - want[name]).abs().max().item() <= 1e-6, name

@@ -20,10 +20,10 @@ def rms(a, b):
     return (a.double().cpu() - b.double().cpu()).pow(2).mean().sqrt().item()
 
 
-def build_model(cfg, seed=synth.SEED):
+def build_model(cfg, seed=synth.SEED, **state_kwargs):
     model = WaveGlow(**cfg)
     model = WaveGlow.remove_weightnorm(model)
-    model.load_state_dict(synth.waveglow_state(seed=seed, cfg=cfg), strict=True)
+    model.load_state_dict(synth.waveglow_state(seed=seed, cfg=cfg, **state_kwargs), strict=True)
     return model.to(DEV).eval().set_precision("fp32")      # this file tests the exact-fp32 FFMA path
 
 
@@ -97,10 +97,13 @@ def test_upsample_squeeze_matches_oracle(frames):
 
 # ---------------------------------------------------------------- whole infer()
 @pytest.mark.parametrize("name", ["waveglow_small_b2_f6.pt", "waveglow_full_b2_f5.pt",
-                                  "waveglow_full_b1_f88_sigma0.pt"])
+                                  "waveglow_full_b1_f88_sigma0.pt", "waveglow_small_b2_f6_general_convinv.pt",
+                                  "waveglow_full_b2_f5_general_convinv.pt"])
 def test_infer_matches_reference_golden(golden_dir, name):
+    """The *_general_convinv cases carry non-orthogonal invertible 1x1 weights (singular values in [0.5, 2]), so a
+    transpose in place of the inverse of glow.py:89-95, or a row/column mix-up of W^-1, fails them."""
     g = torch.load(os.path.join(golden_dir, name))
-    model = build_model(g["cfg"])
+    model = build_model(g["cfg"], **g.get("state_kwargs", {}))
     mel = synth.synthetic_mel(g["batch"], g["frames"], seed=g["mel_seed"]).to(DEV)
     audio = model.infer(mel, sigma=g["sigma"], noise=[z.to(DEV) for z in g["noise"]])
     assert audio.shape == g["audio"].shape
