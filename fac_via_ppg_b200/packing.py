@@ -274,9 +274,36 @@ class PackedWaveGlow:
                     l32.view(flat32, f"{k}.{i}.res_b").copy_(b_rs[:Cn])
                     flow.res_b[i] = l32.ptr(flat32, f"{k}.{i}.res_b")
             l32.view(flat32, f"{k}.out_bias")[: 2 * n_half].copy_(bias8.float())
-            flow.out_bias = l32.ptr(flat32, f"{k}.out_bias")
+        table = self._tc_table(flat16, flat32)
         self._tc = (flat16, flat32, table)
         return table
+
+    def _tc_table(self, flat16, flat32):
+        """``fac_wg_tc_weights`` pointer table over the two derived buffers (a pure function of the layouts)."""
+        l16, l32 = self.tc_layouts()
+        L = self.cfg["WN_config"]["n_layers"]
+        table = _ext.WgTcWeights()
+        table.up_hi, table.up_lo, table.mel_pad = l16.ptr(flat16, "up_hi"), l16.ptr(flat16, "up_lo"), self.mel_pad
+        for k in range(self.cfg["n_flows"]):
+            flow = table.flows[k]
+            flow.out_bias = l32.ptr(flat32, f"{k}.out_bias")
+            for i in range(L):
+                flow.w1_hi[i], flow.w1_lo[i] = l16.ptr(flat16, f"{k}.{i}.w1_hi"), l16.ptr(flat16, f"{k}.{i}.w1_lo")
+                flow.wc[i] = l32.ptr(flat32, f"{k}.{i}.wc")
+                if i < L - 1:
+                    flow.w2_hi[i], flow.w2_lo[i] = l16.ptr(flat16, f"{k}.{i}.w2_hi"), l16.ptr(flat16, f"{k}.{i}.w2_lo")
+                    flow.res_b[i] = l32.ptr(flat32, f"{k}.{i}.res_b")
+        return table
+
+    def to(self, device):
+        """A copy of the packed weights (and of the derived tensor-core buffers, when built) on ``device``: pack
+        once on the host -- or load from the pack cache -- and ship three flat buffers."""
+        new = PackedWaveGlow(self.cfg, device)
+        new.flat.copy_(self.flat)
+        if getattr(self, "_tc", None) is not None:
+            f16, f32 = self._tc[0].to(device), self._tc[1].to(device)
+            new._tc = (f16, f32, new._tc_table(f16, f32))
+        return new
 
     @classmethod
     def from_state(cls, sd, cfg, device, cache_dir=None):
@@ -510,3 +537,12 @@ class PackedTacotron:
     @classmethod
     def from_state(cls, sd, hp, device):
         return cls(hp, device).load_state(sd)
+
+    def to(self, device):
+        """A copy on ``device`` (flat buffer + the derived tensor-core operand matrices, when built)."""
+        new = PackedTacotron(self.hp, device)
+        new.flat.copy_(self.flat)
+        if getattr(self, "_tc", None) is not None:
+            new._tc = {name: {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in w.items()}
+                       for name, w in self._tc.items()}
+        return new
