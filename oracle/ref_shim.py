@@ -66,6 +66,10 @@ def install():
     if not available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
     # (1) bare 'common' package + librosa stub
+    # (drop-in aliases of fac_via_ppg_b200.install_aliases() under the same names would shadow the reference)
+    for name in [n for n in sys.modules if n.split(".")[0] in ("common", "waveglow")
+                 and "fac_via_ppg_b200" in (getattr(sys.modules[n], "__name__", "") or "")]:
+        del sys.modules[name]
     common = types.ModuleType("common")
     common.__path__ = [os.path.join(REFERENCE_SRC, "common")]
     sys.modules.setdefault("common", common)

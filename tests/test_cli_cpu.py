@@ -27,7 +27,18 @@ def test_recording_without_reference_front_end_fails_loudly(tmp_path, monkeypatc
     assert "FAC_REFERENCE_SRC" in str(exc.value)
 
 
-def test_recording_uses_the_reference_front_end_despite_the_aliases(tmp_path, monkeypatch):
+@pytest.fixture
+def alias_sandbox():
+    """The drop-in aliases live in sys.modules: keep them from leaking into tests that import the real reference."""
+    names = lambda: [n for n in sys.modules if n.split(".")[0] in ("common", "waveglow", "ppg")]   # noqa: E731
+    saved = {n: sys.modules[n] for n in names()}
+    yield
+    for n in names():
+        del sys.modules[n]
+    sys.modules.update(saved)
+
+
+def test_recording_uses_the_reference_front_end_despite_the_aliases(tmp_path, monkeypatch, alias_sandbox):
     """The drop-in aliases bind `common` to this package (no data_utils there); the reference's own `common` and
     `ppg` packages must still be importable for get_ppg, and the aliases must be back afterwards."""
     src = tmp_path / "src"
