@@ -102,6 +102,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- gate (reference src/waveglow/glow.py:33-40)
+__device__ __forceinline__ float ex2_approx(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+// tanh(a) * sigmoid(b) = (e^{2a} - 1) / ((e^{2a} + 1) (1 + e^{-b})), ~3e-7 absolute error.
+__device__ __forceinline__ float gate_act(float a, float b) {
+  a = fminf(fmaxf(a, -15.f), 15.f);
+  const float ea = ex2_approx(a * 2.8853900817779268f);
+  const float eb = ex2_approx(b * -1.4426950408889634f);
+  return __fdividef(ea - 1.f, (ea + 1.f) * (1.f + eb));
+}
+
 // ---------------------------------------------------------------- descriptors
 // K-major operand tile in shared memory, rows of `row_bytes` (32 / 64 / 128 = the TMA swizzle
 // span), 8-row groups `8*row_bytes` apart (dense TMA box).  Bit layout: start address [0,14)

@@ -24,19 +24,18 @@
 // contraction in chains of <= k_chunk elements that alternate the two TMEM accumulators (see conv_gemm_tc).
 #include "fac_common.cuh"
 #include "tc_common.cuh"
+#include "tc_host.cuh"
 
 namespace fac {
 namespace {
 
 using namespace tc;
 
-constexpr int TC_BM = 128;       // time rows per tile (UMMA M)
 // K per pipeline stage (BK): 64 (128-byte rows, SWIZZLE_128B) by default, 32 (64-byte rows, SWIZZLE_64B) optional:
 // the TMA issue rate is per row request, so rows should be as wide as the stage budget allows.
 constexpr int TC_BK_MAX = 64;
 constexpr int UMMA_K = 16;
 constexpr int TC_NMAX = 512;     // accumulator columns per tile (all of TMEM)
-constexpr int TC_NHALF = 256;    // N of one UMMA
 constexpr int TC_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each owning half of the columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_NOUT = 8;       // channels of the collapsed skip path (= max 2*n_half)
@@ -95,19 +94,6 @@ struct TcParams {
   const int* row_lengths;  // TC_LINEAR, optional [B]: rows t >= row_lengths[b] are written as zeros (ragged batches)
   long long* prof;         // optional [grid][8] cycle counters
 };
-
-__device__ __forceinline__ float ex2_approx(float v) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-  return r;
-}
-// tanh(a) * sigmoid(b) = (e^{2a} - 1) / ((e^{2a} + 1) (1 + e^{-b})), ~3e-7 absolute error.
-__device__ __forceinline__ float gate_act(float a, float b) {
-  a = fminf(fmaxf(a, -15.f), 15.f);
-  const float ea = ex2_approx(a * 2.8853900817779268f);
-  const float eb = ex2_approx(b * -1.4426950408889634f);
-  return __fdividef(ea - 1.f, (ea + 1.f) * (1.f + eb));
-}
 
 template <int CG, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -602,71 +588,15 @@ __global__ void wn_end_tc_kernel(const float* __restrict__ out8, const float* __
   }
 }
 
-// ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-inline CUtensorMapSwizzle tc_swizzle(int bk) {
-  return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-}
+// ---------------------------------------------------------------- host side (tensor maps: tc_host.cuh)
 int g_tc_bk = 0;   // 0 = automatic
 inline int tc_pick_bk(int) { return g_tc_bk ? g_tc_bk : 64; }   // measured: 64 wins in both modes (profiles/README.md)
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = [] {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      ptr = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(ptr);
-  }();
-  return fn;
-}
-
-// (B, T, C) channels-last bf16 activation: box = 16 channels x 128 rows of one utterance.
-int make_act_map(CUtensorMap* m, const void* ptr, int B, int T, int C, int bk) {
-  EncodeTiledFn fn = encode_fn();
-  FAC_REQUIRE(fn != nullptr, "tensor-core path: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
-  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
-  cuuint32_t box[3] = {(cuuint32_t)bk, TC_BM, 1};
-  cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, tc_swizzle(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  FAC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", B, T, C, (int)r);
-  return 0;
-}
 int g_tc_batch_group = 0; // utterances per pass of fac_waveglow_infer_tc over a flow; 0 = the whole batch
 int g_tc_cta_group = 0;   // 0 = automatic: CTA pairs for the split-bf16 mode, single CTAs for plain bf16
 
 // Measured on B200 (profiles/README.md): pairs win 9 % in split-bf16 (operand traffic and shared-memory reads
 // per UMMA drop by a third, 6-stage ring); plain bf16 is TMA-feed-bound either way and is 3 % faster unpaired.
 inline int tc_pick_cg(int nsplit) { return g_tc_cta_group ? g_tc_cta_group : (nsplit == 2 ? 2 : 1); }
-
-// (N, K) row-major bf16 weight: box = 32 k x (min(256, N) / cta_group) rows.
-int make_weight_map(CUtensorMap* m, const void* ptr, int N, int K, int cg, int bk) {
-  EncodeTiledFn fn = encode_fn();
-  FAC_REQUIRE(fn != nullptr, "tensor-core path: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)((N < TC_NHALF ? N : TC_NHALF) / cg)};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, tc_swizzle(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  FAC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight %dx%d) failed: %d", N, K, (int)r);
-  return 0;
-}
-
-int sm_count() {
-  static int sms[FAC_MAX_DEVICES] = {};
-  const int dev = current_device_slot();
-  if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-  return sms[dev];
-}
 
 template <int CG, int BK>
 int launch_tc_cg(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st) {
