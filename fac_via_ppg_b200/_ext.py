@@ -63,6 +63,7 @@ class WgWorkspace(C.Structure):
 class WgTcFlow(C.Structure):
     _fields_ = [("w1_hi", _fp * FAC_MAX_LAYERS), ("w1_lo", _fp * FAC_MAX_LAYERS),
                 ("w2_hi", _fp * FAC_MAX_LAYERS), ("w2_lo", _fp * FAC_MAX_LAYERS),
+                ("w2r_hi", _fp * FAC_MAX_LAYERS), ("w2r_lo", _fp * FAC_MAX_LAYERS),
                 ("wc", _fp * FAC_MAX_LAYERS), ("res_b", _fp * FAC_MAX_LAYERS), ("out_bias", _fp)]
 
 
@@ -73,7 +74,7 @@ class WgTcWeights(C.Structure):
 
 class WgTcWorkspace(C.Structure):
     _fields_ = [(n, _fp) for n in ("mel_hi", "mel_lo", "spect_hi", "spect_lo", "x_hi", "x_lo", "acts_hi", "acts_lo",
-                                   "out8")]
+                                   "out8", "x2_hi", "x2_lo")]
 
 
 class TacoDecoderWeights(C.Structure):
@@ -118,6 +119,7 @@ SIGNATURES = {
     "fac_tc_set_cta_group": (C.c_int, [C.c_int]),
     "fac_tc_set_batch_group": (C.c_int, [C.c_int]),
     "fac_tc_set_k_block": (C.c_int, [C.c_int]),
+    "fac_tc_set_fused": (C.c_int, [C.c_int]),
     "fac_selftest_grid_barrier": (C.c_int, [_fp, C.c_int, _fp]),
     "fac_denoise_spectrum_f32": (C.c_int, [_fp, _fp, C.c_float, C.c_longlong, C.c_int, C.c_int, _fp]),
     "fac_lstm_bidir_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
@@ -160,6 +162,8 @@ def load(build_if_missing: bool = True):
         check(lib.fac_tc_set_cta_group(int(cta_group)), "fac_tc_set_cta_group")
     if k_block:
         check(lib.fac_tc_set_k_block(int(k_block)), "fac_tc_set_k_block")
+    if os.environ.get("FAC_TC_FUSED"):
+        check(lib.fac_tc_set_fused(int(os.environ["FAC_TC_FUSED"])), "fac_tc_set_fused")
     return lib
 
 

@@ -42,6 +42,7 @@ int tc_pad_split(const float*, void*, void*, long long, int, int, int, cudaStrea
 int denoise_spectrum(float*, const float*, float, long long, int, int, cudaStream_t);
 int tc_set_cta_group(int);
 int tc_set_k_block(int);
+int tc_set_fused(int);
 int selftest_grid_barrier(unsigned int*, int, cudaStream_t);
 int lstm_bidir(const float*, const float*, float*, const int*, int, int, int, cudaStream_t);
 int taco_decoder_run(const fac_taco_decoder_weights*, const float*, const float*, const int*, const unsigned char*,
@@ -116,6 +117,7 @@ void fac_taco_set_profile_buffer(long long* device_buf) { fac::taco_set_prof(dev
 int fac_tc_set_batch_group(int utterances) { return fac::tc_set_batch_group(utterances); }
 int fac_tc_set_cta_group(int cta_group) { return fac::tc_set_cta_group(cta_group); }
 int fac_tc_set_k_block(int k_block) { return fac::tc_set_k_block(k_block); }
+int fac_tc_set_fused(int enabled) { return fac::tc_set_fused(enabled); }
 int fac_selftest_grid_barrier(unsigned int* zeroed_counter, int iters, void* stream) {
   return fac::selftest_grid_barrier(zeroed_counter, iters, (cudaStream_t)stream);
 }

@@ -1,0 +1,537 @@
+// One WaveGlow WN layer (reference src/waveglow/glow.py:158-174) as ONE launch on the 5th-generation tensor
+// cores: the in+cond GEMM, the gate, the collapsed skip update AND the residual GEMM + residual add, with the
+// gated activations handed from the first GEMM's epilogue to the second GEMM through shared memory.
+//
+// The two-launch form (waveglow_tc.cu) writes `acts` (hi+lo) to HBM and reads it straight back, re-reads and
+// re-writes the residual stream x in a second pass and spends ~5 % of its UMMAs on an identity block that
+// performs x + res on the tensor core.  Here, per CTA pair (cta_group::2, UMMA M = 256 = two adjacent 128-row
+// time tiles) and per tile:
+//   U(u)  u = 0,1: pre[256 x 256] = [x(t-d) | x(t) | x(t+d) | spect(t)] W1[u]^T      (K = 3C + n_cond, split-bf16:
+//                  3 UMMAs per product) into TMEM region 0
+//   E(u)          the 8 epilogue warps DRAIN region 0 into registers (128 fp32 per thread) and release it at
+//                  once, then gate tanh*sigmoid -> acts (128 channels of this unit), out8 += Wc acts (fp32), and
+//                  write acts as bf16 hi/lo straight into shared memory in the UMMA operand layout (the TMA
+//                  swizzle applied by hand)
+//   P(u)          res[256 x C] (+)= acts_u W_res[:, u]^T into TMEM region 1 (K = the unit's 128 channels)
+//   EG            x_new = res + b_res + x (glow.py:166) -> bf16 hi/lo of the NEXT layer's input buffer
+// The UMMA issue order is U(q), P(q-1), U(q+1), P(q) ... over the flattened unit sequence q: every unit is
+// followed by a short residual part in the OTHER TMEM region, which hides the register drain of the unit just
+// finished, so a single 256-column accumulator region serves the first GEMM without stalls and the other 256
+// columns hold the residual accumulator -- all 512 TMEM columns, no double buffering needed.  acts never
+// touches HBM; x is read by TMA (taps) + once more by EG from L2 and written once, into a second buffer (the
+// neighbouring tiles still read the old x for their dilated taps: layers ping-pong between two x buffers).
+// Shared memory: operand ring (128 KB: 2 stages of K = 64 or 4 stages of K = 32) + the acts operand tile
+// (64 KB) + Wc / out8 exchange.  Registers: the epilogue warpgroups take 232 registers per thread from the
+// producer / issuer warpgroup (setmaxnreg), which is what makes a 128-register drain possible.
+// Layer without a residual output (the last one, glow.py:168-169): U / E only.
+#include "fac_common.cuh"
+#include "tc_common.cuh"
+#include "tc_host.cuh"
+
+namespace fac {
+namespace {
+
+using namespace tc;
+
+constexpr int FU_THREADS = 384;        // warpgroup 0 = {TMA producer, UMMA issuer, 2 idle warps}, warpgroups 1-2 = epilogue
+constexpr int FU_EPI_WARPS = 8;
+constexpr int FU_EPI_THREADS = 32 * FU_EPI_WARPS;
+constexpr int FU_NOUT = 8;             // channels of the collapsed skip path
+constexpr int FU_CMAX = 256;
+constexpr int FU_MAX_STAGES = 8;
+constexpr int FU_RING_BYTES = 128 * 1024;
+constexpr int FU_ACTS_BYTES = 64 * 1024;          // 128 rows x 128 channels x (hi + lo) x 2 B
+constexpr int FU_BAR_BYTES = 256;
+constexpr int FU_WC_BYTES = FU_NOUT * FU_CMAX * 4;
+constexpr int FU_X8_BYTES = TC_BM * FU_NOUT * 4;
+constexpr int FU_SMEM = FU_RING_BYTES + FU_ACTS_BYTES + FU_BAR_BYTES + FU_WC_BYTES + FU_X8_BYTES + 1024;
+constexpr int FU_REGS_LOW = 40, FU_REGS_HIGH = 232;   // 128 x 40 + 256 x 232 = 384 x 168
+
+struct FusedParams {
+  int T, B, tiles_per_batch, n_tiles;
+  int C, n_cond, taps, dilation, center;
+  int k1_steps;              // K steps of the first GEMM: (taps * C + n_cond) / BK
+  int has_res;               // 0: last layer (no residual GEMM)
+  const float* bias1;        // [2C] in.bias + cond.bias, gate-interleaved
+  const float* res_b;        // [C]
+  const float* wc;           // [8][C] collapsed skip weights
+  float* out8;               // (B, T, 8)
+  int accumulate_out8;
+  const __nv_bfloat16* x_hi;     // residual stream read by EG (the same buffer the x tensor maps describe)
+  const __nv_bfloat16* x_lo;
+  __nv_bfloat16* xo_hi;          // residual stream written for the next layer
+  __nv_bfloat16* xo_lo;
+  __nv_bfloat16* acts_hi;        // optional (tests): the gated activations, (B, T, C)
+  __nv_bfloat16* acts_lo;
+};
+
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// wait with cluster-scope acquire: the arrivals come from the peer CTA's threads after their shared-memory writes
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  while (!mbar_try_wait_cluster(addr, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// byte offset inside a K-major operand tile of `ROWB`-byte rows (dense, 1024-byte aligned) -> the offset the TMA
+// swizzle mode of that row width (128B / 64B) would have stored it at: address bits [4,7) ^= bits [7,10) (128B),
+// bits [4,6) ^= bits [7,9) (64B)
+template <int ROWB>
+__device__ __forceinline__ uint32_t swizzle_off(uint32_t off) {
+  return ROWB == 128 ? off ^ (((off >> 7) & 7u) << 4) : off ^ (((off >> 7) & 3u) << 4);
+}
+
+template <int BK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FU_THREADS, 1)
+wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid_constant__ CUtensorMap x_lo_map,
+                      const __grid_constant__ CUtensorMap s_hi_map, const __grid_constant__ CUtensorMap s_lo_map,
+                      const __grid_constant__ CUtensorMap w1_hi_map, const __grid_constant__ CUtensorMap w1_lo_map,
+                      const __grid_constant__ CUtensorMap w2_hi_map, const __grid_constant__ CUtensorMap w2_lo_map,
+                      const FusedParams p) {
+  constexpr int ROWB = BK * 2;                       // bytes of one operand row
+  constexpr int A_BYTES = TC_BM * ROWB;              // one 128-row activation tile (hi or lo)
+  constexpr int W_BYTES = (TC_NHALF / 2) * ROWB;     // this CTA's half of a 256-row weight block (hi or lo)
+  constexpr int STAGE_BYTES = 2 * (A_BYTES + W_BYTES);
+  constexpr int STAGES = FU_RING_BYTES / STAGE_BYTES;
+  constexpr int W_OFF = 2 * A_BYTES;                 // stage layout: A_hi A_lo W_hi W_lo
+  static_assert(STAGES >= 2 && STAGES <= FU_MAX_STAGES, "ring");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* acts_s = smem + FU_RING_BYTES;            // [k step][hi | lo][128 rows][ROWB], 1024-byte aligned
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + FU_RING_BYTES + FU_ACTS_BYTES);
+  uint64_t* empty = full + FU_MAX_STAGES;
+  uint64_t* tmem_full = empty + FU_MAX_STAGES;       // [2]: region 0 = first GEMM, region 1 = residual GEMM
+  uint64_t* tmem_empty = tmem_full + 2;              // [2]
+  uint64_t* acts_ready = tmem_empty + 2;             // epilogue -> issuer (leader's copy is used)
+  uint64_t* acts_free = acts_ready + 1;              // issuer -> epilogue (both CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acts_free + 1);
+  float* wc_s = reinterpret_cast<float*>(smem + FU_RING_BYTES + FU_ACTS_BYTES + FU_BAR_BYTES);
+  float* x8_s = wc_s + FU_NOUT * FU_CMAX;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int tile_first = ((int)blockIdx.x / 2) * 2;
+  const int C = p.C;
+  const int n_total = 2 * C;
+  const int n_units = (n_total + TC_NHALF - 1) / TC_NHALF;          // accumulator blocks of the first GEMM per tile
+  const int n_cols = n_total < TC_NHALF ? n_total : TC_NHALF;       // columns of one block
+  const int chpu = n_cols / 2;                                      // channels one unit contributes
+  const int kp_steps = chpu / BK;                                   // K steps of one residual part
+  int my_tiles = 0;
+  for (int tb = tile_first; tb < p.n_tiles; tb += (int)gridDim.x) ++my_tiles;
+  const int Q = my_tiles * n_units;                                 // units of this CTA pair
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int r = 0; r < 2; ++r) {
+      mbar_init(&tmem_full[r], 1);
+      mbar_init(&tmem_empty[r], FU_EPI_WARPS * 2);
+    }
+    mbar_init(acts_ready, FU_EPI_WARPS * 2);
+    mbar_init(acts_free, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&x_hi_map);
+    tma_prefetch_desc(&w1_hi_map);
+  }
+  for (int i = threadIdx.x; i < FU_NOUT * C; i += FU_THREADS) wc_s[i] = __ldg(p.wc + i);
+  if (warp == 1) tmem_alloc_cg2(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FU_REGS_LOW));
+    if (warp == 0 && lane == 0) {
+      // ===================================================== TMA producer
+      const int w1_rows = n_cols / 2, w2_rows = C / 2;            // weight rows staged by this CTA
+      const int steps_x = p.taps * (C / BK);
+      int stage = 0;
+      uint32_t phase = 0;
+      auto acquire = [&](uint32_t bytes) -> uint8_t* {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * bytes);   // both CTAs' loads land on the leader's barrier
+        return smem + stage * STAGE_BYTES;
+      };
+      auto advance = [&]() {
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int q = 0; q <= Q; ++q) {
+        if (q < Q) {
+          const int tile = tile_first + (q / n_units) * (int)gridDim.x + rank;   // may be one past the end: OOB -> zeros
+          const int u = q % n_units;
+          const int b = tile / p.tiles_per_batch, t0 = (tile % p.tiles_per_batch) * TC_BM;
+          const int w_row = u * TC_NHALF + rank * w1_rows;
+          for (int ks = 0; ks < p.k1_steps; ++ks) {
+            uint8_t* st = acquire((uint32_t)(2 * A_BYTES + 2 * w1_rows * ROWB));
+            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+            if (ks < steps_x) {
+              const int cps = C / BK, tap = ks / cps, c0 = (ks - tap * cps) * BK;
+              const int row0 = t0 + tap * p.dilation - p.center;
+              tma_load_3d_cg2(st, &x_hi_map, lead_full, c0, row0, b);
+              tma_load_3d_cg2(st + A_BYTES, &x_lo_map, lead_full, c0, row0, b);
+            } else {
+              const int c0 = (ks - steps_x) * BK;
+              tma_load_3d_cg2(st, &s_hi_map, lead_full, c0, t0, b);
+              tma_load_3d_cg2(st + A_BYTES, &s_lo_map, lead_full, c0, t0, b);
+            }
+            tma_load_2d_cg2(st + W_OFF, &w1_hi_map, lead_full, ks * BK, w_row);
+            tma_load_2d_cg2(st + W_OFF + W_BYTES, &w1_lo_map, lead_full, ks * BK, w_row);
+            advance();
+          }
+        }
+        if (q > 0 && p.has_res) {
+          const int u = (q - 1) % n_units;
+          for (int s = 0; s < kp_steps; ++s) {
+            uint8_t* st = acquire((uint32_t)(2 * w2_rows * ROWB));
+            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+            const int k0 = u * chpu + s * BK;
+            tma_load_2d_cg2(st + W_OFF, &w2_hi_map, lead_full, k0, rank * w2_rows);
+            tma_load_2d_cg2(st + W_OFF + W_BYTES, &w2_lo_map, lead_full, k0, rank * w2_rows);
+            advance();
+          }
+        }
+      }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+      // ===================================================== UMMA issuer (the leader issues for the pair)
+      const uint32_t idesc1 = make_idesc_bf16(2 * TC_BM, n_cols), idesc2 = make_idesc_bf16(2 * TC_BM, C);
+      const uint32_t d1 = tmem_base, d2 = tmem_base + TC_NHALF;
+      const uint32_t acts_a = smem_u32(acts_s);
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int q = 0; q <= Q; ++q) {
+        if (q < Q) {
+          // first GEMM of unit q into region 0 (drained -- into registers -- by the epilogue of unit q-1)
+          mbar_wait(&tmem_empty[0], (uint32_t)((q & 1) ^ 1));
+          tc_fence_after();
+          for (int ks = 0; ks < p.k1_steps; ++ks) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint32_t koff = kk * 32;
+              const uint64_t a_h = make_smem_desc(st + koff, ROWB), a_l = make_smem_desc(st + A_BYTES + koff, ROWB);
+              const uint64_t w_h = make_smem_desc(st + W_OFF + koff, ROWB);
+              const uint64_t w_l = make_smem_desc(st + W_OFF + W_BYTES + koff, ROWB);
+              umma_bf16_cg2(d1, a_h, w_h, idesc1, (ks > 0 || kk > 0) ? 1u : 0u);
+              umma_bf16_cg2(d1, a_l, w_h, idesc1, 1u);
+              umma_bf16_cg2(d1, a_h, w_l, idesc1, 1u);
+            }
+            umma_commit_cg2(&empty[stage], (uint16_t)0x3);
+            advance();
+          }
+          umma_commit_cg2(&tmem_full[0], (uint16_t)0x3);
+        }
+        if (q > 0 && p.has_res) {
+          // residual part of unit q-1 into region 1: its acts were written while unit q was being multiplied
+          const int qq = q - 1, u = qq % n_units, tile_j = qq / n_units;
+          mbar_wait_cluster(acts_ready, (uint32_t)(qq & 1));
+          if (u == 0) mbar_wait(&tmem_empty[1], (uint32_t)((tile_j & 1) ^ 1));     // EG of the previous tile
+          tc_fence_after();
+          for (int s = 0; s < kp_steps; ++s) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t as = acts_a + s * 2 * A_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint32_t koff = kk * 32;
+              const uint64_t a_h = make_smem_desc(as + koff, ROWB), a_l = make_smem_desc(as + A_BYTES + koff, ROWB);
+              const uint64_t w_h = make_smem_desc(st + W_OFF + koff, ROWB);
+              const uint64_t w_l = make_smem_desc(st + W_OFF + W_BYTES + koff, ROWB);
+              umma_bf16_cg2(d2, a_h, w_h, idesc2, (u > 0 || s > 0 || kk > 0) ? 1u : 0u);
+              umma_bf16_cg2(d2, a_l, w_h, idesc2, 1u);
+              umma_bf16_cg2(d2, a_h, w_l, idesc2, 1u);
+            }
+            umma_commit_cg2(&empty[stage], (uint16_t)0x3);
+            advance();
+          }
+          umma_commit_cg2(acts_free, (uint16_t)0x3);                 // the acts tile may be overwritten
+          if (u == n_units - 1) umma_commit_cg2(&tmem_full[1], (uint16_t)0x3);
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FU_REGS_HIGH));
+    // ===================================================== epilogue: 8 warps = TMEM lane quarter x column half
+    const int qd = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = qd * 32 + lane;
+    const int ncol_half = n_cols / 2;                  // accumulator columns of this thread in the first GEMM
+    const int c_begin = half * ncol_half;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(qd * 32) << 16);
+    const uint32_t lead_empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    const uint32_t lead_empty1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+    const uint32_t lead_ready = mapa_u32(smem_u32(acts_ready), 0);
+    const uint32_t acts_a = smem_u32(acts_s);
+    for (int q = 0; q <= Q; ++q) {
+      if (q < Q) {
+        // ------------------------------------------------- E(q): drain, gate, out8, acts -> shared memory
+        const int tile_j = q / n_units, u = q % n_units;
+        const int tile = tile_first + tile_j * (int)gridDim.x + rank;
+        const int b = tile / p.tiles_per_batch;
+        const int t = (tile % p.tiles_per_batch) * TC_BM + row;
+        const bool valid = tile < p.n_tiles && t < p.T;
+        const long long col = (long long)b * p.T + t;
+        mbar_wait(&tmem_full[0], (uint32_t)(q & 1));
+        tc_fence_after();
+        uint32_t acc[4][32];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4)
+          if (c4 * 32 < ncol_half) tmem_ld32(lane_base + c_begin + c4 * 32, acc[c4]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_empty0);        // region 0 is free again: the next unit may start
+        float acc8[FU_NOUT];
+#pragma unroll
+        for (int o = 0; o < FU_NOUT; ++o) acc8[o] = 0.f;
+        bool waited = !p.has_res || q == 0;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          if (c4 * 32 < ncol_half) {
+            const int n0 = u * TC_NHALF + c_begin + c4 * 32;     // first output column of this chunk
+            const int ch_u = (c_begin + c4 * 32) >> 1;           // first channel inside the unit (16 per chunk)
+            const int ch0 = n0 >> 1;                             // global channel
+            float g[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias1 + n0 + 2 * j));
+              g[j] = gate_act(__uint_as_float(acc[c4][2 * j]) + bv.x, __uint_as_float(acc[c4][2 * j + 1]) + bv.y);
+              g[j + 1] = gate_act(__uint_as_float(acc[c4][2 * j + 2]) + bv.z, __uint_as_float(acc[c4][2 * j + 3]) + bv.w);
+            }
+            // collapsed skip path: out8 += Wc[:, ch0:ch0+16] g   (fp32, exact gate outputs)
+#pragma unroll
+            for (int o = 0; o < FU_NOUT; ++o) {
+              const float4* wrow = reinterpret_cast<const float4*>(wc_s + o * C + ch0);
+              float a = acc8[o];
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 w4 = wrow[j4];
+                a = fmaf(w4.x, g[4 * j4 + 0], a);
+                a = fmaf(w4.y, g[4 * j4 + 1], a);
+                a = fmaf(w4.z, g[4 * j4 + 2], a);
+                a = fmaf(w4.w, g[4 * j4 + 3], a);
+              }
+              acc8[o] = a;
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split2(g[2 * j], g[2 * j + 1], hi[j], lo[j]);
+            if (p.has_res) {
+              if (!waited) {      // the previous residual part has read the acts tile (completes right after unit q)
+                mbar_wait(acts_free, (uint32_t)((q - 1) & 1));
+                waited = true;
+              }
+              // rows outside the utterance hold zeros (their x_new rows are never stored)
+              const uint32_t s = (uint32_t)(ch_u / BK);
+              const uint32_t off = (uint32_t)row * ROWB + (uint32_t)(ch_u % BK) * 2;
+              const uint32_t base = acts_a + s * 2 * A_BYTES;
+              const uint32_t o0 = swizzle_off<ROWB>(off), o1 = swizzle_off<ROWB>(off + 16);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + o0), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + o1), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + A_BYTES + o0), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + A_BYTES + o1), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+            }
+            if (p.acts_hi != nullptr && valid) {
+              const long long goff = col * C + ch0;
+              uint4* dh = reinterpret_cast<uint4*>(p.acts_hi + goff);
+              dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              uint4* dl = reinterpret_cast<uint4*>(p.acts_lo + goff);
+              dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+          }
+        }
+        if (p.has_res) {
+          fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(lead_ready);
+        }
+        // out8: the warp owning the upper column half hands its partial sums to its partner (fixed order:
+        // deterministic rounding); unit 0 of a tile starts or continues the layer sum, later units continue
+        if (half == 1) {
+#pragma unroll
+          for (int o = 0; o < FU_NOUT; ++o) x8_s[row * FU_NOUT + o] = acc8[o];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(FU_EPI_THREADS) : "memory");
+        if (half == 0 && valid) {
+#pragma unroll
+          for (int o = 0; o < FU_NOUT; ++o) acc8[o] += x8_s[row * FU_NOUT + o];
+          float4* o8 = reinterpret_cast<float4*>(p.out8 + col * FU_NOUT);
+          float4 o0 = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
+          float4 o1 = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
+          if (p.accumulate_out8 || u > 0) {
+            const float4 p0 = o8[0], p1 = o8[1];
+            o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+            o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+          }
+          o8[0] = o0;
+          o8[1] = o1;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(FU_EPI_THREADS) : "memory");
+      }
+      if (q > 0 && p.has_res && (q - 1) % n_units == n_units - 1) {
+        // ------------------------------------------------- EG: x_new = res + b_res + x (glow.py:166)
+        const int tile_j = (q - 1) / n_units;
+        const int tile = tile_first + tile_j * (int)gridDim.x + rank;
+        const int b = tile / p.tiles_per_batch;
+        const int t = (tile % p.tiles_per_batch) * TC_BM + row;
+        const bool valid = tile < p.n_tiles && t < p.T;
+        const long long col = (long long)b * p.T + t;
+        mbar_wait(&tmem_full[1], (uint32_t)(tile_j & 1));
+        tc_fence_after();
+        const int cw = C / 2;                               // residual columns of this thread
+        for (int c = 0; c < cw; c += 32) {
+          uint32_t rr[32];
+          const int n0 = half * cw + c;
+          tmem_ld32(lane_base + TC_NHALF + n0, rr);
+          tmem_ld_wait();
+          if (!valid) continue;
+          const long long off = col * C + n0;
+          const uint4* xh = reinterpret_cast<const uint4*>(p.x_hi + off);
+          const uint4* xl = reinterpret_cast<const uint4*>(p.x_lo + off);
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint4 h4 = __ldg(xh + j4), l4 = __ldg(xl + j4);
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int j = 8 * j4 + 2 * k;                                  // column pair (j, j + 1)
+              const float2 bb = __ldg(reinterpret_cast<const float2*>(p.res_b + n0 + j));
+              const float2 xhf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[k]));
+              const float2 xlf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[k]));
+              const float v0 = (__uint_as_float(rr[j]) + bb.x) + (xhf.x + xlf.x);
+              const float v1 = (__uint_as_float(rr[j + 1]) + bb.y) + (xhf.y + xlf.y);
+              split2(v0, v1, hi[4 * j4 + k], lo[4 * j4 + k]);
+            }
+          }
+          uint4* dh = reinterpret_cast<uint4*>(p.xo_hi + off);
+          uint4* dl = reinterpret_cast<uint4*>(p.xo_lo + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_empty1);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // nobody leaves while the peer may still signal / read this CTA
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc_cg2(tmem_base, 512);
+}
+
+template <int BK>
+int launch_fused(const CUtensorMap maps[8], const FusedParams& p, cudaStream_t st) {
+  static bool attr_set_on[FAC_MAX_DEVICES] = {};
+  bool& attr_set = attr_set_on[current_device_slot()];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wn_layer_fused_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM);
+    if (e != cudaSuccess) {
+      set_error("wn_layer_fused: cannot reserve %d bytes of shared memory: %s", FU_SMEM, cudaGetErrorString(e));
+      return 2;
+    }
+    attr_set = true;
+  }
+  const int pairs = ceil_div(p.n_tiles, 2), max_pairs = sm_count() / 2;
+  const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+  wn_layer_fused_kernel<BK><<<grid, FU_THREADS, FU_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+                                                              maps[6], maps[7], p);
+  count_launch();
+  return check_launch("wn_layer_fused_kernel");
+}
+
+}  // namespace
+
+bool wn_fused_supported(int C, int n_cond, int bk) {
+  const int n_cols = 2 * C < TC_NHALF ? 2 * C : TC_NHALF;
+  return (bk == 32 || bk == 64) && C % bk == 0 && n_cond % bk == 0 && C <= FU_CMAX && (2 * C) % n_cols == 0 &&
+         (n_cols / 2) % bk == 0 && (n_cols / 2) % 32 == 0 && (C / 2) % 32 == 0 && C % 16 == 0;
+}
+
+// One fused WN layer: x_in (hi, lo) -> x_out (hi, lo), out8 (+)= Wc acts.  acts_hi/lo optional (tests).
+int wn_layer_fused(const void* x_in_hi, const void* x_in_lo, void* x_out_hi, void* x_out_lo, const void* spect_hi,
+                   const void* spect_lo, const void* w1_hi, const void* w1_lo, const void* w2_hi, const void* w2_lo,
+                   const float* bias1, const float* res_b, const float* wc, float* out8, int accumulate_out8,
+                   void* acts_hi, void* acts_lo, int B, int T, int C, int n_cond, int taps, int dilation, int has_res,
+                   int bk, cudaStream_t st) {
+  FAC_REQUIRE(wn_fused_supported(C, n_cond, bk), "wn_layer_fused: unsupported geometry C=%d n_cond=%d bk=%d", C, n_cond, bk);
+  FAC_REQUIRE(x_in_hi && x_in_lo && spect_hi && spect_lo && w1_hi && w1_lo && bias1 && wc && out8,
+              "wn_layer_fused: NULL argument");
+  FAC_REQUIRE(!has_res || (x_out_hi && x_out_lo && w2_hi && w2_lo && res_b), "wn_layer_fused: residual operands missing");
+  FAC_REQUIRE(!has_res || x_out_hi != x_in_hi, "wn_layer_fused: the residual stream cannot be updated in place");
+  CUtensorMap maps[8];
+  const int K1 = taps * C + n_cond;
+  if (int rc = make_act_map(&maps[0], x_in_hi, B, T, C, bk)) return rc;
+  if (int rc = make_act_map(&maps[1], x_in_lo, B, T, C, bk)) return rc;
+  if (int rc = make_act_map(&maps[2], spect_hi, B, T, n_cond, bk)) return rc;
+  if (int rc = make_act_map(&maps[3], spect_lo, B, T, n_cond, bk)) return rc;
+  if (int rc = make_weight_map(&maps[4], w1_hi, 2 * C, K1, 2, bk)) return rc;
+  if (int rc = make_weight_map(&maps[5], w1_lo, 2 * C, K1, 2, bk)) return rc;
+  if (has_res) {
+    if (int rc = make_weight_map(&maps[6], w2_hi, C, C, 2, bk)) return rc;
+    if (int rc = make_weight_map(&maps[7], w2_lo, C, C, 2, bk)) return rc;
+  } else {
+    maps[6] = maps[4];
+    maps[7] = maps[5];
+  }
+  FusedParams p{};
+  p.T = T;
+  p.B = B;
+  p.tiles_per_batch = ceil_div(T, TC_BM);
+  p.n_tiles = B * p.tiles_per_batch;
+  p.C = C;
+  p.n_cond = n_cond;
+  p.taps = taps;
+  p.dilation = dilation;
+  p.center = dilation * (taps - 1) / 2;
+  p.k1_steps = K1 / bk;
+  p.has_res = has_res;
+  p.bias1 = bias1;
+  p.res_b = res_b;
+  p.wc = wc;
+  p.out8 = out8;
+  p.accumulate_out8 = accumulate_out8;
+  p.x_hi = reinterpret_cast<const __nv_bfloat16*>(x_in_hi);
+  p.x_lo = reinterpret_cast<const __nv_bfloat16*>(x_in_lo);
+  p.xo_hi = reinterpret_cast<__nv_bfloat16*>(x_out_hi);
+  p.xo_lo = reinterpret_cast<__nv_bfloat16*>(x_out_lo);
+  p.acts_hi = reinterpret_cast<__nv_bfloat16*>(acts_hi);
+  p.acts_lo = reinterpret_cast<__nv_bfloat16*>(acts_lo);
+  return bk == 64 ? launch_fused<64>(maps, p, st) : launch_fused<32>(maps, p, st);
+}
+
+}  // namespace fac

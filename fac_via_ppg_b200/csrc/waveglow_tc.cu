@@ -788,6 +788,11 @@ int tc_set_batch_group(int n) {
   g_tc_batch_group = n;
   return 0;
 }
+int g_tc_fused = 1;
+int tc_set_fused(int enabled) {
+  g_tc_fused = enabled != 0;
+  return 0;
+}
 int tc_set_cta_group(int cg) {
   FAC_REQUIRE(cg >= 0 && cg <= 2, "cta group must be 0 (auto), 1 or 2 (got %d)", cg);
   g_tc_cta_group = cg;
@@ -795,6 +800,12 @@ int tc_set_cta_group(int cg) {
 }
 
 int wg_check_model(const fac_wg_model* m);
+bool wn_fused_supported(int C, int n_cond, int bk);
+int wn_layer_fused(const void* x_in_hi, const void* x_in_lo, void* x_out_hi, void* x_out_lo, const void* spect_hi,
+                   const void* spect_lo, const void* w1_hi, const void* w1_lo, const void* w2_hi, const void* w2_lo,
+                   const float* bias1, const float* res_b, const float* wc, float* out8, int accumulate_out8,
+                   void* acts_hi, void* acts_lo, int B, int T, int C, int n_cond, int taps, int dilation, int has_res,
+                   int bk, cudaStream_t st);
 
 static int tc_check(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac_wg_tc_workspace* ws, int nsplit) {
   if (int rc = wg_check_model(m)) return rc;
@@ -804,9 +815,18 @@ static int tc_check(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac
   FAC_REQUIRE(C % TC_BK_MAX == 0 && n_cond % TC_BK_MAX == 0 && 2 * C <= TC_NMAX && C <= TC_CMAX,
               "tensor-core path: needs n_channels %% 16 == 0 (<= %d) and n_cond %% 16 == 0", TC_CMAX);
   FAC_REQUIRE(m->n_group <= TC_NOUT, "tensor-core path: n_group %d > %d", m->n_group, TC_NOUT);
-  FAC_REQUIRE(ws->spect_hi && ws->x_hi && ws->acts_hi && ws->out8, "tensor-core path: workspace incomplete");
-  if (nsplit == 2) FAC_REQUIRE(ws->spect_lo && ws->x_lo && ws->acts_lo, "tensor-core path: lo buffers missing");
+  const bool fused_ws = nsplit == 2 && ws->x2_hi && ws->x2_lo;
+  FAC_REQUIRE(ws->spect_hi && ws->x_hi && (ws->acts_hi || fused_ws) && ws->out8, "tensor-core path: workspace incomplete");
+  if (nsplit == 2) FAC_REQUIRE(ws->spect_lo && ws->x_lo && (ws->acts_lo || fused_ws), "tensor-core path: lo buffers missing");
   return 0;
+}
+
+// One fused launch per layer (waveglow_fused.cu) when the workspace carries the second residual-stream pair.
+static bool tc_use_fused(const fac_wg_model* m, const fac_wg_tc_flow& wf, const fac_wg_tc_workspace* ws, int nsplit,
+                         int layer) {
+  return g_tc_fused && nsplit == 2 && tc_pick_cg(nsplit) == 2 && ws->x2_hi && ws->x2_lo && wf.w1_lo[layer] &&
+         (layer == m->n_layers - 1 || (wf.w2r_hi[layer] && wf.w2r_lo[layer])) &&
+         wn_fused_supported(m->n_channels, m->n_mel * m->n_group, tc_pick_bk(nsplit));
 }
 
 int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac_wg_tc_workspace* ws,
@@ -897,6 +917,16 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
   const int C = m->n_channels, n_cond = m->n_mel * m->n_group, ks = m->kernel_size;
   const int dil = 1 << layer;
   const bool last = layer == m->n_layers - 1;
+  if (tc_use_fused(m, wf, ws, nsplit, layer)) {
+    // the residual stream ping-pongs: layer i reads x (i even) / x2 (i odd) and writes the other pair
+    const bool even = (layer & 1) == 0;
+    return wn_layer_fused(even ? ws->x_hi : ws->x2_hi, even ? ws->x_lo : ws->x2_lo, even ? ws->x2_hi : ws->x_hi,
+                          even ? ws->x2_lo : ws->x_lo, ws->spect_hi, ws->spect_lo, wf.w1_hi[layer], wf.w1_lo[layer],
+                          last ? nullptr : wf.w2r_hi[layer], last ? nullptr : wf.w2r_lo[layer], f.in_cond_b[layer],
+                          last ? nullptr : wf.res_b[layer], wf.wc[layer], ws->out8, layer > 0, ws->acts_hi, ws->acts_lo, B,
+                          Tg, C, n_cond, ks, dil, last ? 0 : 1, tc_pick_bk(nsplit), st);
+  }
+  FAC_REQUIRE(ws->acts_hi && (nsplit == 1 || ws->acts_lo), "wn_layer_tc: the two-launch form needs the acts buffers");
   CUtensorMap maps[6];
   TcParams p{};
   p.T = Tg;
@@ -979,6 +1009,8 @@ int wg_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* 
       g.x_lo = shift(ws->x_lo, col0 * C);
       g.acts_hi = shift(ws->acts_hi, col0 * C);
       g.acts_lo = shift(ws->acts_lo, col0 * C);
+      g.x2_hi = shift(ws->x2_hi, col0 * C);
+      g.x2_lo = shift(ws->x2_lo, col0 * C);
       g.out8 = ws->out8 + col0 * TC_NOUT;
       float* audio_g = audio + col0 * m->n_group;
       if (int rc = wg_tc_start(m, k, audio_g, &g, nb, Tg, nsplit, st)) return rc;

@@ -210,6 +210,7 @@ class PackedWaveGlow:
                     l16.add(f"{k}.{i}.w1_{part}", (2 * Cn, ks * Cn + n_cond))
                     if i < L - 1:
                         l16.add(f"{k}.{i}.w2_{part}", (Cn, 2 * Cn))
+                        l16.add(f"{k}.{i}.w2r_{part}", (Cn, Cn))
                 l32.add(f"{k}.{i}.wc", (8, Cn))
                 if i < L - 1:
                     l32.add(f"{k}.{i}.res_b", (Cn,))
@@ -271,6 +272,7 @@ class PackedWaveGlow:
                 bias8 += end_w @ b_skip.double()
                 if not last:
                     put16(f"{k}.{i}.w2", torch.cat([w_rs[:Cn], eye], dim=1).contiguous(), flow, i)
+                    put16(f"{k}.{i}.w2r", w_rs[:Cn].contiguous(), flow, i)
                     l32.view(flat32, f"{k}.{i}.res_b").copy_(b_rs[:Cn])
                     flow.res_b[i] = l32.ptr(flat32, f"{k}.{i}.res_b")
             l32.view(flat32, f"{k}.out_bias")[: 2 * n_half].copy_(bias8.float())
@@ -292,6 +294,7 @@ class PackedWaveGlow:
                 flow.wc[i] = l32.ptr(flat32, f"{k}.{i}.wc")
                 if i < L - 1:
                     flow.w2_hi[i], flow.w2_lo[i] = l16.ptr(flat16, f"{k}.{i}.w2_hi"), l16.ptr(flat16, f"{k}.{i}.w2_lo")
+                    flow.w2r_hi[i], flow.w2r_lo[i] = l16.ptr(flat16, f"{k}.{i}.w2r_hi"), l16.ptr(flat16, f"{k}.{i}.w2r_lo")
                     flow.res_b[i] = l32.ptr(flat32, f"{k}.{i}.res_b")
         return table
 

@@ -163,6 +163,7 @@ class WaveGlow(torch.nn.Module):
     #   "bf16"   tcgen05 tensor cores, plain bf16 operands (BASELINE configs[2] precision)
     PRECISIONS = ("fp32", "bf16x3", "bf16")
     precision = "bf16x3"      # default: tensor cores with fp32-grade results
+    fused_layers = True       # bf16x3: one fused launch per WN layer (csrc/waveglow_fused.cu); False: two launches
 
     def set_precision(self, precision):
         if precision in (None, "auto"):
@@ -205,7 +206,11 @@ class WaveGlow(torch.nn.Module):
             bufs["ws"] = _ext.WgWorkspace(bufs["spect"].data_ptr(), bufs["x"].data_ptr(), bufs["acts"].data_ptr(),
                                           bufs["skip"].data_ptr())
         else:
-            for name, c in (("spect_hi", n_cond), ("x_hi", Cn), ("acts_hi", Cn)):
+            # split mode: a layer is ONE fused launch that ping-pongs the residual stream between x and x2 and
+            # keeps the gated activations on the SM; plain bf16: two launches per layer with acts through HBM
+            fused = nsplit == 2 and self.fused_layers
+            names = (("spect_hi", n_cond), ("x_hi", Cn)) + ((("x2_hi", Cn),) if fused else (("acts_hi", Cn),))
+            for name, c in names:
                 bufs[name] = b16(c)
                 bufs[name[:-2] + "lo"] = b16(c) if nsplit == 2 else None
             bufs["out8"] = f32(8)
@@ -216,7 +221,8 @@ class WaveGlow(torch.nn.Module):
                 bufs["mel_hi"].data_ptr(), _ext.ptr(bufs["mel_lo"]),
                 bufs["spect_hi"].data_ptr(), _ext.ptr(bufs["spect_lo"]),
                 bufs["x_hi"].data_ptr(), _ext.ptr(bufs["x_lo"]),
-                bufs["acts_hi"].data_ptr(), _ext.ptr(bufs["acts_lo"]), bufs["out8"].data_ptr())
+                _ext.ptr(bufs.get("acts_hi")), _ext.ptr(bufs.get("acts_lo")), bufs["out8"].data_ptr(),
+                _ext.ptr(bufs.get("x2_hi")), _ext.ptr(bufs.get("x2_lo")))
         return bufs, B, F, Tg
 
     # Small inputs are launch-bound (a 2 s utterance is ~240 launches of a few microseconds of work each, plus

@@ -141,7 +141,9 @@ int fac_waveglow_infer_f32(const fac_wg_model* m, const float* mel_cl, float* au
  *        tap0|tap1|tap2|cond (glow.py:159-162)
  *   w2 = [residual half of res_skip | identity]: N = C, K = 2C, so that the tensor core itself
  *        performs x <- x + res (glow.py:164-166); lo has zeros in the identity half; unused for
- *        the last layer, whose res_skip feeds the skip path only
+ *        the last layer, whose res_skip feeds the skip path only (two-launch form of a layer)
+ *   w2r = residual half of res_skip alone: N = C, K = C (fused one-launch form: the residual add happens in
+ *        the epilogue of the second GEMM)
  *   wc = end.weight @ (skip half of res_skip): the skip path collapsed into an 8-channel update
  *        per layer (glow.py:167-175: end() is linear in the skip sum); fp32 [8][C], rows >= 2*n_half zero
  *   out_bias = end.bias + end.weight @ sum_i (skip half of res_skip bias_i); fp32 [8]
@@ -149,6 +151,7 @@ int fac_waveglow_infer_f32(const fac_wg_model* m, const float* mel_cl, float* au
 typedef struct fac_wg_tc_flow {
   const void* w1_hi[FAC_MAX_LAYERS]; const void* w1_lo[FAC_MAX_LAYERS];
   const void* w2_hi[FAC_MAX_LAYERS]; const void* w2_lo[FAC_MAX_LAYERS];
+  const void* w2r_hi[FAC_MAX_LAYERS]; const void* w2r_lo[FAC_MAX_LAYERS];
   const float* wc[FAC_MAX_LAYERS];
   const float* res_b[FAC_MAX_LAYERS];
   const float* out_bias;
@@ -164,13 +167,19 @@ typedef struct fac_wg_tc_weights {
 /* Scratch of the tensor-core path for B utterances of T_g columns: the padded mel copies, the
  * bf16 hi/lo operand copies the TMA loads read ((B,T_g,channels) channels-last; the residual
  * stream x lives ONLY as its hi+lo pair) and out8 (B,T_g,8) fp32, the running end() pre-activation.
- * The *_lo buffers may be NULL when nsplit == 1. */
+ * The *_lo buffers may be NULL when nsplit == 1.
+ * x2 (optional): a second residual-stream pair.  When present (and nsplit == 2) a layer runs as ONE fused launch
+ * (csrc/waveglow_fused.cu: first GEMM -> gate -> residual GEMM -> residual add, acts never leaves the SM) that
+ * reads the stream from one pair and writes the other, because neighbouring time tiles still read the old
+ * values for their dilated taps: layer i reads x when i is even and x2 when i is odd, and writes the other one
+ * (fac_wn_start_tc always writes x).  acts_hi/acts_lo may then be NULL (a test hook when not). */
 typedef struct fac_wg_tc_workspace {
   void* mel_hi; void* mel_lo;          /* (B, F, mel_pad) bf16 */
   void* spect_hi; void* spect_lo;
   void* x_hi; void* x_lo;
   void* acts_hi; void* acts_lo;
   float* out8;
+  void* x2_hi; void* x2_lo;
 } fac_wg_tc_workspace;
 
 /* nsplit = 1: bf16 operands; nsplit = 2: split-bf16 (3 UMMAs per product, fp32-grade result). */
@@ -179,8 +188,9 @@ int fac_waveglow_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights
                                   const float* mel_cl, int B, int F, int nsplit, void* stream);
 int fac_wn_start_tc(const fac_wg_model* m, int flow, const float* audio, const fac_wg_tc_workspace* ws,
                     int B, int Tg, int nsplit, void* stream);
-/* glow.py:158-174 for one layer: TMA-fed tcgen05 GEMM + gate epilogue (+ out8 update), then the
- * residual GEMM (skipped for the last layer). */
+/* glow.py:158-174 for one layer: TMA-fed tcgen05 GEMM + gate epilogue (+ out8 update) and the residual GEMM
+ * (skipped for the last layer) -- one fused launch when the workspace carries x2 (see above), else two launches
+ * with x updated in place. */
 int fac_wn_layer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int layer,
                     const fac_wg_tc_workspace* ws, int B, int Tg, int nsplit, void* stream);
 /* glow.py:175 + 278-283 from out8: coupling inverse and invertible 1x1 (reverse), in place on audio. */
@@ -192,6 +202,8 @@ void fac_tc_set_profile_buffer(long long* device_buf);
 /* 0 (default): automatic; 1: one CTA per 128-column tile; 2: CTA pairs (thread-block cluster of 2,
  * tcgen05 cta_group::2, UMMA M = 256, each CTA stages half of the weight rows). */
 int fac_tc_set_cta_group(int cta_group);
+/* 1 (default): layers run fused whenever the workspace allows it; 0: always the two-launch form (A/B measurements). */
+int fac_tc_set_fused(int enabled);
 /* Utterances per pass of fac_waveglow_infer_tc over a flow (they are independent): 0 (default) = the whole
  * batch; a group whose residual stream and gated activations fit the L2 keeps them out of HBM between the
  * GEMMs of a layer. */

@@ -34,12 +34,14 @@ def build_model(cfg, precision, **state_kwargs):
     return _models[key]
 
 
-@pytest.mark.parametrize("cfg_name,cols", [("small", 70), ("small", 300), ("full", 200)])
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
-def test_tc_layer_matches_fp32_layer(cfg_name, cols, precision):
-    """One WN layer (flow 0; dilation 1 and 4/8) on the tensor cores vs the exact-fp32 kernels on
-    identical inputs: gated activations, residual stream (kept as a bf16 hi+lo pair) and the
-    collapsed skip path (out8 += W_end W_skip acts must equal W_end applied to the fp32 skip)."""
+@pytest.mark.parametrize("cfg_name,cols", [("small", 70), ("small", 300), ("full", 200), ("full", 700)])
+@pytest.mark.parametrize("precision,fused", [("bf16x3", True), ("bf16x3", False), ("bf16", False)])
+def test_tc_layer_matches_fp32_layer(cfg_name, cols, precision, fused):
+    """One WN layer (flow 0; dilation 1 and 2/8, and the last layer, which has no residual output) on the tensor
+    cores vs the exact-fp32 kernels on identical inputs: gated activations, residual stream (kept as a bf16
+    hi+lo pair) and the collapsed skip path (out8 += W_end W_skip acts must equal W_end applied to the fp32 skip).
+    fused = the one-launch form of csrc/waveglow_fused.cu (the residual stream moves from x to x2 or back,
+    depending on the layer's parity); otherwise the two-launch form that updates x in place."""
     cfg = synth.WAVEGLOW_CONFIG_SMALL if cfg_name == "small" else synth.WAVEGLOW_CONFIG
     model = build_model(cfg, precision)
     lib, packed = _ext.load(), model.packed()
@@ -56,27 +58,42 @@ def test_tc_layer_matches_fp32_layer(cfg_name, cols, precision):
     tol = 2e-4 if precision == "bf16x3" else 8e-2
     hi = lambda t: t.to(torch.bfloat16)                                   # noqa: E731
     lo = lambda t: (t - t.to(torch.bfloat16).float()).to(torch.bfloat16)  # noqa: E731
-    for layer in (0, 3 if cfg["WN_config"]["n_layers"] > 3 else 1):
+    n_layers = cfg["WN_config"]["n_layers"]
+    for layer in (0, 3 if n_layers > 3 else 1, n_layers - 1):
+        last = layer == n_layers - 1
         # exact fp32 reference kernels (skip accumulates on top of skip0 for layer > 0)
         xr, sr, ar = x0.clone(), skip0.clone(), torch.empty_like(x0)
         ws = _ext.WgWorkspace(spect.data_ptr(), xr.data_ptr(), ar.data_ptr(), sr.data_ptr())
         _ext.check(lib.fac_wn_layer_f32(C.byref(packed.cmodel), 0, layer, C.byref(ws), B, cols, st), "f32 layer")
         skip_delta = sr - skip0 if layer > 0 else sr
         # the tensor-core path folds the skip biases into out_bias, so out8 carries none
-        skip_delta = skip_delta - packed.layout.view(packed.flat, f"0.{layer}.res_skip_b")[Cn:2 * Cn]
+        b_rs = packed.layout.view(packed.flat, f"0.{layer}.res_skip_b")
+        skip_delta = skip_delta - (b_rs[:Cn] if last else b_rs[Cn:2 * Cn])
         out8_ref = skip_delta @ end_w.t() + (out8_0[..., : 2 * n_half] if layer > 0 else 0)
         # tensor-core kernels
-        x_hi, x_lo, s_hi, s_lo = hi(x0), lo(x0), hi(spect), lo(spect)
-        a_hi, a_lo = torch.zeros_like(x_hi), torch.zeros_like(x_hi)
+        s_hi, s_lo = hi(spect), lo(spect)
+        a_hi, a_lo = torch.zeros_like(s_hi[..., :Cn]), torch.zeros_like(s_hi[..., :Cn])
         out8 = out8_0.clone()
-        wst = _ext.WgTcWorkspace(None, None, s_hi.data_ptr(), s_lo.data_ptr(), x_hi.data_ptr(), x_lo.data_ptr(),
-                                 a_hi.data_ptr(), a_lo.data_ptr(), out8.data_ptr())
+        if fused:        # layer i reads x (i even) / x2 (i odd) and writes the other pair
+            src, dst = (hi(x0), lo(x0)), (torch.full_like(a_hi, 7.0), torch.full_like(a_hi, 7.0))
+            xa, xb = (src, dst) if layer % 2 == 0 else (dst, src)
+            wst = _ext.WgTcWorkspace(None, None, s_hi.data_ptr(), s_lo.data_ptr(), xa[0].data_ptr(), xa[1].data_ptr(),
+                                     a_hi.data_ptr(), a_lo.data_ptr(), out8.data_ptr(), xb[0].data_ptr(), xb[1].data_ptr())
+            x_hi, x_lo = src if last else dst            # the last layer leaves the stream alone
+        else:
+            x_hi, x_lo = hi(x0), lo(x0)
+            wst = _ext.WgTcWorkspace(None, None, s_hi.data_ptr(), s_lo.data_ptr(), x_hi.data_ptr(), x_lo.data_ptr(),
+                                     a_hi.data_ptr(), a_lo.data_ptr(), out8.data_ptr(), None, None)
+        before = lib.fac_launch_count()
         rc = lib.fac_wn_layer_tc(C.byref(packed.cmodel), C.byref(packed.tc_weights()), 0, layer, C.byref(wst), B, cols,
                                  nsplit, st)
         _ext.check(rc, "tc layer")
         torch.cuda.synchronize()
+        assert lib.fac_launch_count() - before == (1 if fused or last else 2)
         acts = a_hi.float() + (a_lo.float() if nsplit == 2 else 0)
         xt = x_hi.float() + (x_lo.float() if nsplit == 2 else 0)
+        if last:
+            xr = x0                                      # glow.py:168-169: no residual output
         assert (acts - ar).abs().max().item() <= tol, ("acts", layer)
         assert (xt - xr).abs().max().item() <= tol, ("x", layer)
         assert (out8[..., : 2 * n_half] - out8_ref).abs().max().item() <= tol, ("out8", layer)
@@ -172,7 +189,7 @@ def test_small_inputs_replay_a_cuda_graph():
     first = model.infer(mel, sigma=0.0)            # captures
     lib.fac_reset_launch_count()
     again = model.infer(mel, sigma=0.0)            # replays
-    assert lib.fac_launch_count() > 200
+    assert lib.fac_launch_count() > 100           # 20 upsampler phases + 12 x (start + 8 fused layers + end) + ...
     assert torch.equal(first, eager) and torch.equal(again, eager)
     mel2 = synth.synthetic_mel(2, 9, seed=5).to(DEV)
     assert torch.equal(model.infer(mel2, sigma=0.0), model._infer_eager(mel2, 0.0, None))   # new input, same graph
