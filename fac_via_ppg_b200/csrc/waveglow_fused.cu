@@ -20,10 +20,17 @@
 // columns hold the residual accumulator -- all 512 TMEM columns, no double buffering needed.  acts never
 // touches HBM; x is read by TMA (taps) + once more by EG from L2 and written once, into a second buffer (the
 // neighbouring tiles still read the old x for their dilated taps: layers ping-pong between two x buffers).
-// Shared memory: operand ring (128 KB: 2 stages of K = 64 or 4 stages of K = 32) + the acts operand tile
-// (64 KB) + Wc / out8 exchange.  Registers: the epilogue warpgroups take 232 registers per thread from the
-// producer / issuer warpgroup (setmaxnreg), which is what makes a 128-register drain possible.
-// Layer without a residual output (the last one, glow.py:168-169): U / E only.
+// EG moves x through shared memory with TMA in both directions: a third producer thread streams the old x of the
+// tile (32-channel boxes, one staging entry per column half) a whole tile ahead, the epilogue threads add in
+// place (their own row) and one thread per half stores the box to the other x buffer with a TMA store -- the
+// row-per-thread global accesses this replaces cost 32 LSU wavefronts per instruction and made EG the longest
+// stage of the epilogue (measured: 33 k cycles per tile; profiles/README.md).
+// Shared memory: operand ring (128 KB = 4 stages of K = 32; with K = 64 only 2 stages fit and the issuer starves:
+// measured) + the acts operand tile (64 KB) + the x staging (32 KB).  The producer also prefetches the first
+// unit's activation boxes of the next tile into L2 (they come from DRAM; the second unit re-reads them from L2).
+// Registers: the epilogue warpgroups take 232 registers per thread from the producer / issuer warpgroup
+// (setmaxnreg), which is what makes a 128-register drain possible.
+// Layer without a residual output (the last one, glow.py:168-169): U / E only, alternating both TMEM regions.
 #include "fac_common.cuh"
 #include "tc_common.cuh"
 #include "tc_host.cuh"
@@ -41,10 +48,11 @@ constexpr int FU_CMAX = 256;
 constexpr int FU_MAX_STAGES = 8;
 constexpr int FU_RING_BYTES = 128 * 1024;
 constexpr int FU_ACTS_BYTES = 64 * 1024;          // 128 rows x 128 channels x (hi + lo) x 2 B
-constexpr int FU_BAR_BYTES = 256;
-constexpr int FU_WC_BYTES = FU_NOUT * FU_CMAX * 4;
-constexpr int FU_X8_BYTES = TC_BM * FU_NOUT * 4;
-constexpr int FU_SMEM = FU_RING_BYTES + FU_ACTS_BYTES + FU_BAR_BYTES + FU_WC_BYTES + FU_X8_BYTES + 1024;
+constexpr int FU_XS_COLS = 32;                    // channels of one x staging box (64-byte rows, SWIZZLE_64B)
+constexpr int FU_XS_ARRAY = TC_BM * FU_XS_COLS * 2;       // 8 KB: one box (hi or lo)
+constexpr int FU_XS_BYTES = 2 * 2 * FU_XS_ARRAY;          // one entry (hi + lo) per column half
+constexpr int FU_BAR_BYTES = 512;
+constexpr int FU_SMEM = FU_RING_BYTES + FU_ACTS_BYTES + FU_XS_BYTES + FU_BAR_BYTES + 1024;
 constexpr int FU_REGS_LOW = 40, FU_REGS_HIGH = 232;   // 128 x 40 + 256 x 232 = 384 x 168
 
 struct FusedParams {
@@ -63,6 +71,33 @@ struct FusedParams {
   __nv_bfloat16* xo_lo;
   __nv_bfloat16* acts_hi;        // optional (tests): the gated activations, (B, T, C)
   __nv_bfloat16* acts_lo;
+  int prefetch_steps;            // L2 prefetch distance of the producer in K steps (0 = off)
+  long long* prof;               // optional [grid][16] clock64 counters (tools/tc_cycle_breakdown.py)
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(m), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// clock64 accumulators of one role; compiled in, costs a few instructions per barrier wait
+struct Tick {
+  long long t;
+  __device__ __forceinline__ void start() { t = clock64(); }
+  __device__ __forceinline__ void lap(long long& acc) {
+    const long long now = clock64();
+    acc += now - t;
+    t = now;
+  }
 };
 
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t addr, uint32_t parity) {
@@ -84,6 +119,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+
 // byte offset inside a K-major operand tile of `ROWB`-byte rows (dense, 1024-byte aligned) -> the offset the TMA
 // swizzle mode of that row width (128B / 64B) would have stored it at: address bits [4,7) ^= bits [7,10) (128B),
 // bits [4,6) ^= bits [7,9) (64B)
@@ -92,13 +134,18 @@ __device__ __forceinline__ uint32_t swizzle_off(uint32_t off) {
   return ROWB == 128 ? off ^ (((off >> 7) & 7u) << 4) : off ^ (((off >> 7) & 3u) << 4);
 }
 
+struct FusedMaps {
+  CUtensorMap x_hi, x_lo;        // residual stream in: boxes of BK channels (operand A of the first GEMM)
+  CUtensorMap s_hi, s_lo;        // spect
+  CUtensorMap w1_hi, w1_lo;      // [2C][taps*C + n_cond]
+  CUtensorMap w2_hi, w2_lo;      // [C][C] residual half of res_skip
+  CUtensorMap xi_hi, xi_lo;      // residual stream in, boxes of FU_XS_COLS channels (EG staging)
+  CUtensorMap xo_hi, xo_lo;      // residual stream out, same boxes (TMA store)
+};
+
 template <int BK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FU_THREADS, 1)
-wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid_constant__ CUtensorMap x_lo_map,
-                      const __grid_constant__ CUtensorMap s_hi_map, const __grid_constant__ CUtensorMap s_lo_map,
-                      const __grid_constant__ CUtensorMap w1_hi_map, const __grid_constant__ CUtensorMap w1_lo_map,
-                      const __grid_constant__ CUtensorMap w2_hi_map, const __grid_constant__ CUtensorMap w2_lo_map,
-                      const FusedParams p) {
+wn_layer_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p) {
   constexpr int ROWB = BK * 2;                       // bytes of one operand row
   constexpr int A_BYTES = TC_BM * ROWB;              // one 128-row activation tile (hi or lo)
   constexpr int W_BYTES = (TC_NHALF / 2) * ROWB;     // this CTA's half of a 256-row weight block (hi or lo)
@@ -109,15 +156,16 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* acts_s = smem + FU_RING_BYTES;            // [k step][hi | lo][128 rows][ROWB], 1024-byte aligned
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + FU_RING_BYTES + FU_ACTS_BYTES);
+  uint8_t* xs_s = acts_s + FU_ACTS_BYTES;            // [column half][hi | lo][128 rows][64 B]
+  uint64_t* full = reinterpret_cast<uint64_t*>(xs_s + FU_XS_BYTES);
   uint64_t* empty = full + FU_MAX_STAGES;
   uint64_t* tmem_full = empty + FU_MAX_STAGES;       // [2]: region 0 = first GEMM, region 1 = residual GEMM
   uint64_t* tmem_empty = tmem_full + 2;              // [2]
   uint64_t* acts_ready = tmem_empty + 2;             // epilogue -> issuer (leader's copy is used)
   uint64_t* acts_free = acts_ready + 1;              // issuer -> epilogue (both CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acts_free + 1);
-  float* wc_s = reinterpret_cast<float*>(smem + FU_RING_BYTES + FU_ACTS_BYTES + FU_BAR_BYTES);
-  float* x8_s = wc_s + FU_NOUT * FU_CMAX;
+  uint64_t* xs_full = acts_free + 1;                 // [2] x producer -> epilogue half
+  uint64_t* xs_empty = xs_full + 2;                  // [2] epilogue half -> x producer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xs_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -128,6 +176,7 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
   const int n_cols = n_total < TC_NHALF ? n_total : TC_NHALF;       // columns of one block
   const int chpu = n_cols / 2;                                      // channels one unit contributes
   const int kp_steps = chpu / BK;                                   // K steps of one residual part
+  const int xs_chunks = (C / 2) / FU_XS_COLS;                       // x staging boxes per column half and tile
   int my_tiles = 0;
   for (int tb = tile_first; tb < p.n_tiles; tb += (int)gridDim.x) ++my_tiles;
   const int Q = my_tiles * n_units;                                 // units of this CTA pair
@@ -140,14 +189,15 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
     for (int r = 0; r < 2; ++r) {
       mbar_init(&tmem_full[r], 1);
       mbar_init(&tmem_empty[r], FU_EPI_WARPS * 2);
+      mbar_init(&xs_full[r], 1);
+      mbar_init(&xs_empty[r], 1);
     }
     mbar_init(acts_ready, FU_EPI_WARPS * 2);
     mbar_init(acts_free, 1);
     fence_barrier_init();
-    tma_prefetch_desc(&x_hi_map);
-    tma_prefetch_desc(&w1_hi_map);
+    tma_prefetch_desc(&maps.x_hi);
+    tma_prefetch_desc(&maps.w1_hi);
   }
-  for (int i = threadIdx.x; i < FU_NOUT * C; i += FU_THREADS) wc_s[i] = __ldg(p.wc + i);
   if (warp == 1) tmem_alloc_cg2(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -158,13 +208,16 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FU_REGS_LOW));
     if (warp == 0 && lane == 0) {
-      // ===================================================== TMA producer
+      // ===================================================== TMA producer (operand ring)
       const int w1_rows = n_cols / 2, w2_rows = C / 2;            // weight rows staged by this CTA
       const int steps_x = p.taps * (C / BK);
       int stage = 0;
       uint32_t phase = 0;
+      long long prod_wait = 0;
       auto acquire = [&](uint32_t bytes) -> uint8_t* {
+        const long long w0 = clock64();
         mbar_wait(&empty[stage], phase ^ 1);
+        prod_wait += clock64() - w0;
         if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * bytes);   // both CTAs' loads land on the leader's barrier
         return smem + stage * STAGE_BYTES;
       };
@@ -174,27 +227,52 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
           phase ^= 1;
         }
       };
+      // activation box of K step ks of unit q: (map pair, channel, first row, utterance)
+      auto a_box = [&](int q, int ks, const CUtensorMap*& mh, const CUtensorMap*& ml, int& c0, int& row0, int& b) {
+        const int tile = tile_first + (q / n_units) * (int)gridDim.x + rank;   // may be one past the end: OOB -> zeros
+        b = tile / p.tiles_per_batch;
+        const int t0 = (tile % p.tiles_per_batch) * TC_BM;
+        if (ks < steps_x) {
+          const int cps = C / BK, tap = ks / cps;
+          c0 = (ks - tap * cps) * BK;
+          row0 = t0 + tap * p.dilation - p.center;
+          mh = &maps.x_hi;
+          ml = &maps.x_lo;
+        } else {
+          c0 = (ks - steps_x) * BK;
+          row0 = t0;
+          mh = &maps.s_hi;
+          ml = &maps.s_lo;
+        }
+      };
       for (int q = 0; q <= Q; ++q) {
         if (q < Q) {
-          const int tile = tile_first + (q / n_units) * (int)gridDim.x + rank;   // may be one past the end: OOB -> zeros
           const int u = q % n_units;
-          const int b = tile / p.tiles_per_batch, t0 = (tile % p.tiles_per_batch) * TC_BM;
           const int w_row = u * TC_NHALF + rank * w1_rows;
           for (int ks = 0; ks < p.k1_steps; ++ks) {
+            const CUtensorMap *mh, *ml;
+            int c0, row0, b;
+            if (p.prefetch_steps > 0) {
+              // L2 prefetch, prefetch_steps ahead in the flattened (unit, K step) order, of boxes that will come
+              // from DRAM: those of a tile's FIRST unit (its later units find them in L2)
+              int q2 = q, ks2 = ks + p.prefetch_steps;
+              if (ks2 >= p.k1_steps) {
+                ks2 -= p.k1_steps;
+                ++q2;
+              }
+              if (q2 < Q && q2 % n_units == 0) {
+                a_box(q2, ks2, mh, ml, c0, row0, b);
+                tma_prefetch_l2_3d(mh, c0, row0, b);
+                tma_prefetch_l2_3d(ml, c0, row0, b);
+              }
+            }
             uint8_t* st = acquire((uint32_t)(2 * A_BYTES + 2 * w1_rows * ROWB));
             const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
-            if (ks < steps_x) {
-              const int cps = C / BK, tap = ks / cps, c0 = (ks - tap * cps) * BK;
-              const int row0 = t0 + tap * p.dilation - p.center;
-              tma_load_3d_cg2(st, &x_hi_map, lead_full, c0, row0, b);
-              tma_load_3d_cg2(st + A_BYTES, &x_lo_map, lead_full, c0, row0, b);
-            } else {
-              const int c0 = (ks - steps_x) * BK;
-              tma_load_3d_cg2(st, &s_hi_map, lead_full, c0, t0, b);
-              tma_load_3d_cg2(st + A_BYTES, &s_lo_map, lead_full, c0, t0, b);
-            }
-            tma_load_2d_cg2(st + W_OFF, &w1_hi_map, lead_full, ks * BK, w_row);
-            tma_load_2d_cg2(st + W_OFF + W_BYTES, &w1_lo_map, lead_full, ks * BK, w_row);
+            a_box(q, ks, mh, ml, c0, row0, b);
+            tma_load_3d_cg2(st, mh, lead_full, c0, row0, b);
+            tma_load_3d_cg2(st + A_BYTES, ml, lead_full, c0, row0, b);
+            tma_load_2d_cg2(st + W_OFF, &maps.w1_hi, lead_full, ks * BK, w_row);
+            tma_load_2d_cg2(st + W_OFF + W_BYTES, &maps.w1_lo, lead_full, ks * BK, w_row);
             advance();
           }
         }
@@ -204,16 +282,16 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
             uint8_t* st = acquire((uint32_t)(2 * w2_rows * ROWB));
             const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
             const int k0 = u * chpu + s * BK;
-            tma_load_2d_cg2(st + W_OFF, &w2_hi_map, lead_full, k0, rank * w2_rows);
-            tma_load_2d_cg2(st + W_OFF + W_BYTES, &w2_lo_map, lead_full, k0, rank * w2_rows);
+            tma_load_2d_cg2(st + W_OFF, &maps.w2_hi, lead_full, k0, rank * w2_rows);
+            tma_load_2d_cg2(st + W_OFF + W_BYTES, &maps.w2_lo, lead_full, k0, rank * w2_rows);
             advance();
           }
         }
       }
+      if (p.prof) p.prof[blockIdx.x * 16 + 0] = prod_wait;
     } else if (warp == 1 && lane == 0 && rank == 0) {
       // ===================================================== UMMA issuer (the leader issues for the pair)
       const uint32_t idesc1 = make_idesc_bf16(2 * TC_BM, n_cols), idesc2 = make_idesc_bf16(2 * TC_BM, C);
-      const uint32_t d1 = tmem_base, d2 = tmem_base + TC_NHALF;
       const uint32_t acts_a = smem_u32(acts_s);
       int stage = 0;
       uint32_t phase = 0;
@@ -223,13 +301,25 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
           phase ^= 1;
         }
       };
+      long long w_tmem0 = 0, w_full = 0, w_acts = 0, w_tmem1 = 0, issue = 0;
+      const long long k_start = clock64();
+      Tick tk;
+      tk.start();
       for (int q = 0; q <= Q; ++q) {
         if (q < Q) {
-          // first GEMM of unit q into region 0 (drained -- into registers -- by the epilogue of unit q-1)
-          mbar_wait(&tmem_empty[0], (uint32_t)((q & 1) ^ 1));
+          // first GEMM of unit q: with a residual part, always region 0 (drained -- into registers -- by the epilogue
+          // of unit q-1 while the residual part of unit q-2 ran); without, the two regions alternate
+          const int r = p.has_res ? 0 : (q & 1);
+          const uint32_t use = p.has_res ? (uint32_t)q : (uint32_t)(q >> 1);     // how often the region was used before
+          tk.lap(issue);
+          mbar_wait(&tmem_empty[r], (use & 1) ^ 1);
+          tk.lap(w_tmem0);
           tc_fence_after();
+          const uint32_t d1 = tmem_base + r * TC_NHALF;
           for (int ks = 0; ks < p.k1_steps; ++ks) {
+            tk.lap(issue);
             mbar_wait(&full[stage], phase);
+            tk.lap(w_full);
             tc_fence_after();
             const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
 #pragma unroll
@@ -245,16 +335,22 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
             umma_commit_cg2(&empty[stage], (uint16_t)0x3);
             advance();
           }
-          umma_commit_cg2(&tmem_full[0], (uint16_t)0x3);
+          umma_commit_cg2(&tmem_full[r], (uint16_t)0x3);
         }
         if (q > 0 && p.has_res) {
           // residual part of unit q-1 into region 1: its acts were written while unit q was being multiplied
           const int qq = q - 1, u = qq % n_units, tile_j = qq / n_units;
+          const uint32_t d2 = tmem_base + TC_NHALF;
+          tk.lap(issue);
           mbar_wait_cluster(acts_ready, (uint32_t)(qq & 1));
+          tk.lap(w_acts);
           if (u == 0) mbar_wait(&tmem_empty[1], (uint32_t)((tile_j & 1) ^ 1));     // EG of the previous tile
+          tk.lap(w_tmem1);
           tc_fence_after();
           for (int s = 0; s < kp_steps; ++s) {
+            tk.lap(issue);
             mbar_wait(&full[stage], phase);
+            tk.lap(w_full);
             tc_fence_after();
             const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
             const uint32_t as = acts_a + s * 2 * A_BYTES;
@@ -275,6 +371,27 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
           if (u == n_units - 1) umma_commit_cg2(&tmem_full[1], (uint16_t)0x3);
         }
       }
+      if (p.prof) {
+        long long* pr = p.prof + blockIdx.x * 16;
+        pr[1] = w_tmem0; pr[2] = w_full; pr[3] = w_acts; pr[4] = w_tmem1; pr[5] = clock64() - k_start;
+      }
+    } else if (warp == 2 && lane == 0 && p.has_res) {
+      // ===================================================== x producer: the tile's old residual stream for EG
+      uint32_t ph[2] = {0, 0};
+      for (int j = 0; j < my_tiles; ++j) {
+        const int tile = tile_first + j * (int)gridDim.x + rank;
+        const int b = tile / p.tiles_per_batch, t0 = (tile % p.tiles_per_batch) * TC_BM;
+        for (int cc = 0; cc < xs_chunks; ++cc)
+          for (int h = 0; h < 2; ++h) {
+            uint8_t* dst = xs_s + h * 2 * FU_XS_ARRAY;
+            const int c0 = h * (C / 2) + cc * FU_XS_COLS;
+            mbar_wait(&xs_empty[h], ph[h] ^ 1);
+            mbar_arrive_expect_tx(&xs_full[h], 2 * FU_XS_ARRAY);
+            tma_load_3d(dst, &maps.xi_hi, &xs_full[h], c0, t0, b);
+            tma_load_3d(dst + FU_XS_ARRAY, &maps.xi_lo, &xs_full[h], c0, t0, b);
+            ph[h] ^= 1;
+          }
+      }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FU_REGS_HIGH));
@@ -289,6 +406,12 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
     const uint32_t lead_empty1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
     const uint32_t lead_ready = mapa_u32(smem_u32(acts_ready), 0);
     const uint32_t acts_a = smem_u32(acts_s);
+    const uint32_t xs_a = smem_u32(xs_s) + half * 2 * FU_XS_ARRAY;
+    uint32_t xs_phase = 0;
+    long long e_wfull0 = 0, e_drain = 0, e_wfree = 0, e_busy = 0, e_wfull1 = 0, eg_busy = 0;
+    const long long e_start = clock64();
+    Tick tk;
+    tk.start();
     for (int q = 0; q <= Q; ++q) {
       if (q < Q) {
         // ------------------------------------------------- E(q): drain, gate, out8, acts -> shared memory
@@ -298,16 +421,21 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
         const int t = (tile % p.tiles_per_batch) * TC_BM + row;
         const bool valid = tile < p.n_tiles && t < p.T;
         const long long col = (long long)b * p.T + t;
-        mbar_wait(&tmem_full[0], (uint32_t)(q & 1));
+        const int r = p.has_res ? 0 : (q & 1);
+        const uint32_t use = p.has_res ? (uint32_t)q : (uint32_t)(q >> 1);
+        tk.lap(e_busy);
+        mbar_wait(&tmem_full[r], use & 1);
+        tk.lap(e_wfull0);
         tc_fence_after();
         uint32_t acc[4][32];
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4)
-          if (c4 * 32 < ncol_half) tmem_ld32(lane_base + c_begin + c4 * 32, acc[c4]);
+          if (c4 * 32 < ncol_half) tmem_ld32(lane_base + r * TC_NHALF + c_begin + c4 * 32, acc[c4]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(lead_empty0);        // region 0 is free again: the next unit may start
+        if (lane == 0) mbar_arrive_cluster(r == 0 ? lead_empty0 : lead_empty1);   // the region is free again
+        tk.lap(e_drain);
         float acc8[FU_NOUT];
 #pragma unroll
         for (int o = 0; o < FU_NOUT; ++o) acc8[o] = 0.f;
@@ -325,14 +453,15 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
               g[j] = gate_act(__uint_as_float(acc[c4][2 * j]) + bv.x, __uint_as_float(acc[c4][2 * j + 1]) + bv.y);
               g[j + 1] = gate_act(__uint_as_float(acc[c4][2 * j + 2]) + bv.z, __uint_as_float(acc[c4][2 * j + 3]) + bv.w);
             }
-            // collapsed skip path: out8 += Wc[:, ch0:ch0+16] g   (fp32, exact gate outputs)
+            // collapsed skip path: out8 += Wc[:, ch0:ch0+16] g   (fp32, exact gate outputs; Wc: warp-uniform
+            // addresses, L1-resident)
 #pragma unroll
             for (int o = 0; o < FU_NOUT; ++o) {
-              const float4* wrow = reinterpret_cast<const float4*>(wc_s + o * C + ch0);
+              const float4* wrow = reinterpret_cast<const float4*>(p.wc + o * C + ch0);
               float a = acc8[o];
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 w4 = wrow[j4];
+                const float4 w4 = __ldg(wrow + j4);
                 a = fmaf(w4.x, g[4 * j4 + 0], a);
                 a = fmaf(w4.y, g[4 * j4 + 1], a);
                 a = fmaf(w4.z, g[4 * j4 + 2], a);
@@ -345,7 +474,9 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
             for (int j = 0; j < 8; ++j) split2(g[2 * j], g[2 * j + 1], hi[j], lo[j]);
             if (p.has_res) {
               if (!waited) {      // the previous residual part has read the acts tile (completes right after unit q)
+                tk.lap(e_busy);
                 mbar_wait(acts_free, (uint32_t)((q - 1) & 1));
+                tk.lap(e_wfree);
                 waited = true;
               }
               // rows outside the utterance hold zeros (their x_new rows are never stored)
@@ -353,10 +484,10 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
               const uint32_t off = (uint32_t)row * ROWB + (uint32_t)(ch_u % BK) * 2;
               const uint32_t base = acts_a + s * 2 * A_BYTES;
               const uint32_t o0 = swizzle_off<ROWB>(off), o1 = swizzle_off<ROWB>(off + 16);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + o0), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + o1), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + A_BYTES + o0), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + A_BYTES + o1), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+              st_shared_v4(base + o0, hi[0], hi[1], hi[2], hi[3]);
+              st_shared_v4(base + o1, hi[4], hi[5], hi[6], hi[7]);
+              st_shared_v4(base + A_BYTES + o0, lo[0], lo[1], lo[2], lo[3]);
+              st_shared_v4(base + A_BYTES + o1, lo[4], lo[5], lo[6], lo[7]);
             }
             if (p.acts_hi != nullptr && valid) {
               const long long goff = col * C + ch0;
@@ -374,77 +505,95 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(lead_ready);
         }
-        // out8: the warp owning the upper column half hands its partial sums to its partner (fixed order:
-        // deterministic rounding); unit 0 of a tile starts or continues the layer sum, later units continue
-        if (half == 1) {
-#pragma unroll
-          for (int o = 0; o < FU_NOUT; ++o) x8_s[row * FU_NOUT + o] = acc8[o];
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(FU_EPI_THREADS) : "memory");
-        if (half == 0 && valid) {
-#pragma unroll
-          for (int o = 0; o < FU_NOUT; ++o) acc8[o] += x8_s[row * FU_NOUT + o];
+        // out8 (+)= partial sums of the two column halves, in a fixed order (deterministic rounding): the lower
+        // half first (it starts or continues the layer sum), then the upper half on top.  L2 is the meeting point
+        // (ld.global.cg), the named barriers order the two read-modify-writes and the next unit's.
+        {
           float4* o8 = reinterpret_cast<float4*>(p.out8 + col * FU_NOUT);
           float4 o0 = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
           float4 o1 = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
-          if (p.accumulate_out8 || u > 0) {
-            const float4 p0 = o8[0], p1 = o8[1];
+          if (half == 0 && valid) {
+            if (p.accumulate_out8 || u > 0) {
+              const float4 p0 = __ldcg(o8), p1 = __ldcg(o8 + 1);
+              o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+              o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+            }
+            o8[0] = o0;
+            o8[1] = o1;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(FU_EPI_THREADS) : "memory");
+          if (half == 1 && valid) {
+            const float4 p0 = __ldcg(o8), p1 = __ldcg(o8 + 1);
             o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
             o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+            o8[0] = o0;
+            o8[1] = o1;
           }
-          o8[0] = o0;
-          o8[1] = o1;
+          asm volatile("bar.sync 2, %0;" ::"n"(FU_EPI_THREADS) : "memory");
         }
-        asm volatile("bar.sync 2, %0;" ::"n"(FU_EPI_THREADS) : "memory");
       }
       if (q > 0 && p.has_res && (q - 1) % n_units == n_units - 1) {
-        // ------------------------------------------------- EG: x_new = res + b_res + x (glow.py:166)
+        // ------------------------------------------------- EG: x_new = res + b_res + x (glow.py:166), through the
+        // x staging: the old x arrives by TMA, is updated in place (own row) and leaves by TMA store
         const int tile_j = (q - 1) / n_units;
         const int tile = tile_first + tile_j * (int)gridDim.x + rank;
-        const int b = tile / p.tiles_per_batch;
-        const int t = (tile % p.tiles_per_batch) * TC_BM + row;
-        const bool valid = tile < p.n_tiles && t < p.T;
-        const long long col = (long long)b * p.T + t;
+        const int b = tile / p.tiles_per_batch, t0 = (tile % p.tiles_per_batch) * TC_BM;
+        tk.lap(e_busy);
         mbar_wait(&tmem_full[1], (uint32_t)(tile_j & 1));
+        tk.lap(e_wfull1);
         tc_fence_after();
-        const int cw = C / 2;                               // residual columns of this thread
-        for (int c = 0; c < cw; c += 32) {
+        for (int cc = 0; cc < xs_chunks; ++cc) {
+          const int n0 = half * (C / 2) + cc * FU_XS_COLS;
           uint32_t rr[32];
-          const int n0 = half * cw + c;
           tmem_ld32(lane_base + TC_NHALF + n0, rr);
+          mbar_wait(&xs_full[half], xs_phase);
+          xs_phase ^= 1;
           tmem_ld_wait();
-          if (!valid) continue;
-          const long long off = col * C + n0;
-          const uint4* xh = reinterpret_cast<const uint4*>(p.x_hi + off);
-          const uint4* xl = reinterpret_cast<const uint4*>(p.x_lo + off);
-          uint32_t hi[16], lo[16];
+          uint32_t hw[16], lw[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const uint4 h4 = __ldg(xh + j4), l4 = __ldg(xl + j4);
-            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int j = 8 * j4 + 2 * k;                                  // column pair (j, j + 1)
-              const float2 bb = __ldg(reinterpret_cast<const float2*>(p.res_b + n0 + j));
-              const float2 xhf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[k]));
-              const float2 xlf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[k]));
-              const float v0 = (__uint_as_float(rr[j]) + bb.x) + (xhf.x + xlf.x);
-              const float v1 = (__uint_as_float(rr[j + 1]) + bb.y) + (xhf.y + xlf.y);
-              split2(v0, v1, hi[4 * j4 + k], lo[4 * j4 + k]);
-            }
+            const uint32_t o = swizzle_off<64>((uint32_t)row * 64 + j4 * 16);
+            ld_shared_v4(xs_a + o, hw[4 * j4], hw[4 * j4 + 1], hw[4 * j4 + 2], hw[4 * j4 + 3]);
+            ld_shared_v4(xs_a + FU_XS_ARRAY + o, lw[4 * j4], lw[4 * j4 + 1], lw[4 * j4 + 2], lw[4 * j4 + 3]);
           }
-          uint4* dh = reinterpret_cast<uint4*>(p.xo_hi + off);
-          uint4* dl = reinterpret_cast<uint4*>(p.xo_lo + off);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          for (int k = 0; k < 16; ++k) {
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(p.res_b + n0 + 2 * k));
+            const float2 xhf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[k]));
+            const float2 xlf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[k]));
+            const float v0 = (__uint_as_float(rr[2 * k]) + bb.x) + (xhf.x + xlf.x);
+            const float v1 = (__uint_as_float(rr[2 * k + 1]) + bb.y) + (xhf.y + xlf.y);
+            split2(v0, v1, hw[k], lw[k]);
+          }
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint32_t o = swizzle_off<64>((uint32_t)row * 64 + j4 * 16);
+            st_shared_v4(xs_a + o, hw[4 * j4], hw[4 * j4 + 1], hw[4 * j4 + 2], hw[4 * j4 + 3]);
+            st_shared_v4(xs_a + FU_XS_ARRAY + o, lw[4 * j4], lw[4 * j4 + 1], lw[4 * j4 + 2], lw[4 * j4 + 3]);
+          }
+          fence_proxy_async_smem();
+          if (half == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 4, 128;" ::: "memory");
+          if (qd == 0 && lane == 0) {
+            // rows outside the utterance (and a tile past the end) are clipped by the tensor map
+            tma_store_3d(&maps.xo_hi, xs_s + half * 2 * FU_XS_ARRAY, n0, t0, b);
+            tma_store_3d(&maps.xo_lo, xs_s + half * 2 * FU_XS_ARRAY + FU_XS_ARRAY, n0, t0, b);
+            tma_store_commit();
+            tma_store_wait_read();               // the staging entry may be refilled
+            mbar_arrive(&xs_empty[half]);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(lead_empty1);
+        tk.lap(eg_busy);
       }
+    }
+    if (qd == 0 && lane == 0) tma_store_wait_all();
+    if (p.prof && warp == 4 && lane == 0) {
+      long long* pr = p.prof + blockIdx.x * 16;
+      pr[6] = e_wfull0; pr[7] = e_drain; pr[8] = e_wfree; pr[9] = e_busy; pr[10] = e_wfull1; pr[11] = eg_busy;
+      pr[12] = clock64() - e_start;
     }
   }
   tc_fence_before();
@@ -455,7 +604,7 @@ wn_layer_fused_kernel(const __grid_constant__ CUtensorMap x_hi_map, const __grid
 }
 
 template <int BK>
-int launch_fused(const CUtensorMap maps[8], const FusedParams& p, cudaStream_t st) {
+int launch_fused(const FusedMaps& maps, const FusedParams& p, cudaStream_t st) {
   static bool attr_set_on[FAC_MAX_DEVICES] = {};
   bool& attr_set = attr_set_on[current_device_slot()];
   if (!attr_set) {
@@ -468,8 +617,7 @@ int launch_fused(const CUtensorMap maps[8], const FusedParams& p, cudaStream_t s
   }
   const int pairs = ceil_div(p.n_tiles, 2), max_pairs = sm_count() / 2;
   const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-  wn_layer_fused_kernel<BK><<<grid, FU_THREADS, FU_SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
-                                                              maps[6], maps[7], p);
+  wn_layer_fused_kernel<BK><<<grid, FU_THREADS, FU_SMEM, st>>>(maps, p);
   count_launch();
   return check_launch("wn_layer_fused_kernel");
 }
@@ -479,7 +627,7 @@ int launch_fused(const CUtensorMap maps[8], const FusedParams& p, cudaStream_t s
 bool wn_fused_supported(int C, int n_cond, int bk) {
   const int n_cols = 2 * C < TC_NHALF ? 2 * C : TC_NHALF;
   return (bk == 32 || bk == 64) && C % bk == 0 && n_cond % bk == 0 && C <= FU_CMAX && (2 * C) % n_cols == 0 &&
-         (n_cols / 2) % bk == 0 && (n_cols / 2) % 32 == 0 && (C / 2) % 32 == 0 && C % 16 == 0;
+         (n_cols / 2) % bk == 0 && (n_cols / 2) % 32 == 0 && (C / 2) % FU_XS_COLS == 0 && C % 16 == 0;
 }
 
 // One fused WN layer: x_in (hi, lo) -> x_out (hi, lo), out8 (+)= Wc acts.  acts_hi/lo optional (tests).
@@ -487,26 +635,32 @@ int wn_layer_fused(const void* x_in_hi, const void* x_in_lo, void* x_out_hi, voi
                    const void* spect_lo, const void* w1_hi, const void* w1_lo, const void* w2_hi, const void* w2_lo,
                    const float* bias1, const float* res_b, const float* wc, float* out8, int accumulate_out8,
                    void* acts_hi, void* acts_lo, int B, int T, int C, int n_cond, int taps, int dilation, int has_res,
-                   int bk, cudaStream_t st) {
+                   int bk, int prefetch_steps, long long* prof, cudaStream_t st) {
   FAC_REQUIRE(wn_fused_supported(C, n_cond, bk), "wn_layer_fused: unsupported geometry C=%d n_cond=%d bk=%d", C, n_cond, bk);
   FAC_REQUIRE(x_in_hi && x_in_lo && spect_hi && spect_lo && w1_hi && w1_lo && bias1 && wc && out8,
               "wn_layer_fused: NULL argument");
   FAC_REQUIRE(!has_res || (x_out_hi && x_out_lo && w2_hi && w2_lo && res_b), "wn_layer_fused: residual operands missing");
   FAC_REQUIRE(!has_res || x_out_hi != x_in_hi, "wn_layer_fused: the residual stream cannot be updated in place");
-  CUtensorMap maps[8];
+  FusedMaps maps;
   const int K1 = taps * C + n_cond;
-  if (int rc = make_act_map(&maps[0], x_in_hi, B, T, C, bk)) return rc;
-  if (int rc = make_act_map(&maps[1], x_in_lo, B, T, C, bk)) return rc;
-  if (int rc = make_act_map(&maps[2], spect_hi, B, T, n_cond, bk)) return rc;
-  if (int rc = make_act_map(&maps[3], spect_lo, B, T, n_cond, bk)) return rc;
-  if (int rc = make_weight_map(&maps[4], w1_hi, 2 * C, K1, 2, bk)) return rc;
-  if (int rc = make_weight_map(&maps[5], w1_lo, 2 * C, K1, 2, bk)) return rc;
+  if (int rc = make_act_map(&maps.x_hi, x_in_hi, B, T, C, bk)) return rc;
+  if (int rc = make_act_map(&maps.x_lo, x_in_lo, B, T, C, bk)) return rc;
+  if (int rc = make_act_map(&maps.s_hi, spect_hi, B, T, n_cond, bk)) return rc;
+  if (int rc = make_act_map(&maps.s_lo, spect_lo, B, T, n_cond, bk)) return rc;
+  if (int rc = make_weight_map(&maps.w1_hi, w1_hi, 2 * C, K1, 2, bk)) return rc;
+  if (int rc = make_weight_map(&maps.w1_lo, w1_lo, 2 * C, K1, 2, bk)) return rc;
   if (has_res) {
-    if (int rc = make_weight_map(&maps[6], w2_hi, C, C, 2, bk)) return rc;
-    if (int rc = make_weight_map(&maps[7], w2_lo, C, C, 2, bk)) return rc;
+    if (int rc = make_weight_map(&maps.w2_hi, w2_hi, C, C, 2, bk)) return rc;
+    if (int rc = make_weight_map(&maps.w2_lo, w2_lo, C, C, 2, bk)) return rc;
+    if (int rc = make_act_map(&maps.xi_hi, x_in_hi, B, T, C, FU_XS_COLS)) return rc;
+    if (int rc = make_act_map(&maps.xi_lo, x_in_lo, B, T, C, FU_XS_COLS)) return rc;
+    if (int rc = make_act_map(&maps.xo_hi, x_out_hi, B, T, C, FU_XS_COLS)) return rc;
+    if (int rc = make_act_map(&maps.xo_lo, x_out_lo, B, T, C, FU_XS_COLS)) return rc;
   } else {
-    maps[6] = maps[4];
-    maps[7] = maps[5];
+    maps.w2_hi = maps.w1_hi;
+    maps.w2_lo = maps.w1_lo;
+    maps.xi_hi = maps.xo_hi = maps.x_hi;
+    maps.xi_lo = maps.xo_lo = maps.x_lo;
   }
   FusedParams p{};
   p.T = T;
@@ -531,6 +685,8 @@ int wn_layer_fused(const void* x_in_hi, const void* x_in_lo, void* x_out_hi, voi
   p.xo_lo = reinterpret_cast<__nv_bfloat16*>(x_out_lo);
   p.acts_hi = reinterpret_cast<__nv_bfloat16*>(acts_hi);
   p.acts_lo = reinterpret_cast<__nv_bfloat16*>(acts_lo);
+  p.prof = prof;
+  p.prefetch_steps = prefetch_steps < p.k1_steps ? prefetch_steps : p.k1_steps - 1;
   return bk == 64 ? launch_fused<64>(maps, p, st) : launch_fused<32>(maps, p, st);
 }
 

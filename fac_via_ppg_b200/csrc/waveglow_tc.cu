@@ -788,9 +788,12 @@ int tc_set_batch_group(int n) {
   g_tc_batch_group = n;
   return 0;
 }
-int g_tc_fused = 1;
+int g_tc_fused = 1, g_tc_prefetch = 0;
+// enabled: 0 = two launches per layer; 1 = fused; 1 + 16 * d = fused with the producer prefetching d K steps ahead
+// into L2 (experiments)
 int tc_set_fused(int enabled) {
-  g_tc_fused = enabled != 0;
+  g_tc_fused = (enabled & 15) != 0;
+  g_tc_prefetch = enabled >> 4;
   return 0;
 }
 int tc_set_cta_group(int cg) {
@@ -805,7 +808,7 @@ int wn_layer_fused(const void* x_in_hi, const void* x_in_lo, void* x_out_hi, voi
                    const void* spect_lo, const void* w1_hi, const void* w1_lo, const void* w2_hi, const void* w2_lo,
                    const float* bias1, const float* res_b, const float* wc, float* out8, int accumulate_out8,
                    void* acts_hi, void* acts_lo, int B, int T, int C, int n_cond, int taps, int dilation, int has_res,
-                   int bk, cudaStream_t st);
+                   int bk, int prefetch_steps, long long* prof, cudaStream_t st);
 
 static int tc_check(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac_wg_tc_workspace* ws, int nsplit) {
   if (int rc = wg_check_model(m)) return rc;
@@ -821,12 +824,16 @@ static int tc_check(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac
   return 0;
 }
 
+// K block of the fused layer kernel: 32 unless overridden (next to its 64 KB acts tile and the x staging the
+// operand ring is 128 KB: 4 stages of K = 32, but only 2 of K = 64, which starves the issuer -- measured)
+static int tc_fused_bk() { return g_tc_bk ? g_tc_bk : 32; }
+
 // One fused launch per layer (waveglow_fused.cu) when the workspace carries the second residual-stream pair.
 static bool tc_use_fused(const fac_wg_model* m, const fac_wg_tc_flow& wf, const fac_wg_tc_workspace* ws, int nsplit,
                          int layer) {
   return g_tc_fused && nsplit == 2 && tc_pick_cg(nsplit) == 2 && ws->x2_hi && ws->x2_lo && wf.w1_lo[layer] &&
          (layer == m->n_layers - 1 || (wf.w2r_hi[layer] && wf.w2r_lo[layer])) &&
-         wn_fused_supported(m->n_channels, m->n_mel * m->n_group, tc_pick_bk(nsplit));
+         wn_fused_supported(m->n_channels, m->n_mel * m->n_group, tc_fused_bk());
 }
 
 int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac_wg_tc_workspace* ws,
@@ -924,7 +931,7 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
                           even ? ws->x2_lo : ws->x_lo, ws->spect_hi, ws->spect_lo, wf.w1_hi[layer], wf.w1_lo[layer],
                           last ? nullptr : wf.w2r_hi[layer], last ? nullptr : wf.w2r_lo[layer], f.in_cond_b[layer],
                           last ? nullptr : wf.res_b[layer], wf.wc[layer], ws->out8, layer > 0, ws->acts_hi, ws->acts_lo, B,
-                          Tg, C, n_cond, ks, dil, last ? 0 : 1, tc_pick_bk(nsplit), st);
+                          Tg, C, n_cond, ks, dil, last ? 0 : 1, tc_fused_bk(), g_tc_prefetch, g_tc_prof, st);
   }
   FAC_REQUIRE(ws->acts_hi && (nsplit == 1 || ws->acts_lo), "wn_layer_tc: the two-launch form needs the acts buffers");
   CUtensorMap maps[6];
