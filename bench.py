@@ -255,7 +255,7 @@ def measure_fp32_mode(env, model, mel, peaks, samples_per_step):
     model.set_precision("fp32")
     try:
         ms, clocks = env.timed_with_clocks(lambda: model.infer(mel, sigma=0.6), 2, warmup=1)
-        roof = model.profile_dominant_kernel(mel, peaks)
+        roof = model.profile_dominant_kernel(mel, peaks, passes=1)
     finally:
         model.set_precision(old)
     ms /= 2
@@ -527,7 +527,7 @@ def main():
 
     # ---- roofline of the dominant kernel (the WN layer GEMMs), timed live with CUDA events
     peaks = measured_peaks()
-    roof = model.profile_dominant_kernel(mel, peaks) if hasattr(model, "profile_dominant_kernel") else None
+    roof = model.profile_dominant_kernel(mel, peaks, passes=max(3, min(args.steps, 10)))
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if roof is not None and os.path.isfile(traffic_path):
         with open(traffic_path) as fh:
