@@ -122,6 +122,9 @@ SIGNATURES = {
     "fac_tc_set_fused": (C.c_int, [C.c_int]),
     "fac_selftest_grid_barrier": (C.c_int, [_fp, C.c_int, _fp]),
     "fac_denoise_spectrum_f32": (C.c_int, [_fp, _fp, C.c_float, C.c_longlong, C.c_int, C.c_int, _fp]),
+    "fac_ppg_sparsify": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),
+    "fac_prenet0_sparse_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, _fp, _fp, _fp, C.c_int, _fp, _fp, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     "fac_lstm_bidir_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "fac_lstm_bidir_var_f32": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "fac_taco_decoder_run": (C.c_int, [_P(TacoDecoderWeights), _fp, _fp, _fp, _fp, _P(TacoDecoderState), _fp, _fp,

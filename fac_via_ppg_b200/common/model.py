@@ -27,6 +27,11 @@ Differences from the reference that a caller can observe:
     on the input's device.  ``rng_mode='reference'`` replays the reference's draw order
     call by call (seed-exact); the default ``'fast'`` makes one draw per tensor kind.
     A recorded tape can be injected with ``inference(inputs, dropout_tape=...)``.
+  * ``inference`` also accepts a pruned posteriorgram (``ops.SparsePPG``: per-frame (index, value) lists, or a
+    dense input pruned on the GPU when ``model.ppg_prune = (k, threshold)`` is set): the first prenet layer then
+    gathers k weight rows per frame instead of running the K = 5816 GEMM, and a host caller ships k * 8 bytes per
+    frame instead of 23 KB.  Exact for the pruned posteriorgram; pruning itself perturbs the first layer's
+    pre-activations by at most (dropped probability mass) x max |W|.
 The training direction (``forward`` / ``parse_batch``) is out of scope and raises.
 """
 from __future__ import annotations
@@ -145,6 +150,7 @@ class Tacotron2(nn.Module):
                                  # (fp32-grade, 3 UMMAs per product) | 'fp32' = exact FFMA implicit GEMM
     collect_timing = False       # True: CUDA-event times of encoder / decoder / postnet in .last_timing (ms)
     return_alignments = True     # dense (B, T_out, T_in) like the reference; False saves memory on long inputs
+    ppg_prune = None             # (k, threshold): prune dense inputs on the GPU and use the gather prenet (see above)
 
     def __init__(self, hparams):
         super().__init__()
@@ -212,11 +218,15 @@ class Tacotron2(nn.Module):
         None): rows beyond an utterance's length are written as zeros by every layer, which is the zero padding
         the next Conv1d would see if the utterance were processed alone."""
         hp = self.hp
-        B, D, T = inputs.shape
+        B, T = (inputs.shape[0], inputs.shape[1]) if isinstance(inputs, ops.SparsePPG) else (inputs.shape[0], inputs.shape[2])
         E = hp["encoder_embedding_dim"]
         tw = packed.tc_weights()
-        a = ops.transpose_split(inputs, tw["enc.pre0"]["c_pad"])
-        _, a = ops.conv_gemm_tc(a, tw["enc.pre0"], act=_ext.ACT_RELU, mask=enc0, row_lengths=lens)
+        if isinstance(inputs, ops.SparsePPG):
+            _, a = ops.prenet0_sparse(inputs, packed.view("enc.pre0_w"), E, mask=enc0, row_lengths=lens,
+                                      pad=tw["enc.pre1"]["c_pad"])
+        else:
+            a = ops.transpose_split(inputs, tw["enc.pre0"]["c_pad"])
+            _, a = ops.conv_gemm_tc(a, tw["enc.pre0"], act=_ext.ACT_RELU, mask=enc0, row_lengths=lens)
         _, a = ops.conv_gemm_tc(a, tw["enc.pre1"], act=_ext.ACT_RELU, mask=enc1, row_lengths=lens)
         for i in range(hp["encoder_n_convolutions"]):
             _, a = ops.conv_gemm_tc(a, tw[f"enc.conv{i}"], act=_ext.ACT_RELU, row_lengths=lens)
@@ -228,15 +238,20 @@ class Tacotron2(nn.Module):
         """reference model.py:237-249 (Encoder.inference): (B, D, T) -> memory (B, T, E); rows beyond an
         utterance's length (ragged batch) are zero."""
         hp = self.hp
-        B, D, T = inputs.shape
+        sparse = isinstance(inputs, ops.SparsePPG)
+        B, T = (inputs.shape[0], inputs.shape[1]) if sparse else (inputs.shape[0], inputs.shape[2])
         E, H = hp["encoder_embedding_dim"], hp["encoder_embedding_dim"] // 2
-        dev = inputs.device
+        dev = inputs.values.device if sparse else inputs.device
         new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         if self.precision == "fp16x3":
             xp = self._encode_tc(packed, inputs, enc0, enc1, lens)
         else:
-            h = ops.conv_gemm([ops.conv_src(inputs, channel_major=True)], packed.view("enc.pre0_w"), None, E,
-                              new(B, T, E), batch=B, rows=T, act=_ext.ACT_RELU, mask=enc0, row_lengths=lens)
+            if sparse:
+                h, _ = ops.prenet0_sparse(inputs, packed.view("enc.pre0_w"), E, mask=enc0, row_lengths=lens,
+                                          out=new(B, T, E), want_split=False)
+            else:
+                h = ops.conv_gemm([ops.conv_src(inputs, channel_major=True)], packed.view("enc.pre0_w"), None, E,
+                                  new(B, T, E), batch=B, rows=T, act=_ext.ACT_RELU, mask=enc0, row_lengths=lens)
             h = ops.conv_gemm([ops.conv_src(h)], packed.view("enc.pre1_w"), None, E, new(B, T, E), batch=B, rows=T,
                               act=_ext.ACT_RELU, mask=enc1, row_lengths=lens)
             k = hp["encoder_kernel_size"]
@@ -345,24 +360,33 @@ class Tacotron2(nn.Module):
         ``input_lengths`` (optional, B ints <= T_in) makes the batch ragged: utterance b only has its first
         input_lengths[b] frames (the rest is padding and is ignored), and its outputs equal those of a B == 1
         call on inputs[b:b+1, :, :input_lengths[b]] with the same dropout masks."""
-        _ext.require_cuda(inputs, "inputs")
-        inputs = self.parse_input(inputs)
-        x = inputs.float().contiguous()
-        B, D, T = x.shape
+        if isinstance(inputs, ops.SparsePPG):
+            _ext.require_cuda(inputs.values, "inputs")
+            _ext.require_cuda(inputs.indices, "inputs")
+            x = inputs
+            (B, T, _), D = x.shape, x.n_symbols
+        else:
+            _ext.require_cuda(inputs, "inputs")
+            inputs = self.parse_input(inputs)
+            x = inputs.float().contiguous()
+            B, D, T = x.shape
         if D != self.hp["n_symbols"]:
             raise ValueError("inputs have %d symbols, model expects %d" % (D, self.hp["n_symbols"]))
         if B == 0 or T == 0:
             raise ValueError("empty input batch")
+        if self.ppg_prune is not None and not isinstance(x, ops.SparsePPG):
+            x = ops.sparsify_ppg(x, *self.ppg_prune)
+        dev = x.values.device if isinstance(x, ops.SparsePPG) else x.device
         lens = None
         if input_lengths is not None:
             lens_host = torch.as_tensor(input_lengths).to("cpu", torch.int64).flatten()
             if lens_host.numel() != B or int(lens_host.min()) < 1 or int(lens_host.max()) > T:
                 raise ValueError("input_lengths must hold %d values in [1, %d]" % (B, T))
             if int(lens_host.min()) < T:                     # all full length: the plain path
-                lens = lens_host.to(device=x.device, dtype=torch.int32)
+                lens = lens_host.to(device=dev, dtype=torch.int32)
         packed = self.packed()
         n_steps = int(self.decoder.max_decoder_steps)
-        enc0, enc1, dec_masks = self._dropout_masks(B, T, n_steps, x.device, dropout_tape)
+        enc0, enc1, dec_masks = self._dropout_masks(B, T, n_steps, dev, dropout_tape)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.collect_timing else None
         if ev:
             ev[0].record()
@@ -379,7 +403,7 @@ class Tacotron2(nn.Module):
         mel_cl = mel_cl[:, :t_out].contiguous()
         ragged_out = B > 1 and int(out_lens.min()) < t_out
         if ragged_out:                                               # per-utterance stop: zero the tail
-            keep = (torch.arange(t_out, device=x.device)[None, :] < out_len[:, None]).unsqueeze(-1)
+            keep = (torch.arange(t_out, device=dev)[None, :] < out_len[:, None]).unsqueeze(-1)
             mel_cl = mel_cl * keep
             gate = gate[:, :t_out] * keep[..., 0]
             if align is not None:

@@ -47,9 +47,19 @@ def waveglow_audio(mel, waveglow, sigma, is_cuda_output=False):
     return (32768 * audio[0]).cpu().numpy().astype("int16")
 
 
-def get_inference(seq, model, is_clip=False):
-    """reference utils.py:155-174: (T, D) numpy PPG -> mel_outputs_postnet (1, 80, T_out) on the GPU."""
-    seq = to_gpu(torch.from_numpy(np.asarray(seq)).float().transpose(0, 1).unsqueeze(0))
+def get_inference(seq, model, is_clip=False, ppg_topk=0, ppg_threshold=0.0):
+    """reference utils.py:155-174: (T, D) numpy PPG -> mel_outputs_postnet (1, 80, T_out) on the GPU.
+    ``ppg_topk`` > 0 (an extension): prune every frame on the host to its ppg_topk largest posteriors (> threshold)
+    and ship the (index, value) lists instead of the dense matrix (ops.SparsePPG)."""
+    seq = torch.from_numpy(np.asarray(seq)).float().transpose(0, 1).unsqueeze(0)
+    if ppg_topk > 0:
+        from fac_via_ppg_b200.ops import SparsePPG
+        lists = SparsePPG.from_dense_host(seq, k=ppg_topk, threshold=ppg_threshold).to("cuda", non_blocking=True)
+        _, mel_outputs_postnet, _, _ = model.inference(lists)
+        if is_clip:
+            return mel_outputs_postnet[:, :, 10:(seq.size(2) - 10)]
+        return mel_outputs_postnet
+    seq = to_gpu(seq)
     _, mel_outputs_postnet, _, _ = model.inference(seq)
     if is_clip:
         return mel_outputs_postnet[:, :, 10:(seq.size(2) - 10)]

@@ -39,6 +39,9 @@ void lstm_set_prof(long long*);
 int conv_gemm_tc(const fac_tc_conv*, cudaStream_t);
 int tc_transpose_split(const float*, void*, void*, int, int, int, int, int, cudaStream_t);
 int tc_pad_split(const float*, void*, void*, long long, int, int, int, cudaStream_t);
+int ppg_sparsify(const float*, int*, float*, int*, int, int, int, int, float, cudaStream_t);
+int prenet0_sparse(const int*, const float*, const float*, int, const float*, const int*, float*, int, void*, void*, int, int,
+                   int, int, int, int, cudaStream_t);
 int denoise_spectrum(float*, const float*, float, long long, int, int, cudaStream_t);
 int tc_set_cta_group(int);
 int tc_set_k_block(int);
@@ -124,6 +127,16 @@ int fac_selftest_grid_barrier(unsigned int* zeroed_counter, int iters, void* str
 int fac_denoise_spectrum_f32(float* spec, const float* bias_mag, float strength, long long n_rows, int n_bins, int ld,
                                void* stream) {
   return fac::denoise_spectrum(spec, bias_mag, strength, n_rows, n_bins, ld, (cudaStream_t)stream);
+}
+int fac_ppg_sparsify(const float* ppg, int* idx, float* val, int* overflow, int B, int D, int T, int k,
+                     float threshold, void* stream) {
+  return fac::ppg_sparsify(ppg, idx, val, overflow, B, D, T, k, threshold, (cudaStream_t)stream);
+}
+int fac_prenet0_sparse_f32(const int* idx, const float* val, const float* w_t, int w_ld, const float* mask,
+                           const int* row_lengths, float* out, int out_ld, void* out_hi, void* out_lo, int B, int T,
+                           int k, int D, int E, int pad, void* stream) {
+  return fac::prenet0_sparse(idx, val, w_t, w_ld, mask, row_lengths, out, out_ld, out_hi, out_lo, B, T, k, D, E, pad,
+                             (cudaStream_t)stream);
 }
 int fac_lstm_bidir_f32(const float* xp, const float* w_hh, float* out, int B, int T, int H, void* stream) {
   return fac::lstm_bidir(xp, w_hh, out, nullptr, B, T, H, (cudaStream_t)stream);

@@ -116,3 +116,85 @@ def conv_gemm_tc(a, w, *, act=_ext.ACT_NONE, mask=None, residual=None, out=None,
     rc = _ext.load().fac_conv_gemm_tc(C.byref(d), _ext.current_stream())
     _ext.check(rc, "fac_conv_gemm_tc")
     return out, (nxt if want_split else None)
+
+
+# ---------------------------------------------------------------------- pruned posteriorgrams
+class SparsePPG:
+    """A posteriorgram as per-frame (index, value) lists: ``indices`` (B, T, k) int32, ``values`` (B, T, k) fp32,
+    padded with (0, 0.0); ``n_symbols`` = the dense width (5816).  What ``Tacotron2.inference`` accepts in place
+    of the dense (B, n_symbols, T) tensor: k * 8 bytes per frame instead of 23 KB."""
+
+    def __init__(self, indices, values, n_symbols):
+        if indices.shape != values.shape or indices.dim() != 3:
+            raise ValueError("indices and values must both be (B, T, k)")
+        if indices.shape[2] > 64:
+            raise ValueError("at most 64 entries per frame")
+        self.indices = indices.to(torch.int32).contiguous()
+        self.values = values.to(torch.float32).contiguous()
+        self.n_symbols = int(n_symbols)
+
+    @property
+    def shape(self):
+        return self.indices.shape
+
+    def to(self, device, non_blocking=False):
+        return SparsePPG(self.indices.to(device, non_blocking=non_blocking),
+                         self.values.to(device, non_blocking=non_blocking), self.n_symbols)
+
+    def pin_memory(self):
+        return SparsePPG(self.indices.pin_memory(), self.values.pin_memory(), self.n_symbols)
+
+    def dense(self):
+        """(B, n_symbols, T) dense tensor holding exactly the listed entries (tests, oracle input)."""
+        B, T, k = self.indices.shape
+        out = torch.zeros(B, T, self.n_symbols, dtype=torch.float32, device=self.values.device)
+        out.scatter_add_(2, self.indices.long(), self.values)
+        return out.transpose(1, 2).contiguous()
+
+    @classmethod
+    def from_dense_host(cls, ppg, k=64, threshold=0.0):
+        """Host-side pruning of a dense (B, n_symbols, T) posteriorgram (numpy / CPU tensor): per frame the k
+        largest entries, of those only the ones > threshold, in ascending channel order."""
+        x = torch.as_tensor(ppg, dtype=torch.float32).cpu()
+        B, D, T = x.shape
+        vals, idx = x.transpose(1, 2).topk(min(k, D), dim=2)
+        vals = torch.where(vals > threshold, vals, torch.zeros_like(vals))
+        idx = torch.where(vals > 0, idx, torch.zeros_like(idx))
+        order = torch.argsort(torch.where(vals > 0, idx, torch.full_like(idx, D)), dim=2)
+        return cls(idx.gather(2, order), vals.gather(2, order), D)
+
+
+def sparsify_ppg(ppg: torch.Tensor, k: int = 64, threshold: float = 1e-4) -> SparsePPG:
+    """Dense (B, n_symbols, T) posteriorgram on the GPU -> SparsePPG holding the entries > threshold
+    (fac_ppg_sparsify).  Raises FacError when a frame has more than k such entries: nothing is truncated
+    silently -- raise the threshold, or keep the dense path."""
+    _ext.require_cuda(ppg, "ppg")
+    x = ppg.float().contiguous()
+    B, D, T = x.shape
+    idx = torch.empty(B, T, k, dtype=torch.int32, device=x.device)
+    val = torch.empty(B, T, k, dtype=torch.float32, device=x.device)
+    overflow = torch.zeros(1, dtype=torch.int32, device=x.device)
+    rc = _ext.load().fac_ppg_sparsify(x.data_ptr(), idx.data_ptr(), val.data_ptr(), overflow.data_ptr(), B, D, T, k,
+                                      float(threshold), _ext.current_stream())
+    _ext.check(rc, "fac_ppg_sparsify")
+    n_over = int(overflow.item())
+    if n_over:
+        raise _ext.FacError("%d of %d frames have more than %d entries above %g: raise the threshold or use the "
+                            "dense path" % (n_over, B * T, k, threshold))
+    return SparsePPG(idx, val, D)
+
+
+def prenet0_sparse(sp: SparsePPG, w_t: torch.Tensor, E: int, *, mask=None, row_lengths=None, out=None, pad=None,
+                   want_split=True):
+    """First encoder prenet layer on a SparsePPG (fac_prenet0_sparse_f32).  ``w_t`` = packed enc.pre0_w
+    (n_symbols, ld).  Returns (out_f32 or None, (hi, lo) fp16 operand copies or None)."""
+    _ext.require_cuda(sp.values, "sparse PPG")
+    B, T, k = sp.indices.shape
+    pad = pad or (E + 63) // 64 * 64
+    nxt = split_pair((B, T, pad), sp.values.device, 2, torch.float16) if want_split else (None, None)
+    rc = _ext.load().fac_prenet0_sparse_f32(sp.indices.data_ptr(), sp.values.data_ptr(), w_t.data_ptr(), w_t.shape[1],
+                                            _ext.ptr(mask), _ext.ptr(row_lengths), _ext.ptr(out),
+                                            0 if out is None else out.shape[-1], _ext.ptr(nxt[0]), _ext.ptr(nxt[1]),
+                                            B, T, k, sp.n_symbols, E, pad, _ext.current_stream())
+    _ext.check(rc, "fac_prenet0_sparse_f32")
+    return out, (nxt if want_split else None)

@@ -9,7 +9,8 @@ is accepted only when ``FAC_REFERENCE_SRC`` points at a reference ``src/`` tree 
 imports: the original ``get_ppg`` then runs unchanged, with the reference's own ``common`` / ``ppg``
 packages imported in isolation from this package's drop-in aliases.  Two extras help on boxes without
 checkpoints: ``--synthetic SECONDS`` ignores the model/utterance paths and runs seeded random-init
-models on a synthetic PPG, and ``--no_denoiser`` skips the post-filter.
+models on a synthetic PPG, and ``--no_denoiser`` skips the post-filter.  ``--ppg_topk K`` prunes every PPG
+frame to its K largest posteriors on the host (k * 8 bytes per frame cross PCIe instead of 23 KB).
 """
 import argparse
 import logging
@@ -79,6 +80,9 @@ def main(argv=None):
     parser.add_argument("--synthetic", type=float, default=0.0, metavar="SECONDS",
                         help="run seeded random-init models on a synthetic PPG of this length")
     parser.add_argument("--no_denoiser", action="store_true")
+    parser.add_argument("--ppg_topk", type=int, default=0, metavar="K",
+                        help="prune every PPG frame to its K (<= 64) largest posteriors on the host and run the "
+                             "gather prenet (0 = dense, the reference's input)")
     args = parser.parse_args(argv)
 
     os.makedirs(args.output_dir, exist_ok=True)
@@ -115,7 +119,7 @@ def main(argv=None):
     denoiser = None if args.no_denoiser else Denoiser(waveglow_model, mode=denoiser_mode)
 
     logging.info("Perform AC on %s", args.teacher_utterance_path)
-    ac_mel = get_inference(teacher_ppg, tacotron_model, is_clip)
+    ac_mel = get_inference(teacher_ppg, tacotron_model, is_clip, ppg_topk=args.ppg_topk)
     ac_wav = waveglow_audio(ac_mel, waveglow_model, waveglow_sigma, True)
     if denoiser is not None:
         ac_wav = denoiser(ac_wav, strength=denoiser_strength)[:, 0]

@@ -251,6 +251,23 @@ int fac_transpose_split_16(const float* in, void* hi, void* lo, int B, int C, in
 /* (n_rows, C) fp32 -> (n_rows, pad) 16-bit hi [+ lo], columns [C, pad) zero. */
 int fac_pad_split_16(const float* in, void* hi, void* lo, long long n_rows, int C, int pad, int fp16, void* stream);
 
+/* ---- pruned posteriorgram input -------------- */
+/* The step before the path (reference src/common/data_utils.py:55-59 get_ppg) hands Tacotron2.inference a dense
+ * (T, 5816) posteriorgram whose frames are almost entirely tail.  fac_ppg_sparsify turns the channel-major
+ * (B, D, T) input into per-frame lists of the entries > threshold: idx / val are (B, T, k), ascending channel
+ * order, padded with (0, 0.0); k <= 64.  *overflow (one int, zeroed by the caller) counts the frames that had
+ * more than k survivors -- those lists are truncated and the caller must not use them. */
+int fac_ppg_sparsify(const float* ppg, int* idx, float* val, int* overflow, int B, int D, int T, int k,
+                     float threshold, void* stream);
+/* First encoder prenet layer (reference src/common/model.py:124-135: bias-free Linear D -> E, ReLU, dropout mask)
+ * on such lists: out[b,t,:] = relu(sum_j val[b,t,j] * w_t[idx[b,t,j], :]) * mask[b,t,:], exact fp32 FMA in list
+ * order.  w_t is [D][w_ld] (the transposed weight, fac_via_ppg_b200/packing.py enc.pre0_w); mask (B,T,E) or NULL;
+ * row_lengths as in fac_tc_conv; out (fp32, row stride out_ld) and/or out_hi/out_lo ((B,T,pad) IEEE-half hi/lo
+ * operand copies for fac_conv_gemm_tc, channels [E, pad) zero). */
+int fac_prenet0_sparse_f32(const int* idx, const float* val, const float* w_t, int w_ld, const float* mask,
+                           const int* row_lengths, float* out, int out_ld, void* out_hi, void* out_lo, int B, int T,
+                           int k, int D, int E, int pad, void* stream);
+
 /* ---- PPG -> Mel (Tacotron2 variant) ------------------------------------- */
 /* Recurrent part of the encoder's bidirectional LSTM (reference src/common/model.py:211-213,
  * 246-247).  xp is (B, T, 2*4H): x W_ih^T + b_ih + b_hh of the forward direction in columns

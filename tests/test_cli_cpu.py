@@ -61,3 +61,27 @@ def test_recording_uses_the_reference_front_end_despite_the_aliases(tmp_path, mo
     from common.utils import get_inference      # the drop-in again  # noqa: F401
     assert os.path.basename(sys.modules["common.utils"].__file__) == "utils.py"
     assert "fac_via_ppg_b200" in sys.modules["common.utils"].__file__
+
+
+def test_sparse_ppg_host_pruning_round_trip():
+    """ops.SparsePPG.from_dense_host: top-k per frame, ascending channel order, zero padding; dense() restores
+    exactly the kept entries."""
+    import torch
+    from fac_via_ppg_b200.ops import SparsePPG
+    g = torch.Generator().manual_seed(0)
+    dense = torch.zeros(2, 50, 7)
+    dense[0, [3, 17, 40], 0] = torch.tensor([0.2, 0.5, 0.3])
+    dense[1, :, 2] = torch.softmax(torch.randn(50, generator=g), 0)
+    sp = SparsePPG.from_dense_host(dense, k=4)
+    assert sp.shape == (2, 7, 4) and sp.n_symbols == 50
+    assert sp.indices[0, 0].tolist() == [3, 17, 40, 0] and sp.values[0, 0].tolist()[3] == 0.0
+    kept = sp.dense()
+    assert torch.equal(kept[0], dense[0])                                   # <= k entries per frame: lossless
+    top4 = dense[1, :, 2].topk(4)
+    assert sorted(sp.indices[1, 2].tolist()) == sorted(top4.indices.tolist())
+    assert sp.indices[1, 2].tolist() == sorted(sp.indices[1, 2].tolist())
+    assert abs(float(kept[1, :, 2].sum()) - float(top4.values.sum())) < 1e-6
+    thr = SparsePPG.from_dense_host(dense, k=4, threshold=0.25)
+    assert thr.values[0, 0].tolist() == [0.5, 0.3, 0.0, 0.0] and thr.indices[0, 0].tolist() == [17, 40, 0, 0]
+    with pytest.raises(ValueError):
+        SparsePPG(torch.zeros(1, 2, 65, dtype=torch.int32), torch.zeros(1, 2, 65), 100)

@@ -336,3 +336,55 @@ def test_ragged_batch_larger_than_one_decoder_launch_is_length_sorted(model):
         alone = model.inference(ppg[k:k + 1, :, :n].contiguous(), dropout_tape=tape)
         assert torch.equal(out[1][k], alone[1][0]), k
         assert torch.equal(out[3][k, :, :n], alone[3][0]), k
+
+
+def test_pruned_posteriorgram_input_matches_dense_path_and_oracle(model):
+    """a posteriorgram whose frames hold at most k entries (what pruning a real PPG leaves) goes
+    through the gather prenet (fac_prenet0_sparse_f32) instead of the K = 5816 GEMM.  Same function: the sparse
+    path, the dense path and the oracle agree on the pruned input (1e-3 on mel, like every other parity case), for
+    lists built on the host and on the GPU, for both encoder precisions and for a ragged batch."""
+    sd = synth.tacotron_state()
+    B, T, k, n_steps = 3, 45, 48, 20
+    force_length(model, n_steps)
+    g = torch.Generator().manual_seed(5)
+    # peaked frames: a few dozen senones carry all the mass (the rest is exactly zero after pruning)
+    dense = torch.zeros(B, 5816, T)
+    for b in range(B):
+        for t in range(T):
+            n = int(torch.randint(1, k + 1, (1,), generator=g))
+            idx = torch.randperm(5816, generator=g)[:n]
+            dense[b, idx, t] = torch.softmax(torch.randn(n, generator=g) * 2, 0)
+    torch.manual_seed(15)
+    masks = tacotron_oracle.record_dropout_tape(B, T, n_steps)
+    ref = tacotron_oracle.tacotron_inference(sd, synth.TACOTRON_HPARAMS, dense, masks, 2.0, n_steps)
+    host = ops.SparsePPG.from_dense_host(dense, k=k)
+    assert torch.equal(host.dense(), dense)
+    dev_lists = ops.sparsify_ppg(dense.to(DEV), k=k, threshold=0.0)
+    assert torch.equal(dev_lists.dense().cpu(), dense)
+    assert torch.equal(dev_lists.indices.cpu(), host.indices) and torch.equal(dev_lists.values.cpu(), host.values)
+    for precision in ("fp16x3", "fp32"):
+        model.set_precision(precision)
+        try:
+            out_dense = model.inference(dense.to(DEV), dropout_tape=masks)
+            out_sparse = model.inference(host.to(DEV), dropout_tape=masks)
+            model.ppg_prune = (k, 0.0)
+            out_auto = model.inference(dense.to(DEV), dropout_tape=masks)
+        finally:
+            model.set_precision("fp16x3")
+            model.ppg_prune = None
+        for name, a, b_, c, r in zip(("mel", "mel_post", "gate", "align"), out_sparse, out_dense, out_auto, ref):
+            assert (a.cpu() - r).abs().max().item() <= MEL_TOL, (precision, name)
+            assert (a - b_).abs().max().item() <= MEL_TOL, (precision, name)
+            assert torch.equal(a, c), (precision, name)
+    # ragged batch through the sparse path == single runs of the dense path
+    lengths = [45, 30, 9]
+    out = model.inference(host.to(DEV), dropout_tape=masks, input_lengths=lengths)
+    for kk, n in enumerate(lengths):
+        tape = [m[kk:kk + 1, :n] for m in masks[:2]] + [m[kk:kk + 1] for m in masks[2:]]
+        alone = model.inference(dense[kk:kk + 1, :, :n].contiguous().to(DEV), dropout_tape=tape)
+        assert (out[1][kk] - alone[1][0]).abs().max().item() <= MEL_TOL, kk
+    # more survivors than the list holds: loud failure, never a silent truncation
+    with pytest.raises(_ext.FacError):
+        ops.sparsify_ppg(synth.synthetic_ppg(1, 8).to(DEV), k=16, threshold=1e-5)
+    with pytest.raises(ValueError):
+        model.inference(ops.SparsePPG(host.indices.to(DEV), host.values.to(DEV), 100))
