@@ -82,6 +82,6 @@ def test_sparse_ppg_host_pruning_round_trip():
     assert sp.indices[1, 2].tolist() == sorted(sp.indices[1, 2].tolist())
     assert abs(float(kept[1, :, 2].sum()) - float(top4.values.sum())) < 1e-6
     thr = SparsePPG.from_dense_host(dense, k=4, threshold=0.25)
-    assert thr.values[0, 0].tolist() == [0.5, 0.3, 0.0, 0.0] and thr.indices[0, 0].tolist() == [17, 40, 0, 0]
+    assert thr.values[0, 0].tolist() == pytest.approx([0.5, 0.3, 0.0, 0.0]) and thr.indices[0, 0].tolist() == [17, 40, 0, 0]
     with pytest.raises(ValueError):
         SparsePPG(torch.zeros(1, 2, 65, dtype=torch.int32), torch.zeros(1, 2, 65), 100)
