@@ -230,7 +230,7 @@ class Tacotron2(nn.Module):
         _, a = ops.conv_gemm_tc(a, tw["enc.pre1"], act=_ext.ACT_RELU, mask=enc1, row_lengths=lens)
         for i in range(hp["encoder_n_convolutions"]):
             _, a = ops.conv_gemm_tc(a, tw[f"enc.conv{i}"], act=_ext.ACT_RELU, row_lengths=lens)
-        xp = torch.empty(B, T, 4 * E, device=inputs.device, dtype=torch.float32)
+        xp = torch.empty(B, T, 4 * E, device=a[0].device, dtype=torch.float32)
         ops.conv_gemm_tc(a, tw["enc.lstm_ih"], out=xp, want_split=False)
         return xp
 

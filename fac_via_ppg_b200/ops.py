@@ -137,6 +137,10 @@ class SparsePPG:
     def shape(self):
         return self.indices.shape
 
+    @property
+    def device(self):
+        return self.values.device
+
     def to(self, device, non_blocking=False):
         return SparsePPG(self.indices.to(device, non_blocking=non_blocking),
                          self.values.to(device, non_blocking=non_blocking), self.n_symbols)
