@@ -74,7 +74,7 @@ class WgTcWeights(C.Structure):
 
 class WgTcWorkspace(C.Structure):
     _fields_ = [(n, _fp) for n in ("mel_hi", "mel_lo", "spect_hi", "spect_lo", "x_hi", "x_lo", "acts_hi", "acts_lo",
-                                   "out8", "x2_hi", "x2_lo")]
+                                   "out8", "x2_hi", "x2_lo", "flow_sync")]
 
 
 class TacoDecoderWeights(C.Structure):
@@ -107,6 +107,8 @@ SIGNATURES = {
     "fac_wn_start_tc": (C.c_int, [_P(WgModel), C.c_int, _fp, _P(WgTcWorkspace), C.c_int, C.c_int, C.c_int, _fp]),
     "fac_wn_layer_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), C.c_int, C.c_int, _P(WgTcWorkspace), C.c_int,
                                   C.c_int, C.c_int, _fp]),
+    "fac_waveglow_flow_step_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), C.c_int, _fp, _P(WgTcWorkspace), C.c_int,
+                                            C.c_int, C.c_int, _fp]),
     "fac_wn_end_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), C.c_int, _fp, _fp, C.c_int, C.c_int, _fp]),
     "fac_waveglow_infer_tc": (C.c_int, [_P(WgModel), _P(WgTcWeights), _fp, _fp, _P(WgTcWorkspace), C.c_int, C.c_int,
                                         C.c_int, _fp]),

@@ -31,6 +31,8 @@ int wg_tc_layer(const fac_wg_model*, const fac_wg_tc_weights*, int, int, const f
                 cudaStream_t);
 int wg_infer_tc(const fac_wg_model*, const fac_wg_tc_weights*, const float*, float*, const fac_wg_tc_workspace*, int,
                 int, int, cudaStream_t);
+int wg_tc_flow_step(const fac_wg_model*, const fac_wg_tc_weights*, int, float*, const fac_wg_tc_workspace*, int, int, int,
+                    cudaStream_t);
 int wg_tc_end(const fac_wg_model*, const fac_wg_tc_weights*, int, const float*, float*, int, int, cudaStream_t);
 int tc_set_batch_group(int);
 void tc_set_prof(long long*);
@@ -106,6 +108,10 @@ int fac_wn_end_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, c
 int fac_waveglow_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* mel_cl, float* audio,
                           const fac_wg_tc_workspace* ws, int B, int F, int nsplit, void* stream) {
   return fac::wg_infer_tc(m, w, mel_cl, audio, ws, B, F, nsplit, (cudaStream_t)stream);
+}
+int fac_waveglow_flow_step_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, float* audio,
+                              const fac_wg_tc_workspace* ws, int B, int Tg, int nsplit, void* stream) {
+  return fac::wg_tc_flow_step(m, w, flow, audio, ws, B, Tg, nsplit, (cudaStream_t)stream);
 }
 void fac_tc_set_profile_buffer(long long* device_buf) { fac::tc_set_prof(device_buf); }
 int fac_conv_gemm_tc(const fac_tc_conv* conv, void* stream) { return fac::conv_gemm_tc(conv, (cudaStream_t)stream); }

@@ -57,22 +57,30 @@ constexpr int FU_REGS_LOW = 40, FU_REGS_HIGH = 232;   // 128 x 40 + 256 x 232 = 
 
 struct FusedParams {
   int T, B, tiles_per_batch, n_tiles;
-  int C, n_cond, taps, dilation, center;
+  int C, n_cond, taps;
   int k1_steps;              // K steps of the first GEMM: (taps * C + n_cond) / BK
-  int has_res;               // 0: last layer (no residual GEMM)
-  const float* bias1;        // [2C] in.bias + cond.bias, gate-interleaved
-  const float* res_b;        // [C]
-  const float* wc;           // [8][C] collapsed skip weights
+  // The launch runs layers [layer_first, layer_first + layer_count) of a WN with n_layers layers (dilation 2^l,
+  // the last one has no residual output), optionally preceded by `start` (glow.py:156) and followed by `end` +
+  // coupling + invertible 1x1 (glow.py:175, 278-283): the whole flow step in one launch.  Consecutive phases
+  // are separated by a grid-wide barrier (cooperative launch); a single layer needs none.
+  int layer_first, layer_count, n_layers;
+  int do_start, do_end;
+  const float* bias1[FAC_MAX_LAYERS];   // [2C] in.bias + cond.bias, gate-interleaved
+  const float* res_b[FAC_MAX_LAYERS];   // [C]
+  const float* wc[FAC_MAX_LAYERS];      // [8][C] collapsed skip weights
   float* out8;               // (B, T, 8)
-  int accumulate_out8;
-  const __nv_bfloat16* x_hi;     // residual stream read by EG (the same buffer the x tensor maps describe)
-  const __nv_bfloat16* x_lo;
-  __nv_bfloat16* xo_hi;          // residual stream written for the next layer
-  __nv_bfloat16* xo_lo;
-  __nv_bfloat16* acts_hi;        // optional (tests): the gated activations, (B, T, C)
+  int accumulate_out8;       // single-layer launches: layer_first > 0
+  const float* start_w;      // [n_half][C]
+  const float* start_b;      // [C]
+  const float* out_bias;     // [8] end.bias + end.weight @ (sum of the skip biases)
+  const float* w_inv;        // [n_rem][n_rem]
+  float* audio;              // (B, T, n_group): the flow's live channels are the LAST n_rem slots of a column
+  int n_group, n_rem, n_half;
+  __nv_bfloat16* acts_hi;    // optional (tests, single layer): the gated activations, (B, T, C)
   __nv_bfloat16* acts_lo;
-  int prefetch_steps;            // L2 prefetch distance of the producer in K steps (0 = off)
-  long long* prof;               // optional [grid][16] clock64 counters (tools/tc_cycle_breakdown.py)
+  unsigned int* grid_bar;    // zeroed by the host; arrival counter of the grid barrier
+  int prefetch_steps;        // L2 prefetch distance of the producer in K steps (0 = off)
+  long long* prof;           // optional [grid][16] clock64 counters (tools/tc_cycle_breakdown.py)
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
@@ -135,17 +143,34 @@ __device__ __forceinline__ uint32_t swizzle_off(uint32_t off) {
 }
 
 struct FusedMaps {
-  CUtensorMap x_hi, x_lo;        // residual stream in: boxes of BK channels (operand A of the first GEMM)
-  CUtensorMap s_hi, s_lo;        // spect
-  CUtensorMap w1_hi, w1_lo;      // [2C][taps*C + n_cond]
-  CUtensorMap w2_hi, w2_lo;      // [C][C] residual half of res_skip
-  CUtensorMap xi_hi, xi_lo;      // residual stream in, boxes of FU_XS_COLS channels (EG staging)
-  CUtensorMap xo_hi, xo_lo;      // residual stream out, same boxes (TMA store)
+  CUtensorMap xa_hi, xa_lo, xb_hi, xb_lo;   // residual stream buffers A (ws->x) and B (ws->x2): boxes of BK channels
+  CUtensorMap s_hi, s_lo;                   // spect
+  CUtensorMap w1_hi, w1_lo;                 // [layer][2C][taps*C + n_cond]
+  CUtensorMap w2_hi, w2_lo;                 // [layer][C][C] residual half of res_skip
+  CUtensorMap ya_hi, ya_lo, yb_hi, yb_lo;   // the same two buffers in boxes of FU_XS_COLS channels (EG staging, TMA store)
 };
+
+// Grid-wide barrier between the phases of a flow step (cooperative launch: every CTA is resident).  The TMA stores
+// of the phase have been waited for by their issuing threads before the CTA barrier; the proxy fences order those
+// async-proxy writes with the generic-proxy release / acquire and the next phase's TMA loads.
+__device__ __forceinline__ void flow_barrier(unsigned int* counter, unsigned int& target) {
+  asm volatile("bar.sync 5, %0;" ::"n"(FU_THREADS) : "memory");
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  asm volatile("bar.sync 5, %0;" ::"n"(FU_THREADS) : "memory");
+}
 
 template <int BK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FU_THREADS, 1)
-wn_layer_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p) {
+wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p) {
   constexpr int ROWB = BK * 2;                       // bytes of one operand row
   constexpr int A_BYTES = TC_BM * ROWB;              // one 128-row activation tile (hi or lo)
   constexpr int W_BYTES = (TC_NHALF / 2) * ROWB;     // this CTA's half of a 256-row weight block (hi or lo)
@@ -159,7 +184,7 @@ wn_layer_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams 
   uint8_t* xs_s = acts_s + FU_ACTS_BYTES;            // [column half][hi | lo][128 rows][64 B]
   uint64_t* full = reinterpret_cast<uint64_t*>(xs_s + FU_XS_BYTES);
   uint64_t* empty = full + FU_MAX_STAGES;
-  uint64_t* tmem_full = empty + FU_MAX_STAGES;       // [2]: region 0 = first GEMM, region 1 = residual GEMM
+  uint64_t* tmem_full = empty + FU_MAX_STAGES;       // [2] accumulator regions (see the issuer)
   uint64_t* tmem_empty = tmem_full + 2;              // [2]
   uint64_t* acts_ready = tmem_empty + 2;             // epilogue -> issuer (leader's copy is used)
   uint64_t* acts_free = acts_ready + 1;              // issuer -> epilogue (both CTAs)
@@ -179,7 +204,12 @@ wn_layer_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams 
   const int xs_chunks = (C / 2) / FU_XS_COLS;                       // x staging boxes per column half and tile
   int my_tiles = 0;
   for (int tb = tile_first; tb < p.n_tiles; tb += (int)gridDim.x) ++my_tiles;
-  const int Q = my_tiles * n_units;                                 // units of this CTA pair
+  const int Q = my_tiles * n_units;                                 // units of this CTA pair per layer
+  unsigned int bar_target = 0;
+  // phases: [start] layer ... layer [end]; a grid barrier separates start from the first layer and a layer with a
+  // residual output from the next one (`end` only touches this CTA's own columns)
+  auto has_res = [&](int l) { return l < p.n_layers - 1; };
+  auto barrier_after_layer = [&](int li) { return li + 1 < p.layer_count && has_res(p.layer_first + li); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -195,7 +225,7 @@ wn_layer_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams 
     mbar_init(acts_ready, FU_EPI_WARPS * 2);
     mbar_init(acts_free, 1);
     fence_barrier_init();
-    tma_prefetch_desc(&maps.x_hi);
+    tma_prefetch_desc(&maps.xa_hi);
     tma_prefetch_desc(&maps.w1_hi);
   }
   if (warp == 1) tmem_alloc_cg2(tmem_slot, 512);
@@ -207,190 +237,198 @@ wn_layer_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams 
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FU_REGS_LOW));
-    if (warp == 0 && lane == 0) {
-      // ===================================================== TMA producer (operand ring)
-      const int w1_rows = n_cols / 2, w2_rows = C / 2;            // weight rows staged by this CTA
-      const int steps_x = p.taps * (C / BK);
-      int stage = 0;
-      uint32_t phase = 0;
-      long long prod_wait = 0;
-      auto acquire = [&](uint32_t bytes) -> uint8_t* {
-        const long long w0 = clock64();
-        mbar_wait(&empty[stage], phase ^ 1);
-        prod_wait += clock64() - w0;
-        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * bytes);   // both CTAs' loads land on the leader's barrier
-        return smem + stage * STAGE_BYTES;
-      };
-      auto advance = [&]() {
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      };
-      // activation box of K step ks of unit q: (map pair, channel, first row, utterance)
-      auto a_box = [&](int q, int ks, const CUtensorMap*& mh, const CUtensorMap*& ml, int& c0, int& row0, int& b) {
-        const int tile = tile_first + (q / n_units) * (int)gridDim.x + rank;   // may be one past the end: OOB -> zeros
-        b = tile / p.tiles_per_batch;
-        const int t0 = (tile % p.tiles_per_batch) * TC_BM;
-        if (ks < steps_x) {
-          const int cps = C / BK, tap = ks / cps;
-          c0 = (ks - tap * cps) * BK;
-          row0 = t0 + tap * p.dilation - p.center;
-          mh = &maps.x_hi;
-          ml = &maps.x_lo;
-        } else {
-          c0 = (ks - steps_x) * BK;
-          row0 = t0;
-          mh = &maps.s_hi;
-          ml = &maps.s_lo;
-        }
-      };
-      for (int q = 0; q <= Q; ++q) {
-        if (q < Q) {
-          const int u = q % n_units;
-          const int w_row = u * TC_NHALF + rank * w1_rows;
-          for (int ks = 0; ks < p.k1_steps; ++ks) {
-            const CUtensorMap *mh, *ml;
-            int c0, row0, b;
-            if (p.prefetch_steps > 0) {
-              // L2 prefetch, prefetch_steps ahead in the flattened (unit, K step) order, of boxes that will come
-              // from DRAM: those of a tile's FIRST unit (its later units find them in L2)
-              int q2 = q, ks2 = ks + p.prefetch_steps;
-              if (ks2 >= p.k1_steps) {
-                ks2 -= p.k1_steps;
-                ++q2;
+    // ring position and the use counters behind every mbarrier parity run on across the layers of the launch
+    int stage = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() {
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    };
+    if (p.do_start) flow_barrier(p.grid_bar, bar_target);
+    long long prod_wait = 0, w_tmem0 = 0, w_full = 0, w_acts = 0, w_tmem1 = 0, issue = 0;
+    const long long k_start = clock64();
+    uint32_t use[2] = {0, 0}, acts_n = 0, xph[2] = {0, 0};
+    for (int li = 0; li < p.layer_count; ++li) {
+      const int layer = p.layer_first + li;
+      const bool res = has_res(layer);
+      const int dil = 1 << layer, center = dil * (p.taps - 1) / 2;
+      const bool in_a = (layer & 1) == 0;              // layer l reads buffer A when l is even and writes the other
+      if (warp == 0 && lane == 0) {
+        // ===================================================== TMA producer (operand ring)
+        const CUtensorMap* xm_hi = in_a ? &maps.xa_hi : &maps.xb_hi;
+        const CUtensorMap* xm_lo = in_a ? &maps.xa_lo : &maps.xb_lo;
+        const int w1_rows = n_cols / 2, w2_rows = C / 2;            // weight rows staged by this CTA
+        const int steps_x = p.taps * (C / BK);
+        auto acquire = [&](uint32_t bytes) -> uint8_t* {
+          const long long w0 = clock64();
+          mbar_wait(&empty[stage], phase ^ 1);
+          prod_wait += clock64() - w0;
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * bytes);   // both CTAs' loads land on the leader's barrier
+          return smem + stage * STAGE_BYTES;
+        };
+        // activation box of K step ks of unit q: (map pair, channel, first row, utterance)
+        auto a_box = [&](int q, int ks, const CUtensorMap*& mh, const CUtensorMap*& ml, int& c0, int& row0, int& b) {
+          const int tile = tile_first + (q / n_units) * (int)gridDim.x + rank;   // may be one past the end: OOB -> zeros
+          b = tile / p.tiles_per_batch;
+          const int t0 = (tile % p.tiles_per_batch) * TC_BM;
+          if (ks < steps_x) {
+            const int cps = C / BK, tap = ks / cps;
+            c0 = (ks - tap * cps) * BK;
+            row0 = t0 + tap * dil - center;
+            mh = xm_hi;
+            ml = xm_lo;
+          } else {
+            c0 = (ks - steps_x) * BK;
+            row0 = t0;
+            mh = &maps.s_hi;
+            ml = &maps.s_lo;
+          }
+        };
+        for (int q = 0; q <= Q; ++q) {
+          if (q < Q) {
+            const int u = q % n_units;
+            const int w_row = u * TC_NHALF + rank * w1_rows;
+            for (int ks = 0; ks < p.k1_steps; ++ks) {
+              const CUtensorMap *mh, *ml;
+              int c0, row0, b;
+              if (p.prefetch_steps > 0) {
+                // L2 prefetch, prefetch_steps ahead in the flattened (unit, K step) order, of boxes that will come
+                // from DRAM: those of a tile's FIRST unit (its later units find them in L2)
+                int q2 = q, ks2 = ks + p.prefetch_steps;
+                if (ks2 >= p.k1_steps) {
+                  ks2 -= p.k1_steps;
+                  ++q2;
+                }
+                if (q2 < Q && q2 % n_units == 0) {
+                  a_box(q2, ks2, mh, ml, c0, row0, b);
+                  tma_prefetch_l2_3d(mh, c0, row0, b);
+                  tma_prefetch_l2_3d(ml, c0, row0, b);
+                }
               }
-              if (q2 < Q && q2 % n_units == 0) {
-                a_box(q2, ks2, mh, ml, c0, row0, b);
-                tma_prefetch_l2_3d(mh, c0, row0, b);
-                tma_prefetch_l2_3d(ml, c0, row0, b);
-              }
+              uint8_t* st = acquire((uint32_t)(2 * A_BYTES + 2 * w1_rows * ROWB));
+              const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+              a_box(q, ks, mh, ml, c0, row0, b);
+              tma_load_3d_cg2(st, mh, lead_full, c0, row0, b);
+              tma_load_3d_cg2(st + A_BYTES, ml, lead_full, c0, row0, b);
+              tma_load_3d_cg2(st + W_OFF, &maps.w1_hi, lead_full, ks * BK, w_row, layer);
+              tma_load_3d_cg2(st + W_OFF + W_BYTES, &maps.w1_lo, lead_full, ks * BK, w_row, layer);
+              advance();
             }
-            uint8_t* st = acquire((uint32_t)(2 * A_BYTES + 2 * w1_rows * ROWB));
-            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
-            a_box(q, ks, mh, ml, c0, row0, b);
-            tma_load_3d_cg2(st, mh, lead_full, c0, row0, b);
-            tma_load_3d_cg2(st + A_BYTES, ml, lead_full, c0, row0, b);
-            tma_load_2d_cg2(st + W_OFF, &maps.w1_hi, lead_full, ks * BK, w_row);
-            tma_load_2d_cg2(st + W_OFF + W_BYTES, &maps.w1_lo, lead_full, ks * BK, w_row);
-            advance();
+          }
+          if (q > 0 && res) {
+            const int u = (q - 1) % n_units;
+            for (int s = 0; s < kp_steps; ++s) {
+              uint8_t* st = acquire((uint32_t)(2 * w2_rows * ROWB));
+              const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+              const int k0 = u * chpu + s * BK;
+              tma_load_3d_cg2(st + W_OFF, &maps.w2_hi, lead_full, k0, rank * w2_rows, layer);
+              tma_load_3d_cg2(st + W_OFF + W_BYTES, &maps.w2_lo, lead_full, k0, rank * w2_rows, layer);
+              advance();
+            }
           }
         }
-        if (q > 0 && p.has_res) {
-          const int u = (q - 1) % n_units;
-          for (int s = 0; s < kp_steps; ++s) {
-            uint8_t* st = acquire((uint32_t)(2 * w2_rows * ROWB));
-            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
-            const int k0 = u * chpu + s * BK;
-            tma_load_2d_cg2(st + W_OFF, &maps.w2_hi, lead_full, k0, rank * w2_rows);
-            tma_load_2d_cg2(st + W_OFF + W_BYTES, &maps.w2_lo, lead_full, k0, rank * w2_rows);
-            advance();
+      } else if (warp == 1 && lane == 0) {
+        // ===================================================== UMMA issuer (the leader issues for the pair)
+        if (rank == 0) {
+          const uint32_t idesc1 = make_idesc_bf16(2 * TC_BM, n_cols), idesc2 = make_idesc_bf16(2 * TC_BM, C);
+          const uint32_t acts_a = smem_u32(acts_s);
+          Tick tk;
+          tk.start();
+          for (int q = 0; q <= Q; ++q) {
+            if (q < Q) {
+              // first GEMM of unit q: with a residual part always region 0 (drained -- into registers -- by the
+              // epilogue of unit q-1 while the residual part of unit q-2 ran); without, the two regions alternate
+              const int r = res ? 0 : (q & 1);
+              tk.lap(issue);
+              mbar_wait(&tmem_empty[r], (use[r]++ & 1) ^ 1);
+              tk.lap(w_tmem0);
+              tc_fence_after();
+              const uint32_t d1 = tmem_base + r * TC_NHALF;
+              for (int ks = 0; ks < p.k1_steps; ++ks) {
+                tk.lap(issue);
+                mbar_wait(&full[stage], phase);
+                tk.lap(w_full);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; ++kk) {
+                  const uint32_t koff = kk * 32;
+                  const uint64_t a_h = make_smem_desc(st + koff, ROWB), a_l = make_smem_desc(st + A_BYTES + koff, ROWB);
+                  const uint64_t w_h = make_smem_desc(st + W_OFF + koff, ROWB);
+                  const uint64_t w_l = make_smem_desc(st + W_OFF + W_BYTES + koff, ROWB);
+                  umma_bf16_cg2(d1, a_h, w_h, idesc1, (ks > 0 || kk > 0) ? 1u : 0u);
+                  umma_bf16_cg2(d1, a_l, w_h, idesc1, 1u);
+                  umma_bf16_cg2(d1, a_h, w_l, idesc1, 1u);
+                }
+                umma_commit_cg2(&empty[stage], (uint16_t)0x3);
+                advance();
+              }
+              umma_commit_cg2(&tmem_full[r], (uint16_t)0x3);
+            }
+            if (q > 0 && res) {
+              // residual part of unit q-1 into region 1: its acts were written while unit q was being multiplied
+              const int u = (q - 1) % n_units;
+              const uint32_t d2 = tmem_base + TC_NHALF;
+              tk.lap(issue);
+              mbar_wait_cluster(acts_ready, acts_n++ & 1);
+              tk.lap(w_acts);
+              if (u == 0) mbar_wait(&tmem_empty[1], (use[1]++ & 1) ^ 1);     // EG of the previous tile
+              tk.lap(w_tmem1);
+              tc_fence_after();
+              for (int s = 0; s < kp_steps; ++s) {
+                tk.lap(issue);
+                mbar_wait(&full[stage], phase);
+                tk.lap(w_full);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
+                const uint32_t as = acts_a + s * 2 * A_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; ++kk) {
+                  const uint32_t koff = kk * 32;
+                  const uint64_t a_h = make_smem_desc(as + koff, ROWB), a_l = make_smem_desc(as + A_BYTES + koff, ROWB);
+                  const uint64_t w_h = make_smem_desc(st + W_OFF + koff, ROWB);
+                  const uint64_t w_l = make_smem_desc(st + W_OFF + W_BYTES + koff, ROWB);
+                  umma_bf16_cg2(d2, a_h, w_h, idesc2, (u > 0 || s > 0 || kk > 0) ? 1u : 0u);
+                  umma_bf16_cg2(d2, a_l, w_h, idesc2, 1u);
+                  umma_bf16_cg2(d2, a_h, w_l, idesc2, 1u);
+                }
+                umma_commit_cg2(&empty[stage], (uint16_t)0x3);
+                advance();
+              }
+              umma_commit_cg2(acts_free, (uint16_t)0x3);                 // the acts tile may be overwritten
+              if (u == n_units - 1) umma_commit_cg2(&tmem_full[1], (uint16_t)0x3);
+            }
           }
+        }
+      } else if (warp == 2 && lane == 0 && res) {
+        // ===================================================== x producer: the tile's old residual stream for EG
+        const CUtensorMap* ym_hi = in_a ? &maps.ya_hi : &maps.yb_hi;
+        const CUtensorMap* ym_lo = in_a ? &maps.ya_lo : &maps.yb_lo;
+        for (int j = 0; j < my_tiles; ++j) {
+          const int tile = tile_first + j * (int)gridDim.x + rank;
+          const int b = tile / p.tiles_per_batch, t0 = (tile % p.tiles_per_batch) * TC_BM;
+          for (int cc = 0; cc < xs_chunks; ++cc)
+            for (int h = 0; h < 2; ++h) {
+              uint8_t* dst = xs_s + h * 2 * FU_XS_ARRAY;
+              const int c0 = h * (C / 2) + cc * FU_XS_COLS;
+              mbar_wait(&xs_empty[h], xph[h] ^ 1);
+              mbar_arrive_expect_tx(&xs_full[h], 2 * FU_XS_ARRAY);
+              tma_load_3d(dst, ym_hi, &xs_full[h], c0, t0, b);
+              tma_load_3d(dst + FU_XS_ARRAY, ym_lo, &xs_full[h], c0, t0, b);
+              xph[h] ^= 1;
+            }
         }
       }
-      if (p.prof) p.prof[blockIdx.x * 16 + 0] = prod_wait;
-    } else if (warp == 1 && lane == 0 && rank == 0) {
-      // ===================================================== UMMA issuer (the leader issues for the pair)
-      const uint32_t idesc1 = make_idesc_bf16(2 * TC_BM, n_cols), idesc2 = make_idesc_bf16(2 * TC_BM, C);
-      const uint32_t acts_a = smem_u32(acts_s);
-      int stage = 0;
-      uint32_t phase = 0;
-      auto advance = [&]() {
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      };
-      long long w_tmem0 = 0, w_full = 0, w_acts = 0, w_tmem1 = 0, issue = 0;
-      const long long k_start = clock64();
-      Tick tk;
-      tk.start();
-      for (int q = 0; q <= Q; ++q) {
-        if (q < Q) {
-          // first GEMM of unit q: with a residual part, always region 0 (drained -- into registers -- by the epilogue
-          // of unit q-1 while the residual part of unit q-2 ran); without, the two regions alternate
-          const int r = p.has_res ? 0 : (q & 1);
-          const uint32_t use = p.has_res ? (uint32_t)q : (uint32_t)(q >> 1);     // how often the region was used before
-          tk.lap(issue);
-          mbar_wait(&tmem_empty[r], (use & 1) ^ 1);
-          tk.lap(w_tmem0);
-          tc_fence_after();
-          const uint32_t d1 = tmem_base + r * TC_NHALF;
-          for (int ks = 0; ks < p.k1_steps; ++ks) {
-            tk.lap(issue);
-            mbar_wait(&full[stage], phase);
-            tk.lap(w_full);
-            tc_fence_after();
-            const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
-#pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {
-              const uint32_t koff = kk * 32;
-              const uint64_t a_h = make_smem_desc(st + koff, ROWB), a_l = make_smem_desc(st + A_BYTES + koff, ROWB);
-              const uint64_t w_h = make_smem_desc(st + W_OFF + koff, ROWB);
-              const uint64_t w_l = make_smem_desc(st + W_OFF + W_BYTES + koff, ROWB);
-              umma_bf16_cg2(d1, a_h, w_h, idesc1, (ks > 0 || kk > 0) ? 1u : 0u);
-              umma_bf16_cg2(d1, a_l, w_h, idesc1, 1u);
-              umma_bf16_cg2(d1, a_h, w_l, idesc1, 1u);
-            }
-            umma_commit_cg2(&empty[stage], (uint16_t)0x3);
-            advance();
-          }
-          umma_commit_cg2(&tmem_full[r], (uint16_t)0x3);
-        }
-        if (q > 0 && p.has_res) {
-          // residual part of unit q-1 into region 1: its acts were written while unit q was being multiplied
-          const int qq = q - 1, u = qq % n_units, tile_j = qq / n_units;
-          const uint32_t d2 = tmem_base + TC_NHALF;
-          tk.lap(issue);
-          mbar_wait_cluster(acts_ready, (uint32_t)(qq & 1));
-          tk.lap(w_acts);
-          if (u == 0) mbar_wait(&tmem_empty[1], (uint32_t)((tile_j & 1) ^ 1));     // EG of the previous tile
-          tk.lap(w_tmem1);
-          tc_fence_after();
-          for (int s = 0; s < kp_steps; ++s) {
-            tk.lap(issue);
-            mbar_wait(&full[stage], phase);
-            tk.lap(w_full);
-            tc_fence_after();
-            const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
-            const uint32_t as = acts_a + s * 2 * A_BYTES;
-#pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {
-              const uint32_t koff = kk * 32;
-              const uint64_t a_h = make_smem_desc(as + koff, ROWB), a_l = make_smem_desc(as + A_BYTES + koff, ROWB);
-              const uint64_t w_h = make_smem_desc(st + W_OFF + koff, ROWB);
-              const uint64_t w_l = make_smem_desc(st + W_OFF + W_BYTES + koff, ROWB);
-              umma_bf16_cg2(d2, a_h, w_h, idesc2, (u > 0 || s > 0 || kk > 0) ? 1u : 0u);
-              umma_bf16_cg2(d2, a_l, w_h, idesc2, 1u);
-              umma_bf16_cg2(d2, a_h, w_l, idesc2, 1u);
-            }
-            umma_commit_cg2(&empty[stage], (uint16_t)0x3);
-            advance();
-          }
-          umma_commit_cg2(acts_free, (uint16_t)0x3);                 // the acts tile may be overwritten
-          if (u == n_units - 1) umma_commit_cg2(&tmem_full[1], (uint16_t)0x3);
-        }
-      }
-      if (p.prof) {
-        long long* pr = p.prof + blockIdx.x * 16;
+      __syncwarp();
+      if (barrier_after_layer(li)) flow_barrier(p.grid_bar, bar_target);
+    }
+    if (p.prof) {
+      long long* pr = p.prof + blockIdx.x * 16;
+      if (warp == 0 && lane == 0) pr[0] = prod_wait;
+      if (warp == 1 && lane == 0 && rank == 0) {
         pr[1] = w_tmem0; pr[2] = w_full; pr[3] = w_acts; pr[4] = w_tmem1; pr[5] = clock64() - k_start;
-      }
-    } else if (warp == 2 && lane == 0 && p.has_res) {
-      // ===================================================== x producer: the tile's old residual stream for EG
-      uint32_t ph[2] = {0, 0};
-      for (int j = 0; j < my_tiles; ++j) {
-        const int tile = tile_first + j * (int)gridDim.x + rank;
-        const int b = tile / p.tiles_per_batch, t0 = (tile % p.tiles_per_batch) * TC_BM;
-        for (int cc = 0; cc < xs_chunks; ++cc)
-          for (int h = 0; h < 2; ++h) {
-            uint8_t* dst = xs_s + h * 2 * FU_XS_ARRAY;
-            const int c0 = h * (C / 2) + cc * FU_XS_COLS;
-            mbar_wait(&xs_empty[h], ph[h] ^ 1);
-            mbar_arrive_expect_tx(&xs_full[h], 2 * FU_XS_ARRAY);
-            tma_load_3d(dst, &maps.xi_hi, &xs_full[h], c0, t0, b);
-            tma_load_3d(dst + FU_XS_ARRAY, &maps.xi_lo, &xs_full[h], c0, t0, b);
-            ph[h] ^= 1;
-          }
       }
     }
   } else {
@@ -407,163 +445,46 @@ wn_layer_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams 
     const uint32_t lead_ready = mapa_u32(smem_u32(acts_ready), 0);
     const uint32_t acts_a = smem_u32(acts_s);
     const uint32_t xs_a = smem_u32(xs_s) + half * 2 * FU_XS_ARRAY;
-    uint32_t xs_phase = 0;
+    uint8_t* xs_mine = xs_s + half * 2 * FU_XS_ARRAY;
+    const bool storer = qd == 0 && lane == 0;          // the thread of this half that issues the TMA stores
+    auto half_sync = [&]() {
+      if (half == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+      else asm volatile("bar.sync 4, 128;" ::: "memory");
+    };
+    uint32_t xs_phase = 0, use[2] = {0, 0}, acts_n = 0;
     long long e_wfull0 = 0, e_drain = 0, e_wfree = 0, e_busy = 0, e_wfull1 = 0, eg_busy = 0;
     const long long e_start = clock64();
     Tick tk;
     tk.start();
-    for (int q = 0; q <= Q; ++q) {
-      if (q < Q) {
-        // ------------------------------------------------- E(q): drain, gate, out8, acts -> shared memory
-        const int tile_j = q / n_units, u = q % n_units;
-        const int tile = tile_first + tile_j * (int)gridDim.x + rank;
-        const int b = tile / p.tiles_per_batch;
-        const int t = (tile % p.tiles_per_batch) * TC_BM + row;
-        const bool valid = tile < p.n_tiles && t < p.T;
-        const long long col = (long long)b * p.T + t;
-        const int r = p.has_res ? 0 : (q & 1);
-        const uint32_t use = p.has_res ? (uint32_t)q : (uint32_t)(q >> 1);
-        tk.lap(e_busy);
-        mbar_wait(&tmem_full[r], use & 1);
-        tk.lap(e_wfull0);
-        tc_fence_after();
-        uint32_t acc[4][32];
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4)
-          if (c4 * 32 < ncol_half) tmem_ld32(lane_base + r * TC_NHALF + c_begin + c4 * 32, acc[c4]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(r == 0 ? lead_empty0 : lead_empty1);   // the region is free again
-        tk.lap(e_drain);
-        float acc8[FU_NOUT];
-#pragma unroll
-        for (int o = 0; o < FU_NOUT; ++o) acc8[o] = 0.f;
-        bool waited = !p.has_res || q == 0;
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          if (c4 * 32 < ncol_half) {
-            const int n0 = u * TC_NHALF + c_begin + c4 * 32;     // first output column of this chunk
-            const int ch_u = (c_begin + c4 * 32) >> 1;           // first channel inside the unit (16 per chunk)
-            const int ch0 = n0 >> 1;                             // global channel
-            float g[16];
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias1 + n0 + 2 * j));
-              g[j] = gate_act(__uint_as_float(acc[c4][2 * j]) + bv.x, __uint_as_float(acc[c4][2 * j + 1]) + bv.y);
-              g[j + 1] = gate_act(__uint_as_float(acc[c4][2 * j + 2]) + bv.z, __uint_as_float(acc[c4][2 * j + 3]) + bv.w);
-            }
-            // collapsed skip path: out8 += Wc[:, ch0:ch0+16] g   (fp32, exact gate outputs; Wc: warp-uniform
-            // addresses, L1-resident)
-#pragma unroll
-            for (int o = 0; o < FU_NOUT; ++o) {
-              const float4* wrow = reinterpret_cast<const float4*>(p.wc + o * C + ch0);
-              float a = acc8[o];
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 w4 = __ldg(wrow + j4);
-                a = fmaf(w4.x, g[4 * j4 + 0], a);
-                a = fmaf(w4.y, g[4 * j4 + 1], a);
-                a = fmaf(w4.z, g[4 * j4 + 2], a);
-                a = fmaf(w4.w, g[4 * j4 + 3], a);
-              }
-              acc8[o] = a;
-            }
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) split2(g[2 * j], g[2 * j + 1], hi[j], lo[j]);
-            if (p.has_res) {
-              if (!waited) {      // the previous residual part has read the acts tile (completes right after unit q)
-                tk.lap(e_busy);
-                mbar_wait(acts_free, (uint32_t)((q - 1) & 1));
-                tk.lap(e_wfree);
-                waited = true;
-              }
-              // rows outside the utterance hold zeros (their x_new rows are never stored)
-              const uint32_t s = (uint32_t)(ch_u / BK);
-              const uint32_t off = (uint32_t)row * ROWB + (uint32_t)(ch_u % BK) * 2;
-              const uint32_t base = acts_a + s * 2 * A_BYTES;
-              const uint32_t o0 = swizzle_off<ROWB>(off), o1 = swizzle_off<ROWB>(off + 16);
-              st_shared_v4(base + o0, hi[0], hi[1], hi[2], hi[3]);
-              st_shared_v4(base + o1, hi[4], hi[5], hi[6], hi[7]);
-              st_shared_v4(base + A_BYTES + o0, lo[0], lo[1], lo[2], lo[3]);
-              st_shared_v4(base + A_BYTES + o1, lo[4], lo[5], lo[6], lo[7]);
-            }
-            if (p.acts_hi != nullptr && valid) {
-              const long long goff = col * C + ch0;
-              uint4* dh = reinterpret_cast<uint4*>(p.acts_hi + goff);
-              dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-              uint4* dl = reinterpret_cast<uint4*>(p.acts_lo + goff);
-              dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            }
-          }
-        }
-        if (p.has_res) {
-          fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(lead_ready);
-        }
-        // out8 (+)= partial sums of the two column halves, in a fixed order (deterministic rounding): the lower
-        // half first (it starts or continues the layer sum), then the upper half on top.  L2 is the meeting point
-        // (ld.global.cg), the named barriers order the two read-modify-writes and the next unit's.
-        {
-          float4* o8 = reinterpret_cast<float4*>(p.out8 + col * FU_NOUT);
-          float4 o0 = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
-          float4 o1 = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
-          if (half == 0 && valid) {
-            if (p.accumulate_out8 || u > 0) {
-              const float4 p0 = __ldcg(o8), p1 = __ldcg(o8 + 1);
-              o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
-              o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
-            }
-            o8[0] = o0;
-            o8[1] = o1;
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(FU_EPI_THREADS) : "memory");
-          if (half == 1 && valid) {
-            const float4 p0 = __ldcg(o8), p1 = __ldcg(o8 + 1);
-            o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
-            o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
-            o8[0] = o0;
-            o8[1] = o1;
-          }
-          asm volatile("bar.sync 2, %0;" ::"n"(FU_EPI_THREADS) : "memory");
-        }
-      }
-      if (q > 0 && p.has_res && (q - 1) % n_units == n_units - 1) {
-        // ------------------------------------------------- EG: x_new = res + b_res + x (glow.py:166), through the
-        // x staging: the old x arrives by TMA, is updated in place (own row) and leaves by TMA store
-        const int tile_j = (q - 1) / n_units;
-        const int tile = tile_first + tile_j * (int)gridDim.x + rank;
+
+    if (p.do_start) {
+      // ------------------------------------------------- x = start(audio_0) (glow.py:156) for this CTA's tiles,
+      // written to buffer A through the x staging and a TMA store
+      const int off = p.n_group - p.n_rem;
+      for (int j = 0; j < my_tiles; ++j) {
+        const int tile = tile_first + j * (int)gridDim.x + rank;
         const int b = tile / p.tiles_per_batch, t0 = (tile % p.tiles_per_batch) * TC_BM;
-        tk.lap(e_busy);
-        mbar_wait(&tmem_full[1], (uint32_t)(tile_j & 1));
-        tk.lap(e_wfull1);
-        tc_fence_after();
+        const int t = t0 + row;
+        const bool valid = tile < p.n_tiles && t < p.T;
+        float a_in[FU_NOUT / 2];
+#pragma unroll
+        for (int i = 0; i < FU_NOUT / 2; ++i)
+          a_in[i] = (valid && i < p.n_half) ? __ldcg(p.audio + ((long long)b * p.T + t) * p.n_group + off + i) : 0.f;
         for (int cc = 0; cc < xs_chunks; ++cc) {
           const int n0 = half * (C / 2) + cc * FU_XS_COLS;
-          uint32_t rr[32];
-          tmem_ld32(lane_base + TC_NHALF + n0, rr);
-          mbar_wait(&xs_full[half], xs_phase);
-          xs_phase ^= 1;
-          tmem_ld_wait();
           uint32_t hw[16], lw[16];
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const uint32_t o = swizzle_off<64>((uint32_t)row * 64 + j4 * 16);
-            ld_shared_v4(xs_a + o, hw[4 * j4], hw[4 * j4 + 1], hw[4 * j4 + 2], hw[4 * j4 + 3]);
-            ld_shared_v4(xs_a + FU_XS_ARRAY + o, lw[4 * j4], lw[4 * j4 + 1], lw[4 * j4 + 2], lw[4 * j4 + 3]);
-          }
-#pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(p.res_b + n0 + 2 * k));
-            const float2 xhf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[k]));
-            const float2 xlf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[k]));
-            const float v0 = (__uint_as_float(rr[2 * k]) + bb.x) + (xhf.x + xlf.x);
-            const float v1 = (__uint_as_float(rr[2 * k + 1]) + bb.y) + (xhf.y + xlf.y);
-            split2(v0, v1, hw[k], lw[k]);
+            float2 v = __ldg(reinterpret_cast<const float2*>(p.start_b + n0 + 2 * k));
+#pragma unroll
+            for (int i = 0; i < FU_NOUT / 2; ++i) {
+              if (i < p.n_half) {
+                const float2 w = __ldg(reinterpret_cast<const float2*>(p.start_w + (long long)i * C + n0 + 2 * k));
+                v.x = fmaf(a_in[i], w.x, v.x);
+                v.y = fmaf(a_in[i], w.y, v.y);
+              }
+            }
+            split2(v.x, v.y, hw[k], lw[k]);
           }
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
@@ -572,24 +493,256 @@ wn_layer_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams 
             st_shared_v4(xs_a + FU_XS_ARRAY + o, lw[4 * j4], lw[4 * j4 + 1], lw[4 * j4 + 2], lw[4 * j4 + 3]);
           }
           fence_proxy_async_smem();
-          if (half == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
-          else asm volatile("bar.sync 4, 128;" ::: "memory");
-          if (qd == 0 && lane == 0) {
-            // rows outside the utterance (and a tile past the end) are clipped by the tensor map
-            tma_store_3d(&maps.xo_hi, xs_s + half * 2 * FU_XS_ARRAY, n0, t0, b);
-            tma_store_3d(&maps.xo_lo, xs_s + half * 2 * FU_XS_ARRAY + FU_XS_ARRAY, n0, t0, b);
+          half_sync();
+          if (storer) {
+            tma_store_3d(&maps.ya_hi, xs_mine, n0, t0, b);
+            tma_store_3d(&maps.ya_lo, xs_mine + FU_XS_ARRAY, n0, t0, b);
             tma_store_commit();
-            tma_store_wait_read();               // the staging entry may be refilled
-            mbar_arrive(&xs_empty[half]);
+            tma_store_wait_read();
+          }
+          half_sync();                         // the staging entry may be rewritten
+        }
+      }
+      if (storer) tma_store_wait_all();
+      flow_barrier(p.grid_bar, bar_target);
+    }
+
+    for (int li = 0; li < p.layer_count; ++li) {
+      const int layer = p.layer_first + li;
+      const bool res = has_res(layer);
+      const bool in_a = (layer & 1) == 0;
+      const CUtensorMap* yo_hi = in_a ? &maps.yb_hi : &maps.ya_hi;       // the buffer this layer writes
+      const CUtensorMap* yo_lo = in_a ? &maps.yb_lo : &maps.ya_lo;
+      const float* bias1 = p.bias1[layer];
+      const float* wcl = p.wc[layer];
+      const float* res_b = p.res_b[layer];
+      const bool acc_out8 = p.layer_count > 1 ? layer > 0 : p.accumulate_out8 != 0;
+      for (int q = 0; q <= Q; ++q) {
+        if (q < Q) {
+          // ------------------------------------------------- E(q): drain, gate, out8, acts -> shared memory
+          const int tile_j = q / n_units, u = q % n_units;
+          const int tile = tile_first + tile_j * (int)gridDim.x + rank;
+          const int b = tile / p.tiles_per_batch;
+          const int t = (tile % p.tiles_per_batch) * TC_BM + row;
+          const bool valid = tile < p.n_tiles && t < p.T;
+          const long long col = (long long)b * p.T + t;
+          const int r = res ? 0 : (q & 1);
+          tk.lap(e_busy);
+          mbar_wait(&tmem_full[r], use[r]++ & 1);
+          tk.lap(e_wfull0);
+          tc_fence_after();
+          uint32_t acc[4][32];
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            if (c4 * 32 < ncol_half) tmem_ld32(lane_base + r * TC_NHALF + c_begin + c4 * 32, acc[c4]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(r == 0 ? lead_empty0 : lead_empty1);   // the region is free again
+          tk.lap(e_drain);
+          float acc8[FU_NOUT];
+#pragma unroll
+          for (int o = 0; o < FU_NOUT; ++o) acc8[o] = 0.f;
+          bool waited = !res;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            if (c4 * 32 < ncol_half) {
+              const int n0 = u * TC_NHALF + c_begin + c4 * 32;     // first output column of this chunk
+              const int ch_u = (c_begin + c4 * 32) >> 1;           // first channel inside the unit (16 per chunk)
+              const int ch0 = n0 >> 1;                             // global channel
+              float g[16];
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias1 + n0 + 2 * j));
+                g[j] = gate_act(__uint_as_float(acc[c4][2 * j]) + bv.x, __uint_as_float(acc[c4][2 * j + 1]) + bv.y);
+                g[j + 1] = gate_act(__uint_as_float(acc[c4][2 * j + 2]) + bv.z, __uint_as_float(acc[c4][2 * j + 3]) + bv.w);
+              }
+              // collapsed skip path: out8 += Wc[:, ch0:ch0+16] g   (fp32, exact gate outputs; Wc: warp-uniform
+              // addresses, L1-resident)
+#pragma unroll
+              for (int o = 0; o < FU_NOUT; ++o) {
+                const float4* wrow = reinterpret_cast<const float4*>(wcl + o * C + ch0);
+                float a = acc8[o];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 w4 = __ldg(wrow + j4);
+                  a = fmaf(w4.x, g[4 * j4 + 0], a);
+                  a = fmaf(w4.y, g[4 * j4 + 1], a);
+                  a = fmaf(w4.z, g[4 * j4 + 2], a);
+                  a = fmaf(w4.w, g[4 * j4 + 3], a);
+                }
+                acc8[o] = a;
+              }
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) split2(g[2 * j], g[2 * j + 1], hi[j], lo[j]);
+              if (res) {
+                if (!waited) {      // the previous residual part has read the acts tile (completes right after unit q)
+                  tk.lap(e_busy);
+                  if (acts_n > 0) mbar_wait(acts_free, (acts_n - 1) & 1);
+                  ++acts_n;
+                  tk.lap(e_wfree);
+                  waited = true;
+                }
+                // rows outside the utterance hold zeros (their x_new rows are clipped by the TMA store)
+                const uint32_t s = (uint32_t)(ch_u / BK);
+                const uint32_t off = (uint32_t)row * ROWB + (uint32_t)(ch_u % BK) * 2;
+                const uint32_t base = acts_a + s * 2 * A_BYTES;
+                const uint32_t o0 = swizzle_off<ROWB>(off), o1 = swizzle_off<ROWB>(off + 16);
+                st_shared_v4(base + o0, hi[0], hi[1], hi[2], hi[3]);
+                st_shared_v4(base + o1, hi[4], hi[5], hi[6], hi[7]);
+                st_shared_v4(base + A_BYTES + o0, lo[0], lo[1], lo[2], lo[3]);
+                st_shared_v4(base + A_BYTES + o1, lo[4], lo[5], lo[6], lo[7]);
+              }
+              if (p.acts_hi != nullptr && valid) {
+                const long long goff = col * C + ch0;
+                uint4* dh = reinterpret_cast<uint4*>(p.acts_hi + goff);
+                dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                uint4* dl = reinterpret_cast<uint4*>(p.acts_lo + goff);
+                dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+              }
+            }
+          }
+          if (res) {
+            fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_ready);
+          }
+          // out8 (+)= partial sums of the two column halves, in a fixed order (deterministic rounding): the lower
+          // half first (it starts or continues the layer sum), then the upper half on top.  L2 is the meeting point
+          // (ld.global.cg), the named barriers order the two read-modify-writes and the next unit's.
+          {
+            float4* o8 = reinterpret_cast<float4*>(p.out8 + col * FU_NOUT);
+            float4 o0 = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
+            float4 o1 = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
+            if (half == 0 && valid) {
+              if (acc_out8 || u > 0) {
+                const float4 p0 = __ldcg(o8), p1 = __ldcg(o8 + 1);
+                o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+                o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+              }
+              o8[0] = o0;
+              o8[1] = o1;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(FU_EPI_THREADS) : "memory");
+            if (half == 1 && valid) {
+              const float4 p0 = __ldcg(o8), p1 = __ldcg(o8 + 1);
+              o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+              o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+              o8[0] = o0;
+              o8[1] = o1;
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(FU_EPI_THREADS) : "memory");
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(lead_empty1);
-        tk.lap(eg_busy);
+        if (q > 0 && res && (q - 1) % n_units == n_units - 1) {
+          // ------------------------------------------------- EG: x_new = res + b_res + x (glow.py:166), through the
+          // x staging: the old x arrives by TMA, is updated in place (own row) and leaves by TMA store
+          const int tile_j = (q - 1) / n_units;
+          const int tile = tile_first + tile_j * (int)gridDim.x + rank;
+          const int b = tile / p.tiles_per_batch, t0 = (tile % p.tiles_per_batch) * TC_BM;
+          tk.lap(e_busy);
+          mbar_wait(&tmem_full[1], use[1]++ & 1);
+          tk.lap(e_wfull1);
+          tc_fence_after();
+          for (int cc = 0; cc < xs_chunks; ++cc) {
+            const int n0 = half * (C / 2) + cc * FU_XS_COLS;
+            uint32_t rr[32];
+            tmem_ld32(lane_base + TC_NHALF + n0, rr);
+            mbar_wait(&xs_full[half], xs_phase);
+            xs_phase ^= 1;
+            tmem_ld_wait();
+            uint32_t hw[16], lw[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint32_t o = swizzle_off<64>((uint32_t)row * 64 + j4 * 16);
+              ld_shared_v4(xs_a + o, hw[4 * j4], hw[4 * j4 + 1], hw[4 * j4 + 2], hw[4 * j4 + 3]);
+              ld_shared_v4(xs_a + FU_XS_ARRAY + o, lw[4 * j4], lw[4 * j4 + 1], lw[4 * j4 + 2], lw[4 * j4 + 3]);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float2 bb = __ldg(reinterpret_cast<const float2*>(res_b + n0 + 2 * k));
+              const float2 xhf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[k]));
+              const float2 xlf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[k]));
+              const float v0 = (__uint_as_float(rr[2 * k]) + bb.x) + (xhf.x + xlf.x);
+              const float v1 = (__uint_as_float(rr[2 * k + 1]) + bb.y) + (xhf.y + xlf.y);
+              split2(v0, v1, hw[k], lw[k]);
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint32_t o = swizzle_off<64>((uint32_t)row * 64 + j4 * 16);
+              st_shared_v4(xs_a + o, hw[4 * j4], hw[4 * j4 + 1], hw[4 * j4 + 2], hw[4 * j4 + 3]);
+              st_shared_v4(xs_a + FU_XS_ARRAY + o, lw[4 * j4], lw[4 * j4 + 1], lw[4 * j4 + 2], lw[4 * j4 + 3]);
+            }
+            fence_proxy_async_smem();
+            half_sync();
+            if (storer) {
+              // rows outside the utterance (and a tile past the end) are clipped by the tensor map
+              tma_store_3d(yo_hi, xs_mine, n0, t0, b);
+              tma_store_3d(yo_lo, xs_mine + FU_XS_ARRAY, n0, t0, b);
+              tma_store_commit();
+              tma_store_wait_read();               // the staging entry may be refilled
+              mbar_arrive(&xs_empty[half]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(lead_empty1);
+          tk.lap(eg_busy);
+        }
+      }
+      if (storer) tma_store_wait_all();
+      if (barrier_after_layer(li)) flow_barrier(p.grid_bar, bar_target);
+    }
+
+    if (p.do_end && half == 0) {
+      // ------------------------------------------------- out = end(skip sum) = out8 + bias8 (glow.py:175); b, s =
+      // halves (278-279); a1 <- (a1 - b) / exp(s) (280); z <- W^-1 [a0; a1] (283, 96): one thread per column of this
+      // CTA's tiles, in place on audio (out8 rows were completed by this CTA's own epilogue)
+      const int off = p.n_group - p.n_rem;
+      for (int j = 0; j < my_tiles; ++j) {
+        const int tile = tile_first + j * (int)gridDim.x + rank;
+        const int b = tile / p.tiles_per_batch;
+        const int t = (tile % p.tiles_per_batch) * TC_BM + row;
+        if (tile >= p.n_tiles || t >= p.T) continue;
+        const long long col = (long long)b * p.T + t;
+        const float4 qa = __ldcg(reinterpret_cast<const float4*>(p.out8 + col * FU_NOUT));
+        const float4 qb = __ldcg(reinterpret_cast<const float4*>(p.out8 + col * FU_NOUT) + 1);
+        const float o[FU_NOUT] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        float* acol = p.audio + col * p.n_group + off;
+        float y[FU_NOUT];
+#pragma unroll
+        for (int i = 0; i < FU_NOUT; ++i) {
+          y[i] = 0.f;
+          if (i < p.n_rem) {
+            const float av = __ldcg(acol + i);
+            if (i < p.n_half) {
+              y[i] = av;
+            } else {
+              float bshift = 0.f, sc = 0.f;
+#pragma unroll
+              for (int k = 0; k < FU_NOUT; ++k) {     // static indexing keeps o[] in registers
+                if (k == i - p.n_half) bshift = o[k] + __ldg(p.out_bias + k);
+                if (k == i) sc = o[k] + __ldg(p.out_bias + k);
+              }
+              y[i] = (av - bshift) / expf(sc);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < FU_NOUT; ++i) {
+          if (i < p.n_rem) {
+            float z = 0.f;
+#pragma unroll
+            for (int k = 0; k < FU_NOUT; ++k)
+              if (k < p.n_rem) z = fmaf(__ldg(p.w_inv + i * p.n_rem + k), y[k], z);
+            acol[i] = z;
+          }
+        }
       }
     }
-    if (qd == 0 && lane == 0) tma_store_wait_all();
     if (p.prof && warp == 4 && lane == 0) {
       long long* pr = p.prof + blockIdx.x * 16;
       pr[6] = e_wfull0; pr[7] = e_drain; pr[8] = e_wfree; pr[9] = e_busy; pr[10] = e_wfull1; pr[11] = eg_busy;
@@ -604,22 +757,50 @@ wn_layer_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams 
 }
 
 template <int BK>
-int launch_fused(const FusedMaps& maps, const FusedParams& p, cudaStream_t st) {
+int launch_fused(const FusedMaps& maps, const FusedParams& p, bool cooperative, cudaStream_t st) {
   static bool attr_set_on[FAC_MAX_DEVICES] = {};
   bool& attr_set = attr_set_on[current_device_slot()];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wn_layer_fused_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(wn_flow_fused_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM);
     if (e != cudaSuccess) {
-      set_error("wn_layer_fused: cannot reserve %d bytes of shared memory: %s", FU_SMEM, cudaGetErrorString(e));
+      set_error("wn_flow_fused: cannot reserve %d bytes of shared memory: %s", FU_SMEM, cudaGetErrorString(e));
       return 2;
     }
     attr_set = true;
   }
   const int pairs = ceil_div(p.n_tiles, 2), max_pairs = sm_count() / 2;
-  const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-  wn_layer_fused_kernel<BK><<<grid, FU_THREADS, FU_SMEM, st>>>(maps, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));     // <= 1 CTA per SM: co-resident
+  cfg.blockDim = dim3(FU_THREADS);
+  cfg.dynamicSmemBytes = FU_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;      // the grid barrier between phases needs every CTA resident
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cooperative ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wn_flow_fused_kernel<BK>, maps, p);
   count_launch();
-  return check_launch("wn_layer_fused_kernel");
+  if (e != cudaSuccess) {
+    set_error("wn_flow_fused_kernel: launch failed: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  return check_launch("wn_flow_fused_kernel");
+}
+
+// [layers][N][K] 16-bit weights of one flow with a uniform layer stride: box = bk k x (min(256, N) / 2) rows.
+int make_weight_map3(CUtensorMap* m, const void* ptr, int N, int K, int layers, long long layer_stride_bytes, int bk) {
+  EncodeTiledFn fn = encode_fn();
+  FAC_REQUIRE(fn != nullptr, "tensor-core path: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)layers};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)layer_stride_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)((N < TC_NHALF ? N : TC_NHALF) / 2), 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, tc_swizzle(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FAC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights %dx%dx%d) failed: %d", layers, N, K, (int)r);
+  return 0;
 }
 
 }  // namespace
@@ -630,38 +811,67 @@ bool wn_fused_supported(int C, int n_cond, int bk) {
          (n_cols / 2) % bk == 0 && (n_cols / 2) % 32 == 0 && (C / 2) % FU_XS_COLS == 0 && C % 16 == 0;
 }
 
-// One fused WN layer: x_in (hi, lo) -> x_out (hi, lo), out8 (+)= Wc acts.  acts_hi/lo optional (tests).
-int wn_layer_fused(const void* x_in_hi, const void* x_in_lo, void* x_out_hi, void* x_out_lo, const void* spect_hi,
-                   const void* spect_lo, const void* w1_hi, const void* w1_lo, const void* w2_hi, const void* w2_lo,
-                   const float* bias1, const float* res_b, const float* wc, float* out8, int accumulate_out8,
-                   void* acts_hi, void* acts_lo, int B, int T, int C, int n_cond, int taps, int dilation, int has_res,
-                   int bk, int prefetch_steps, long long* prof, cudaStream_t st) {
-  FAC_REQUIRE(wn_fused_supported(C, n_cond, bk), "wn_layer_fused: unsupported geometry C=%d n_cond=%d bk=%d", C, n_cond, bk);
-  FAC_REQUIRE(x_in_hi && x_in_lo && spect_hi && spect_lo && w1_hi && w1_lo && bias1 && wc && out8,
-              "wn_layer_fused: NULL argument");
-  FAC_REQUIRE(!has_res || (x_out_hi && x_out_lo && w2_hi && w2_lo && res_b), "wn_layer_fused: residual operands missing");
-  FAC_REQUIRE(!has_res || x_out_hi != x_in_hi, "wn_layer_fused: the residual stream cannot be updated in place");
+// The tensor-core weights of a flow are usable by the fused kernel when every layer's matrices sit at a uniform
+// stride (packing.py lays them out that way): one 3-D tensor map then serves all layers.
+bool wn_fused_weights_ok(const fac_wg_model* m, const fac_wg_tc_flow& wf) {
+  const int L = m->n_layers;
+  if (!wf.w1_hi[0] || !wf.w1_lo[0]) return false;
+  if (L == 1) return true;
+  if (!wf.w2r_hi[0] || !wf.w2r_lo[0]) return false;
+  const long long stride = (const char*)wf.w1_hi[1] - (const char*)wf.w1_hi[0];
+  if (stride <= 0 || stride % 16) return false;
+  for (int i = 0; i < L; ++i) {
+    if ((const char*)wf.w1_hi[i] != (const char*)wf.w1_hi[0] + i * stride) return false;
+    if ((const char*)wf.w1_lo[i] != (const char*)wf.w1_lo[0] + i * stride) return false;
+    if (i < L - 1) {
+      if ((const char*)wf.w2r_hi[i] != (const char*)wf.w2r_hi[0] + i * stride) return false;
+      if ((const char*)wf.w2r_lo[i] != (const char*)wf.w2r_lo[0] + i * stride) return false;
+      if (!wf.res_b[i]) return false;
+    }
+    if (!wf.wc[i]) return false;
+  }
+  return true;
+}
+
+// Layers [layer_first, layer_first + layer_count) of flow `flow`, optionally with start (before) and end +
+// coupling + invertible 1x1 (after), as ONE launch.  The residual stream of layer l is read from ws->x when l is
+// even and from ws->x2 when l is odd, and written to the other pair; start writes ws->x.
+int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, const fac_wg_tc_workspace* ws,
+                  float* audio, int B, int T, int layer_first, int layer_count, int do_start, int do_end, int bk,
+                  int prefetch_steps, long long* prof, cudaStream_t st) {
+  const fac_wg_flow& f = m->flows[flow];
+  const fac_wg_tc_flow& wf = w->flows[flow];
+  const int C = m->n_channels, n_cond = m->n_mel * m->n_group, taps = m->kernel_size, L = m->n_layers;
+  FAC_REQUIRE(wn_fused_supported(C, n_cond, bk), "wn_flow_fused: unsupported geometry C=%d n_cond=%d bk=%d", C, n_cond, bk);
+  FAC_REQUIRE(wn_fused_weights_ok(m, wf), "wn_flow_fused: the flow's tensor-core weights are not uniformly strided");
+  FAC_REQUIRE(layer_first >= 0 && layer_count >= 1 && layer_first + layer_count <= L, "wn_flow_fused: layer range");
+  FAC_REQUIRE(ws->x_hi && ws->x_lo && ws->x2_hi && ws->x2_lo && ws->spect_hi && ws->spect_lo && ws->out8,
+              "wn_flow_fused: workspace incomplete");
+  const bool phases = do_start || (layer_count > 1);
+  FAC_REQUIRE(!phases || ws->flow_sync, "wn_flow_fused: a multi-phase launch needs ws->flow_sync");
+  FAC_REQUIRE(!(do_start || do_end) || audio, "wn_flow_fused: audio missing");
   FusedMaps maps;
   const int K1 = taps * C + n_cond;
-  if (int rc = make_act_map(&maps.x_hi, x_in_hi, B, T, C, bk)) return rc;
-  if (int rc = make_act_map(&maps.x_lo, x_in_lo, B, T, C, bk)) return rc;
-  if (int rc = make_act_map(&maps.s_hi, spect_hi, B, T, n_cond, bk)) return rc;
-  if (int rc = make_act_map(&maps.s_lo, spect_lo, B, T, n_cond, bk)) return rc;
-  if (int rc = make_weight_map(&maps.w1_hi, w1_hi, 2 * C, K1, 2, bk)) return rc;
-  if (int rc = make_weight_map(&maps.w1_lo, w1_lo, 2 * C, K1, 2, bk)) return rc;
-  if (has_res) {
-    if (int rc = make_weight_map(&maps.w2_hi, w2_hi, C, C, 2, bk)) return rc;
-    if (int rc = make_weight_map(&maps.w2_lo, w2_lo, C, C, 2, bk)) return rc;
-    if (int rc = make_act_map(&maps.xi_hi, x_in_hi, B, T, C, FU_XS_COLS)) return rc;
-    if (int rc = make_act_map(&maps.xi_lo, x_in_lo, B, T, C, FU_XS_COLS)) return rc;
-    if (int rc = make_act_map(&maps.xo_hi, x_out_hi, B, T, C, FU_XS_COLS)) return rc;
-    if (int rc = make_act_map(&maps.xo_lo, x_out_lo, B, T, C, FU_XS_COLS)) return rc;
+  const long long stride = L > 1 ? (const char*)wf.w1_hi[1] - (const char*)wf.w1_hi[0] : (long long)2 * C * K1 * 2;
+  if (int rc = make_act_map(&maps.xa_hi, ws->x_hi, B, T, C, bk)) return rc;
+  if (int rc = make_act_map(&maps.xa_lo, ws->x_lo, B, T, C, bk)) return rc;
+  if (int rc = make_act_map(&maps.xb_hi, ws->x2_hi, B, T, C, bk)) return rc;
+  if (int rc = make_act_map(&maps.xb_lo, ws->x2_lo, B, T, C, bk)) return rc;
+  if (int rc = make_act_map(&maps.s_hi, ws->spect_hi, B, T, n_cond, bk)) return rc;
+  if (int rc = make_act_map(&maps.s_lo, ws->spect_lo, B, T, n_cond, bk)) return rc;
+  if (int rc = make_weight_map3(&maps.w1_hi, wf.w1_hi[0], 2 * C, K1, L, stride, bk)) return rc;
+  if (int rc = make_weight_map3(&maps.w1_lo, wf.w1_lo[0], 2 * C, K1, L, stride, bk)) return rc;
+  if (L > 1) {
+    if (int rc = make_weight_map3(&maps.w2_hi, wf.w2r_hi[0], C, C, L - 1, stride, bk)) return rc;
+    if (int rc = make_weight_map3(&maps.w2_lo, wf.w2r_lo[0], C, C, L - 1, stride, bk)) return rc;
   } else {
     maps.w2_hi = maps.w1_hi;
     maps.w2_lo = maps.w1_lo;
-    maps.xi_hi = maps.xo_hi = maps.x_hi;
-    maps.xi_lo = maps.xo_lo = maps.x_lo;
   }
+  if (int rc = make_act_map(&maps.ya_hi, ws->x_hi, B, T, C, FU_XS_COLS)) return rc;
+  if (int rc = make_act_map(&maps.ya_lo, ws->x_lo, B, T, C, FU_XS_COLS)) return rc;
+  if (int rc = make_act_map(&maps.yb_hi, ws->x2_hi, B, T, C, FU_XS_COLS)) return rc;
+  if (int rc = make_act_map(&maps.yb_lo, ws->x2_lo, B, T, C, FU_XS_COLS)) return rc;
   FusedParams p{};
   p.T = T;
   p.B = B;
@@ -670,24 +880,41 @@ int wn_layer_fused(const void* x_in_hi, const void* x_in_lo, void* x_out_hi, voi
   p.C = C;
   p.n_cond = n_cond;
   p.taps = taps;
-  p.dilation = dilation;
-  p.center = dilation * (taps - 1) / 2;
   p.k1_steps = K1 / bk;
-  p.has_res = has_res;
-  p.bias1 = bias1;
-  p.res_b = res_b;
-  p.wc = wc;
-  p.out8 = out8;
-  p.accumulate_out8 = accumulate_out8;
-  p.x_hi = reinterpret_cast<const __nv_bfloat16*>(x_in_hi);
-  p.x_lo = reinterpret_cast<const __nv_bfloat16*>(x_in_lo);
-  p.xo_hi = reinterpret_cast<__nv_bfloat16*>(x_out_hi);
-  p.xo_lo = reinterpret_cast<__nv_bfloat16*>(x_out_lo);
-  p.acts_hi = reinterpret_cast<__nv_bfloat16*>(acts_hi);
-  p.acts_lo = reinterpret_cast<__nv_bfloat16*>(acts_lo);
-  p.prof = prof;
+  p.layer_first = layer_first;
+  p.layer_count = layer_count;
+  p.n_layers = L;
+  p.do_start = do_start;
+  p.do_end = do_end;
+  for (int i = 0; i < L; ++i) {
+    p.bias1[i] = f.in_cond_b[i];
+    p.res_b[i] = i < L - 1 ? wf.res_b[i] : nullptr;
+    p.wc[i] = wf.wc[i];
+  }
+  p.out8 = ws->out8;
+  p.accumulate_out8 = layer_first > 0;
+  p.start_w = f.start_w;
+  p.start_b = f.start_b;
+  p.out_bias = wf.out_bias;
+  p.w_inv = f.w_inv;
+  p.audio = audio;
+  p.n_group = m->n_group;
+  p.n_rem = f.n_rem;
+  p.n_half = f.n_half;
+  p.acts_hi = layer_count == 1 ? reinterpret_cast<__nv_bfloat16*>(ws->acts_hi) : nullptr;
+  p.acts_lo = layer_count == 1 ? reinterpret_cast<__nv_bfloat16*>(ws->acts_lo) : nullptr;
+  if (p.acts_hi == nullptr || p.acts_lo == nullptr) p.acts_hi = p.acts_lo = nullptr;
+  p.grid_bar = reinterpret_cast<unsigned int*>(ws->flow_sync);
   p.prefetch_steps = prefetch_steps < p.k1_steps ? prefetch_steps : p.k1_steps - 1;
-  return bk == 64 ? launch_fused<64>(maps, p, st) : launch_fused<32>(maps, p, st);
+  p.prof = prof;
+  if (phases) {
+    cudaError_t e = cudaMemsetAsync(ws->flow_sync, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) {
+      set_error("wn_flow_fused: cannot reset the grid barrier: %s", cudaGetErrorString(e));
+      return 2;
+    }
+  }
+  return bk == 64 ? launch_fused<64>(maps, p, phases, st) : launch_fused<32>(maps, p, phases, st);
 }
 
 }  // namespace fac

@@ -788,12 +788,13 @@ int tc_set_batch_group(int n) {
   g_tc_batch_group = n;
   return 0;
 }
-int g_tc_fused = 1, g_tc_prefetch = 0;
-// enabled: 0 = two launches per layer; 1 = fused; 1 + 16 * d = fused with the producer prefetching d K steps ahead
-// into L2 (experiments)
-int tc_set_fused(int enabled) {
-  g_tc_fused = (enabled & 15) != 0;
-  g_tc_prefetch = enabled >> 4;
+int g_tc_fused = 2, g_tc_prefetch = 0;
+// mode & 15: 0 = two launches per layer; 1 = one fused launch per layer; 2 = one launch per flow step where possible.
+// mode >> 4: L2 prefetch distance of the fused kernel's producer in K steps (experiments)
+int tc_set_fused(int mode) {
+  FAC_REQUIRE((mode & 15) <= 2 && mode >= 0, "fused mode must be 0, 1 or 2 (+ 16 x prefetch distance), got %d", mode);
+  g_tc_fused = mode & 15;
+  g_tc_prefetch = mode >> 4;
   return 0;
 }
 int tc_set_cta_group(int cg) {
@@ -804,11 +805,10 @@ int tc_set_cta_group(int cg) {
 
 int wg_check_model(const fac_wg_model* m);
 bool wn_fused_supported(int C, int n_cond, int bk);
-int wn_layer_fused(const void* x_in_hi, const void* x_in_lo, void* x_out_hi, void* x_out_lo, const void* spect_hi,
-                   const void* spect_lo, const void* w1_hi, const void* w1_lo, const void* w2_hi, const void* w2_lo,
-                   const float* bias1, const float* res_b, const float* wc, float* out8, int accumulate_out8,
-                   void* acts_hi, void* acts_lo, int B, int T, int C, int n_cond, int taps, int dilation, int has_res,
-                   int bk, int prefetch_steps, long long* prof, cudaStream_t st);
+bool wn_fused_weights_ok(const fac_wg_model* m, const fac_wg_tc_flow& wf);
+int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, const fac_wg_tc_workspace* ws,
+                  float* audio, int B, int T, int layer_first, int layer_count, int do_start, int do_end, int bk,
+                  int prefetch_steps, long long* prof, cudaStream_t st);
 
 static int tc_check(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac_wg_tc_workspace* ws, int nsplit) {
   if (int rc = wg_check_model(m)) return rc;
@@ -831,8 +831,7 @@ static int tc_fused_bk() { return g_tc_bk ? g_tc_bk : 32; }
 // One fused launch per layer (waveglow_fused.cu) when the workspace carries the second residual-stream pair.
 static bool tc_use_fused(const fac_wg_model* m, const fac_wg_tc_flow& wf, const fac_wg_tc_workspace* ws, int nsplit,
                          int layer) {
-  return g_tc_fused && nsplit == 2 && tc_pick_cg(nsplit) == 2 && ws->x2_hi && ws->x2_lo && wf.w1_lo[layer] &&
-         (layer == m->n_layers - 1 || (wf.w2r_hi[layer] && wf.w2r_lo[layer])) &&
+  return g_tc_fused && nsplit == 2 && tc_pick_cg(nsplit) == 2 && ws->x2_hi && ws->x2_lo && wn_fused_weights_ok(m, wf) &&
          wn_fused_supported(m->n_channels, m->n_mel * m->n_group, tc_fused_bk());
 }
 
@@ -926,12 +925,7 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
   const bool last = layer == m->n_layers - 1;
   if (tc_use_fused(m, wf, ws, nsplit, layer)) {
     // the residual stream ping-pongs: layer i reads x (i even) / x2 (i odd) and writes the other pair
-    const bool even = (layer & 1) == 0;
-    return wn_layer_fused(even ? ws->x_hi : ws->x2_hi, even ? ws->x_lo : ws->x2_lo, even ? ws->x2_hi : ws->x_hi,
-                          even ? ws->x2_lo : ws->x_lo, ws->spect_hi, ws->spect_lo, wf.w1_hi[layer], wf.w1_lo[layer],
-                          last ? nullptr : wf.w2r_hi[layer], last ? nullptr : wf.w2r_lo[layer], f.in_cond_b[layer],
-                          last ? nullptr : wf.res_b[layer], wf.wc[layer], ws->out8, layer > 0, ws->acts_hi, ws->acts_lo, B,
-                          Tg, C, n_cond, ks, dil, last ? 0 : 1, tc_fused_bk(), g_tc_prefetch, g_tc_prof, st);
+    return wn_flow_fused(m, w, flow, ws, nullptr, B, Tg, layer, 1, 0, 0, tc_fused_bk(), g_tc_prefetch, g_tc_prof, st);
   }
   FAC_REQUIRE(ws->acts_hi && (nsplit == 1 || ws->acts_lo), "wn_layer_tc: the two-launch form needs the acts buffers");
   CUtensorMap maps[6];
@@ -991,6 +985,18 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
   return launch_tc(maps, p, st, cg);
 }
 
+int wg_tc_flow_step(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, float* audio,
+                    const fac_wg_tc_workspace* ws, int B, int Tg, int nsplit, cudaStream_t st) {
+  if (int rc = tc_check(m, w, ws, nsplit)) return rc;
+  FAC_REQUIRE(flow >= 0 && flow < m->n_flows && audio, "waveglow_flow_step_tc: bad arguments");
+  if (g_tc_fused == 2 && ws->flow_sync && tc_use_fused(m, w->flows[flow], ws, nsplit, 0))
+    return wn_flow_fused(m, w, flow, ws, audio, B, Tg, 0, m->n_layers, 1, 1, tc_fused_bk(), g_tc_prefetch, g_tc_prof, st);
+  if (int rc = wg_tc_start(m, flow, audio, ws, B, Tg, nsplit, st)) return rc;
+  for (int i = 0; i < m->n_layers; ++i)
+    if (int rc = wg_tc_layer(m, w, flow, i, ws, B, Tg, nsplit, st)) return rc;
+  return wg_tc_end(m, w, flow, ws->out8, audio, B, Tg, st);
+}
+
 int wg_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* mel_cl, float* audio,
                 const fac_wg_tc_workspace* ws, int B, int F, int nsplit, cudaStream_t st) {
   if (int rc = tc_check(m, w, ws, nsplit)) return rc;
@@ -1020,10 +1026,7 @@ int wg_infer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, const float* 
       g.x2_lo = shift(ws->x2_lo, col0 * C);
       g.out8 = ws->out8 + col0 * TC_NOUT;
       float* audio_g = audio + col0 * m->n_group;
-      if (int rc = wg_tc_start(m, k, audio_g, &g, nb, Tg, nsplit, st)) return rc;
-      for (int i = 0; i < m->n_layers; ++i)
-        if (int rc = wg_tc_layer(m, w, k, i, &g, nb, Tg, nsplit, st)) return rc;
-      if (int rc = wg_tc_end(m, w, k, g.out8, audio_g, nb, Tg, st)) return rc;
+      if (int rc = wg_tc_flow_step(m, w, k, audio_g, &g, nb, Tg, nsplit, st)) return rc;
     }
   }
   return 0;

@@ -206,11 +206,12 @@ class PackedWaveGlow:
         for k in range(cfg["n_flows"]):
             l32.add(f"{k}.out_bias", (8,))
             for i in range(L):
+                # every layer occupies the same block (the last one leaves its residual matrices zero): a uniform
+                # layer stride lets ONE 3-D tensor map per matrix kind serve all layers of a flow (waveglow_fused.cu)
                 for part in ("hi", "lo"):
                     l16.add(f"{k}.{i}.w1_{part}", (2 * Cn, ks * Cn + n_cond))
-                    if i < L - 1:
-                        l16.add(f"{k}.{i}.w2_{part}", (Cn, 2 * Cn))
-                        l16.add(f"{k}.{i}.w2r_{part}", (Cn, Cn))
+                    l16.add(f"{k}.{i}.w2_{part}", (Cn, 2 * Cn))
+                    l16.add(f"{k}.{i}.w2r_{part}", (Cn, Cn))
                 l32.add(f"{k}.{i}.wc", (8, Cn))
                 if i < L - 1:
                     l32.add(f"{k}.{i}.res_b", (Cn,))

@@ -172,7 +172,9 @@ typedef struct fac_wg_tc_weights {
  * (csrc/waveglow_fused.cu: first GEMM -> gate -> residual GEMM -> residual add, acts never leaves the SM) that
  * reads the stream from one pair and writes the other, because neighbouring time tiles still read the old
  * values for their dilated taps: layer i reads x when i is even and x2 when i is odd, and writes the other one
- * (fac_wn_start_tc always writes x).  acts_hi/acts_lo may then be NULL (a test hook when not). */
+ * (fac_wn_start_tc always writes x).  acts_hi/acts_lo may then be NULL (a test hook when not).
+ * flow_sync (optional, with x2): 4 bytes for the grid barrier of fac_waveglow_flow_step_tc, which then runs a
+ * whole flow step -- start, every WN layer, end + coupling + invertible 1x1 -- as ONE cooperative launch. */
 typedef struct fac_wg_tc_workspace {
   void* mel_hi; void* mel_lo;          /* (B, F, mel_pad) bf16 */
   void* spect_hi; void* spect_lo;
@@ -180,6 +182,7 @@ typedef struct fac_wg_tc_workspace {
   void* acts_hi; void* acts_lo;
   float* out8;
   void* x2_hi; void* x2_lo;
+  void* flow_sync;
 } fac_wg_tc_workspace;
 
 /* nsplit = 1: bf16 operands; nsplit = 2: split-bf16 (3 UMMAs per product, fp32-grade result). */
@@ -196,13 +199,23 @@ int fac_wn_layer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow,
 /* glow.py:175 + 278-283 from out8: coupling inverse and invertible 1x1 (reverse), in place on audio. */
 int fac_wn_end_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, const float* out8, float* audio,
                   int B, int Tg, void* stream);
+/* One step of the reverse flow (reference src/waveglow/glow.py:272-290 for flow k: WN.forward :154-175 on audio_0,
+ * affine coupling inverse :278-281, Invertible1x1Conv reverse :283) in place on `audio` (B, T_g, n_group), whose
+ * live channels are the last n_rem slots of every column.  With nsplit == 2 and a workspace that carries x2 and
+ * flow_sync this is ONE kernel launch (csrc/waveglow_fused.cu: start -> 8 fused layers separated by grid barriers
+ * -> end / coupling / W^-1, activations L2-resident between layers, weights TMA-streamed); otherwise it is the
+ * sequence fac_wn_start_tc, fac_wn_layer_tc x n_layers, fac_wn_end_tc. */
+int fac_waveglow_flow_step_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, float* audio,
+                              const fac_wg_tc_workspace* ws, int B, int Tg, int nsplit, void* stream);
 /* Optional cycle counters of the tensor-core kernel: device buffer of 2*256*8 int64 ([G1|G2][cta][8]:
  * producer wait-empty, MMA wait-tmem, MMA wait-full, MMA total, epilogue wait, epilogue busy); NULL disables. */
 void fac_tc_set_profile_buffer(long long* device_buf);
 /* 0 (default): automatic; 1: one CTA per 128-column tile; 2: CTA pairs (thread-block cluster of 2,
  * tcgen05 cta_group::2, UMMA M = 256, each CTA stages half of the weight rows). */
 int fac_tc_set_cta_group(int cta_group);
-/* 1 (default): layers run fused whenever the workspace allows it; 0: always the two-launch form (A/B measurements). */
+/* 0: always the two-launch form of a layer; 1: one fused launch per layer; 2 (default): additionally one launch per
+ * flow step where the workspace allows it.  Bits 4 and up: L2 prefetch distance of the fused kernel's producer in K
+ * steps (A/B measurements). */
 int fac_tc_set_fused(int enabled);
 /* Utterances per pass of fac_waveglow_infer_tc over a flow (they are independent): 0 (default) = the whole
  * batch; a group whose residual stream and gated activations fit the L2 keeps them out of HBM between the

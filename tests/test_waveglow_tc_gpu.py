@@ -99,6 +99,47 @@ def test_tc_layer_matches_fp32_layer(cfg_name, cols, precision, fused):
         assert (out8[..., : 2 * n_half] - out8_ref).abs().max().item() <= tol, ("out8", layer)
 
 
+@pytest.mark.parametrize("cfg_name,B,cols", [("small", 2, 300), ("full", 1, 130), ("full", 3, 1000)])
+def test_flow_step_is_one_launch_and_equals_the_layer_by_layer_sequence(cfg_name, B, cols):
+    """fac_waveglow_flow_step_tc (reference glow.py:272-283 for one flow: WN.forward, coupling inverse, invertible
+    1x1) as ONE cooperative launch -- start, 8 fused layers separated by grid barriers, end -- against the same
+    step run as start / layer / ... / end launches: identical bits (same kernel code per tile), for the first flow
+    (4 + 4 channels) and the last one (2 + 2)."""
+    cfg = synth.WAVEGLOW_CONFIG_SMALL if cfg_name == "small" else synth.WAVEGLOW_CONFIG
+    model = build_model(cfg, "bf16x3")
+    lib, packed = _ext.load(), model.packed()
+    Cn, n_cond, L = cfg["WN_config"]["n_channels"], 640, cfg["WN_config"]["n_layers"]
+    g = torch.Generator().manual_seed(cols)
+    spect = (torch.randn(B, cols, n_cond, generator=g) * 2).to(DEV)
+    audio0 = torch.randn(B, cols, 8, generator=g).to(DEV)
+    s_hi = spect.to(torch.bfloat16)
+    s_lo = (spect - s_hi.float()).to(torch.bfloat16)
+    st, m, tcw = _ext.current_stream(), C.byref(packed.cmodel), C.byref(packed.tc_weights())
+    b16 = lambda: torch.zeros(B, cols, Cn, device=DEV, dtype=torch.bfloat16)      # noqa: E731
+
+    def workspace(sync):
+        bufs = [b16() for _ in range(4)] + [torch.zeros(B, cols, 8, device=DEV), sync]
+        ws = _ext.WgTcWorkspace(None, None, s_hi.data_ptr(), s_lo.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(),
+                                None, None, bufs[4].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(), _ext.ptr(sync))
+        return ws, bufs
+
+    for flow in (cfg["n_flows"] - 1, 0):
+        a_one, a_seq = audio0.clone(), audio0.clone()
+        ws1, keep1 = workspace(torch.zeros(1, dtype=torch.int32, device=DEV))
+        before = lib.fac_launch_count()
+        _ext.check(lib.fac_waveglow_flow_step_tc(m, tcw, flow, a_one.data_ptr(), C.byref(ws1), B, cols, 2, st), "flow step")
+        torch.cuda.synchronize()
+        assert lib.fac_launch_count() - before == 1
+        ws2, keep2 = workspace(None)                      # no flow_sync: start + one fused launch per layer + end
+        before = lib.fac_launch_count()
+        _ext.check(lib.fac_waveglow_flow_step_tc(m, tcw, flow, a_seq.data_ptr(), C.byref(ws2), B, cols, 2, st), "flow seq")
+        torch.cuda.synchronize()
+        assert lib.fac_launch_count() - before == L + 2
+        assert torch.isfinite(a_one).all() and not torch.equal(a_one, audio0)
+        assert torch.equal(a_one, a_seq), flow
+        assert torch.equal(keep1[4], keep2[4])            # out8
+
+
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
 @pytest.mark.parametrize("name", ["waveglow_small_b2_f6.pt", "waveglow_full_b2_f5.pt",
                                   "waveglow_full_b1_f88_sigma0.pt", "waveglow_small_b2_f6_general_convinv.pt",
@@ -189,7 +230,7 @@ def test_small_inputs_replay_a_cuda_graph():
     first = model.infer(mel, sigma=0.0)            # captures
     lib.fac_reset_launch_count()
     again = model.infer(mel, sigma=0.0)            # replays
-    assert lib.fac_launch_count() > 100           # 20 upsampler phases + 12 x (start + 8 fused layers + end) + ...
+    assert lib.fac_launch_count() >= 33           # 20 upsampler phases + mel split + one launch per flow step
     assert torch.equal(first, eager) and torch.equal(again, eager)
     mel2 = synth.synthetic_mel(2, 9, seed=5).to(DEV)
     assert torch.equal(model.infer(mel2, sigma=0.0), model._infer_eager(mel2, 0.0, None))   # new input, same graph
