@@ -97,14 +97,20 @@ __device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0,
                : "memory");
 }
 
-// clock64 accumulators of one role; compiled in, costs a few instructions per barrier wait
-struct Tick {
+// clock64 accumulators of one role (tools/tc_cycle_breakdown.py).  Only the PROF instantiation of the kernel carries
+// them: in the single-thread producer / issuer roles they cost a third of the 40 registers those warps keep.
+template <bool ON>
+struct TickT {
   long long t;
-  __device__ __forceinline__ void start() { t = clock64(); }
+  __device__ __forceinline__ void start() {
+    if (ON) t = clock64();
+  }
   __device__ __forceinline__ void lap(long long& acc) {
-    const long long now = clock64();
-    acc += now - t;
-    t = now;
+    if (ON) {
+      const long long now = clock64();
+      acc += now - t;
+      t = now;
+    }
   }
 };
 
@@ -168,9 +174,12 @@ __device__ __forceinline__ void flow_barrier(unsigned int* counter, unsigned int
   asm volatile("bar.sync 5, %0;" ::"n"(FU_THREADS) : "memory");
 }
 
-template <int BK>
+// FLOW = false: the single-layer form (layer_count == 1, no start / end / grid barrier): the same code with the
+// phase logic compiled out, which keeps the register allocation of the hot loops as tight as it can be.
+template <int BK, bool FLOW, bool PROF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FU_THREADS, 1)
 wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p) {
+  using Tick = TickT<PROF>;
   constexpr int ROWB = BK * 2;                       // bytes of one operand row
   constexpr int A_BYTES = TC_BM * ROWB;              // one 128-row activation tile (hi or lo)
   constexpr int W_BYTES = (TC_NHALF / 2) * ROWB;     // this CTA's half of a 256-row weight block (hi or lo)
@@ -208,8 +217,10 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
   unsigned int bar_target = 0;
   // phases: [start] layer ... layer [end]; a grid barrier separates start from the first layer and a layer with a
   // residual output from the next one (`end` only touches this CTA's own columns)
+  const int layer_count = FLOW ? p.layer_count : 1;
+  const bool do_start = FLOW && p.do_start, do_end = FLOW && p.do_end;
   auto has_res = [&](int l) { return l < p.n_layers - 1; };
-  auto barrier_after_layer = [&](int li) { return li + 1 < p.layer_count && has_res(p.layer_first + li); };
+  auto barrier_after_layer = [&](int li) { return FLOW && li + 1 < layer_count && has_res(p.layer_first + li); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -246,11 +257,11 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
         phase ^= 1;
       }
     };
-    if (p.do_start) flow_barrier(p.grid_bar, bar_target);
+    if (do_start) flow_barrier(p.grid_bar, bar_target);
     long long prod_wait = 0, w_tmem0 = 0, w_full = 0, w_acts = 0, w_tmem1 = 0, issue = 0;
-    const long long k_start = clock64();
+    const long long k_start = PROF ? clock64() : 0;
     uint32_t use[2] = {0, 0}, acts_n = 0, xph[2] = {0, 0};
-    for (int li = 0; li < p.layer_count; ++li) {
+    for (int li = 0; li < layer_count; ++li) {
       const int layer = p.layer_first + li;
       const bool res = has_res(layer);
       const int dil = 1 << layer, center = dil * (p.taps - 1) / 2;
@@ -262,9 +273,9 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
         const int w1_rows = n_cols / 2, w2_rows = C / 2;            // weight rows staged by this CTA
         const int steps_x = p.taps * (C / BK);
         auto acquire = [&](uint32_t bytes) -> uint8_t* {
-          const long long w0 = clock64();
+          const long long w0 = PROF ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
-          prod_wait += clock64() - w0;
+          if (PROF) prod_wait += clock64() - w0;
           if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * bytes);   // both CTAs' loads land on the leader's barrier
           return smem + stage * STAGE_BYTES;
         };
@@ -424,7 +435,7 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
       __syncwarp();
       if (barrier_after_layer(li)) flow_barrier(p.grid_bar, bar_target);
     }
-    if (p.prof) {
+    if (PROF && p.prof) {
       long long* pr = p.prof + blockIdx.x * 16;
       if (warp == 0 && lane == 0) pr[0] = prod_wait;
       if (warp == 1 && lane == 0 && rank == 0) {
@@ -453,11 +464,11 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
     };
     uint32_t xs_phase = 0, use[2] = {0, 0}, acts_n = 0;
     long long e_wfull0 = 0, e_drain = 0, e_wfree = 0, e_busy = 0, e_wfull1 = 0, eg_busy = 0;
-    const long long e_start = clock64();
+    const long long e_start = PROF ? clock64() : 0;
     Tick tk;
     tk.start();
 
-    if (p.do_start) {
+    if (do_start) {
       // ------------------------------------------------- x = start(audio_0) (glow.py:156) for this CTA's tiles,
       // written to buffer A through the x staging and a TMA store
       const int off = p.n_group - p.n_rem;
@@ -507,7 +518,7 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
       flow_barrier(p.grid_bar, bar_target);
     }
 
-    for (int li = 0; li < p.layer_count; ++li) {
+    for (int li = 0; li < layer_count; ++li) {
       const int layer = p.layer_first + li;
       const bool res = has_res(layer);
       const bool in_a = (layer & 1) == 0;
@@ -516,7 +527,7 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
       const float* bias1 = p.bias1[layer];
       const float* wcl = p.wc[layer];
       const float* res_b = p.res_b[layer];
-      const bool acc_out8 = p.layer_count > 1 ? layer > 0 : p.accumulate_out8 != 0;
+      const bool acc_out8 = layer_count > 1 ? layer > 0 : p.accumulate_out8 != 0;
       for (int q = 0; q <= Q; ++q) {
         if (q < Q) {
           // ------------------------------------------------- E(q): drain, gate, out8, acts -> shared memory
@@ -697,7 +708,7 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
       if (barrier_after_layer(li)) flow_barrier(p.grid_bar, bar_target);
     }
 
-    if (p.do_end && half == 0) {
+    if (do_end && half == 0) {
       // ------------------------------------------------- out = end(skip sum) = out8 + bias8 (glow.py:175); b, s =
       // halves (278-279); a1 <- (a1 - b) / exp(s) (280); z <- W^-1 [a0; a1] (283, 96): one thread per column of this
       // CTA's tiles, in place on audio (out8 rows were completed by this CTA's own epilogue)
@@ -743,7 +754,7 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
         }
       }
     }
-    if (p.prof && warp == 4 && lane == 0) {
+    if (PROF && p.prof && warp == 4 && lane == 0) {
       long long* pr = p.prof + blockIdx.x * 16;
       pr[6] = e_wfull0; pr[7] = e_drain; pr[8] = e_wfree; pr[9] = e_busy; pr[10] = e_wfull1; pr[11] = eg_busy;
       pr[12] = clock64() - e_start;
@@ -756,12 +767,12 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
   if (warp == 1) tmem_dealloc_cg2(tmem_base, 512);
 }
 
-template <int BK>
-int launch_fused(const FusedMaps& maps, const FusedParams& p, bool cooperative, cudaStream_t st) {
+template <int BK, bool FLOW, bool PROF>
+int launch_fused(const FusedMaps& maps, const FusedParams& p, cudaStream_t st) {
   static bool attr_set_on[FAC_MAX_DEVICES] = {};
   bool& attr_set = attr_set_on[current_device_slot()];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wn_flow_fused_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(wn_flow_fused_kernel<BK, FLOW, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM);
     if (e != cudaSuccess) {
       set_error("wn_flow_fused: cannot reserve %d bytes of shared memory: %s", FU_SMEM, cudaGetErrorString(e));
       return 2;
@@ -778,8 +789,8 @@ int launch_fused(const FusedMaps& maps, const FusedParams& p, bool cooperative, 
   attr[0].id = cudaLaunchAttributeCooperative;      // the grid barrier between phases needs every CTA resident
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = cooperative ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wn_flow_fused_kernel<BK>, maps, p);
+  cfg.numAttrs = FLOW ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wn_flow_fused_kernel<BK, FLOW, PROF>, maps, p);
   count_launch();
   if (e != cudaSuccess) {
     set_error("wn_flow_fused_kernel: launch failed: %s", cudaGetErrorString(e));
@@ -914,7 +925,12 @@ int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, c
       return 2;
     }
   }
-  return bk == 64 ? launch_fused<64>(maps, p, phases, st) : launch_fused<32>(maps, p, phases, st);
+  if (prof != nullptr) {     // the instrumented instantiations (K = 32 only)
+    FAC_REQUIRE(bk == 32, "wn_flow_fused: cycle counters are compiled for the K = 32 kernel only");
+    return phases ? launch_fused<32, true, true>(maps, p, st) : launch_fused<32, false, true>(maps, p, st);
+  }
+  if (phases) return bk == 64 ? launch_fused<64, true, false>(maps, p, st) : launch_fused<32, true, false>(maps, p, st);
+  return bk == 64 ? launch_fused<64, false, false>(maps, p, st) : launch_fused<32, false, false>(maps, p, st);
 }
 
 }  // namespace fac

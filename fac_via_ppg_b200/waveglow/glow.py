@@ -13,6 +13,7 @@ include/fac_b200.h.  There is no PyTorch or CPU fallback; the training direction
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -163,7 +164,12 @@ class WaveGlow(torch.nn.Module):
     #   "bf16"   tcgen05 tensor cores, plain bf16 operands (BASELINE configs[2] precision)
     PRECISIONS = ("fp32", "bf16x3", "bf16")
     precision = "bf16x3"      # default: tensor cores with fp32-grade results
-    fused_layers = True       # bf16x3: one fused launch per WN layer (csrc/waveglow_fused.cu); False: two launches
+    # bf16x3: one fused launch per WN layer (csrc/waveglow_fused.cu); False: two launches per layer
+    fused_layers = os.environ.get("FAC_TC_FUSED", "1") != "0"
+    # True: a whole flow step (start, 8 layers, end / coupling / 1x1) is ONE cooperative launch with grid barriers
+    # between the layers (fac_waveglow_flow_step_tc).  Measured on B200 it is 1.5 % slower than one launch per
+    # layer at 8 x 10 s and 10 % slower for a single short utterance (profiles/README.md), so it is opt-in.
+    flow_step_launch = os.environ.get("FAC_TC_FUSED", "1") == "2"
 
     def set_precision(self, precision):
         if precision in (None, "auto"):
@@ -214,7 +220,8 @@ class WaveGlow(torch.nn.Module):
                 bufs[name] = b16(c)
                 bufs[name[:-2] + "lo"] = b16(c) if nsplit == 2 else None
             bufs["out8"] = f32(8)
-            bufs["flow_sync"] = torch.zeros(1, device=dev, dtype=torch.int32) if fused else None
+            bufs["flow_sync"] = (torch.zeros(1, device=dev, dtype=torch.int32)
+                                 if fused and self.flow_step_launch else None)
             pad = self.packed().mel_pad
             bufs["mel_hi"] = torch.empty(B, F, pad, device=dev, dtype=torch.bfloat16)
             bufs["mel_lo"] = torch.empty_like(bufs["mel_hi"]) if nsplit == 2 else None

@@ -215,6 +215,26 @@ def test_tc_full_size_whole_tensor_and_oracle_windows():
         assert torch.equal(alone[0], full[row]), row
 
 
+def test_flow_step_launch_mode_of_infer_matches_the_default(golden_dir):
+    """WaveGlow.flow_step_launch: infer() with one cooperative launch per flow step (33 launches per call instead of
+    141) produces the same bits as the default one-launch-per-layer mode, and the reference golden within 1e-4."""
+    g = torch.load(os.path.join(golden_dir, "waveglow_full_b2_f5.pt"))
+    model = build_model(g["cfg"], "bf16x3")
+    mel = synth.synthetic_mel(g["batch"], g["frames"], seed=g["mel_seed"]).to(DEV)
+    noise = [z.to(DEV) for z in g["noise"]]
+    lib = _ext.load()
+    base = model.infer(mel, sigma=g["sigma"], noise=noise)
+    model.flow_step_launch = True
+    try:
+        lib.fac_reset_launch_count()
+        flow = model.infer(mel, sigma=g["sigma"], noise=noise)
+        assert lib.fac_launch_count() == 20 + 1 + g["cfg"]["n_flows"]
+    finally:
+        model.flow_step_launch = False
+    assert torch.equal(flow, base)
+    assert rms(flow, g["audio"]) <= 1e-4
+
+
 def test_small_inputs_replay_a_cuda_graph():
     """Launch-bound sizes are captured once per shape in a CUDA graph: same bits as the eager path (sigma = 0
     removes the noise), fresh noise on every replay, launches still accounted for."""
@@ -230,7 +250,7 @@ def test_small_inputs_replay_a_cuda_graph():
     first = model.infer(mel, sigma=0.0)            # captures
     lib.fac_reset_launch_count()
     again = model.infer(mel, sigma=0.0)            # replays
-    assert lib.fac_launch_count() >= 33           # 20 upsampler phases + mel split + one launch per flow step
+    assert lib.fac_launch_count() >= 141          # 20 upsampler phases + mel split + 12 x (start + 8 fused layers + end)
     assert torch.equal(first, eager) and torch.equal(again, eager)
     mel2 = synth.synthetic_mel(2, 9, seed=5).to(DEV)
     assert torch.equal(model.infer(mel2, sigma=0.0), model._infer_eager(mel2, 0.0, None))   # new input, same graph

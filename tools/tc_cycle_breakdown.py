@@ -17,7 +17,8 @@ m = WaveGlow.remove_weightnorm(WaveGlow(**cfg))
 m.load_state_dict(synth.waveglow_state(cfg=cfg))
 m = m.cuda().eval()
 lib = _ext.load()
-mel = synth.synthetic_mel(8, 1379).cuda()
+shape = [int(v) for v in os.environ.get("FAC_BREAKDOWN_SHAPE", "8,1379").split(",")]      # utterances, frames
+mel = synth.synthetic_mel(shape[0], shape[1]).cuda()
 names2 = ["prod_wait_empty", "mma_wait_tmem", "mma_wait_full", "mma_total", "epi_wait_full", "epi_busy"]
 namesf = ["prod_wait_empty", "mma_wait_tmem0", "mma_wait_full", "mma_wait_acts", "mma_wait_tmem1", "mma_total",
           "epi_wait_full0", "epi_drain", "epi_wait_acts_free", "epi_busy", "epi_wait_full1", "eg_busy", "epi_total"]
