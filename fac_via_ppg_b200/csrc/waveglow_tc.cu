@@ -519,30 +519,39 @@ __global__ void mel_pad_split_kernel(const float* __restrict__ mel, __nv_bfloat1
   if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-// x = start(audio_0) (glow.py:156), written as the bf16 operand copies of the first layer.
+// x = start(audio_0) (glow.py:156), written as the bf16 operand copies of the first layer.  A pure streaming
+// kernel (reads 16-32 B, writes 1 KB per column): thread = 8 channels of one column, 16-byte stores.
 __global__ void wn_start_tc_kernel(const float* __restrict__ audio, const float* __restrict__ w,
                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ x_hi,
                                    __nv_bfloat16* __restrict__ x_lo, long long n_cols, int C, int n_group, int off,
                                    int n_half) {
-  const int c4 = C >> 2;
+  const int c8 = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_cols * c4) return;
-  const long long col = idx / c4;
-  const int c = (int)(idx % c4) * 4;
-  float4 o = __ldg(reinterpret_cast<const float4*>(bias + c));
+  if (idx >= n_cols * c8) return;
+  const long long col = idx / c8;
+  const int c = (int)(idx % c8) * 8;
+  float4 o0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+  float4 o1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
   for (int j = 0; j < n_half; ++j) {
     const float a = __ldg(audio + col * n_group + off + j);
-    const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long long)j * C + c));
-    o.x = fmaf(a, wv.x, o.x);
-    o.y = fmaf(a, wv.y, o.y);
-    o.z = fmaf(a, wv.z, o.z);
-    o.w = fmaf(a, wv.w, o.w);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (long long)j * C + c));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (long long)j * C + c + 4));
+    o0.x = fmaf(a, w0.x, o0.x);
+    o0.y = fmaf(a, w0.y, o0.y);
+    o0.z = fmaf(a, w0.z, o0.z);
+    o0.w = fmaf(a, w0.w, o0.w);
+    o1.x = fmaf(a, w1.x, o1.x);
+    o1.y = fmaf(a, w1.y, o1.y);
+    o1.z = fmaf(a, w1.z, o1.z);
+    o1.w = fmaf(a, w1.w, o1.w);
   }
-  uint32_t h0, l0, h1, l1;
-  split2(o.x, o.y, h0, l0);
-  split2(o.z, o.w, h1, l1);
-  *reinterpret_cast<uint2*>(x_hi + col * C + c) = make_uint2(h0, h1);
-  if (x_lo) *reinterpret_cast<uint2*>(x_lo + col * C + c) = make_uint2(l0, l1);
+  uint32_t h[4], l[4];
+  split2(o0.x, o0.y, h[0], l[0]);
+  split2(o0.z, o0.w, h[1], l[1]);
+  split2(o1.x, o1.y, h[2], l[2]);
+  split2(o1.z, o1.w, h[3], l[3]);
+  *reinterpret_cast<uint4*>(x_hi + col * C + c) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (x_lo) *reinterpret_cast<uint4*>(x_lo + col * C + c) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // out = out8 + bias8 is end(skip sum) (glow.py:175); b, s = halves (glow.py:278-279);
@@ -893,7 +902,7 @@ int wg_tc_start(const fac_wg_model* m, int flow, const float* audio, const fac_w
   FAC_REQUIRE(flow >= 0 && flow < m->n_flows && ws && ws->x_hi, "wn_start_tc: bad arguments");
   const fac_wg_flow& f = m->flows[flow];
   const long long n_cols = (long long)B * Tg;
-  const long long total = n_cols * (m->n_channels / 4);
+  const long long total = n_cols * (m->n_channels / 8);
   wn_start_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
       audio, f.start_w, f.start_b, reinterpret_cast<__nv_bfloat16*>(ws->x_hi),
       nsplit == 2 ? reinterpret_cast<__nv_bfloat16*>(ws->x_lo) : nullptr, n_cols, m->n_channels, m->n_group,
