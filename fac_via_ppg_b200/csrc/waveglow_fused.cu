@@ -80,6 +80,7 @@ struct FusedParams {
   __nv_bfloat16* acts_lo;
   unsigned int* grid_bar;    // zeroed by the host; arrival counter of the grid barrier
   int prefetch_steps;        // L2 prefetch distance of the producer in K steps (0 = off)
+  int l2_hints;              // eviction-priority hints on the TMA loads: 1 keep re-read boxes, 2 single-use boxes first, 4 keep weights
   long long* prof;           // optional [grid][16] clock64 counters (tools/tc_cycle_breakdown.py)
 };
 
@@ -272,6 +273,10 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
         const CUtensorMap* xm_lo = in_a ? &maps.xa_lo : &maps.xb_lo;
         const int w1_rows = n_cols / 2, w2_rows = C / 2;            // weight rows staged by this CTA
         const int steps_x = p.taps * (C / BK);
+        // L2 residency: the activation boxes of a tile's first unit are read again by its later units (and, for x,
+        // by the neighbouring tiles' taps) -> keep; the last unit's are not needed again in this layer -> evict first;
+        // the weights are shared by every CTA of the grid -> keep
+        const uint64_t keep = p.l2_hints ? l2_policy_evict_last() : 0, once = p.l2_hints ? l2_policy_evict_first() : 0;
         auto acquire = [&](uint32_t bytes) -> uint8_t* {
           const long long w0 = PROF ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
@@ -321,10 +326,30 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
               uint8_t* st = acquire((uint32_t)(2 * A_BYTES + 2 * w1_rows * ROWB));
               const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
               a_box(q, ks, mh, ml, c0, row0, b);
-              tma_load_3d_cg2(st, mh, lead_full, c0, row0, b);
-              tma_load_3d_cg2(st + A_BYTES, ml, lead_full, c0, row0, b);
-              tma_load_3d_cg2(st + W_OFF, &maps.w1_hi, lead_full, ks * BK, w_row, layer);
-              tma_load_3d_cg2(st + W_OFF + W_BYTES, &maps.w1_lo, lead_full, ks * BK, w_row, layer);
+              const bool reread = u < n_units - 1 || ks < steps_x;
+              if ((p.l2_hints & 1) && reread) {
+                tma_load_3d_cg2_hint(st, mh, lead_full, c0, row0, b, keep);
+                tma_load_3d_cg2_hint(st + A_BYTES, ml, lead_full, c0, row0, b, keep);
+              } else if ((p.l2_hints & 2) && !reread) {
+                tma_load_3d_cg2_hint(st, mh, lead_full, c0, row0, b, once);
+                tma_load_3d_cg2_hint(st + A_BYTES, ml, lead_full, c0, row0, b, once);
+              } else {
+                tma_load_3d_cg2(st, mh, lead_full, c0, row0, b);
+                tma_load_3d_cg2(st + A_BYTES, ml, lead_full, c0, row0, b);
+              }
+              if (p.l2_hints & 4) {
+                tma_load_3d_cg2_hint(st + W_OFF, &maps.w1_hi, lead_full, ks * BK, w_row, layer, keep);
+                tma_load_3d_cg2_hint(st + W_OFF + W_BYTES, &maps.w1_lo, lead_full, ks * BK, w_row, layer, keep);
+              } else {
+                tma_load_3d_cg2(st + W_OFF, &maps.w1_hi, lead_full, ks * BK, w_row, layer);
+                tma_load_3d_cg2(st + W_OFF + W_BYTES, &maps.w1_lo, lead_full, ks * BK, w_row, layer);
+              }
+              if (false) {
+                tma_load_3d_cg2(st, mh, lead_full, c0, row0, b);
+                tma_load_3d_cg2(st + A_BYTES, ml, lead_full, c0, row0, b);
+                tma_load_3d_cg2(st + W_OFF, &maps.w1_hi, lead_full, ks * BK, w_row, layer);
+                tma_load_3d_cg2(st + W_OFF + W_BYTES, &maps.w1_lo, lead_full, ks * BK, w_row, layer);
+              }
               advance();
             }
           }
@@ -426,8 +451,14 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
               const int c0 = h * (C / 2) + cc * FU_XS_COLS;
               mbar_wait(&xs_empty[h], xph[h] ^ 1);
               mbar_arrive_expect_tx(&xs_full[h], 2 * FU_XS_ARRAY);
-              tma_load_3d(dst, ym_hi, &xs_full[h], c0, t0, b);
-              tma_load_3d(dst + FU_XS_ARRAY, ym_lo, &xs_full[h], c0, t0, b);
+              if (p.l2_hints & 2) {    // the last read of the old x in this layer
+                const uint64_t once = l2_policy_evict_first();
+                tma_load_3d_hint(dst, ym_hi, &xs_full[h], c0, t0, b, once);
+                tma_load_3d_hint(dst + FU_XS_ARRAY, ym_lo, &xs_full[h], c0, t0, b, once);
+              } else {
+                tma_load_3d(dst, ym_hi, &xs_full[h], c0, t0, b);
+                tma_load_3d(dst + FU_XS_ARRAY, ym_lo, &xs_full[h], c0, t0, b);
+              }
               xph[h] ^= 1;
             }
         }
@@ -849,7 +880,7 @@ bool wn_fused_weights_ok(const fac_wg_model* m, const fac_wg_tc_flow& wf) {
 // even and from ws->x2 when l is odd, and written to the other pair; start writes ws->x.
 int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, const fac_wg_tc_workspace* ws,
                   float* audio, int B, int T, int layer_first, int layer_count, int do_start, int do_end, int bk,
-                  int prefetch_steps, long long* prof, cudaStream_t st) {
+                  int prefetch_steps, int l2_hints, long long* prof, cudaStream_t st) {
   const fac_wg_flow& f = m->flows[flow];
   const fac_wg_tc_flow& wf = w->flows[flow];
   const int C = m->n_channels, n_cond = m->n_mel * m->n_group, taps = m->kernel_size, L = m->n_layers;
@@ -917,6 +948,7 @@ int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, c
   if (p.acts_hi == nullptr || p.acts_lo == nullptr) p.acts_hi = p.acts_lo = nullptr;
   p.grid_bar = reinterpret_cast<unsigned int*>(ws->flow_sync);
   p.prefetch_steps = prefetch_steps < p.k1_steps ? prefetch_steps : p.k1_steps - 1;
+  p.l2_hints = l2_hints;
   p.prof = prof;
   if (phases) {
     cudaError_t e = cudaMemsetAsync(ws->flow_sync, 0, sizeof(unsigned int), st);
