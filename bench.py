@@ -16,7 +16,7 @@ Side objects on the same JSON line (each timed with CUDA events after its own wa
 nvidia-smi clock sample; none of them is inside the headline's timed region):
   N = 1 : `fp32` (the exact-fp32 FFMA mode on the headline workload), `library_gpu` (the reference's arithmetic
           as stock PyTorch/cuDNN calls on the same B200, TF32 off and on -- SURVEY.md section 8d),
-          `ppg2mel` (Tacotron2.inference, mel frames/s), `pipeline` (BASELINE configs[2]), `cpu_baseline`.
+          `ppg2mel` (Tacotron2.inference, mel frames/s), `pipeline` (BASELINE configs[2]), `denoiser`, `cpu_baseline`.
   every N: `cfg4` (BASELINE configs[3]: WaveGlow.infer on 32 x 10 s per GPU = 256 utterances on 8 GPUs) and
           `cfg5` (BASELINE configs[4]: 8 x 60 s per GPU = 64 utterances on 8 GPUs, PPG -> Mel -> WaveGlow ->
           Denoiser as generate_synthesis.py:86-98 runs them, through pinned host buffers, whole-job RTF).
@@ -293,6 +293,23 @@ def measure_library_gpu(env, mel, samples_per_step):
     return out
 
 
+def measure_denoiser(env, model, batch=8, seconds=10.0):
+    """The step right after WaveGlow.infer on the CLI path (reference src/waveglow/denoiser.py:58-68 with the dense-DFT
+    STFT of src/common/stft.py:79-138): STFT GEMM -> spectral subtraction -> inverse STFT GEMM on 8 x 10 s of audio,
+    tensor-core form (default) and exact FFMA form."""
+    from fac_via_ppg_b200.waveglow.denoiser import Denoiser
+    den = Denoiser(model, mode="zeros")
+    n = synth.frames_for_seconds(seconds) * 160
+    audio = torch.randn(batch, n, device=env.dev) * 0.1
+    out = {"workload": "Denoiser(strength 0.005) on %d x %.0f s of audio (STFT 1024 / hop 160)" % (batch, seconds),
+           "unit": "samples/s", "timing": "CUDA events, mean of 5 after 1 warm-up"}
+    for precision in ("fp16x3", "fp32"):
+        den.stft.precision = precision
+        ms, clocks = env.timed_with_clocks(lambda: den(audio, strength=0.005), 5, warmup=1)
+        out[precision] = {"value": batch * n / (ms / 5e3), "ms": ms / 5, "clocks": clocks}
+    return out
+
+
 def measure_cfg4(env, model, batch=32, seconds=10.0):
     """BASELINE configs[3]: WaveGlow.infer on 256 x 10 s sharded over 8 GPUs = 32 utterances per GPU (weak scaling:
     every rank runs its own 32), mel resident, and through pinned host buffers."""
@@ -537,11 +554,12 @@ def main():
             roof["traffic_source"] = t["source"]
 
     side = world == 1 and not args.no_side
-    fp32 = library = ppg2mel = pipeline = cpu = None
+    fp32 = library = ppg2mel = pipeline = cpu = denoiser = None
     if side and precision != "fp32":
         fp32 = measure_fp32_mode(env, model, mel, peaks, samples_per_step)
     if side:
         library = measure_library_gpu(env, mel, samples_per_step)
+        denoiser = measure_denoiser(env, model)
     # ---- PPG -> Mel side metric (mel frames/s) and BASELINE configs[2] ----------
     if side and not args.no_ppg2mel:
         ppg2mel = measure_ppg2mel(env)
@@ -575,6 +593,7 @@ def main():
         "library_gpu": library,
         "ppg2mel": ppg2mel,
         "pipeline": pipeline,
+        "denoiser": denoiser,
         "cfg4": cfg4,
         "cfg5": cfg5,
         "tflops_algorithmic": value * WG_FLOP_PER_SAMPLE / 1e12,

@@ -111,7 +111,7 @@ def conv_gemm_tc(a, w, *, act=_ext.ACT_NONE, mask=None, residual=None, out=None,
     d = _ext.TcConv(a_hi.data_ptr(), _ext.ptr(a_lo), w["hi"].data_ptr(), w["lo"].data_ptr() if nsplit == 2 else None,
                     _ext.ptr(w["bias"]), _ext.ptr(mask), _ext.ptr(residual), _ext.ptr(out), _ext.ptr(nxt[0]),
                     _ext.ptr(nxt[1]), ld(mask), ld(residual), ld(out), B, T, c_pad, w["taps"],
-                    (w["taps"] - 1) // 2, w["n_pad"], w["n_valid"], act, nsplit, int(a_hi.dtype == torch.float16),
+                    w.get("center_override", (w["taps"] - 1) // 2), w["n_pad"], w["n_valid"], act, nsplit, int(a_hi.dtype == torch.float16),
                     k_chunk or 0, 0, _ext.ptr(scratch), _ext.ptr(row_lengths))
     rc = _ext.load().fac_conv_gemm_tc(C.byref(d), _ext.current_stream())
     _ext.check(rc, "fac_conv_gemm_tc")

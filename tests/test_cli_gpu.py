@@ -93,11 +93,21 @@ def test_denoiser_matches_reference_restatement():
     bias_audio = wg.infer(torch.zeros(1, 80, 88, device="cuda"), sigma=0.0).float().cpu()
     g = torch.Generator().manual_seed(1)
     audio = torch.randn(2, 4800, generator=g) * 0.2
-    for strength in (0.005, 0.5):
-        ref = denoiser_oracle.denoise(audio, bias_audio, strength)
-        out = den(audio.cuda(), strength=strength)
-        assert out.shape == ref.shape == (2, 1, 4800)
-        assert (out.cpu() - ref).abs().max().item() <= 2e-4, strength
+    for precision in ("fp16x3", "fp32"):          # tensor-core STFT GEMMs (default) and the exact FFMA form
+        den.stft.precision = precision
+        for strength in (0.005, 0.5):
+            ref = denoiser_oracle.denoise(audio, bias_audio, strength)
+            out = den(audio.cuda(), strength=strength)
+            assert out.shape == ref.shape == (2, 1, 4800)
+            err = (out.cpu() - ref).abs().max().item()
+            print("denoiser %s strength %g: max-abs vs oracle %.2e" % (precision, strength, err))
+            assert err <= 2e-4, (precision, strength)
+    den.stft.precision = "fp16x3"
+    mag_tc, ph_tc = den.stft.transform(audio.cuda())
+    den.stft.precision = "fp32"
+    mag_f, ph_f = den.stft.transform(audio.cuda())
+    den.stft.precision = "fp16x3"
+    assert mag_tc.shape == mag_f.shape == (2, 513, 31) and (mag_tc - mag_f).abs().max().item() <= 1e-4
 
 
 def test_cli_with_checkpoints_and_npy_ppg(tmp_path, monkeypatch):
