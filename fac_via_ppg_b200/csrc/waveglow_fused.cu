@@ -177,16 +177,18 @@ __device__ __forceinline__ void flow_barrier(unsigned int* counter, unsigned int
 
 // FLOW = false: the single-layer form (layer_count == 1, no start / end / grid barrier): the same code with the
 // phase logic compiled out, which keeps the register allocation of the hot loops as tight as it can be.
-template <int BK, bool FLOW, bool PROF>
+// NS = 2: split-bf16 operands (hi + lo pairs, 3 UMMAs per product, fp32-grade); NS = 1: plain bf16 (hi only).
+template <int BK, int NS, bool FLOW, bool PROF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FU_THREADS, 1)
 wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p) {
   using Tick = TickT<PROF>;
+  constexpr bool SPLIT = NS == 2;
   constexpr int ROWB = BK * 2;                       // bytes of one operand row
   constexpr int A_BYTES = TC_BM * ROWB;              // one 128-row activation tile (hi or lo)
   constexpr int W_BYTES = (TC_NHALF / 2) * ROWB;     // this CTA's half of a 256-row weight block (hi or lo)
-  constexpr int STAGE_BYTES = 2 * (A_BYTES + W_BYTES);
-  constexpr int STAGES = FU_RING_BYTES / STAGE_BYTES;
-  constexpr int W_OFF = 2 * A_BYTES;                 // stage layout: A_hi A_lo W_hi W_lo
+  constexpr int STAGE_BYTES = NS * (A_BYTES + W_BYTES);
+  constexpr int STAGES = FU_RING_BYTES / STAGE_BYTES < FU_MAX_STAGES ? FU_RING_BYTES / STAGE_BYTES : FU_MAX_STAGES;
+  constexpr int W_OFF = NS * A_BYTES;                // stage layout: A_hi [A_lo] W_hi [W_lo]
   static_assert(STAGES >= 2 && STAGES <= FU_MAX_STAGES, "ring");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -323,32 +325,26 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
                   tma_prefetch_l2_3d(ml, c0, row0, b);
                 }
               }
-              uint8_t* st = acquire((uint32_t)(2 * A_BYTES + 2 * w1_rows * ROWB));
+              uint8_t* st = acquire((uint32_t)(NS * (A_BYTES + w1_rows * ROWB)));
               const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
               a_box(q, ks, mh, ml, c0, row0, b);
               const bool reread = u < n_units - 1 || ks < steps_x;
               if ((p.l2_hints & 1) && reread) {
                 tma_load_3d_cg2_hint(st, mh, lead_full, c0, row0, b, keep);
-                tma_load_3d_cg2_hint(st + A_BYTES, ml, lead_full, c0, row0, b, keep);
+                if (SPLIT) tma_load_3d_cg2_hint(st + A_BYTES, ml, lead_full, c0, row0, b, keep);
               } else if ((p.l2_hints & 2) && !reread) {
                 tma_load_3d_cg2_hint(st, mh, lead_full, c0, row0, b, once);
-                tma_load_3d_cg2_hint(st + A_BYTES, ml, lead_full, c0, row0, b, once);
+                if (SPLIT) tma_load_3d_cg2_hint(st + A_BYTES, ml, lead_full, c0, row0, b, once);
               } else {
                 tma_load_3d_cg2(st, mh, lead_full, c0, row0, b);
-                tma_load_3d_cg2(st + A_BYTES, ml, lead_full, c0, row0, b);
+                if (SPLIT) tma_load_3d_cg2(st + A_BYTES, ml, lead_full, c0, row0, b);
               }
               if (p.l2_hints & 4) {
                 tma_load_3d_cg2_hint(st + W_OFF, &maps.w1_hi, lead_full, ks * BK, w_row, layer, keep);
-                tma_load_3d_cg2_hint(st + W_OFF + W_BYTES, &maps.w1_lo, lead_full, ks * BK, w_row, layer, keep);
+                if (SPLIT) tma_load_3d_cg2_hint(st + W_OFF + W_BYTES, &maps.w1_lo, lead_full, ks * BK, w_row, layer, keep);
               } else {
                 tma_load_3d_cg2(st + W_OFF, &maps.w1_hi, lead_full, ks * BK, w_row, layer);
-                tma_load_3d_cg2(st + W_OFF + W_BYTES, &maps.w1_lo, lead_full, ks * BK, w_row, layer);
-              }
-              if (false) {
-                tma_load_3d_cg2(st, mh, lead_full, c0, row0, b);
-                tma_load_3d_cg2(st + A_BYTES, ml, lead_full, c0, row0, b);
-                tma_load_3d_cg2(st + W_OFF, &maps.w1_hi, lead_full, ks * BK, w_row, layer);
-                tma_load_3d_cg2(st + W_OFF + W_BYTES, &maps.w1_lo, lead_full, ks * BK, w_row, layer);
+                if (SPLIT) tma_load_3d_cg2(st + W_OFF + W_BYTES, &maps.w1_lo, lead_full, ks * BK, w_row, layer);
               }
               advance();
             }
@@ -356,11 +352,11 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
           if (q > 0 && res) {
             const int u = (q - 1) % n_units;
             for (int s = 0; s < kp_steps; ++s) {
-              uint8_t* st = acquire((uint32_t)(2 * w2_rows * ROWB));
+              uint8_t* st = acquire((uint32_t)(NS * w2_rows * ROWB));
               const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
               const int k0 = u * chpu + s * BK;
               tma_load_3d_cg2(st + W_OFF, &maps.w2_hi, lead_full, k0, rank * w2_rows, layer);
-              tma_load_3d_cg2(st + W_OFF + W_BYTES, &maps.w2_lo, lead_full, k0, rank * w2_rows, layer);
+              if (SPLIT) tma_load_3d_cg2(st + W_OFF + W_BYTES, &maps.w2_lo, lead_full, k0, rank * w2_rows, layer);
               advance();
             }
           }
@@ -391,12 +387,14 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
 #pragma unroll
                 for (int kk = 0; kk < BK / 16; ++kk) {
                   const uint32_t koff = kk * 32;
-                  const uint64_t a_h = make_smem_desc(st + koff, ROWB), a_l = make_smem_desc(st + A_BYTES + koff, ROWB);
-                  const uint64_t w_h = make_smem_desc(st + W_OFF + koff, ROWB);
-                  const uint64_t w_l = make_smem_desc(st + W_OFF + W_BYTES + koff, ROWB);
+                  const uint64_t a_h = make_smem_desc(st + koff, ROWB), w_h = make_smem_desc(st + W_OFF + koff, ROWB);
                   umma_bf16_cg2(d1, a_h, w_h, idesc1, (ks > 0 || kk > 0) ? 1u : 0u);
-                  umma_bf16_cg2(d1, a_l, w_h, idesc1, 1u);
-                  umma_bf16_cg2(d1, a_h, w_l, idesc1, 1u);
+                  if (SPLIT) {
+                    const uint64_t a_l = make_smem_desc(st + A_BYTES + koff, ROWB);
+                    const uint64_t w_l = make_smem_desc(st + W_OFF + W_BYTES + koff, ROWB);
+                    umma_bf16_cg2(d1, a_l, w_h, idesc1, 1u);
+                    umma_bf16_cg2(d1, a_h, w_l, idesc1, 1u);
+                  }
                 }
                 umma_commit_cg2(&empty[stage], (uint16_t)0x3);
                 advance();
@@ -419,16 +417,18 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
                 tk.lap(w_full);
                 tc_fence_after();
                 const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
-                const uint32_t as = acts_a + s * 2 * A_BYTES;
+                const uint32_t as = acts_a + s * NS * A_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < BK / 16; ++kk) {
                   const uint32_t koff = kk * 32;
-                  const uint64_t a_h = make_smem_desc(as + koff, ROWB), a_l = make_smem_desc(as + A_BYTES + koff, ROWB);
-                  const uint64_t w_h = make_smem_desc(st + W_OFF + koff, ROWB);
-                  const uint64_t w_l = make_smem_desc(st + W_OFF + W_BYTES + koff, ROWB);
+                  const uint64_t a_h = make_smem_desc(as + koff, ROWB), w_h = make_smem_desc(st + W_OFF + koff, ROWB);
                   umma_bf16_cg2(d2, a_h, w_h, idesc2, (u > 0 || s > 0 || kk > 0) ? 1u : 0u);
-                  umma_bf16_cg2(d2, a_l, w_h, idesc2, 1u);
-                  umma_bf16_cg2(d2, a_h, w_l, idesc2, 1u);
+                  if (SPLIT) {
+                    const uint64_t a_l = make_smem_desc(as + A_BYTES + koff, ROWB);
+                    const uint64_t w_l = make_smem_desc(st + W_OFF + W_BYTES + koff, ROWB);
+                    umma_bf16_cg2(d2, a_l, w_h, idesc2, 1u);
+                    umma_bf16_cg2(d2, a_h, w_l, idesc2, 1u);
+                  }
                 }
                 umma_commit_cg2(&empty[stage], (uint16_t)0x3);
                 advance();
@@ -450,14 +450,14 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
               uint8_t* dst = xs_s + h * 2 * FU_XS_ARRAY;
               const int c0 = h * (C / 2) + cc * FU_XS_COLS;
               mbar_wait(&xs_empty[h], xph[h] ^ 1);
-              mbar_arrive_expect_tx(&xs_full[h], 2 * FU_XS_ARRAY);
+              mbar_arrive_expect_tx(&xs_full[h], NS * FU_XS_ARRAY);
               if (p.l2_hints & 2) {    // the last read of the old x in this layer
                 const uint64_t once = l2_policy_evict_first();
                 tma_load_3d_hint(dst, ym_hi, &xs_full[h], c0, t0, b, once);
-                tma_load_3d_hint(dst + FU_XS_ARRAY, ym_lo, &xs_full[h], c0, t0, b, once);
+                if (SPLIT) tma_load_3d_hint(dst + FU_XS_ARRAY, ym_lo, &xs_full[h], c0, t0, b, once);
               } else {
                 tma_load_3d(dst, ym_hi, &xs_full[h], c0, t0, b);
-                tma_load_3d(dst + FU_XS_ARRAY, ym_lo, &xs_full[h], c0, t0, b);
+                if (SPLIT) tma_load_3d(dst + FU_XS_ARRAY, ym_lo, &xs_full[h], c0, t0, b);
               }
               xph[h] ^= 1;
             }
@@ -532,13 +532,13 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
           for (int j4 = 0; j4 < 4; ++j4) {
             const uint32_t o = swizzle_off<64>((uint32_t)row * 64 + j4 * 16);
             st_shared_v4(xs_a + o, hw[4 * j4], hw[4 * j4 + 1], hw[4 * j4 + 2], hw[4 * j4 + 3]);
-            st_shared_v4(xs_a + FU_XS_ARRAY + o, lw[4 * j4], lw[4 * j4 + 1], lw[4 * j4 + 2], lw[4 * j4 + 3]);
+            if (SPLIT) st_shared_v4(xs_a + FU_XS_ARRAY + o, lw[4 * j4], lw[4 * j4 + 1], lw[4 * j4 + 2], lw[4 * j4 + 3]);
           }
           fence_proxy_async_smem();
           half_sync();
           if (storer) {
             tma_store_3d(&maps.ya_hi, xs_mine, n0, t0, b);
-            tma_store_3d(&maps.ya_lo, xs_mine + FU_XS_ARRAY, n0, t0, b);
+            if (SPLIT) tma_store_3d(&maps.ya_lo, xs_mine + FU_XS_ARRAY, n0, t0, b);
             tma_store_commit();
             tma_store_wait_read();
           }
@@ -629,21 +629,25 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
                 // rows outside the utterance hold zeros (their x_new rows are clipped by the TMA store)
                 const uint32_t s = (uint32_t)(ch_u / BK);
                 const uint32_t off = (uint32_t)row * ROWB + (uint32_t)(ch_u % BK) * 2;
-                const uint32_t base = acts_a + s * 2 * A_BYTES;
+                const uint32_t base = acts_a + s * NS * A_BYTES;
                 const uint32_t o0 = swizzle_off<ROWB>(off), o1 = swizzle_off<ROWB>(off + 16);
                 st_shared_v4(base + o0, hi[0], hi[1], hi[2], hi[3]);
                 st_shared_v4(base + o1, hi[4], hi[5], hi[6], hi[7]);
-                st_shared_v4(base + A_BYTES + o0, lo[0], lo[1], lo[2], lo[3]);
-                st_shared_v4(base + A_BYTES + o1, lo[4], lo[5], lo[6], lo[7]);
+                if (SPLIT) {
+                  st_shared_v4(base + A_BYTES + o0, lo[0], lo[1], lo[2], lo[3]);
+                  st_shared_v4(base + A_BYTES + o1, lo[4], lo[5], lo[6], lo[7]);
+                }
               }
               if (p.acts_hi != nullptr && valid) {
                 const long long goff = col * C + ch0;
                 uint4* dh = reinterpret_cast<uint4*>(p.acts_hi + goff);
                 dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                uint4* dl = reinterpret_cast<uint4*>(p.acts_lo + goff);
-                dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                if (SPLIT) {
+                  uint4* dl = reinterpret_cast<uint4*>(p.acts_lo + goff);
+                  dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                  dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
               }
             }
           }
@@ -701,7 +705,8 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
             for (int j4 = 0; j4 < 4; ++j4) {
               const uint32_t o = swizzle_off<64>((uint32_t)row * 64 + j4 * 16);
               ld_shared_v4(xs_a + o, hw[4 * j4], hw[4 * j4 + 1], hw[4 * j4 + 2], hw[4 * j4 + 3]);
-              ld_shared_v4(xs_a + FU_XS_ARRAY + o, lw[4 * j4], lw[4 * j4 + 1], lw[4 * j4 + 2], lw[4 * j4 + 3]);
+              if (SPLIT) ld_shared_v4(xs_a + FU_XS_ARRAY + o, lw[4 * j4], lw[4 * j4 + 1], lw[4 * j4 + 2], lw[4 * j4 + 3]);
+              else lw[4 * j4] = lw[4 * j4 + 1] = lw[4 * j4 + 2] = lw[4 * j4 + 3] = 0u;
             }
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -716,14 +721,14 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
             for (int j4 = 0; j4 < 4; ++j4) {
               const uint32_t o = swizzle_off<64>((uint32_t)row * 64 + j4 * 16);
               st_shared_v4(xs_a + o, hw[4 * j4], hw[4 * j4 + 1], hw[4 * j4 + 2], hw[4 * j4 + 3]);
-              st_shared_v4(xs_a + FU_XS_ARRAY + o, lw[4 * j4], lw[4 * j4 + 1], lw[4 * j4 + 2], lw[4 * j4 + 3]);
+              if (SPLIT) st_shared_v4(xs_a + FU_XS_ARRAY + o, lw[4 * j4], lw[4 * j4 + 1], lw[4 * j4 + 2], lw[4 * j4 + 3]);
             }
             fence_proxy_async_smem();
             half_sync();
             if (storer) {
               // rows outside the utterance (and a tile past the end) are clipped by the tensor map
               tma_store_3d(yo_hi, xs_mine, n0, t0, b);
-              tma_store_3d(yo_lo, xs_mine + FU_XS_ARRAY, n0, t0, b);
+              if (SPLIT) tma_store_3d(yo_lo, xs_mine + FU_XS_ARRAY, n0, t0, b);
               tma_store_commit();
               tma_store_wait_read();               // the staging entry may be refilled
               mbar_arrive(&xs_empty[half]);
@@ -798,12 +803,12 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
   if (warp == 1) tmem_dealloc_cg2(tmem_base, 512);
 }
 
-template <int BK, bool FLOW, bool PROF>
+template <int BK, int NS, bool FLOW, bool PROF>
 int launch_fused(const FusedMaps& maps, const FusedParams& p, cudaStream_t st) {
   static bool attr_set_on[FAC_MAX_DEVICES] = {};
   bool& attr_set = attr_set_on[current_device_slot()];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wn_flow_fused_kernel<BK, FLOW, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(wn_flow_fused_kernel<BK, NS, FLOW, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, FU_SMEM);
     if (e != cudaSuccess) {
       set_error("wn_flow_fused: cannot reserve %d bytes of shared memory: %s", FU_SMEM, cudaGetErrorString(e));
       return 2;
@@ -821,7 +826,7 @@ int launch_fused(const FusedMaps& maps, const FusedParams& p, cudaStream_t st) {
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = FLOW ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wn_flow_fused_kernel<BK, FLOW, PROF>, maps, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wn_flow_fused_kernel<BK, NS, FLOW, PROF>, maps, p);
   count_launch();
   if (e != cudaSuccess) {
     set_error("wn_flow_fused_kernel: launch failed: %s", cudaGetErrorString(e));
@@ -879,16 +884,21 @@ bool wn_fused_weights_ok(const fac_wg_model* m, const fac_wg_tc_flow& wf) {
 // coupling + invertible 1x1 (after), as ONE launch.  The residual stream of layer l is read from ws->x when l is
 // even and from ws->x2 when l is odd, and written to the other pair; start writes ws->x.
 int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, const fac_wg_tc_workspace* ws,
-                  float* audio, int B, int T, int layer_first, int layer_count, int do_start, int do_end, int bk,
-                  int prefetch_steps, int l2_hints, long long* prof, cudaStream_t st) {
+                  float* audio, int B, int T, int nsplit, int layer_first, int layer_count, int do_start, int do_end,
+                  int bk, int prefetch_steps, int l2_hints, long long* prof, cudaStream_t st) {
   const fac_wg_flow& f = m->flows[flow];
   const fac_wg_tc_flow& wf = w->flows[flow];
   const int C = m->n_channels, n_cond = m->n_mel * m->n_group, taps = m->kernel_size, L = m->n_layers;
   FAC_REQUIRE(wn_fused_supported(C, n_cond, bk), "wn_flow_fused: unsupported geometry C=%d n_cond=%d bk=%d", C, n_cond, bk);
+  FAC_REQUIRE(nsplit == 1 || nsplit == 2, "wn_flow_fused: nsplit must be 1 or 2");
   FAC_REQUIRE(wn_fused_weights_ok(m, wf), "wn_flow_fused: the flow's tensor-core weights are not uniformly strided");
   FAC_REQUIRE(layer_first >= 0 && layer_count >= 1 && layer_first + layer_count <= L, "wn_flow_fused: layer range");
-  FAC_REQUIRE(ws->x_hi && ws->x_lo && ws->x2_hi && ws->x2_lo && ws->spect_hi && ws->spect_lo && ws->out8,
-              "wn_flow_fused: workspace incomplete");
+  FAC_REQUIRE(ws->x_hi && ws->x2_hi && ws->spect_hi && ws->out8, "wn_flow_fused: workspace incomplete");
+  FAC_REQUIRE(nsplit == 1 || (ws->x_lo && ws->x2_lo && ws->spect_lo), "wn_flow_fused: lo buffers missing");
+  // plain bf16: the lo maps are never dereferenced; they alias the hi ones
+  const void* x_lo = nsplit == 2 ? ws->x_lo : ws->x_hi;
+  const void* x2_lo = nsplit == 2 ? ws->x2_lo : ws->x2_hi;
+  const void* spect_lo = nsplit == 2 ? ws->spect_lo : ws->spect_hi;
   const bool phases = do_start || (layer_count > 1);
   FAC_REQUIRE(!phases || ws->flow_sync, "wn_flow_fused: a multi-phase launch needs ws->flow_sync");
   FAC_REQUIRE(!(do_start || do_end) || audio, "wn_flow_fused: audio missing");
@@ -896,11 +906,11 @@ int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, c
   const int K1 = taps * C + n_cond;
   const long long stride = L > 1 ? (const char*)wf.w1_hi[1] - (const char*)wf.w1_hi[0] : (long long)2 * C * K1 * 2;
   if (int rc = make_act_map(&maps.xa_hi, ws->x_hi, B, T, C, bk)) return rc;
-  if (int rc = make_act_map(&maps.xa_lo, ws->x_lo, B, T, C, bk)) return rc;
+  if (int rc = make_act_map(&maps.xa_lo, x_lo, B, T, C, bk)) return rc;
   if (int rc = make_act_map(&maps.xb_hi, ws->x2_hi, B, T, C, bk)) return rc;
-  if (int rc = make_act_map(&maps.xb_lo, ws->x2_lo, B, T, C, bk)) return rc;
+  if (int rc = make_act_map(&maps.xb_lo, x2_lo, B, T, C, bk)) return rc;
   if (int rc = make_act_map(&maps.s_hi, ws->spect_hi, B, T, n_cond, bk)) return rc;
-  if (int rc = make_act_map(&maps.s_lo, ws->spect_lo, B, T, n_cond, bk)) return rc;
+  if (int rc = make_act_map(&maps.s_lo, spect_lo, B, T, n_cond, bk)) return rc;
   if (int rc = make_weight_map3(&maps.w1_hi, wf.w1_hi[0], 2 * C, K1, L, stride, bk)) return rc;
   if (int rc = make_weight_map3(&maps.w1_lo, wf.w1_lo[0], 2 * C, K1, L, stride, bk)) return rc;
   if (L > 1) {
@@ -911,9 +921,9 @@ int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, c
     maps.w2_lo = maps.w1_lo;
   }
   if (int rc = make_act_map(&maps.ya_hi, ws->x_hi, B, T, C, FU_XS_COLS)) return rc;
-  if (int rc = make_act_map(&maps.ya_lo, ws->x_lo, B, T, C, FU_XS_COLS)) return rc;
+  if (int rc = make_act_map(&maps.ya_lo, x_lo, B, T, C, FU_XS_COLS)) return rc;
   if (int rc = make_act_map(&maps.yb_hi, ws->x2_hi, B, T, C, FU_XS_COLS)) return rc;
-  if (int rc = make_act_map(&maps.yb_lo, ws->x2_lo, B, T, C, FU_XS_COLS)) return rc;
+  if (int rc = make_act_map(&maps.yb_lo, x2_lo, B, T, C, FU_XS_COLS)) return rc;
   FusedParams p{};
   p.T = T;
   p.B = B;
@@ -945,7 +955,7 @@ int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, c
   p.n_half = f.n_half;
   p.acts_hi = layer_count == 1 ? reinterpret_cast<__nv_bfloat16*>(ws->acts_hi) : nullptr;
   p.acts_lo = layer_count == 1 ? reinterpret_cast<__nv_bfloat16*>(ws->acts_lo) : nullptr;
-  if (p.acts_hi == nullptr || p.acts_lo == nullptr) p.acts_hi = p.acts_lo = nullptr;
+  if (p.acts_hi == nullptr || (nsplit == 2 && p.acts_lo == nullptr)) p.acts_hi = p.acts_lo = nullptr;
   p.grid_bar = reinterpret_cast<unsigned int*>(ws->flow_sync);
   p.prefetch_steps = prefetch_steps < p.k1_steps ? prefetch_steps : p.k1_steps - 1;
   p.l2_hints = l2_hints;
@@ -957,12 +967,16 @@ int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, c
       return 2;
     }
   }
+  if (nsplit == 1) {         // plain bf16 (K = 32 only: 8 ring stages)
+    FAC_REQUIRE(bk == 32 && prof == nullptr, "wn_flow_fused: the bf16 form is compiled for K = 32 without cycle counters");
+    return phases ? launch_fused<32, 1, true, false>(maps, p, st) : launch_fused<32, 1, false, false>(maps, p, st);
+  }
   if (prof != nullptr) {     // the instrumented instantiations (K = 32 only)
     FAC_REQUIRE(bk == 32, "wn_flow_fused: cycle counters are compiled for the K = 32 kernel only");
-    return phases ? launch_fused<32, true, true>(maps, p, st) : launch_fused<32, false, true>(maps, p, st);
+    return phases ? launch_fused<32, 2, true, true>(maps, p, st) : launch_fused<32, 2, false, true>(maps, p, st);
   }
-  if (phases) return bk == 64 ? launch_fused<64, true, false>(maps, p, st) : launch_fused<32, true, false>(maps, p, st);
-  return bk == 64 ? launch_fused<64, false, false>(maps, p, st) : launch_fused<32, false, false>(maps, p, st);
+  if (phases) return bk == 64 ? launch_fused<64, 2, true, false>(maps, p, st) : launch_fused<32, 2, true, false>(maps, p, st);
+  return bk == 64 ? launch_fused<64, 2, false, false>(maps, p, st) : launch_fused<32, 2, false, false>(maps, p, st);
 }
 
 }  // namespace fac

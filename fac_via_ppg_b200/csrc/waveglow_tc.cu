@@ -820,8 +820,8 @@ int wg_check_model(const fac_wg_model* m);
 bool wn_fused_supported(int C, int n_cond, int bk);
 bool wn_fused_weights_ok(const fac_wg_model* m, const fac_wg_tc_flow& wf);
 int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, const fac_wg_tc_workspace* ws,
-                  float* audio, int B, int T, int layer_first, int layer_count, int do_start, int do_end, int bk,
-                  int prefetch_steps, int l2_hints, long long* prof, cudaStream_t st);
+                  float* audio, int B, int T, int nsplit, int layer_first, int layer_count, int do_start, int do_end,
+                  int bk, int prefetch_steps, int l2_hints, long long* prof, cudaStream_t st);
 
 static int tc_check(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac_wg_tc_workspace* ws, int nsplit) {
   if (int rc = wg_check_model(m)) return rc;
@@ -831,7 +831,7 @@ static int tc_check(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac
   FAC_REQUIRE(C % TC_BK_MAX == 0 && n_cond % TC_BK_MAX == 0 && 2 * C <= TC_NMAX && C <= TC_CMAX,
               "tensor-core path: needs n_channels %% 16 == 0 (<= %d) and n_cond %% 16 == 0", TC_CMAX);
   FAC_REQUIRE(m->n_group <= TC_NOUT, "tensor-core path: n_group %d > %d", m->n_group, TC_NOUT);
-  const bool fused_ws = nsplit == 2 && ws->x2_hi && ws->x2_lo;
+  const bool fused_ws = ws->x2_hi && (nsplit == 1 || ws->x2_lo);
   FAC_REQUIRE(ws->spect_hi && ws->x_hi && (ws->acts_hi || fused_ws) && ws->out8, "tensor-core path: workspace incomplete");
   if (nsplit == 2) FAC_REQUIRE(ws->spect_lo && ws->x_lo && (ws->acts_lo || fused_ws), "tensor-core path: lo buffers missing");
   return 0;
@@ -844,8 +844,11 @@ static int tc_fused_bk() { return g_tc_bk ? g_tc_bk : 32; }
 // One fused launch per layer (waveglow_fused.cu) when the workspace carries the second residual-stream pair.
 static bool tc_use_fused(const fac_wg_model* m, const fac_wg_tc_flow& wf, const fac_wg_tc_workspace* ws, int nsplit,
                          int layer) {
-  return g_tc_fused && nsplit == 2 && tc_pick_cg(nsplit) == 2 && ws->x2_hi && ws->x2_lo && wn_fused_weights_ok(m, wf) &&
-         wn_fused_supported(m->n_channels, m->n_mel * m->n_group, tc_fused_bk());
+  // (the fused kernel always works in CTA pairs; a forced cta_group of 1 selects the two-launch form)
+  const bool pairs = g_tc_cta_group == 0 || g_tc_cta_group == 2;
+  const int bk = tc_fused_bk();
+  return g_tc_fused && pairs && ws->x2_hi && (nsplit == 1 ? bk == 32 : ws->x2_lo != nullptr) && wn_fused_weights_ok(m, wf) &&
+         wn_fused_supported(m->n_channels, m->n_mel * m->n_group, bk);
 }
 
 int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights* w, const fac_wg_tc_workspace* ws,
@@ -938,7 +941,7 @@ int wg_tc_layer(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, int
   const bool last = layer == m->n_layers - 1;
   if (tc_use_fused(m, wf, ws, nsplit, layer)) {
     // the residual stream ping-pongs: layer i reads x (i even) / x2 (i odd) and writes the other pair
-    return wn_flow_fused(m, w, flow, ws, nullptr, B, Tg, layer, 1, 0, 0, tc_fused_bk(), g_tc_prefetch & 63, g_tc_l2_hints, g_tc_prof, st);
+    return wn_flow_fused(m, w, flow, ws, nullptr, B, Tg, nsplit, layer, 1, 0, 0, tc_fused_bk(), g_tc_prefetch & 63, g_tc_l2_hints, g_tc_prof, st);
   }
   FAC_REQUIRE(ws->acts_hi && (nsplit == 1 || ws->acts_lo), "wn_layer_tc: the two-launch form needs the acts buffers");
   CUtensorMap maps[6];
@@ -1003,7 +1006,7 @@ int wg_tc_flow_step(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow,
   if (int rc = tc_check(m, w, ws, nsplit)) return rc;
   FAC_REQUIRE(flow >= 0 && flow < m->n_flows && audio, "waveglow_flow_step_tc: bad arguments");
   if (g_tc_fused == 2 && ws->flow_sync && tc_use_fused(m, w->flows[flow], ws, nsplit, 0))
-    return wn_flow_fused(m, w, flow, ws, audio, B, Tg, 0, m->n_layers, 1, 1, tc_fused_bk(), g_tc_prefetch & 63, g_tc_l2_hints, g_tc_prof, st);
+    return wn_flow_fused(m, w, flow, ws, audio, B, Tg, nsplit, 0, m->n_layers, 1, 1, tc_fused_bk(), g_tc_prefetch & 63, g_tc_l2_hints, g_tc_prof, st);
   if (int rc = wg_tc_start(m, flow, audio, ws, B, Tg, nsplit, st)) return rc;
   for (int i = 0; i < m->n_layers; ++i)
     if (int rc = wg_tc_layer(m, w, flow, i, ws, B, Tg, nsplit, st)) return rc;

@@ -212,9 +212,9 @@ class WaveGlow(torch.nn.Module):
             bufs["ws"] = _ext.WgWorkspace(bufs["spect"].data_ptr(), bufs["x"].data_ptr(), bufs["acts"].data_ptr(),
                                           bufs["skip"].data_ptr())
         else:
-            # split mode: a layer is ONE fused launch that ping-pongs the residual stream between x and x2 and
-            # keeps the gated activations on the SM; plain bf16: two launches per layer with acts through HBM
-            fused = nsplit == 2 and self.fused_layers
+            # a layer is ONE fused launch that ping-pongs the residual stream between x and x2 and keeps the gated
+            # activations on the SM (fused_layers = False: two launches per layer with acts through HBM)
+            fused = self.fused_layers
             names = (("spect_hi", n_cond), ("x_hi", Cn)) + ((("x2_hi", Cn),) if fused else (("acts_hi", Cn),))
             for name, c in names:
                 bufs[name] = b16(c)

@@ -35,7 +35,7 @@ def build_model(cfg, precision, **state_kwargs):
 
 
 @pytest.mark.parametrize("cfg_name,cols", [("small", 70), ("small", 300), ("full", 200), ("full", 700)])
-@pytest.mark.parametrize("precision,fused", [("bf16x3", True), ("bf16x3", False), ("bf16", False)])
+@pytest.mark.parametrize("precision,fused", [("bf16x3", True), ("bf16x3", False), ("bf16", True), ("bf16", False)])
 def test_tc_layer_matches_fp32_layer(cfg_name, cols, precision, fused):
     """One WN layer (flow 0; dilation 1 and 2/8, and the last layer, which has no residual output) on the tensor
     cores vs the exact-fp32 kernels on identical inputs: gated activations, residual stream (kept as a bf16

@@ -24,7 +24,7 @@ namesf = ["prod_wait_empty", "mma_wait_tmem0", "mma_wait_full", "mma_wait_acts",
           "epi_wait_full0", "epi_drain", "epi_wait_acts_free", "epi_busy", "epi_wait_full1", "eg_busy", "epi_total"]
 for mode in (sys.argv[1:] or ["fused", "split", "bf16"]):
     m.set_precision("bf16" if mode == "bf16" else "bf16x3")
-    m.fused_layers = mode == "fused"
+    m.fused_layers = mode == "fused"              # (bf16: the two-launch form; its fused form carries no counters)
     if os.environ.get("FAC_TC_FUSED"):
         lib.fac_tc_set_fused(int(os.environ["FAC_TC_FUSED"]))
     packed = m.packed()
