@@ -170,6 +170,7 @@ class WaveGlow(torch.nn.Module):
     # between the layers (fac_waveglow_flow_step_tc).  Measured on B200 it is 1.5 % slower than one launch per
     # layer at 8 x 10 s and 10 % slower for a single short utterance (profiles/README.md), so it is opt-in.
     flow_step_launch = os.environ.get("FAC_TC_FUSED", "1") == "2"
+    fused_bf16 = False        # plain bf16 through the fused kernel too (slower, see _alloc_io)
 
     def set_precision(self, precision):
         if precision in (None, "auto"):
@@ -213,8 +214,10 @@ class WaveGlow(torch.nn.Module):
                                           bufs["skip"].data_ptr())
         else:
             # a layer is ONE fused launch that ping-pongs the residual stream between x and x2 and keeps the gated
-            # activations on the SM (fused_layers = False: two launches per layer with acts through HBM)
-            fused = self.fused_layers
+            # activations on the SM (otherwise: two launches per layer with acts through HBM).  Plain bf16 stays on
+            # the two-launch form by default: with a third of the UMMA time per unit the fused kernel's serialized
+            # register-drain epilogue becomes the bottleneck (measured 52 vs 39 ms per 8 x 10 s step)
+            fused = self.fused_layers and (nsplit == 2 or self.fused_bf16)
             names = (("spect_hi", n_cond), ("x_hi", Cn)) + ((("x2_hi", Cn),) if fused else (("acts_hi", Cn),))
             for name, c in names:
                 bufs[name] = b16(c)
