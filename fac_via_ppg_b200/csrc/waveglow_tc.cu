@@ -520,38 +520,53 @@ __global__ void mel_pad_split_kernel(const float* __restrict__ mel, __nv_bfloat1
 }
 
 // x = start(audio_0) (glow.py:156), written as the bf16 operand copies of the first layer.  A pure streaming
-// kernel (reads 16-32 B, writes 1 KB per column): thread = 8 channels of one column, 16-byte stores.
-__global__ void wn_start_tc_kernel(const float* __restrict__ audio, const float* __restrict__ w,
-                                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ x_hi,
-                                   __nv_bfloat16* __restrict__ x_lo, long long n_cols, int C, int n_group, int off,
-                                   int n_half) {
+// kernel (reads 16-32 B, writes 1 KB per column): thread = 8 channels x WN_START_COLS consecutive columns (the
+// weights stay in registers), 16-byte stores.
+constexpr int WN_START_COLS = 4;
+__global__ void __launch_bounds__(256) wn_start_tc_kernel(const float* __restrict__ audio, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ x_hi,
+                                                          __nv_bfloat16* __restrict__ x_lo, long long n_cols, int C,
+                                                          int n_group, int off, int n_half) {
   const int c8 = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_cols * c8) return;
-  const long long col = idx / c8;
+  const long long col0 = (idx / c8) * WN_START_COLS;
+  if (col0 >= n_cols) return;
   const int c = (int)(idx % c8) * 8;
-  float4 o0 = __ldg(reinterpret_cast<const float4*>(bias + c));
-  float4 o1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
-  for (int j = 0; j < n_half; ++j) {
-    const float a = __ldg(audio + col * n_group + off + j);
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (long long)j * C + c));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (long long)j * C + c + 4));
-    o0.x = fmaf(a, w0.x, o0.x);
-    o0.y = fmaf(a, w0.y, o0.y);
-    o0.z = fmaf(a, w0.z, o0.z);
-    o0.w = fmaf(a, w0.w, o0.w);
-    o1.x = fmaf(a, w1.x, o1.x);
-    o1.y = fmaf(a, w1.y, o1.y);
-    o1.z = fmaf(a, w1.z, o1.z);
-    o1.w = fmaf(a, w1.w, o1.w);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+  float4 w0[4], w1[4];                      // n_half <= 4 (n_group <= 8)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    w0[j] = j < n_half ? __ldg(reinterpret_cast<const float4*>(w + (long long)j * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    w1[j] = j < n_half ? __ldg(reinterpret_cast<const float4*>(w + (long long)j * C + c + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  uint32_t h[4], l[4];
-  split2(o0.x, o0.y, h[0], l[0]);
-  split2(o0.z, o0.w, h[1], l[1]);
-  split2(o1.x, o1.y, h[2], l[2]);
-  split2(o1.z, o1.w, h[3], l[3]);
-  *reinterpret_cast<uint4*>(x_hi + col * C + c) = make_uint4(h[0], h[1], h[2], h[3]);
-  if (x_lo) *reinterpret_cast<uint4*>(x_lo + col * C + c) = make_uint4(l[0], l[1], l[2], l[3]);
+#pragma unroll
+  for (int i = 0; i < WN_START_COLS; ++i) {
+    const long long col = col0 + i;
+    if (col >= n_cols) break;
+    float4 o0 = b0, o1 = b1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < n_half) {
+        const float a = __ldg(audio + col * n_group + off + j);
+        o0.x = fmaf(a, w0[j].x, o0.x);
+        o0.y = fmaf(a, w0[j].y, o0.y);
+        o0.z = fmaf(a, w0[j].z, o0.z);
+        o0.w = fmaf(a, w0[j].w, o0.w);
+        o1.x = fmaf(a, w1[j].x, o1.x);
+        o1.y = fmaf(a, w1[j].y, o1.y);
+        o1.z = fmaf(a, w1[j].z, o1.z);
+        o1.w = fmaf(a, w1[j].w, o1.w);
+      }
+    }
+    uint32_t h[4], l[4];
+    split2(o0.x, o0.y, h[0], l[0]);
+    split2(o0.z, o0.w, h[1], l[1]);
+    split2(o1.x, o1.y, h[2], l[2]);
+    split2(o1.z, o1.w, h[3], l[3]);
+    *reinterpret_cast<uint4*>(x_hi + col * C + c) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (x_lo) *reinterpret_cast<uint4*>(x_lo + col * C + c) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
 }
 
 // out = out8 + bias8 is end(skip sum) (glow.py:175); b, s = halves (glow.py:278-279);
@@ -909,7 +924,8 @@ int wg_tc_start(const fac_wg_model* m, int flow, const float* audio, const fac_w
   FAC_REQUIRE(flow >= 0 && flow < m->n_flows && ws && ws->x_hi, "wn_start_tc: bad arguments");
   const fac_wg_flow& f = m->flows[flow];
   const long long n_cols = (long long)B * Tg;
-  const long long total = n_cols * (m->n_channels / 8);
+  FAC_REQUIRE(f.n_half <= 4, "wn_start_tc: n_half %d > 4", f.n_half);
+  const long long total = ((n_cols + WN_START_COLS - 1) / WN_START_COLS) * (m->n_channels / 8);
   wn_start_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
       audio, f.start_w, f.start_b, reinterpret_cast<__nv_bfloat16*>(ws->x_hi),
       nsplit == 2 ? reinterpret_cast<__nv_bfloat16*>(ws->x_lo) : nullptr, n_cols, m->n_channels, m->n_group,
