@@ -84,7 +84,7 @@ class TacoDecoderWeights(C.Structure):
 
 class TacoDecoderState(C.Structure):
     _fields_ = [(n, _fp) for n in ("h_att", "c_att", "h_dec", "c_dec", "ctx", "pre", "p1", "h_tag", "w_prev", "w_cum",
-                                   "done", "out_len")]
+                                   "done", "out_len", "align_win", "align_start")]
 
 
 # name -> (restype, argtypes); every symbol include/fac_b200.h declares.

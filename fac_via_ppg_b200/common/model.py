@@ -149,7 +149,10 @@ class Tacotron2(nn.Module):
     precision = "fp16x3"         # encoder / postnet GEMMs: 'fp16x3' = split-fp16 (IEEE half hi + lo) on the tcgen05 tensor cores
                                  # (fp32-grade, 3 UMMAs per product) | 'fp32' = exact FFMA implicit GEMM
     collect_timing = False       # True: CUDA-event times of encoder / decoder / postnet in .last_timing (ms)
-    return_alignments = True     # dense (B, T_out, T_in) like the reference; False saves memory on long inputs
+    # True: dense (B, T_out, T_in) like the reference; False: None (saves 273 MB per 60 s utterance); 'window': the
+    # sparse form -- a pair (weights (B, T_out, 2w+1), start (B, T_out)): step t attends input positions
+    # start[b, t] + [0, 2w], the only ones the attention window leaves unmasked (reference utils.py:46-78)
+    return_alignments = True
     ppg_prune = None             # (k, threshold): prune dense inputs on the GPU and use the gather prenet (see above)
 
     def __init__(self, hparams):
@@ -287,11 +290,18 @@ class Tacotron2(nn.Module):
                                     None if lens is None else lens[i:i + group].contiguous())
                  for i in range(0, B, group)]
         mel, gate, align, out_len, done = zip(*parts)
-        out = [torch.cat(mel), torch.cat(gate), torch.cat(align) if align[0] is not None else None, torch.cat(out_len)]
+        if align[0] is None:
+            align_all = None
+        elif isinstance(align[0], tuple):
+            align_all = (torch.cat([a[0] for a in align]), torch.cat([a[1] for a in align]))
+        else:
+            align_all = torch.cat(align)
+        out = [torch.cat(mel), torch.cat(gate), align_all, torch.cat(out_len)]
         if order is not None:
             inv = torch.empty_like(order)
             inv[order] = torch.arange(B, device=order.device)
-            out = [None if t is None else t[inv] for t in out]
+            pick = lambda t: None if t is None else (tuple(x[inv] for x in t) if isinstance(t, tuple) else t[inv])  # noqa: E731
+            out = [pick(t) for t in out]
         return (*out, torch.stack(done).sum(0))
 
     def _decode_group(self, packed, memory, dec_masks, n_steps, lens=None):
@@ -307,16 +317,21 @@ class Tacotron2(nn.Module):
               "w_cum": z(B, T),
               "done": torch.zeros(8, dtype=torch.int32, device=dev),
               "out_len": torch.zeros(B, dtype=torch.int32, device=dev)}
-        cstate = _ext.TacoDecoderState(*[st[n].data_ptr() for n, _ in _ext.TacoDecoderState._fields_])
+        cstate = _ext.TacoDecoderState(*[_ext.ptr(st.get(n)) for n, _ in _ext.TacoDecoderState._fields_])
         lengths = lens if lens is not None else torch.full((B,), T, dtype=torch.int32, device=dev)   # model.py:599
         mel = z(B, n_steps, M)
         gate = z(B, n_steps)
-        align = z(B, n_steps, T) if self.return_alignments else None
+        align = z(B, n_steps, T) if self.return_alignments is True else None
+        if self.return_alignments == "window":
+            st["align_win"] = z(B, n_steps, 2 * hp["attention_window_size"] + 1)
+            st["align_start"] = torch.zeros(B, n_steps, dtype=torch.int32, device=dev)
         rc = _ext.load().fac_taco_decoder_run(
             C.byref(packed.cdecoder), memory.data_ptr(), pmem.data_ptr(), lengths.data_ptr(), dec_masks.data_ptr(),
             C.byref(cstate), mel.data_ptr(), gate.data_ptr(), _ext.ptr(align), B, T, n_steps,
             hp["attention_window_size"], float(self.decoder.gate_threshold), _ext.current_stream())
         _ext.check(rc, "fac_taco_decoder_run")
+        if self.return_alignments == "window":
+            align = (st["align_win"], st["align_start"])
         return mel, gate, align, st["out_len"], st["done"]
 
     def _postnet(self, packed, mel_cl, out_len=None):
@@ -351,7 +366,9 @@ class Tacotron2(nn.Module):
         return inputs.half() if self.fp16_run else inputs            # fp16_optimizer.py:53-63
 
     def parse_output(self, outputs, output_lengths=None):
-        return [o if o is None else o.float() for o in outputs] if self.fp16_run else outputs   # model.py:566-578 (no masking at inference)
+        if not self.fp16_run:
+            return outputs                                          # model.py:566-578 (no masking at inference)
+        return [o.float() if torch.is_tensor(o) else o for o in outputs]
 
     @torch.no_grad()
     def inference(self, inputs, dropout_tape=None, input_lengths=None):
@@ -406,7 +423,9 @@ class Tacotron2(nn.Module):
             keep = (torch.arange(t_out, device=dev)[None, :] < out_len[:, None]).unsqueeze(-1)
             mel_cl = mel_cl * keep
             gate = gate[:, :t_out] * keep[..., 0]
-            if align is not None:
+            if isinstance(align, tuple):
+                align = (align[0][:, :t_out] * keep, align[1][:, :t_out] * keep[..., 0].to(torch.int32))
+            elif align is not None:
                 align = align[:, :t_out] * keep
         self.last_output_lengths = out_lens
         post_cl = self._postnet(packed, mel_cl, out_len.contiguous() if ragged_out else None)
@@ -415,8 +434,11 @@ class Tacotron2(nn.Module):
             torch.cuda.synchronize()
             self.last_timing = {"encoder_ms": ev[0].elapsed_time(ev[1]), "decoder_ms": ev[1].elapsed_time(ev[2]),
                                 "postnet_ms": ev[2].elapsed_time(ev[3]), "decoder_steps": t_out}
-        outputs = [mel_cl.transpose(1, 2), post_cl.transpose(1, 2), gate[:, :t_out].unsqueeze(-1),
-                   align[:, :t_out] if align is not None else None]
+        if isinstance(align, tuple):
+            align_out = (align[0][:, :t_out], align[1][:, :t_out])
+        else:
+            align_out = align[:, :t_out] if align is not None else None
+        outputs = [mel_cl.transpose(1, 2), post_cl.transpose(1, 2), gate[:, :t_out].unsqueeze(-1), align_out]
         return self.parse_output(outputs)
 
     def forward(self, inputs):

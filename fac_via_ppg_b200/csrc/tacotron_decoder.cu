@@ -708,6 +708,7 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
     __syncthreads();
     prof.sub<13>(tp);
     for (int c = tid; c < E; c += DEC_THREADS) p.s.ctx[b * E + c] = sm.x.ctxp[0][c] + sm.x.ctxp[1][c] + sm.x.ctxp[2][c];
+    if (tid == 0 && p.s.align_start) p.s.align_start[(long long)b * p.max_steps + t] = start;
     // new attention_weights (zero outside the window), cumulative weights (model.py:424), alignments
     int ostart = 0, oend = -1;
     if (t > 0) window_bounds(t - 1, p.window, len, ostart, oend);
@@ -718,6 +719,7 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
       wprev[start + tid] = wv;
       wcum[start + tid] += wv;
       if (p.align) p.align[((long long)b * p.max_steps + t) * p.T_in + start + tid] = wv;
+      if (p.s.align_win) p.s.align_win[((long long)b * p.max_steps + t) * (2 * p.window + 1) + tid] = wv;
     }
   };
 

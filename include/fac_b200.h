@@ -334,6 +334,12 @@ typedef struct fac_taco_decoder_state {
   int* done;      /* [8]: #utterances stopped by the gate, #stopped by max_steps, steps run, two grid-barrier
                      counters, 3 spare */
   int* out_len;   /* [B] number of frames of each utterance (0 while running) */
+  /* optional sparse form of the alignments (NULL = off): only the <= 2*window+1 positions of the attention window
+   * carry weight (everything else is masked to -inf by reference utils.py:46-78), so step t of utterance b is
+   * align_win[b][t][0 .. 2*window] (zero-padded) starting at input position align_start[b][t] -- 41 floats per
+   * step instead of T_in (273 MB per 60 s utterance dense) */
+  float* align_win;   /* (B, max_steps, 2*window+1) pre-zeroed */
+  int* align_start;   /* (B, max_steps) */
 } fac_taco_decoder_state;
 
 /* Diagnostic: runs `iters` grid-wide barriers of the decoder kernel's kind on a full cooperative grid;

@@ -388,3 +388,28 @@ def test_pruned_posteriorgram_input_matches_dense_path_and_oracle(model):
         ops.sparsify_ppg(synth.synthetic_ppg(1, 8).to(DEV), k=16, threshold=1e-5)
     with pytest.raises(ValueError):
         model.inference(ops.SparsePPG(host.indices.to(DEV), host.values.to(DEV), 100))
+
+
+def test_windowed_alignments_equal_the_dense_ones(model):
+    """return_alignments = 'window': the sparse form (weights of the 2w+1 window positions + their start index per
+    step) scatters back to exactly the dense (B, T_out, T_in) tensor the reference returns -- everything outside
+    the window is masked to -inf by reference utils.py:46-78, i.e. has weight exactly 0."""
+    B, t_in, n_steps = 3, 70, 55
+    force_length(model, n_steps)
+    ppg = synth.synthetic_ppg(B, t_in, seed=31).to(DEV)
+    torch.manual_seed(31)
+    masks = tacotron_oracle.record_dropout_tape(B, t_in, n_steps)
+    dense = model.inference(ppg, dropout_tape=masks, input_lengths=[70, 64, 30])
+    model.return_alignments = "window"
+    try:
+        out = model.inference(ppg, dropout_tape=masks, input_lengths=[70, 64, 30])
+    finally:
+        model.return_alignments = True
+    win, start = out[3]
+    assert win.shape == (B, n_steps, 41) and start.shape == (B, n_steps) and start.dtype == torch.int32
+    assert torch.equal(out[1], dense[1])
+    rebuilt = torch.zeros_like(dense[3])
+    pos = (start.long().unsqueeze(-1) + torch.arange(41, device=DEV)).clamp_(max=t_in - 1)
+    rebuilt.scatter_add_(2, pos, win)
+    assert torch.equal(rebuilt, dense[3])
+    assert float(win.sum(-1).min()) > 0.999            # a softmax over the window
