@@ -317,7 +317,6 @@ class Tacotron2(nn.Module):
               "w_cum": z(B, T),
               "done": torch.zeros(8, dtype=torch.int32, device=dev),
               "out_len": torch.zeros(B, dtype=torch.int32, device=dev)}
-        cstate = _ext.TacoDecoderState(*[_ext.ptr(st.get(n)) for n, _ in _ext.TacoDecoderState._fields_])
         lengths = lens if lens is not None else torch.full((B,), T, dtype=torch.int32, device=dev)   # model.py:599
         mel = z(B, n_steps, M)
         gate = z(B, n_steps)
@@ -325,6 +324,7 @@ class Tacotron2(nn.Module):
         if self.return_alignments == "window":
             st["align_win"] = z(B, n_steps, 2 * hp["attention_window_size"] + 1)
             st["align_start"] = torch.zeros(B, n_steps, dtype=torch.int32, device=dev)
+        cstate = _ext.TacoDecoderState(*[_ext.ptr(st.get(n)) for n, _ in _ext.TacoDecoderState._fields_])
         rc = _ext.load().fac_taco_decoder_run(
             C.byref(packed.cdecoder), memory.data_ptr(), pmem.data_ptr(), lengths.data_ptr(), dec_masks.data_ptr(),
             C.byref(cstate), mel.data_ptr(), gate.data_ptr(), _ext.ptr(align), B, T, n_steps,
