@@ -83,8 +83,11 @@ class TacoDecoderWeights(C.Structure):
 
 
 class TacoDecoderState(C.Structure):
-    _fields_ = [(n, _fp) for n in ("h_att", "c_att", "h_dec", "c_dec", "ctx", "pre", "p1", "h_tag", "w_prev", "w_cum",
-                                   "done", "out_len", "align_win", "align_start")]
+    _fields_ = [(n, _fp) for n in ("c_att", "c_dec", "xchg", "w_prev", "w_cum", "done", "out_len", "align_win",
+                                   "align_start")]
+
+
+TACO_XCHG_WORDS, TACO_XCHG_HINTS = 1800, 64        # include/fac_b200.h FAC_TACO_XCHG_*
 
 
 # name -> (restype, argtypes); every symbol include/fac_b200.h declares.

@@ -312,9 +312,10 @@ class Tacotron2(nn.Module):
         pmem = ops.conv_gemm([ops.conv_src(memory)], packed.view("dec.mem_w"), None, A,
                              torch.empty(B, T, A, device=dev), batch=B, rows=T)
         z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)  # noqa: E731
-        st = {"h_att": z(2, B, R), "c_att": z(B, R), "h_dec": z(2, B, R), "c_dec": z(B, R), "ctx": z(B, E),
-              "pre": z(B, hp["prenet_dim"]), "p1": z(B, hp["prenet_dim"]), "h_tag": z(B, R, 2), "w_prev": z(B, T),
-              "w_cum": z(B, T),
+        st = {"c_att": z(B, R), "c_dec": z(B, R),
+              # every vector that crosses CTAs, as (value, version) 8-byte words, two copies (include/fac_b200.h)
+              "xchg": torch.zeros(2 * _ext.TACO_XCHG_WORDS * B + _ext.TACO_XCHG_HINTS, dtype=torch.int64, device=dev),
+              "w_prev": z(B, T), "w_cum": z(B, T),
               "done": torch.zeros(8, dtype=torch.int32, device=dev),
               "out_len": torch.zeros(B, dtype=torch.int32, device=dev)}
         lengths = lens if lens is not None else torch.full((B,), T, dtype=torch.int32, device=dev)   # model.py:599
@@ -415,7 +416,11 @@ class Tacotron2(nn.Module):
             ev[2].record()
         out_lens = out_len.cpu()                                      # the one device->host sync of the call
         t_out = int(out_lens.max())
-        if int(done.cpu()[1]) > 0:
+        done_host = done.cpu()
+        if int(done_host[7]) > 0:
+            raise _ext.FacError("fac_taco_decoder_run: a hand-over between the decoder's CTAs timed out (the GPU is "
+                                "shared with another kernel, or the state buffers were not zero-filled)")
+        if int(done_host[1]) > 0:
             print("Warning! Reached max decoder steps", file=sys.stderr)   # model.py:526-528 (stderr: keeps stdout machine-readable)
         mel_cl = mel_cl[:, :t_out].contiguous()
         ragged_out = B > 1 and int(out_lens.min()) < t_out

@@ -9,22 +9,33 @@
 //     their shared memory for the whole sequence: the two LSTMCells (11.5 MB fp32),
 //     [mel projection | stop gate | prenet layer 0 composed with the projection] and prenet layer 1.
 //     prenet0 has no bias or nonlinearity between it and the projection (model.py:132-135, 436-438),
-//     so W_pre0 (W_proj hc + b) is evaluated as one composed matrix.  A step is four batched mat-vec
-//     phases: attention LSTM | decoder LSTM | projection+gate+prenet0 | prenet1.
+//     so W_pre0 (W_proj hc + b) is evaluated as one composed matrix.  A step is four batched mat-vecs:
+//     attention LSTM | decoder LSTM | projection+gate+prenet0 | prenet1.
 //   * ATTENTION CTAs (one per utterance) own the location-sensitive attention of their utterance.
 //     The query matrix W_q (180 KB) is resident in their shared memory, and everything that does not
 //     depend on this step's attention-LSTM output -- location conv of the previous/cumulative weights,
 //     location_dense, processed_memory, the encoder rows of the window (held in registers) -- is
-//     prepared while the matrix CTAs run the other three phases.  On the critical path remain
+//     prepared while the matrix CTAs run the other three mat-vecs.  On the critical path remain
 //     W_q h, 41 x 150 tanh, a 41-way softmax and the 41 x 600 context sum.  Only the <= 2w+1 window
 //     positions are evaluated: everything outside [t-w, t+w] is masked to -inf by utils.py:46-78,
 //     i.e. has softmax weight exactly 0.
-//   * phases hand over through lightweight grid barriers (one release-add + acquire spin); the two
-//     barriers between matrix-only phases do not involve the attention CTAs.
-//   * the stop decision (sigmoid(gate) > threshold) is taken on the device.
+//   * DATAFLOW, no grid barrier (profiles/r2_grid_handover_bench.txt: a barrier costs 2.5 k cycles before
+//     a byte moves, 3.8 k with the payload of a phase; a tagged word is seen after ~490): every vector that
+//     crosses CTAs (prenet output, attention hidden, context, decoder hidden, prenet layer-0 output) lives in
+//     global memory as (value, version) 8-byte words, double-buffered by version parity.  A consumer polls
+//     the words it needs until they carry the version it expects -- data and flag arrive in ONE store, no
+//     fence, no atomic.  Every mat-vec needs the FULL input vector, so the data dependencies themselves
+//     keep the CTAs within one step of each other (which is what makes two buffers enough).
+//   * SPLIT mat-vecs: the K range of a matrix is cut at the vector boundaries (segments padded to whole
+//     k16 steps).  The products with vectors that are complete EARLY (the hidden states and the previous
+//     context) are accumulated while the CTA would otherwise wait for a hand-over; after the awaited vector
+//     arrives only its own segment is left: 304 of 1216 columns for the attention LSTM, 608 for the decoder
+//     LSTM, 304 of 912 for the projection.
+//   * the stop decision (sigmoid(gate) > threshold) is taken on the device and travels as a tagged word too.
 #include "fac_common.cuh"
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace fac {
 
@@ -40,7 +51,8 @@ struct DecParams {
   float* align;  // (B, max_steps, T_in) pre-zeroed, or NULL
   int B, T_in, max_steps, window;
   float gate_threshold;
-  long long* prof;            // optional [grid][16] cycle counters: phase body / barrier wait x 5, total
+  long long* prof;            // optional [grid][32] cycle counters (tools/decoder_cycle_breakdown.py)
+  int flags;                  // tuning (FAC_TACO_FLAGS): bit 0..3 = wait on the arrival counter before sweeping pre / ctx / hdec / p1
 };
 
 namespace {
@@ -57,32 +69,66 @@ constexpr int KIN = R + E + R;  // 1200: LSTMCell input | hidden concatenation
 constexpr int KHC = R + E;      // 900: [h_dec | context]
 constexpr int NPP = M + 1 + R;  // 381 rows: mel projection, gate, composed prenet layer 0
 constexpr int MIN_MATRIX_CTAS = 100;
-constexpr int MAXU = 3;         // hidden units per matrix CTA (>= 100 matrix CTAs)
-constexpr int MAXPP = 4;        // projection rows per matrix CTA
-constexpr int MAXP2 = 3;        // prenet-1 rows per matrix CTA
-constexpr int CHUNK = 8;        // utterances per staging buffer = one mma n-tile
-constexpr int PASS = 2 * CHUNK; // utterances per arithmetic pass (both staging buffers)
+// matrix CTAs are specialised by matrix: N_PP_CTAS hold [projection | gate | prenet 0], N_P2_CTAS prenet layer 1,
+// the rest is split evenly between the two LSTMCells (>= 38 CTAs each: <= 8 hidden units = 32 gate rows per CTA)
+constexpr int N_PP_CTAS = 13, N_P2_CTAS = 11;
+constexpr int MAXROWS = 32;     // resident rows per matrix CTA = two mma m-tiles
+constexpr int PASS = 8;         // utterances per arithmetic pass = one mma n-tile
+constexpr int MAXPASS = 6;      // B <= 48
 constexpr int MAXW = 48;        // max window positions (2*window+1 <= 48)
-constexpr int KS_LSTM = KIN + 8;        // halfs per resident LSTM weight row (+8: ldmatrix rows hit distinct banks)
-constexpr int KP_PP = 912, KS_PP = KP_PP + 8;   // projection K padded to whole k16 steps
-constexpr int KP_P2 = 304, KS_P2 = KP_P2 + 8;   // prenet-1 K padded
-constexpr int XS = KIN + 8;             // floats per staged input row
+// K segments: every vector padded to whole k16 steps, so that a mat-vec can be cut at the vector boundaries
+constexpr int SEG = 304, SEGC = 608;              // a 300-vector / the 600-float context
+constexpr int ST_SEG = SEG / 16, ST_SEGC = SEGC / 16;
+constexpr int KP_LSTM = SEG + SEGC + SEG, KS_LSTM = KP_LSTM + 8;  // halfs per resident LSTM weight row (+8: ldmatrix rows hit distinct banks)
+constexpr int KP_PP = SEG + SEGC, KS_PP = KP_PP + 8;             // projection: [h_dec | context]
+constexpr int KP_P2 = SEG, KS_P2 = KP_P2 + 8;                    // prenet layer 1
+// staging slots (columns of MatSmem::xs): two 300-vectors and the context
+constexpr int X0 = 0, X1 = SEG, XC = 2 * SEG, XSTRIDE = 2 * SEG + SEGC + 8;
 constexpr float W_SCALE = 256.f;        // resident weights are stored times 2^8 so that their fp16 lo parts stay normal
 constexpr int CTXP = 3;         // q-range split of the context sum
 constexpr int QPP = MAXW / CTXP;  // window positions per part
 
+// Exchange area (fac_taco_decoder_state::xchg): (value, version) words, two copies by version parity.  Version v
+// of a vector is what step v consumes as the state BEFORE the step: pre_v, hatt_v, ctx_v, hdec_v feed step v;
+// step v produces hatt_{v+1}, ctx_{v+1}, hdec_{v+1}, p1_{v+1}, pre_{v+1}.  Version 0 is the zero fill of the host
+// (model.py:304-335 initialises every state to zero; prenet(0) = 0 because the prenet has no bias).
+enum Vec { V_PRE = 0, V_HATT = 1, V_HDEC = 2, V_P1 = 3, V_CTX = 4 };
+constexpr int XCHG_WORDS = 4 * R + E;   // per utterance and parity
+__device__ __forceinline__ unsigned long long* xchg_vec(unsigned long long* base, int B, int kind, unsigned int version) {
+  return base + ((size_t)(version & 1u) * XCHG_WORDS + (size_t)kind * R) * B;
+}
+__device__ __forceinline__ unsigned long long tagged(float v, unsigned int version) {
+  return ((unsigned long long)version << 32) | __float_as_uint(v);
+}
+// Behind the two copies: one arrival counter per vector kind, 32 bytes apart.  A producer CTA adds 1 after its
+// stores (relaxed, NO fence: the words carry their own version); a waiting CTA polls that one counter with one
+// thread instead of sweeping the payload with 512 -- measured: 140 CTAs polling the payload itself congest the
+// L2 slices of those lines and delay the very stores they wait for (5 k cycles per hand-over instead of 1 k).
+// The counter is only a hint; what a consumer accepts is decided by the version in each word.
+constexpr int XCHG_HINTS = 64;          // 8-byte words reserved for the counters (FAC_TACO_XCHG_HINTS)
+static_assert(XCHG_HINTS * 8 >= 5 * 32 && XCHG_HINTS == FAC_TACO_XCHG_HINTS && XCHG_WORDS == FAC_TACO_XCHG_WORDS, "exchange area");
+__device__ __forceinline__ unsigned int* xchg_hint(unsigned long long* base, int B, int kind) {
+  return reinterpret_cast<unsigned int*>(base + (size_t)2 * XCHG_WORDS * B) + kind * 8;
+}
+__device__ __forceinline__ void hint_arrive(unsigned int* counter) {
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+constexpr int SPIN_LIMIT = 1 << 17;     // polls before a hand-over is declared dead (>= 30 ms; a step takes ~10 us)
+constexpr int DONE_ABORT = 7;           // done[7] != 0: a hand-over timed out, every CTA leaves the loop
+
+constexpr int PROF_SLOTS = 32;
+constexpr int MAT_WARPS = 8;      // warps that multiply (the others wait at the barrier)
 struct MatSmem {                  // matrix CTAs
-  // resident weights as IEEE-half hi/lo pairs (w * 2^8 = hi + lo to ~2^-22): the operands of mma.sync
-  __half w_att[2][MAXU * 4][KS_LSTM];
-  __half w_dec[2][MAXU * 4][KS_LSTM];
-  __half w_pp[2][MAXPP][KS_PP];
-  __half w_p2[2][MAXP2][KS_P2];
-  float b_att[MAXU * 4], b_dec[MAXU * 4], b_pp[MAXPP];
-  alignas(16) float part[DEC_WARPS][16][PASS];   // per-warp partial 16 x 16 tiles (K split over the warps)
-  float sums[16][PASS];
-  int n_done;
-  unsigned int prof[16];
-  alignas(16) float in[2][CHUNK][XS];   // staged input vectors of a chunk of utterances, double-buffered
+  // resident rows of this CTA's matrix as IEEE-half hi/lo pairs (w * 2^8 = hi + lo to ~2^-22): the operands of
+  // mma.sync; the row stride is the matrix's own (KS_LSTM / KS_PP / KS_P2)
+  __half w[2][MAXROWS * KS_LSTM];
+  float bias[MAXROWS];
+  alignas(16) float part[MAT_WARPS][MAXROWS][PASS];   // per-warp partial 32 x 8 tiles (K split over the warps)
+  float sums[MAXROWS][PASS];
+  int n_done, done_count, ok, prof_on;
+  unsigned int prof[PROF_SLOTS];
+  alignas(16) float xs[PASS][XSTRIDE];  // staged input vectors of a pass of utterances: slots X0 | X1 | XC
 };
 struct AttSmem {                  // attention CTAs
   float wq[A][R];                 // query_layer weight, resident
@@ -93,8 +139,8 @@ struct AttSmem {                  // attention CTAs
   float e[MAXW];
   float wts[DEC_WARPS][MAXW];     // softmax weights, one copy per warp
   float cat[2][MAXW + KF - 1 + 2];
-  int n_done;
-  unsigned int prof[16];
+  int n_done, ok;
+  unsigned int prof[PROF_SLOTS];
   alignas(16) union {
     float loc[MAXW][NF];          // preparation
     float ctxp[CTXP][E];          // critical path
@@ -108,37 +154,6 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Barrier over `n` CTAs: monotonically increasing arrival counter (zeroed by the host).  The arrival is a
-// release (every write of this CTA that bar.sync ordered before it is visible to whoever acquires the
-// final count), the spin an acquire.  (Measured: several staggered pollers per CTA are slower, not faster.)
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target, unsigned int n) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    target += n;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-    unsigned int seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-    } while (seen < target);
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-struct Seg {           // one piece of a concatenated input vector: utterance b reads ptr[b*stride + k]
-  const float* ptr;
-  int len, stride;     // multiples of 4 floats
-};
-
-// Staging = asynchronous copies (L2 -> shared memory, bypassing L1: the vectors were written by other CTAs in
-// an earlier phase) of the concatenated input vectors; `mask` selects the segments (bit s = segment s).
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -172,14 +187,14 @@ __device__ __forceinline__ void put_weight(__half* hi, __half* lo, float w) {
 }
 
 struct Prof {                 // thread 0's cycles between consecutive marks, per slot (accumulators in shared memory)
-  unsigned int* acc;          // [16]: slots 0..9, total, 11..13 = fetch wait / arithmetic / epilogue of the mat-vec phases
+  unsigned int* acc;          // [16]: see tools/decoder_cycle_breakdown.py; [10] = total of all marks
   long long prev;
   bool on;
   __device__ __forceinline__ void init(bool enabled, unsigned int* smem_acc) {
     on = enabled && threadIdx.x == 0;
     acc = smem_acc;
     if (on) {
-      for (int i = 0; i < 16; ++i) acc[i] = 0;
+      for (int i = 0; i < PROF_SLOTS; ++i) acc[i] = 0;
       prev = clock64();
     }
   }
@@ -188,7 +203,7 @@ struct Prof {                 // thread 0's cycles between consecutive marks, pe
     if (on) {
       const long long now = clock64();
       acc[SLOT] += (unsigned int)(now - prev);
-      if (SLOT < 10) acc[10] += (unsigned int)(now - prev);
+      acc[10] += (unsigned int)(now - prev);
       prev = now;
     }
   }
@@ -204,157 +219,190 @@ struct Prof {                 // thread 0's cycles between consecutive marks, pe
   __device__ __forceinline__ long long now() const { return on ? clock64() : 0; }
   __device__ __forceinline__ void flush(long long* out) {
     if (on)
-      for (int i = 0; i < 16; ++i) out[blockIdx.x * 16 + i] = acc[i];
+      for (int i = 0; i < PROF_SLOTS; ++i) out[blockIdx.x * PROF_SLOTS + i] = acc[i];
   }
 };
 
-// One batched mat-vec phase over a matrix CTA's resident rows (<= 16: the 4 gate rows of its LSTM units, or its
-// projection / prenet rows) on the tensor cores.  The B utterances go in passes of 16 (two mma n-tiles = the two
-// staging buffers); the fp32 input vectors of the next pass are copied into shared memory asynchronously behind
-// the reduction and the epilogue of the current one.
-// The K range is split over the 16 warps in whole k16 steps (a fixed split: the summation order of an output
-// never depends on B); per step a warp loads the hi and lo weight fragments with ldmatrix, splits its slice
-// of the inputs into half hi/lo pairs in registers and issues the three products hi*hi + lo*hi + hi*lo
-// (fp32-grade: ~2^-21 relative).  The 16 partial 16 x 8 tiles meet in shared memory in fp32.
-//   pre(n0, nb): called right after the copies are in flight (global loads the epilogue wants early)
-//   epi(n0, nb): reads sm.sums[row][utterance] (scaled by W_SCALE)
-//   early: segments of the first chunk that matvec_prefetch() already requested BEFORE the grid barrier
-//          (vectors that were complete one barrier earlier), so that only the fresh segment is fetched after it
-template <int NSEG>
-__device__ __forceinline__ void stage_pass(MatSmem& sm, const Seg (&segs)[NSEG], int n0, int B, unsigned int mask) {
-  // utterances [n0, n0 + 16) -> staging buffers 0 and 1, one cp.async group
-  int base = 0;
-  const int nb = min(PASS, B - n0);
-#pragma unroll
-  for (int s = 0; s < NSEG; ++s) {
-    if (mask >> s & 1) {
-      const int l4 = segs[s].len >> 2;
-      for (int i = threadIdx.x; i < nb * l4; i += DEC_THREADS) {
-        const int n = i / l4, k4 = i - n * l4;
-        cp_async16(&sm.in[n >> 3][n & 7][base + 4 * k4], segs[s].ptr + (long long)(n0 + n) * segs[s].stride + 4 * k4);
-      }
-    }
-    base += segs[s].len;
-  }
-  cp_async_commit();
+// ---- hand-over primitives
+__device__ __forceinline__ void ld_tagged2(const unsigned long long* src, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
 }
-template <int NSEG>
-__device__ __forceinline__ void matvec_prefetch(MatSmem& sm, const Seg (&segs)[NSEG], int B, unsigned int early) {
-  stage_pass(sm, segs, 0, B, early);
+__device__ __forceinline__ unsigned long long ld_tagged(const unsigned long long* src) {
+  unsigned long long a;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(a) : "l"(src) : "memory");
+  return a;
 }
-template <int NSEG, typename PreFn, typename EpiFn>
-__device__ __forceinline__ void matvec_phase(MatSmem& sm, Prof& prof, const Seg (&segs)[NSEG], unsigned int early,
-                                             const __half* w_hi, const __half* w_lo, int ks, int n_rows, int k_steps,
-                                             int B, PreFn pre, EpiFn epi) {
-  long long tp = prof.now();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int base = k_steps / DEC_WARPS, extra = k_steps % DEC_WARPS;
-  const int my_steps = base + (warp < extra ? 1 : 0), my_first = warp * base + min(warp, extra);
-  // ldmatrix: lane l addresses row (l & 7) + 8 * ((l >> 3) & 1) of the 8 x 8 block at k offset 8 * (l >> 4)
-  int arow = (lane & 7) + ((lane >> 3) & 1) * 8;
-  if (arow >= n_rows) arow = 0;                       // rows past the end: any valid row, results ignored
-  const uint32_t a_off = (uint32_t)(arow * ks + (lane >> 4) * 8 + my_first * 16) * 2;
-  const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(w_hi) + a_off;
-  const uint32_t a_lo = (uint32_t)__cvta_generic_to_shared(w_lo) + a_off;
-  stage_pass(sm, segs, 0, B, ~early);
-  for (int n0 = 0; n0 < B; n0 += PASS) {
-    const int nb = min(PASS, B - n0);
-    pre(n0, nb);
-    cp_async_wait<0>();
-    __syncthreads();
-    prof.sub<11>(tp);
-    {
-      // B fragments: column (utterance) lane >> 2 of each n-tile, k pairs 2 * (lane & 3) and + 8
-      const int xo = my_first * 16 + 2 * (lane & 3);
-      const float* xrow0 = &sm.in[0][min(lane >> 2, nb - 1)][xo];
-      const float* xrow1 = &sm.in[1][min(lane >> 2, max(nb - 9, 0))][xo];
-      const bool two = nb > CHUNK;
-      // independent accumulation chains (hi*hi, lo*hi, hi*lo per n-tile), added in a fixed order at the end
-      float acc[2][3][4];
-#pragma unroll
-      for (int i = 0; i < 24; ++i) (&acc[0][0][0])[i] = 0.f;
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        if (i < my_steps) {
-          uint32_t ah[4], al[4], bh[2], bl[2];
-          ldmatrix_x4(ah, a_hi + i * 32);
-          ldmatrix_x4(al, a_lo + i * 32);
-          split_half2(*reinterpret_cast<const float2*>(xrow0 + i * 16), bh[0], bl[0]);
-          split_half2(*reinterpret_cast<const float2*>(xrow0 + i * 16 + 8), bh[1], bl[1]);
-          mma_f16(acc[0][0], ah, bh);
-          mma_f16(acc[0][1], al, bh);
-          mma_f16(acc[0][2], ah, bl);
-          if (two) {
-            split_half2(*reinterpret_cast<const float2*>(xrow1 + i * 16), bh[0], bl[0]);
-            split_half2(*reinterpret_cast<const float2*>(xrow1 + i * 16 + 8), bh[1], bl[1]);
-            mma_f16(acc[1][0], ah, bh);
-            mma_f16(acc[1][1], al, bh);
-            mma_f16(acc[1][2], ah, bl);
-          }
-        }
-      }
-      // accumulator layout: rows lane >> 2 and + 8, columns 2 * (lane & 3) + {0, 1} of the n-tile
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        if (nt == 0 || two) {
-          float v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = acc[nt][0][j] + (acc[nt][1][j] + acc[nt][2][j]);
-          *reinterpret_cast<float2*>(&sm.part[warp][lane >> 2][nt * 8 + 2 * (lane & 3)]) = make_float2(v[0], v[1]);
-          *reinterpret_cast<float2*>(&sm.part[warp][(lane >> 2) + 8][nt * 8 + 2 * (lane & 3)]) = make_float2(v[2], v[3]);
-        }
-      }
-    }
-    long long tq = tp;
-    prof.sub<14>(tq);
-    __syncthreads();
-    prof.sub<15>(tq);
-    // the staging buffers are free again: fetch the next pass behind the reduction and the epilogue
-    if (n0 + PASS < B) stage_pass(sm, segs, n0 + PASS, B, ~0u);
-    if (tid < 16 * PASS) {
-      const int r = tid >> 4, c = tid & 15;
-      if (c < nb) {
-        float a = 0.f;
-#pragma unroll
-        for (int w = 0; w < DEC_WARPS; ++w) a += sm.part[w][r][c];
-        sm.sums[r][c] = a * (1.0f / W_SCALE);
-      }
-    }
-    __syncthreads();
-    prof.sub<12>(tp);
-    epi(n0, nb);
-    prof.sub<13>(tp);
+__device__ __forceinline__ void st_tagged(unsigned long long* dst, float v, unsigned int version) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(tagged(v, version)) : "memory");
+}
+// a spinning thread gives up when somebody else already did (checked now and then) or after SPIN_LIMIT polls
+__device__ __forceinline__ bool spin_dead(int& spins, int* done) {
+  ++spins;
+  if ((spins & 255) == 0 && *reinterpret_cast<volatile int*>(done + DONE_ABORT) != 0) return true;
+  if (spins > SPIN_LIMIT) {
+    *reinterpret_cast<volatile int*>(done + DONE_ABORT) = 1;
+    return true;
   }
+  return false;
 }
 
-// One LSTMCell (model.py:400-402 / 425-428) for the units [u0, u0+nu) of this CTA and all B utterances.
-__device__ __forceinline__ void lstm_phase(MatSmem& sm, Prof& prof, const __half (*w_s)[MAXU * 4][KS_LSTM],
-                                           const float* bias_s, const Seg (&segs)[3], unsigned int early,
-                                           float* h_next, float* c, int B, int u0, int nu,
-                                           unsigned long long* h_tag = nullptr, unsigned int tag = 0) {
-  const int tid = threadIdx.x;
-  float c_old = 0.f;
-  matvec_phase(
-      sm, prof, segs, early, &w_s[0][0][0], &w_s[1][0][0], KS_LSTM, 4 * nu, KIN / 16, B,
-      [&](int n0, int nb) {
-        if (tid < nu * nb) c_old = c[(n0 + tid / nu) * R + u0 + tid % nu];   // only this thread ever touches it
-      },
-      [&](int n0, int nb) {
-        if (tid < nu * nb) {                        // cell update: one thread per (unit, utterance)
-          const int u = tid % nu, n = tid / nu, j = u0 + u, b = n0 + n;
-          float gv[4];
+// Poll-fetch of version `ver` of a 300- or 600-float vector for the utterances [n0, n0 + nb) into staging slot
+// `slot`.  With `hint` (the arrival counter of the vector) thread 0 first waits until all producers have announced
+// their stores, so that the sweep is normally a single round.  The sweep: 2 .. 16 warps per utterance, a lane owns
+// the 16-byte pieces (two tagged words) lane, lane + 32, ... of its warp's share -- all of them in flight at
+// once, no index arithmetic beyond immediates --, keeps re-reading the ones whose versions do not match yet and
+// drops the values into shared memory.
+// Ends with a CTA barrier; false = the hand-over was declared dead (every thread of the CTA agrees).
+constexpr int FETCH_ROUNDS = 5;       // 300 pieces (the context) of one utterance on two warps
+__device__ __noinline__ bool fetch(MatSmem& sm, const unsigned long long* vec, int len, unsigned int ver, int n0, int nb,
+                                   int slot, const unsigned int* hint, unsigned int hint_target, int* done) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool dead = false;
+  int spins = 0;
+  const bool timed = sm.prof_on && threadIdx.x == 0;
+  long long tq = timed ? clock64() : 0;
+  if (hint != nullptr) {              // wait quietly: one thread, one word
+    if (threadIdx.x == 0) {
+      unsigned int seen;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(hint) : "memory");
+      } while (seen < hint_target && !(dead = spin_dead(spins, done)));
+    }
+    __syncthreads();
+    if (timed) {
+      const long long now = clock64();
+      sm.prof[13] += (unsigned int)(now - tq);
+      tq = now;
+    }
+  }
+  // warps per utterance: 2, 4, 8 or 16
+  const int sh = nb > 4 ? 1 : nb > 2 ? 2 : nb > 1 ? 3 : 4;
+  const int n = warp >> sh, part = warp & ((1 << sh) - 1);
+  const int half = len >> 1, share = (half + (1 << sh) - 1) >> sh;     // pieces per warp
+  const int first = part * share, count = n < nb ? min(share, half - first) : 0;
+  const unsigned long long* src = vec + (size_t)(n0 + n) * len + 2 * (first + lane);
+  float* dst = &sm.xs[n < nb ? n : 0][slot + 2 * (first + lane)];
+  unsigned int need = 0;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) gv[g] = bias_s[g * nu + u] + sm.sums[g * nu + u][n];
-          const float cn = sigmoidf_fast(gv[1]) * c_old + sigmoidf_fast(gv[0]) * tanhf_fast(gv[2]);
-          c[b * R + j] = cn;
-          const float h = sigmoidf_fast(gv[3]) * tanhf_fast(cn);
-          h_next[b * R + j] = h;
-          if (h_tag != nullptr)      // (value, tag) in ONE 8-byte store: whoever reads the tag has the value
-            *reinterpret_cast<volatile unsigned long long*>(h_tag + b * R + j) =
-                ((unsigned long long)tag << 32) | __float_as_uint(h);
-        }
-      });
+  for (int j = 0; j < FETCH_ROUNDS; ++j)
+    if (lane + 32 * j < count) need |= 1u << j;
+  while (need != 0 && !dead) {
+    unsigned long long a[FETCH_ROUNDS], b[FETCH_ROUNDS];
+#pragma unroll
+    for (int j = 0; j < FETCH_ROUNDS; ++j)
+      if (need >> j & 1) ld_tagged2(src + 64 * j, a[j], b[j]);
+#pragma unroll
+    for (int j = 0; j < FETCH_ROUNDS; ++j)
+      if ((need >> j & 1) && (unsigned int)(a[j] >> 32) == ver && (unsigned int)(b[j] >> 32) == ver) {
+        *reinterpret_cast<float2*>(dst + 64 * j) =
+            make_float2(__uint_as_float((unsigned int)a[j]), __uint_as_float((unsigned int)b[j]));
+        need &= ~(1u << j);
+      }
+    if (need != 0) dead = spin_dead(spins, done);
+  }
+  const bool any_dead = __syncthreads_or(dead);
+  if (timed) sm.prof[15] += (unsigned int)(clock64() - tq);
+  return !any_dead;
 }
+
+// One piece of a mat-vec: `steps` k16 steps of the resident rows, weight columns from `koff`, inputs from staging
+// slot column `slot`.
+struct SegDesc {
+  int koff, slot, steps;
+};
+
+// Partial products of a matrix CTA's resident rows (<= 32 = two m-tiles) with the staged vectors of one pass of
+// <= 8 utterances (one n-tile), on the tensor cores.  These pieces are small (19 .. 57 k16 steps) and the CTA's
+// instruction issue and latencies, not the tensor pipe, bound them: at most MAT_WARPS warps take part, the
+// others go straight to the barrier.  The steps of the one or two listed segments are dealt round-robin to
+// those warps (a fixed deal: the summation order of an output never depends on B); per step a warp loads the hi
+// and lo weight fragments with ldmatrix, splits its slice of the inputs into half hi/lo pairs in registers and
+// issues the three products hi*hi + lo*hi + hi*lo per m-tile (fp32-grade: ~2^-21 relative).  The partial tiles
+// meet in shared memory in fp32; returns, in the threads tid < 256 (row tid >> 3, utterance tid & 7), the sum
+// scaled back by 1 / W_SCALE (with `to_sums` also sm.sums[row][utterance] = sum + add).  Two CTA barriers inside.
+__device__ __noinline__ float mat_part(MatSmem& sm, int ks, int n_rows, const SegDesc s0, const SegDesc s1, int nb,
+                                       float add = 0.f, bool to_sums = false) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int total = s0.steps + s1.steps;
+  const int n_warps = min(MAT_WARPS, (total + 2) / 3);
+  const bool m2 = n_rows > 16;
+  if (warp < n_warps) {
+    // ldmatrix: lane l addresses row (l & 7) + 8 * ((l >> 3) & 1) of the 8 x 8 block at k offset 8 * (l >> 4)
+    const int arow = (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int arow0 = arow < n_rows ? arow : 0, arow1 = 16 + arow < n_rows ? 16 + arow : 0;   // past the end: any valid row
+    const uint32_t w_hi = (uint32_t)__cvta_generic_to_shared(&sm.w[0][0]), w_lo = (uint32_t)__cvta_generic_to_shared(&sm.w[1][0]);
+    const uint32_t off0 = (uint32_t)(arow0 * ks + (lane >> 4) * 8) * 2, off1 = (uint32_t)(arow1 * ks + (lane >> 4) * 8) * 2;
+    // B fragments: column (utterance) lane >> 2, k pairs 2 * (lane & 3) and + 8
+    const float* xrow = &sm.xs[min(lane >> 2, nb - 1)][2 * (lane & 3)];
+    // independent accumulation chains (hi*hi, lo*hi, hi*lo per m-tile), added in a fixed order at the end
+    float acc[2][3][4];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) (&acc[0][0][0])[i] = 0.f;
+#pragma unroll 2
+    for (int s = warp; s < total; s += n_warps) {
+      int ls = s, koff = s0.koff, xo = s0.slot;
+      if (ls >= s0.steps) {
+        ls -= s0.steps;
+        koff = s1.koff;
+        xo = s1.slot;
+      }
+      koff = (koff + 16 * ls) * 2;
+      xo += 16 * ls;
+      uint32_t ah[4], al[4], bh[2], bl[2];
+      ldmatrix_x4(ah, w_hi + off0 + koff);
+      ldmatrix_x4(al, w_lo + off0 + koff);
+      split_half2(*reinterpret_cast<const float2*>(xrow + xo), bh[0], bl[0]);
+      split_half2(*reinterpret_cast<const float2*>(xrow + xo + 8), bh[1], bl[1]);
+      mma_f16(acc[0][0], ah, bh);
+      mma_f16(acc[0][1], al, bh);
+      mma_f16(acc[0][2], ah, bl);
+      if (m2) {
+        ldmatrix_x4(ah, w_hi + off1 + koff);
+        ldmatrix_x4(al, w_lo + off1 + koff);
+        mma_f16(acc[1][0], ah, bh);
+        mma_f16(acc[1][1], al, bh);
+        mma_f16(acc[1][2], ah, bl);
+      }
+    }
+    // accumulator layout: rows lane >> 2 and + 8, columns 2 * (lane & 3) + {0, 1}
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      if (mt == 0 || m2) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = acc[mt][0][j] + (acc[mt][1][j] + acc[mt][2][j]);
+        *reinterpret_cast<float2*>(&sm.part[warp][mt * 16 + (lane >> 2)][2 * (lane & 3)]) = make_float2(v[0], v[1]);
+        *reinterpret_cast<float2*>(&sm.part[warp][mt * 16 + (lane >> 2) + 8][2 * (lane & 3)]) = make_float2(v[2], v[3]);
+      }
+    }
+  }
+  __syncthreads();
+  float a = 0.f;
+  if (tid < MAXROWS * PASS && (tid & 7) < nb && (tid >> 3) < n_rows) {
+    const int r = tid >> 3, c = tid & 7;
+    for (int w = 0; w < n_warps; ++w) a += sm.part[w][r][c];
+    a *= 1.0f / W_SCALE;
+    if (to_sums) sm.sums[r][c] = a + add;             // the epilogue's input: early columns + this piece
+  }
+  __syncthreads();                                    // sm.part is free again, sm.sums complete
+  return a;
+}
+
+// per-pass register of the threads that hold a reduced (row, utterance) element
+struct PassReg {
+  float v[MAXPASS];
+  __device__ __forceinline__ float get(int ps) const {
+    return ps == 0 ? v[0] : ps == 1 ? v[1] : ps == 2 ? v[2] : ps == 3 ? v[3] : ps == 4 ? v[4] : v[5];
+  }
+  __device__ __forceinline__ void set(int ps, float x) {
+    if (ps == 0) v[0] = x;
+    else if (ps == 1) v[1] = x;
+    else if (ps == 2) v[2] = x;
+    else if (ps == 3) v[3] = x;
+    else if (ps == 4) v[4] = x;
+    else v[5] = x;
+  }
+};
 
 __device__ __forceinline__ void window_bounds(int t, int window, int len, int& start, int& end) {
   // src/common/utils.py:70-74
@@ -369,152 +417,264 @@ __device__ __forceinline__ void row_range(int idx, int n_ctas, int n_rows, int& 
 }
 
 // ------------------------------------------------------------------------------------------ matrix CTAs
-__device__ void matrix_role(const DecParams& p, MatSmem& sm, int mi, int GM) {
-  const int tid = threadIdx.x;
-  const unsigned int G = gridDim.x;
-  int u0, nu, pp0, npp, p20, np2;
-  row_range(mi, GM, R, u0, nu);
-  row_range(mi, GM, NPP, pp0, npp);
-  row_range(mi, GM, R, p20, np2);
+// Every matrix CTA owns a slice of the rows of ONE matrix for the whole sequence and runs one mat-vec per step:
+//   role A  attention_rnn   (model.py:400-402)  waits for pre_t      publishes hatt_{t+1}
+//   role D  decoder_rnn     (model.py:425-428)  waits for ctx_{t+1}  publishes hdec_{t+1}
+//   role P  [linear_projection | gate_layer | prenet layer 0 o projection] (model.py:436-441, 507, 132-135)
+//                                               waits for hdec_{t+1} publishes mel, gate, stop count, p1_{t+1}
+//   role Q  prenet layer 1  (model.py:132-135)  waits for p1_{t+1}   publishes pre_{t+1}
+// A CTA is idle three quarters of a step, so the columns of its matrix that meet vectors known EARLY (hidden
+// states, the previous context) are multiplied while it waits; on the critical path of a step stay four times
+// [arrival counter | sweep of the awaited vector | its 19 or 38 k16 steps | epilogue] plus the attention.
+// the stop counter of step t (published by the CTA that owns the gate row): false = leave the loop
+__device__ __forceinline__ bool step_continues(const DecParams& p, int* n_done_s, int* ok_s, unsigned int v1, Prof& prof) {
+  if (threadIdx.x == 0) {
+    const unsigned long long* done_word = reinterpret_cast<const unsigned long long*>(p.s.done + 4);
+    int spins = 0;
+    bool dead = false;
+    unsigned long long w;
+    do {
+      w = ld_tagged(done_word);
+    } while ((unsigned int)(w >> 32) != v1 && !(dead = spin_dead(spins, p.s.done)));
+    *n_done_s = (int)(unsigned int)w;
+    *ok_s = !dead;
+  }
+  __syncthreads();
+  prof.mark<12>();
+  const bool go = *ok_s && *n_done_s < p.B;
+  __syncthreads();                   // the two words are rewritten next step
+  return go;
+}
 
-  // ---- resident weights: this CTA's rows of every matrix of the step, as half hi/lo pairs; zero K padding
-  for (int i = tid; i < nu * 4 * KS_LSTM; i += DEC_THREADS) {
-    const int q = i / KS_LSTM, k = i - q * KS_LSTM;
-    const int g = q / nu, u = q - g * nu;
-    const long long src = (long long)(g * R + u0 + u) * KIN + k;
-    put_weight(&sm.w_att[0][q][k], &sm.w_att[1][q][k], k < KIN ? __ldg(p.w.w_att + src) : 0.f);
-    put_weight(&sm.w_dec[0][q][k], &sm.w_dec[1][q][k], k < KIN ? __ldg(p.w.w_dec + src) : 0.f);
+// resident rows: `n_rows` rows of a [rows][k_src] fp32 matrix -> padded-segment half hi/lo pairs
+//   layout 0: [300 -> 304 | 600 -> 608 | 300 -> 304] (LSTMCells, projection: the first two)   1: [300 -> 304]
+template <typename RowFn>
+__device__ __forceinline__ void load_rows(MatSmem& sm, const float* w, int k_src, int ks, int kp, int n_rows, RowFn src_row) {
+  for (int i = threadIdx.x; i < n_rows * ks; i += DEC_THREADS) {
+    const int q = i / ks, k = i - q * ks;
+    int ksrc = -1;
+    if (k < kp) {
+      if (k < SEG) ksrc = k < R ? k : -1;
+      else if (k < SEG + SEGC) ksrc = k - SEG < E ? R + k - SEG : -1;
+      else ksrc = k - SEG - SEGC < R ? R + E + k - SEG - SEGC : -1;
+    }
+    put_weight(&sm.w[0][q * ks + k], &sm.w[1][q * ks + k], ksrc >= 0 ? __ldg(w + (long long)src_row(q) * k_src + ksrc) : 0.f);
   }
-  for (int i = tid; i < nu * 4; i += DEC_THREADS) {
-    const int g = i / nu, u = i - g * nu;
-    sm.b_att[i] = __ldg(p.w.b_att + g * R + u0 + u);
-    sm.b_dec[i] = __ldg(p.w.b_dec + g * R + u0 + u);
+}
+
+__device__ __forceinline__ void mat_common_init(const DecParams& p, MatSmem& sm) {
+  // the K padding of the staged inputs must hold finite values (it meets zero weights); nothing writes it later
+  for (int i = threadIdx.x; i < PASS * XSTRIDE; i += DEC_THREADS) (&sm.xs[0][0])[i] = 0.f;
+  if (threadIdx.x == 0) {
+    sm.done_count = 0;
+    sm.prof_on = p.prof != nullptr;
   }
-  for (int i = tid; i < npp * KS_PP; i += DEC_THREADS) {
-    const int q = i / KS_PP, k = i - q * KS_PP;
-    put_weight(&sm.w_pp[0][q][k], &sm.w_pp[1][q][k], k < KHC ? __ldg(p.w.w_pp + (long long)(pp0 + q) * KHC + k) : 0.f);
-  }
-  for (int i = tid; i < npp; i += DEC_THREADS) sm.b_pp[i] = __ldg(p.w.b_pp + pp0 + i);
-  for (int i = tid; i < np2 * KS_P2; i += DEC_THREADS) {
-    const int q = i / KS_P2, k = i - q * KS_P2;
-    put_weight(&sm.w_p2[0][q][k], &sm.w_p2[1][q][k], k < R ? __ldg(p.w.w_pre2 + (long long)(p20 + q) * R + k) : 0.f);
-  }
-  // the K padding of the staged inputs must hold finite values (it meets zero weights)
-  for (int i = tid; i < 2 * CHUNK * XS; i += DEC_THREADS) (&sm.in[0][0][0])[i] = 0.f;
+}
+
+// roles A and D: one LSTMCell for the units [u0, u0 + nu) of this CTA and all B utterances
+//   A: input [pre_t | ctx_t], hidden hatt_t -> hatt_{t+1};  early columns: ctx_t, hatt_t;   awaited: pre_t
+//   D: input [hatt_{t+1} | ctx_{t+1}], hidden hdec_t -> hdec_{t+1};  early: hatt_{t+1}, hdec_t;  awaited: ctx_{t+1}
+template <bool IS_ATT>
+__device__ void lstm_role(const DecParams& p, MatSmem& sm, int idx, int n_ctas, int n_att_ctas) {
+  const int tid = threadIdx.x, B = p.B;
+  int u0, nu;
+  row_range(idx, n_ctas, R, u0, nu);
+  const int n_rows = 4 * nu;
+  load_rows(sm, IS_ATT ? p.w.w_att : p.w.w_dec, KIN, KS_LSTM, KP_LSTM, n_rows,
+            [&](int q) { return (q / nu) * R + u0 + q % nu; });
+  for (int i = tid; i < n_rows; i += DEC_THREADS) sm.bias[i] = __ldg((IS_ATT ? p.w.b_att : p.w.b_dec) + (i / nu) * R + u0 + i % nu);
+  mat_common_init(p, sm);
   __syncthreads();
 
-  unsigned int* bar_all = reinterpret_cast<unsigned int*>(p.s.done + 3);
-  unsigned int* bar_mat = reinterpret_cast<unsigned int*>(p.s.done + 4);
-  unsigned int target_all = 0, target_mat = 0;
-  int cur = 0;
+  unsigned long long* const xb = p.s.xchg;
+  float* const cell = IS_ATT ? p.s.c_att : p.s.c_dec;
+  const unsigned int n_lstm = (unsigned int)n_ctas, n_att = (unsigned int)n_att_ctas;
+  // K layout of both cells: [first input 304 | context 608 | hidden 304]
+  const SegDesc none = {0, 0, 0}, k_in = {0, X0, ST_SEG}, k_ctx = {SEG, XC, ST_SEGC}, k_hid = {SEG + SEGC, X1, ST_SEG};
+  PassReg early;
+#pragma unroll
+  for (int i = 0; i < MAXPASS; ++i) early.v[i] = 0.f;
+  Prof prof;
+  prof.init(p.prof != nullptr, sm.prof);
+  // early columns of step `t` (role A: called right after the critical part of step t - 1, i.e. speculatively
+  // before the stop count of that step is known -- both vectors exist by then whether or not there is a step t)
+  auto early_columns = [&](int t) -> bool {
+    const unsigned int v0 = (unsigned int)t, v1 = v0 + 1;
+    bool ok = true;
+    for (int ps = 0, n0 = 0; n0 < B && ok; ++ps, n0 += PASS) {
+      const int nb = min(PASS, B - n0);
+      if (IS_ATT) {
+        // ctx_t and hatt_t
+        ok = fetch(sm, xchg_vec(xb, B, V_HATT, v0), R, v0, n0, nb, X1, ps == 0 ? xchg_hint(xb, B, V_HATT) : nullptr, n_lstm * v0, p.s.done) &&
+             fetch(sm, xchg_vec(xb, B, V_CTX, v0), E, v0, n0, nb, XC, ps == 0 ? xchg_hint(xb, B, V_CTX) : nullptr, n_att * v0, p.s.done);
+        if (ok) early.set(ps, mat_part(sm, KS_LSTM, n_rows, k_ctx, k_hid, nb));
+      } else {
+        // hatt_{t+1} (just being published by the role-A CTAs) and hdec_t
+        ok = fetch(sm, xchg_vec(xb, B, V_HDEC, v0), R, v0, n0, nb, X1, nullptr, 0, p.s.done) &&
+             fetch(sm, xchg_vec(xb, B, V_HATT, v1), R, v1, n0, nb, X0, ps == 0 ? xchg_hint(xb, B, V_HATT) : nullptr, n_lstm * v1, p.s.done);
+        if (ok) early.set(ps, mat_part(sm, KS_LSTM, n_rows, k_in, k_hid, nb));
+      }
+    }
+    prof.mark<2>();
+    return ok;
+  };
+  for (int t = 0; t < p.max_steps; ++t) {
+    const unsigned int v0 = (unsigned int)t, v1 = v0 + 1;
+    bool ok = true;
+    if (!IS_ATT && !early_columns(t)) break;      // (role A, step 0: the zero state, nothing to add)
+    // ---- the awaited vector, cell update, publication
+    for (int ps = 0, n0 = 0; n0 < B && ok; ++ps, n0 += PASS) {
+      const int nb = min(PASS, B - n0);
+      float c_old = 0.f;
+      if (tid < nu * nb) c_old = cell[(n0 + tid / nu) * R + u0 + tid % nu];     // only this thread ever touches it
+      if (IS_ATT)
+        ok = fetch(sm, xchg_vec(xb, B, V_PRE, v0), R, v0, n0, nb, X0, ps == 0 && (p.flags & 1) ? xchg_hint(xb, B, V_PRE) : nullptr,
+                   (unsigned int)N_P2_CTAS * v0, p.s.done);
+      else
+        ok = fetch(sm, xchg_vec(xb, B, V_CTX, v1), E, v1, n0, nb, XC, ps == 0 && (p.flags & 2) ? xchg_hint(xb, B, V_CTX) : nullptr, n_att * v1, p.s.done);
+      prof.mark<0>();
+      if (!ok) break;
+      mat_part(sm, KS_LSTM, n_rows, IS_ATT ? k_in : k_ctx, none, nb, early.get(ps), true);
+      if (tid < nu * nb) {                        // cell update: one thread per (unit, utterance)
+        const int u = tid % nu, n = tid / nu, j = u0 + u, b = n0 + n;
+        float gv[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) gv[g] = sm.bias[g * nu + u] + sm.sums[g * nu + u][n];
+        const float cn = sigmoidf_fast(gv[1]) * c_old + sigmoidf_fast(gv[0]) * tanhf_fast(gv[2]);
+        cell[b * R + j] = cn;
+        st_tagged(xchg_vec(xb, B, IS_ATT ? V_HATT : V_HDEC, v1) + b * R + j, sigmoidf_fast(gv[3]) * tanhf_fast(cn), v1);
+      }
+      prof.mark<1>();
+    }
+    if (!ok) break;
+    hint_arrive(xchg_hint(xb, B, IS_ATT ? V_HATT : V_HDEC));
+    if (IS_ATT && t + 1 < p.max_steps && !early_columns(t + 1)) break;
+    if (!step_continues(p, &sm.n_done, &sm.ok, v1, prof)) break;
+  }
+  prof.flush(p.prof);
+}
+
+// role P: rows [pp0, pp0 + npp) of [linear_projection | gate_layer | prenet layer 0 o projection] on hc = [h_dec | context]
+__device__ void proj_role(const DecParams& p, MatSmem& sm, int idx, int n_lstm_ctas) {
+  const int tid = threadIdx.x, B = p.B;
+  int pp0, npp;
+  row_range(idx, N_PP_CTAS, NPP, pp0, npp);
+  load_rows(sm, p.w.w_pp, KHC, KS_PP, KP_PP, npp, [&](int q) { return pp0 + q; });
+  for (int i = tid; i < npp; i += DEC_THREADS) sm.bias[i] = __ldg(p.w.b_pp + pp0 + i);
+  mat_common_init(p, sm);
+  __syncthreads();
+
+  unsigned long long* const xb = p.s.xchg;
+  unsigned long long* const done_word = reinterpret_cast<unsigned long long*>(p.s.done + 4);
+  const bool owns_gate = pp0 <= M && M < pp0 + npp;
+  const unsigned int n_lstm = (unsigned int)n_lstm_ctas;
+  const SegDesc none = {0, 0, 0}, k_hdec = {0, X0, ST_SEG}, k_ctx = {SEG, XC, ST_SEGC};
+  PassReg early;
+#pragma unroll
+  for (int i = 0; i < MAXPASS; ++i) early.v[i] = 0.f;
   Prof prof;
   prof.init(p.prof != nullptr, sm.prof);
   for (int t = 0; t < p.max_steps; ++t) {
-    float* h_att_cur = p.s.h_att + cur * p.B * R;
-    float* h_att_nxt = p.s.h_att + (cur ^ 1) * p.B * R;
-    float* h_dec_cur = p.s.h_dec + cur * p.B * R;
-    float* h_dec_nxt = p.s.h_dec + (cur ^ 1) * p.B * R;
-    // (1) attention_rnn (model.py:400-402): input [prenet | context], hidden h_att.  The context and the
-    //     hidden state were requested before the barrier that ended the previous step (see below).
-    {
-      const Seg segs[3] = {{p.s.pre, R, R}, {p.s.ctx, E, E}, {h_att_cur, R, R}};
-      lstm_phase(sm, prof, sm.w_att, sm.b_att, segs, t > 0 ? 6u : 0u, h_att_nxt, p.s.c_att, p.B, u0, nu,
-                 reinterpret_cast<unsigned long long*>(p.s.h_tag), (unsigned int)(t + 1));
+    const unsigned int v1 = (unsigned int)t + 1;
+    const bool more = t + 1 < p.max_steps;
+    bool ok = true;
+    // ---- early: the context columns
+    for (int ps = 0, n0 = 0; n0 < B && ok; ++ps, n0 += PASS) {
+      const int nb = min(PASS, B - n0);
+      ok = fetch(sm, xchg_vec(xb, B, V_CTX, v1), E, v1, n0, nb, XC, ps == 0 ? xchg_hint(xb, B, V_CTX) : nullptr, (unsigned int)B * v1, p.s.done);
+      if (ok) early.set(ps, mat_part(sm, KS_PP, npp, k_ctx, none, nb));
     }
-    prof.mark<0>();
-    // the attention CTAs pick h_att(t) up from the tagged copy without a barrier; this one (matrix CTAs only,
-    // hidden behind the attention) orders the plain copy for the prefetch below
-    grid_barrier(bar_mat, target_mat, GM);
-    prof.mark<1>();
-    // (2) attention CTAs at work; meanwhile fetch the two decoder_rnn inputs that are already complete
-    const Seg segs_dec[3] = {{h_att_nxt, R, R}, {p.s.ctx, E, E}, {h_dec_cur, R, R}};
-    matvec_prefetch(sm, segs_dec, p.B, 5u);
-    grid_barrier(bar_all, target_all, G);      // context(t) complete
-    prof.mark<3>();
-    // (3) decoder_rnn (model.py:425-428): input [h_att | context], hidden h_dec
-    lstm_phase(sm, prof, sm.w_dec, sm.b_dec, segs_dec, 5u, h_dec_nxt, p.s.c_dec, p.B, u0, nu);
-    const Seg segs_pp[2] = {{h_dec_nxt, R, R}, {p.s.ctx, E, E}};
-    matvec_prefetch(sm, segs_pp, p.B, 2u);     // the context, ahead of the barrier
-    prof.mark<4>();
-    grid_barrier(bar_mat, target_mat, GM);
-    prof.mark<5>();
-    // (4) [linear_projection | gate_layer | prenet layer 0 o projection] on hc = [h_dec | context]
-    //     (model.py:436-441, 507, 132-135)
-    {
-      const Seg (&segs)[2] = segs_pp;
-      const bool more = t + 1 < p.max_steps;
-      unsigned char drop0 = 0;
-      matvec_phase(
-          sm, prof, segs, 2u, &sm.w_pp[0][0][0], &sm.w_pp[1][0][0], KS_PP, npp, KP_PP / 16, p.B,
-          [&](int n0, int nb) {     // the dropout mask byte comes from DRAM: ask for it before the arithmetic
-            if (tid < npp * nb) {
-              const int row = pp0 + tid % npp;
-              if (row > M && more)
-                drop0 = p.drop[(((long long)(t + 1) * 2 + 0) * p.B + n0 + tid / npp) * R + row - M - 1];
+    prof.mark<2>();
+    if (!ok) break;
+    for (int ps = 0, n0 = 0; n0 < B && ok; ++ps, n0 += PASS) {
+      const int nb = min(PASS, B - n0);
+      unsigned char drop0 = 0;                    // the dropout mask byte comes from DRAM: ask for it early
+      if (tid < npp * nb) {
+        const int row = pp0 + tid % npp;
+        if (row > M && more) drop0 = p.drop[(((long long)(t + 1) * 2 + 0) * B + n0 + tid / npp) * R + row - M - 1];
+      }
+      ok = fetch(sm, xchg_vec(xb, B, V_HDEC, v1), R, v1, n0, nb, X0, ps == 0 && (p.flags & 4) ? xchg_hint(xb, B, V_HDEC) : nullptr, n_lstm * v1, p.s.done);
+      prof.mark<0>();
+      if (!ok) break;
+      mat_part(sm, KS_PP, npp, k_hdec, none, nb, early.get(ps), true);
+      if (tid < npp * nb) {
+        const int r = tid % npp, n = tid / npp, row = pp0 + r, b = n0 + n;
+        const float v = sm.bias[r] + sm.sums[r][n];
+        if (row < M) {
+          p.mel[((long long)b * p.max_steps + t) * M + row] = v;
+        } else if (row == M) {
+          p.gate[(long long)b * p.max_steps + t] = v;
+          if (p.s.out_len[b] == 0) {              // stop test (model.py:524), per utterance
+            if (sigmoidf_exact(v) > p.gate_threshold) {
+              p.s.out_len[b] = t + 1;
+              atomicAdd(p.s.done, 1);
+              atomicAdd(&sm.done_count, 1);
+            } else if (!more) {
+              p.s.out_len[b] = p.max_steps;       // model.py:526-528 "Reached max decoder steps"
+              atomicAdd(p.s.done + 1, 1);
+              atomicAdd(&sm.done_count, 1);
             }
-          },
-          [&](int n0, int nb) {
-            if (tid < npp * nb) {
-              const int r = tid % npp, n = tid / npp, row = pp0 + r, b = n0 + n;
-              const float v = sm.b_pp[r] + sm.sums[r][n];
-              if (row < M) {
-                p.mel[((long long)b * p.max_steps + t) * M + row] = v;
-              } else if (row == M) {
-                p.gate[(long long)b * p.max_steps + t] = v;
-                if (p.s.out_len[b] == 0) {          // stop test (model.py:524), per utterance
-                  if (sigmoidf_exact(v) > p.gate_threshold) {
-                    p.s.out_len[b] = t + 1;
-                    atomicAdd(p.s.done, 1);
-                  } else if (!more) {
-                    p.s.out_len[b] = p.max_steps;     // model.py:526-528 "Reached max decoder steps"
-                    atomicAdd(p.s.done + 1, 1);
-                  }
-                }
-              } else if (more) {
-                // prenet layer 0 of the NEXT step; dropout p = 0.5 is always on -> mask * 2
-                p.s.p1[b * R + row - M - 1] = fmaxf(v, 0.f) * (2.0f * (float)drop0);
-              }
-            }
-          });
+          }
+        } else if (more) {
+          // prenet layer 0 of the NEXT step; dropout p = 0.5 is always on -> mask * 2
+          st_tagged(xchg_vec(xb, B, V_P1, v1) + b * R + row - M - 1, fmaxf(v, 0.f) * (2.0f * (float)drop0), v1);
+        }
+      }
+      prof.mark<1>();
     }
-    prof.mark<6>();
-    grid_barrier(bar_mat, target_mat, GM);
-    prof.mark<7>();
-    // (5) prenet layer 1 of the next step; the stop counters are final since the last barrier
-    if (tid == DEC_THREADS - 1) {
-      const volatile int* done = p.s.done;
-      sm.n_done = done[0] + done[1];
+    if (!ok) break;
+    hint_arrive(xchg_hint(xb, B, V_P1));
+    if (owns_gate) {                              // how many utterances have stopped, as a tagged word of this step
+      if (tid == 0)                               // (hint_arrive's barrier ordered the epilogue's counting)
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(done_word),
+                     "l"(((unsigned long long)v1 << 32) | (unsigned int)sm.done_count)
+                     : "memory");
     }
-    if (t + 1 < p.max_steps) {
-      const Seg segs[1] = {{p.s.p1, R, R}};
-      unsigned char drop1 = 0;
-      matvec_phase(
-          sm, prof, segs, 0u, &sm.w_p2[0][0][0], &sm.w_p2[1][0][0], KS_P2, np2, KP_P2 / 16, p.B,
-          [&](int n0, int nb) {
-            if (tid < np2 * nb)
-              drop1 = p.drop[(((long long)(t + 1) * 2 + 1) * p.B + n0 + tid / np2) * R + p20 + tid % np2];
-          },
-          [&](int n0, int nb) {
-            if (tid < np2 * nb) {
-              const int r = tid % np2, n = tid / np2;
-              const float v = sm.sums[r][n];
-              p.s.pre[(n0 + n) * R + p20 + r] = fmaxf(v, 0.f) * (2.0f * (float)drop1);
-            }
-          });
-    }
-    prof.mark<8>();
-    {
-      // the next attention_rnn's context and hidden state are complete: request them ahead of the barrier
-      // (a group left in flight by the last step is drained by the exit of the kernel)
-      const Seg segs[3] = {{p.s.pre, R, R}, {p.s.ctx, E, E}, {h_att_nxt, R, R}};
-      matvec_prefetch(sm, segs, p.B, 6u);
-    }
-    grid_barrier(bar_all, target_all, G);
-    prof.mark<9>();
-    cur ^= 1;
-    if (sm.n_done >= p.B) break;     // every utterance has fired its stop gate (or hit max_steps)
+    if (!step_continues(p, &sm.n_done, &sm.ok, v1, prof)) break;
   }
-  cp_async_wait<0>();                // the last prefetch
+  prof.flush(p.prof);
+}
+
+// role Q: rows [r0, r0 + nr) of prenet layer 1
+__device__ void prenet_role(const DecParams& p, MatSmem& sm, int idx) {
+  const int tid = threadIdx.x, B = p.B;
+  int r0, nr;
+  row_range(idx, N_P2_CTAS, R, r0, nr);
+  for (int i = tid; i < nr * KS_P2; i += DEC_THREADS) {
+    const int q = i / KS_P2, k = i - q * KS_P2;
+    put_weight(&sm.w[0][q * KS_P2 + k], &sm.w[1][q * KS_P2 + k], k < R ? __ldg(p.w.w_pre2 + (long long)(r0 + q) * R + k) : 0.f);
+  }
+  mat_common_init(p, sm);
+  __syncthreads();
+
+  unsigned long long* const xb = p.s.xchg;
+  const SegDesc none = {0, 0, 0}, k_all = {0, X0, ST_SEG};
+  Prof prof;
+  prof.init(p.prof != nullptr, sm.prof);
+  for (int t = 0; t < p.max_steps; ++t) {
+    const unsigned int v1 = (unsigned int)t + 1;
+    bool ok = true;
+    if (t + 1 < p.max_steps) {
+      for (int ps = 0, n0 = 0; n0 < B && ok; ++ps, n0 += PASS) {
+        const int nb = min(PASS, B - n0);
+        unsigned char drop1 = 0;
+        if (tid < nr * nb) drop1 = p.drop[(((long long)(t + 1) * 2 + 1) * B + n0 + tid / nr) * R + r0 + tid % nr];
+        ok = fetch(sm, xchg_vec(xb, B, V_P1, v1), R, v1, n0, nb, X0, ps == 0 && (p.flags & 8) ? xchg_hint(xb, B, V_P1) : nullptr,
+                   (unsigned int)N_PP_CTAS * v1, p.s.done);
+        prof.mark<0>();
+        if (!ok) break;
+        mat_part(sm, KS_P2, nr, k_all, none, nb, 0.f, true);
+        if (tid < nr * nb) {
+          const int r = tid % nr, n = tid / nr;
+          st_tagged(xchg_vec(xb, B, V_PRE, v1) + (n0 + n) * R + r0 + r, fmaxf(sm.sums[r][n], 0.f) * (2.0f * (float)drop1), v1);
+        }
+        prof.mark<1>();
+      }
+      if (!ok) break;
+      hint_arrive(xchg_hint(xb, B, V_PRE));
+    }
+    if (!step_continues(p, &sm.n_done, &sm.ok, v1, prof)) break;
+  }
   prof.flush(p.prof);
 }
 
@@ -524,7 +684,6 @@ __device__ void matrix_role(const DecParams& p, MatSmem& sm, int mi, int GM) {
 //   critical(t): the part that needs h_att(t)
 __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned int G = gridDim.x;
   const int len = p.lengths[b];
   float* wprev = p.s.w_prev + (long long)b * p.T_in;
   float* wcum = p.s.w_cum + (long long)b * p.T_in;
@@ -556,6 +715,7 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
   prof.init(p.prof != nullptr, sm.prof);
 
   auto prepare = [&](int t) {
+    long long tp = prof.now();
     int end;
     window_bounds(t, p.window, len, start, end);
     nw = end - start + 1;
@@ -568,6 +728,7 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
       sm.cat[c][q] = v;
     }
     __syncthreads();
+    prof.sub<16>(tp);
     // location_conv (model.py:57): loc[q][f] = sum_{c,k} w[c][k][f] * cat[c][q + k]
     for (int i = tid; i < nw * NF; i += DEC_THREADS) {
       const int q = i / NF, f = i - q * NF;
@@ -580,6 +741,7 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
       sm.x.loc[q][f] = acc0 + acc1;
     }
     __syncthreads();
+    prof.sub<17>(tp);
     // S[q][a] = location_dense(loc[q])[a] + processed_memory[q][a] (model.py:94-96): warp = 3 positions,
     // lane = 5 channels
     {
@@ -611,6 +773,7 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
           if (q < nw && a < A) sm.S[q][a] = exp2x(acc[qi][j]);
         }
     }
+    prof.sub<18>(tp);
     // encoder outputs of the window -> registers (consumed by the context sum of step t)
     {
       const float4* mrow = reinterpret_cast<const float4*>(memory + (long long)start * E) + c4;
@@ -621,22 +784,26 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
       }
     }
     __syncthreads();
+    prof.sub<19>(tp);
   };
 
-  auto critical = [&](int t) {
+  auto critical = [&](int t) -> bool {
     long long tp = prof.now();
     // query projection (model.py:92): pq = W_q h_att; warp per row, 75 float4 per row over the lanes
     {
-      // h_att(t): spin on the (value, tag) pairs the matrix CTAs publish -- one-way latency, no barrier
+      // h_att_{t+1}: spin on the (value, version) words the matrix CTAs publish -- one-way latency
+      bool dead = false;
       if (tid < R) {
-        const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(p.s.h_tag) + b * R + tid;
+        const unsigned long long* src = xchg_vec(p.s.xchg, p.B, V_HATT, (unsigned int)t + 1) + b * R + tid;
         unsigned long long v;
+        int spins = 0;
         do {
-          v = *src;
-        } while ((unsigned int)(v >> 32) != (unsigned int)(t + 1));
+          v = ld_tagged(src);
+        } while ((unsigned int)(v >> 32) != (unsigned int)(t + 1) && !(dead = spin_dead(spins, p.s.done)));
         sm.h[tid] = __uint_as_float((unsigned int)v);
       }
-      __syncthreads();
+      if (__syncthreads_or(dead)) return false;
+      prof.sub<14>(tp);
       const float4* h4 = reinterpret_cast<const float4*>(sm.h);
       const float4 hz = make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 hv0 = h4[lane], hv1 = h4[lane + 32], hv2 = lane < 11 ? h4[lane + 64] : hz;
@@ -707,7 +874,12 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
     }
     __syncthreads();
     prof.sub<13>(tp);
-    for (int c = tid; c < E; c += DEC_THREADS) p.s.ctx[b * E + c] = sm.x.ctxp[0][c] + sm.x.ctxp[1][c] + sm.x.ctxp[2][c];
+    {
+      unsigned long long* dst = xchg_vec(p.s.xchg, p.B, V_CTX, (unsigned int)t + 1) + b * E;
+      for (int c = tid; c < E; c += DEC_THREADS)
+        st_tagged(dst + c, sm.x.ctxp[0][c] + sm.x.ctxp[1][c] + sm.x.ctxp[2][c], (unsigned int)t + 1);
+      hint_arrive(xchg_hint(p.s.xchg, p.B, V_CTX));
+    }
     if (tid == 0 && p.s.align_start) p.s.align_start[(long long)b * p.max_steps + t] = start;
     // new attention_weights (zero outside the window), cumulative weights (model.py:424), alignments
     int ostart = 0, oend = -1;
@@ -721,42 +893,70 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
       if (p.align) p.align[((long long)b * p.max_steps + t) * p.T_in + start + tid] = wv;
       if (p.s.align_win) p.s.align_win[((long long)b * p.max_steps + t) * (2 * p.window + 1) + tid] = wv;
     }
+    __syncthreads();                 // prepare(t + 1) reads the weights just written (other threads)
+    return true;
   };
 
-  unsigned int* bar_all = reinterpret_cast<unsigned int*>(p.s.done + 3);
-  unsigned int target_all = 0;
-  int cur = 0;
+  const unsigned long long* done_word = reinterpret_cast<const unsigned long long*>(p.s.done + 4);
   prepare(0);
   for (int t = 0; t < p.max_steps; ++t) {
     prof.mark<0>();
-    critical(t);
+    if (!critical(t)) break;
     prof.mark<2>();
-    grid_barrier(bar_all, target_all, G);      // context(t) complete -> matrix CTAs
-    prof.mark<3>();
     if (t + 1 < p.max_steps) prepare(t + 1);
     prof.mark<4>();
-    grid_barrier(bar_all, target_all, G);      // end of step
-    prof.mark<9>();
-    cur ^= 1;
+    // the stop counter of this step (a tagged word from the matrix CTA that owns the gate row)
     if (tid == 0) {
-      const volatile int* done = p.s.done;
-      sm.n_done = done[0] + done[1];
+      int spins = 0;
+      bool dead = false;
+      unsigned long long w;
+      do {
+        w = ld_tagged(done_word);
+      } while ((unsigned int)(w >> 32) != (unsigned int)(t + 1) && !(dead = spin_dead(spins, p.s.done)));
+      sm.n_done = (int)(unsigned int)w;
+      sm.ok = !dead;
     }
     __syncthreads();
-    if (sm.n_done >= p.B) {
+    prof.mark<9>();
+    const bool stop = sm.n_done >= p.B || !sm.ok;
+    if (stop) {
       if (blockIdx.x == 0 && tid == 0) p.s.done[2] = t + 1;
       break;
     }
+    __syncthreads();                 // sm.n_done / sm.ok are rewritten next step
   }
   prof.flush(p.prof);
 }
 
 __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  if ((int)blockIdx.x < p.B)
+  const int mi = (int)blockIdx.x - p.B, GM = (int)gridDim.x - p.B;
+  const int n_lstm = (GM - N_PP_CTAS - N_P2_CTAS) / 2;          // CTAs per LSTMCell
+  if (mi < 0) {
     attention_role(p, *reinterpret_cast<AttSmem*>(smem_raw), blockIdx.x);
-  else
-    matrix_role(p, *reinterpret_cast<MatSmem*>(smem_raw), blockIdx.x - p.B, gridDim.x - p.B);
+  } else {
+    MatSmem& sm = *reinterpret_cast<MatSmem*>(smem_raw);
+    if (mi < n_lstm) lstm_role<true>(p, sm, mi, n_lstm, p.B);
+    else if (mi < 2 * n_lstm) lstm_role<false>(p, sm, mi - n_lstm, n_lstm, p.B);
+    else if (mi < 2 * n_lstm + N_PP_CTAS) proj_role(p, sm, mi - 2 * n_lstm, n_lstm);
+    else if (mi < 2 * n_lstm + N_PP_CTAS + N_P2_CTAS) prenet_role(p, sm, mi - 2 * n_lstm - N_PP_CTAS);
+    // (an odd CTA out, if any, has nothing to do)
+  }
+}
+
+// Barrier over `n` CTAs as round 1's decoder used it between phases (kept as a diagnostic: its cost is what the
+// dataflow design avoids): monotonically increasing arrival counter, release on the add, acquire spin.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target, unsigned int n) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += n;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(DEC_THREADS, 1) grid_barrier_selftest_kernel(unsigned int* counter, int iters) {
@@ -790,6 +990,9 @@ int taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, con
                      const unsigned char* drop, const fac_taco_decoder_state* s, float* mel, float* gate, float* align,
                      int B, int T_in, int max_steps, int window, float gate_threshold, cudaStream_t st) {
   FAC_REQUIRE(w && memory && pmem && lengths && drop && s && mel && gate, "taco_decoder: NULL argument");
+  FAC_REQUIRE(s->c_att && s->c_dec && s->xchg && s->w_prev && s->w_cum && s->done && s->out_len,
+              "taco_decoder: NULL state buffer");
+  FAC_REQUIRE(B <= PASS * MAXPASS, "taco_decoder: at most %d utterances per launch", PASS * MAXPASS);
   FAC_REQUIRE(B > 0 && T_in > 0 && max_steps > 0, "taco_decoder: empty problem");
   FAC_REQUIRE(window >= 0 && 2 * window + 1 <= MAXW, "taco_decoder: attention window %d unsupported (max %d)", window,
               (MAXW - 1) / 2);
@@ -815,8 +1018,12 @@ int taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, con
   p.mel = mel; p.gate = gate; p.align = align;
   p.B = B; p.T_in = T_in; p.max_steps = max_steps; p.window = window; p.gate_threshold = gate_threshold;
   p.prof = g_dec_prof;
+  {
+    const char* f = getenv("FAC_TACO_FLAGS");
+    p.flags = f ? atoi(f) : 0;
+  }
   void* args[] = {&p};
-  // cooperative launch = co-residency guarantee for the grid barrier
+  // cooperative launch = co-residency guarantee for the CTAs that poll each other's words
   e = cudaLaunchCooperativeKernel((void*)taco_decoder_kernel, dim3(sms), dim3(DEC_THREADS), args, smem, st);
   count_launch();
   if (e != cudaSuccess) {

@@ -317,22 +317,23 @@ typedef struct fac_taco_decoder_weights {
   const float* w_pre2;   /* [300][300]  decoder.prenet.layers.1 weight                                          */
 } fac_taco_decoder_weights;
 
+#define FAC_TACO_XCHG_WORDS 1800   /* 4 x 300 + 600 words per utterance and parity */
+#define FAC_TACO_XCHG_HINTS 64     /* arrival counters behind the two copies */
+
 /* Decoder state the caller allocates ZERO-FILLED (reference model.py:304-335 initialises every
  * state to zero); the kernel owns it while running. */
 typedef struct fac_taco_decoder_state {
-  float* h_att;   /* [2][B][300] double-buffered attention_hidden            */
   float* c_att;   /* [B][300]    attention_cell                              */
-  float* h_dec;   /* [2][B][300] decoder_hidden                              */
   float* c_dec;   /* [B][300]    decoder_cell                                */
-  float* ctx;     /* [B][600]    attention_context                           */
-  float* pre;     /* [B][300]    prenet output feeding the next step         */
-  float* p1;      /* [B][300]    prenet layer-0 output (scratch)             */
-  float* h_tag;   /* [B][300][2] attention_hidden of the current step as (value, step tag) 8-byte pairs: the
-                     matrix CTAs publish it, the utterance's attention CTA polls it (no barrier in between) */
+  unsigned long long* xchg; /* 2 * FAC_TACO_XCHG_WORDS * B + FAC_TACO_XCHG_HINTS words, exchange area: every vector that crosses CTAs (prenet
+                     output, attention_hidden, decoder_hidden, prenet layer-0 output, attention_context) as
+                     (value, version) 8-byte words, two copies by version parity; producers publish with ONE
+                     store, consumers poll for the version they expect -- the kernel has no grid barrier */
   float* w_prev;  /* [B][T_in]   attention_weights                           */
   float* w_cum;   /* [B][T_in]   attention_weights_cum                       */
-  int* done;      /* [8]: #utterances stopped by the gate, #stopped by max_steps, steps run, two grid-barrier
-                     counters, 3 spare */
+  int* done;      /* [8]: #utterances stopped by the gate, #stopped by max_steps, steps run, spare, [4..5] the
+                     (count, version) word that carries the stop count of a step, spare, [7] != 0: a hand-over
+                     timed out (the run is invalid; fac_taco_decoder_run's caller must check it) */
   int* out_len;   /* [B] number of frames of each utterance (0 while running) */
   /* optional sparse form of the alignments (NULL = off): only the <= 2*window+1 positions of the attention window
    * carry weight (everything else is masked to -inf by reference utils.py:46-78), so step t of utterance b is

@@ -38,7 +38,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_ext.WgModel) == 10 * 4 + 2 * 8 + 16 * C.sizeof(_ext.WgFlow)
     assert C.sizeof(_ext.TcConv) == 10 * 8 + 3 * 8 + 12 * 4 + 8 + 8
     assert C.sizeof(_ext.ConvEpilogue) == 2 * 4 + 8 + 2 * 8 + 3 * 8 + 2 * 4 + 8
-    assert C.sizeof(_ext.TacoDecoderState) == 14 * 8
+    assert C.sizeof(_ext.TacoDecoderState) == 9 * 8
 
 
 def test_build_digest_does_not_depend_on_the_checkout_path(monkeypatch):

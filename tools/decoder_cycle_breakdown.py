@@ -15,23 +15,28 @@ m = Tacotron2(create_hparams_stage())
 m.load_state_dict(synth.tacotron_state())
 m = m.cuda().eval()
 m.collect_timing, m.return_alignments = True, False
-names = ["lstm_att", "attention", "lstm_dec", "projection", "prenet1"]
+SLOTS = [("early columns", 2), ("awaited vector (wait + sweep)", 0), ("products + epilogue", 1), ("stop count", 12),
+         ("of which: arrival counters", 13), ("sweeps", 15)]
+ATT = [("wait h_att", 14), ("query projection", 11), ("energies", 12), ("softmax+context", 13), ("prepare", 4),
+       ("wait stop", 9)]
 args = [int(a) for a in sys.argv[1:]] or [1, 690, 8, 690, 32, 690]
 for B, T in zip(args[0::2], args[1::2]):
     m.decoder.gate_threshold, m.decoder.max_decoder_steps = 2.0, T
     ppg = synth.synthetic_ppg(B, T).cuda()
     m.inference(ppg)
-    prof = torch.zeros(256 * 16, dtype=torch.int64, device="cuda")
+    prof = torch.zeros(256 * 32, dtype=torch.int64, device="cuda")
     lib.fac_taco_set_profile_buffer(prof.data_ptr())
     m.inference(ppg)
     torch.cuda.synchronize()
     lib.fac_taco_set_profile_buffer(None)
-    p = prof.view(256, 16)[:148].double().cpu() / T
+    p = prof.view(256, 32)[:148].double().cpu() / T
     us = m.last_timing["decoder_ms"] * 1e3 / T
-    print("B=%d T=%d: %.2f us/step, %.0f cycles/step (CTA 0)" % (B, T, us, p[0, 10]))
-    for cta in (0, 147):
-        print("  CTA %3d: " % cta + "  ".join("%s %d+%d" % (n, p[cta, 2 * i], p[cta, 2 * i + 1]) for i, n in enumerate(names)))
-    print("  CTA 147 mat-vec phases (all four): fetch wait %d, arithmetic %d, epilogue %d" % tuple(p[147, 11:14]))
-    print("  CTA 147 arithmetic detail: mma section (warp 0) %d, wait for the other warps %d" % tuple(p[147, 14:16]))
-    print("  CTA 0 attention critical path: h load + query projection %d, energies %d, softmax + context %d" % tuple(p[0, 11:14]))
-    print("  mean   : " + "  ".join("%s %d+%d" % (n, p[:, 2 * i].mean(), p[:, 2 * i + 1].mean()) for i, n in enumerate(names)))
+    n_lstm = (148 - B - 24) // 2
+    roles = [("A attention LSTM", B, B + n_lstm), ("D decoder LSTM", B + n_lstm, B + 2 * n_lstm),
+             ("P projection", B + 2 * n_lstm, B + 2 * n_lstm + 13), ("Q prenet 1", B + 2 * n_lstm + 13, B + 2 * n_lstm + 24)]
+    print("B=%d T=%d: %.2f us/step, %.0f cycles/step (attention CTA 0)" % (B, T, us, p[0, 10]))
+    for name, lo, hi in roles:
+        print("  %-18s (%2d CTAs, mean): " % (name, hi - lo) + "  ".join("%s %d" % (n, p[lo:hi, i].mean()) for n, i in SLOTS))
+    print("  attention CTA 0: " + "  ".join("%s %d" % (n, p[0, i]) for n, i in ATT))
+    print("  attention CTA 0, prepare: weights around the window %d, location conv %d, location dense + exp %d, encoder rows %d"
+          % tuple(p[0, 16:20]))
