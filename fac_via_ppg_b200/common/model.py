@@ -272,13 +272,14 @@ class Tacotron2(nn.Module):
 
     def _decode(self, packed, memory, dec_masks, n_steps, lens=None):
         """reference model.py:489-535 (Decoder.inference) -> mel_cl (B, n_steps, M), gate, align, lengths.
-        One launch decodes at most (SMs - 100) utterances (one attention CTA each next to >= 100 matrix
-        CTAs); larger batches run as consecutive groups.  A ragged batch is length-sorted into the groups
+        One launch can decode (SMs - 100) utterances (one attention CTA each next to >= 100 matrix CTAs), but
+        beyond 36 a matrix CTA takes them in passes of 8 instead of 16 (csrc/tacotron_decoder.cu), which is slower
+        per utterance than two launches: larger batches run as consecutive groups of 32.  A ragged batch is length-sorted into the groups
         (src/common/data_utils.py sorts training batches the same way), so that a group of short utterances
         retires as soon as its own longest member has fired its stop gate; an utterance's result does not
         depend on the group it runs in (the decoder's arithmetic is batch-invariant)."""
         B = memory.shape[0]
-        limit = max(1, torch.cuda.get_device_properties(memory.device).multi_processor_count - 100)
+        limit = max(1, min(torch.cuda.get_device_properties(memory.device).multi_processor_count - 100, 36))
         group = min(limit, 32)
         if B <= limit:
             return self._decode_group(packed, memory, dec_masks, n_steps, lens)

@@ -35,7 +35,6 @@
 #include "fac_common.cuh"
 #include <cuda_fp16.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 namespace fac {
 
@@ -52,7 +51,6 @@ struct DecParams {
   int B, T_in, max_steps, window;
   float gate_threshold;
   long long* prof;            // optional [grid][32] cycle counters (tools/decoder_cycle_breakdown.py)
-  int flags;                  // tuning (FAC_TACO_FLAGS): bit 0..3 = wait on the arrival counter before sweeping pre / ctx / hdec / p1
 };
 
 namespace {
@@ -72,9 +70,17 @@ constexpr int MIN_MATRIX_CTAS = 100;
 // matrix CTAs are specialised by matrix: N_PP_CTAS hold [projection | gate | prenet 0], N_P2_CTAS prenet layer 1,
 // the rest is split evenly between the two LSTMCells (>= 38 CTAs each: <= 8 hidden units = 32 gate rows per CTA)
 constexpr int N_PP_CTAS = 13, N_P2_CTAS = 11;
-constexpr int MAXROWS = 32;     // resident rows per matrix CTA = two mma m-tiles
-constexpr int PASS = 8;         // utterances per arithmetic pass = one mma n-tile
-constexpr int MAXPASS = 6;      // B <= 48
+// Two builds of the kernel: utterances go through a matrix CTA in passes of 8 (one mma n-tile; up to 32 resident
+// rows) or, for 8 < B <= 36, in passes of 16 (two n-tiles; the staging needs the room of 4 rows, and B <= 36 keeps
+// an LSTM CTA at <= 7 units = 28 rows).  B <= 48 in all.
+template <bool P16>
+struct Cfg {
+  static constexpr int PASS = P16 ? 16 : 8;
+  static constexpr int MAXROWS = P16 ? 28 : 32;
+  static constexpr int PSHIFT = P16 ? 4 : 3;
+};
+constexpr int MAXPASS = 6;       // passes of 8; passes of 16: 3
+constexpr int MAX_B_P16 = 36;
 constexpr int MAXW = 48;        // max window positions (2*window+1 <= 48)
 // K segments: every vector padded to whole k16 steps, so that a mat-vec can be cut at the vector boundaries
 constexpr int SEG = 304, SEGC = 608;              // a 300-vector / the 600-float context
@@ -82,8 +88,9 @@ constexpr int ST_SEG = SEG / 16, ST_SEGC = SEGC / 16;
 constexpr int KP_LSTM = SEG + SEGC + SEG, KS_LSTM = KP_LSTM + 8;  // halfs per resident LSTM weight row (+8: ldmatrix rows hit distinct banks)
 constexpr int KP_PP = SEG + SEGC, KS_PP = KP_PP + 8;             // projection: [h_dec | context]
 constexpr int KP_P2 = SEG, KS_P2 = KP_P2 + 8;                    // prenet layer 1
-// staging slots (columns of MatSmem::xs): two 300-vectors and the context
-constexpr int X0 = 0, X1 = SEG, XC = 2 * SEG, XSTRIDE = 2 * SEG + SEGC + 8;
+// staging row of one utterance: the context plus one 300-vector (what is staged early and what is awaited never
+// live at the same time, so they share columns; each role lays its slots out itself)
+constexpr int XSTRIDE = SEGC + SEG + 8;
 constexpr float W_SCALE = 256.f;        // resident weights are stored times 2^8 so that their fp16 lo parts stay normal
 constexpr int CTXP = 3;         // q-range split of the context sum
 constexpr int QPP = MAXW / CTXP;  // window positions per part
@@ -101,10 +108,12 @@ __device__ __forceinline__ unsigned long long tagged(float v, unsigned int versi
   return ((unsigned long long)version << 32) | __float_as_uint(v);
 }
 // Behind the two copies: one arrival counter per vector kind, 32 bytes apart.  A producer CTA adds 1 after its
-// stores (relaxed, NO fence: the words carry their own version); a waiting CTA polls that one counter with one
-// thread instead of sweeping the payload with 512 -- measured: 140 CTAs polling the payload itself congest the
-// L2 slices of those lines and delay the very stores they wait for (5 k cycles per hand-over instead of 1 k).
-// The counter is only a hint; what a consumer accepts is decided by the version in each word.
+// stores (relaxed, NO fence: the words carry their own version).  A CTA that fetches a vector EARLY, long before
+// it is complete, waits on that one counter with one thread instead of sweeping the payload with 512 --
+// measured: ~140 CTAs polling a payload for thousands of cycles congest the L2 slices of those lines and delay
+// the very stores they wait for (5 k cycles per hand-over instead of 1 k).  The one role that is next on the
+// critical path polls the words themselves: one hop instead of two.  The counter is only a hint; what a consumer
+// accepts is decided by the version in each word.
 constexpr int XCHG_HINTS = 64;          // 8-byte words reserved for the counters (FAC_TACO_XCHG_HINTS)
 static_assert(XCHG_HINTS * 8 >= 5 * 32 && XCHG_HINTS == FAC_TACO_XCHG_HINTS && XCHG_WORDS == FAC_TACO_XCHG_WORDS, "exchange area");
 __device__ __forceinline__ unsigned int* xchg_hint(unsigned long long* base, int B, int kind) {
@@ -119,16 +128,18 @@ constexpr int DONE_ABORT = 7;           // done[7] != 0: a hand-over timed out, 
 
 constexpr int PROF_SLOTS = 32;
 constexpr int MAT_WARPS = 8;      // warps that multiply (the others wait at the barrier)
+template <bool P16>
 struct MatSmem {                  // matrix CTAs
+  static constexpr int PASS = Cfg<P16>::PASS, MAXROWS = Cfg<P16>::MAXROWS;
   // resident rows of this CTA's matrix as IEEE-half hi/lo pairs (w * 2^8 = hi + lo to ~2^-22): the operands of
   // mma.sync; the row stride is the matrix's own (KS_LSTM / KS_PP / KS_P2)
   __half w[2][MAXROWS * KS_LSTM];
-  float bias[MAXROWS];
-  alignas(16) float part[MAT_WARPS][MAXROWS][PASS];   // per-warp partial 32 x 8 tiles (K split over the warps)
-  float sums[MAXROWS][PASS];
-  int n_done, done_count, ok, prof_on;
+  float bias[32];
+  alignas(16) float part[MAT_WARPS][32][PASS];        // per-warp partial tiles (K split over the warps)
+  float sums[32][PASS];
+  int n_done, done_count, ok;
   unsigned int prof[PROF_SLOTS];
-  alignas(16) float xs[PASS][XSTRIDE];  // staged input vectors of a pass of utterances: slots X0 | X1 | XC
+  alignas(16) float xs[PASS][XSTRIDE];  // staged input vectors of a pass of utterances
 };
 struct AttSmem {                  // attention CTAs
   float wq[A][R];                 // query_layer weight, resident
@@ -146,7 +157,8 @@ struct AttSmem {                  // attention CTAs
     float ctxp[CTXP][E];          // critical path
   } x;
 };
-static_assert(sizeof(MatSmem) <= 227 * 1024 && sizeof(AttSmem) <= 227 * 1024, "decoder shared memory");
+static_assert(sizeof(MatSmem<false>) <= 227 * 1024 && sizeof(MatSmem<true>) <= 227 * 1024 && sizeof(AttSmem) <= 227 * 1024,
+              "decoder shared memory");
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -155,14 +167,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  // (no memory clobber: it only ever reads the resident weights, which never change after the prologue)
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr)
-               : "memory");
+               : "r"(addr));
 }
 // D (16 x 8, fp32) += A (16 x 16, row-major halfs) * B (16 x 8, halfs; lane holds two k-pairs of one column)
 __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
@@ -253,14 +265,12 @@ __device__ __forceinline__ bool spin_dead(int& spins, int* done) {
 // once, no index arithmetic beyond immediates --, keeps re-reading the ones whose versions do not match yet and
 // drops the values into shared memory.
 // Ends with a CTA barrier; false = the hand-over was declared dead (every thread of the CTA agrees).
-constexpr int FETCH_ROUNDS = 5;       // 300 pieces (the context) of one utterance on two warps
-__device__ __noinline__ bool fetch(MatSmem& sm, const unsigned long long* vec, int len, unsigned int ver, int n0, int nb,
+template <bool P16>
+__device__ __noinline__ bool fetch(MatSmem<P16>& sm, const unsigned long long* vec, int len, unsigned int ver, int n0, int nb,
                                    int slot, const unsigned int* hint, unsigned int hint_target, int* done) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   bool dead = false;
   int spins = 0;
-  const bool timed = sm.prof_on && threadIdx.x == 0;
-  long long tq = timed ? clock64() : 0;
   if (hint != nullptr) {              // wait quietly: one thread, one word
     if (threadIdx.x == 0) {
       unsigned int seen;
@@ -269,14 +279,10 @@ __device__ __noinline__ bool fetch(MatSmem& sm, const unsigned long long* vec, i
       } while (seen < hint_target && !(dead = spin_dead(spins, done)));
     }
     __syncthreads();
-    if (timed) {
-      const long long now = clock64();
-      sm.prof[13] += (unsigned int)(now - tq);
-      tq = now;
-    }
   }
-  // warps per utterance: 2, 4, 8 or 16
-  const int sh = nb > 4 ? 1 : nb > 2 ? 2 : nb > 1 ? 3 : 4;
+  constexpr int FETCH_ROUNDS = P16 ? 10 : 5;   // 300 pieces (the context) of one utterance on one / two warps
+  // warps per utterance: 1, 2, 4, 8 or 16
+  const int sh = nb > 8 ? 0 : nb > 4 ? 1 : nb > 2 ? 2 : nb > 1 ? 3 : 4;
   const int n = warp >> sh, part = warp & ((1 << sh) - 1);
   const int half = len >> 1, share = (half + (1 << sh) - 1) >> sh;     // pieces per warp
   const int first = part * share, count = n < nb ? min(share, half - first) : 0;
@@ -300,9 +306,7 @@ __device__ __noinline__ bool fetch(MatSmem& sm, const unsigned long long* vec, i
       }
     if (need != 0) dead = spin_dead(spins, done);
   }
-  const bool any_dead = __syncthreads_or(dead);
-  if (timed) sm.prof[15] += (unsigned int)(clock64() - tq);
-  return !any_dead;
+  return !__syncthreads_or(dead);
 }
 
 // One piece of a mat-vec: `steps` k16 steps of the resident rows, weight columns from `koff`, inputs from staging
@@ -312,34 +316,41 @@ struct SegDesc {
 };
 
 // Partial products of a matrix CTA's resident rows (<= 32 = two m-tiles) with the staged vectors of one pass of
-// <= 8 utterances (one n-tile), on the tensor cores.  These pieces are small (19 .. 57 k16 steps) and the CTA's
-// instruction issue and latencies, not the tensor pipe, bound them: at most MAT_WARPS warps take part, the
-// others go straight to the barrier.  The steps of the one or two listed segments are dealt round-robin to
-// those warps (a fixed deal: the summation order of an output never depends on B); per step a warp loads the hi
+// <= 8 / 16 utterances (one / two n-tiles), on the tensor cores.  These pieces are small (19 .. 57 k16 steps) and the CTA's
+// instruction issue and latencies, not the tensor pipe, bound them.  The steps of the one or two listed segments
+// are dealt round-robin to at most MAT_WARPS slots (a fixed deal: the summation order of an output never depends
+// on B), <= 3 steps per slot where possible; a slot is a pair of warps that share its steps' tiles; per step a warp loads the hi
 // and lo weight fragments with ldmatrix, splits its slice of the inputs into half hi/lo pairs in registers and
 // issues the three products hi*hi + lo*hi + hi*lo per m-tile (fp32-grade: ~2^-21 relative).  The partial tiles
-// meet in shared memory in fp32; returns, in the threads tid < 256 (row tid >> 3, utterance tid & 7), the sum
+// meet in shared memory in fp32; returns, in thread (row * PASS + utterance), the sum
 // scaled back by 1 / W_SCALE (with `to_sums` also sm.sums[row][utterance] = sum + add).  Two CTA barriers inside.
-__device__ __noinline__ float mat_part(MatSmem& sm, int ks, int n_rows, const SegDesc s0, const SegDesc s1, int nb,
+template <bool P16>
+__device__ __noinline__ float mat_part(MatSmem<P16>& sm, int ks, int n_rows, const SegDesc s0, const SegDesc s1, int nb,
                                        float add = 0.f, bool to_sums = false) {
+  constexpr int PSHIFT = Cfg<P16>::PSHIFT, PASS = Cfg<P16>::PASS;
+  constexpr int MT = P16 ? 2 : 1;                    // m-tiles per warp
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int total = s0.steps + s1.steps;
-  const int n_warps = min(MAT_WARPS, (total + 2) / 3);
-  const bool m2 = n_rows > 16;
-  if (warp < n_warps) {
+  const int n_slots = min(MAT_WARPS, (total + 2) / 3);
+  // warp = (deal slot, half): passes of 8 split the two m-tiles over the halves, passes of 16 the two n-tiles
+  const int slot = warp & (MAT_WARPS - 1), sel = warp >> 3;
+  const bool m2 = n_rows > 16, n2 = P16 && nb > 8;
+  if (slot < n_slots && (sel == 0 || (P16 ? n2 : m2))) {
     // ldmatrix: lane l addresses row (l & 7) + 8 * ((l >> 3) & 1) of the 8 x 8 block at k offset 8 * (l >> 4)
     const int arow = (lane & 7) + ((lane >> 3) & 1) * 8;
-    const int arow0 = arow < n_rows ? arow : 0, arow1 = 16 + arow < n_rows ? 16 + arow : 0;   // past the end: any valid row
+    const int mt0 = P16 ? 0 : sel;                    // first (P16: of two) m-tile of this warp
+    const int arow0 = mt0 * 16 + arow < n_rows ? mt0 * 16 + arow : 0, arow1 = 16 + arow < n_rows ? 16 + arow : 0;   // past the end: any valid row
     const uint32_t w_hi = (uint32_t)__cvta_generic_to_shared(&sm.w[0][0]), w_lo = (uint32_t)__cvta_generic_to_shared(&sm.w[1][0]);
     const uint32_t off0 = (uint32_t)(arow0 * ks + (lane >> 4) * 8) * 2, off1 = (uint32_t)(arow1 * ks + (lane >> 4) * 8) * 2;
-    // B fragments: column (utterance) lane >> 2, k pairs 2 * (lane & 3) and + 8
-    const float* xrow = &sm.xs[min(lane >> 2, nb - 1)][2 * (lane & 3)];
+    // B fragments: column (utterance) lane >> 2 of the n-tile, k pairs 2 * (lane & 3) and + 8
+    const int nt = P16 ? sel : 0;
+    const float* xrow = &sm.xs[nt * 8 + min(lane >> 2, max(nb - nt * 8 - 1, 0))][2 * (lane & 3)];
     // independent accumulation chains (hi*hi, lo*hi, hi*lo per m-tile), added in a fixed order at the end
-    float acc[2][3][4];
+    float acc[MT][3][4];
 #pragma unroll
-    for (int i = 0; i < 24; ++i) (&acc[0][0][0])[i] = 0.f;
-#pragma unroll 2
-    for (int s = warp; s < total; s += n_warps) {
+    for (int i = 0; i < 12 * MT; ++i) (&acc[0][0][0])[i] = 0.f;
+#pragma unroll 1
+    for (int s = slot; s < total; s += n_slots) {
       int ls = s, koff = s0.koff, xo = s0.slot;
       if (ls >= s0.steps) {
         ls -= s0.steps;
@@ -348,39 +359,40 @@ __device__ __noinline__ float mat_part(MatSmem& sm, int ks, int n_rows, const Se
       }
       koff = (koff + 16 * ls) * 2;
       xo += 16 * ls;
-      uint32_t ah[4], al[4], bh[2], bl[2];
-      ldmatrix_x4(ah, w_hi + off0 + koff);
-      ldmatrix_x4(al, w_lo + off0 + koff);
+      uint32_t ah[MT][4], al[MT][4], bh[2], bl[2];
+      ldmatrix_x4(ah[0], w_hi + off0 + koff);
+      ldmatrix_x4(al[0], w_lo + off0 + koff);
+      if (P16 && m2) {
+        ldmatrix_x4(ah[MT - 1], w_hi + off1 + koff);
+        ldmatrix_x4(al[MT - 1], w_lo + off1 + koff);
+      }
       split_half2(*reinterpret_cast<const float2*>(xrow + xo), bh[0], bl[0]);
       split_half2(*reinterpret_cast<const float2*>(xrow + xo + 8), bh[1], bl[1]);
-      mma_f16(acc[0][0], ah, bh);
-      mma_f16(acc[0][1], al, bh);
-      mma_f16(acc[0][2], ah, bl);
-      if (m2) {
-        ldmatrix_x4(ah, w_hi + off1 + koff);
-        ldmatrix_x4(al, w_lo + off1 + koff);
-        mma_f16(acc[1][0], ah, bh);
-        mma_f16(acc[1][1], al, bh);
-        mma_f16(acc[1][2], ah, bl);
-      }
-    }
-    // accumulator layout: rows lane >> 2 and + 8, columns 2 * (lane & 3) + {0, 1}
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt)
+        if (mt == 0 || m2) {
+          mma_f16(acc[mt][0], ah[mt], bh);
+          mma_f16(acc[mt][1], al[mt], bh);
+          mma_f16(acc[mt][2], ah[mt], bl);
+        }
+    }
+    // accumulator layout: rows lane >> 2 and + 8, columns 2 * (lane & 3) + {0, 1} of the n-tile
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
       if (mt == 0 || m2) {
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = acc[mt][0][j] + (acc[mt][1][j] + acc[mt][2][j]);
-        *reinterpret_cast<float2*>(&sm.part[warp][mt * 16 + (lane >> 2)][2 * (lane & 3)]) = make_float2(v[0], v[1]);
-        *reinterpret_cast<float2*>(&sm.part[warp][mt * 16 + (lane >> 2) + 8][2 * (lane & 3)]) = make_float2(v[2], v[3]);
+        const int row = (P16 ? mt : mt0) * 16 + (lane >> 2);
+        *reinterpret_cast<float2*>(&sm.part[slot][row][nt * 8 + 2 * (lane & 3)]) = make_float2(v[0], v[1]);
+        *reinterpret_cast<float2*>(&sm.part[slot][row + 8][nt * 8 + 2 * (lane & 3)]) = make_float2(v[2], v[3]);
       }
-    }
   }
   __syncthreads();
   float a = 0.f;
-  if (tid < MAXROWS * PASS && (tid & 7) < nb && (tid >> 3) < n_rows) {
-    const int r = tid >> 3, c = tid & 7;
-    for (int w = 0; w < n_warps; ++w) a += sm.part[w][r][c];
+  if ((tid & (PASS - 1)) < nb && (tid >> PSHIFT) < n_rows) {
+    const int r = tid >> PSHIFT, c = tid & (PASS - 1);
+    for (int w = 0; w < n_slots; ++w) a += sm.part[w][r][c];
     a *= 1.0f / W_SCALE;
     if (to_sums) sm.sums[r][c] = a + add;             // the epilogue's input: early columns + this piece
   }
@@ -448,8 +460,8 @@ __device__ __forceinline__ bool step_continues(const DecParams& p, int* n_done_s
 
 // resident rows: `n_rows` rows of a [rows][k_src] fp32 matrix -> padded-segment half hi/lo pairs
 //   layout 0: [300 -> 304 | 600 -> 608 | 300 -> 304] (LSTMCells, projection: the first two)   1: [300 -> 304]
-template <typename RowFn>
-__device__ __forceinline__ void load_rows(MatSmem& sm, const float* w, int k_src, int ks, int kp, int n_rows, RowFn src_row) {
+template <bool P16, typename RowFn>
+__device__ __forceinline__ void load_rows(MatSmem<P16>& sm, const float* w, int k_src, int ks, int kp, int n_rows, RowFn src_row) {
   for (int i = threadIdx.x; i < n_rows * ks; i += DEC_THREADS) {
     const int q = i / ks, k = i - q * ks;
     int ksrc = -1;
@@ -462,20 +474,22 @@ __device__ __forceinline__ void load_rows(MatSmem& sm, const float* w, int k_src
   }
 }
 
-__device__ __forceinline__ void mat_common_init(const DecParams& p, MatSmem& sm) {
-  // the K padding of the staged inputs must hold finite values (it meets zero weights); nothing writes it later
-  for (int i = threadIdx.x; i < PASS * XSTRIDE; i += DEC_THREADS) (&sm.xs[0][0])[i] = 0.f;
-  if (threadIdx.x == 0) {
-    sm.done_count = 0;
-    sm.prof_on = p.prof != nullptr;
-  }
+template <bool P16>
+__device__ __forceinline__ void mat_common_init(const DecParams& p, MatSmem<P16>& sm) {
+  // the K padding of the staged inputs must hold finite values (it meets zero weights): zeros now, later at most
+  // elements of another (finite) vector that shared the columns
+  for (int i = threadIdx.x; i < Cfg<P16>::PASS * XSTRIDE; i += DEC_THREADS) (&sm.xs[0][0])[i] = 0.f;
+  if (threadIdx.x == 0) sm.done_count = 0;
 }
 
 // roles A and D: one LSTMCell for the units [u0, u0 + nu) of this CTA and all B utterances
 //   A: input [pre_t | ctx_t], hidden hatt_t -> hatt_{t+1};  early columns: ctx_t, hatt_t;   awaited: pre_t
 //   D: input [hatt_{t+1} | ctx_{t+1}], hidden hdec_t -> hdec_{t+1};  early: hatt_{t+1}, hdec_t;  awaited: ctx_{t+1}
-template <bool IS_ATT>
-__device__ void lstm_role(const DecParams& p, MatSmem& sm, int idx, int n_ctas, int n_att_ctas) {
+template <bool P16, bool IS_ATT>
+__device__ void lstm_role(const DecParams& p, MatSmem<P16>& sm, int idx, int n_ctas, int n_att_ctas) {
+  constexpr int PASS = Cfg<P16>::PASS;
+  // staging columns: A stages [ctx | hatt] early and pre over hatt; D stages [hatt | hdec] early and ctx over both
+  constexpr int XC = 0, X0 = IS_ATT ? SEGC : 0, X1 = IS_ATT ? SEGC : SEG;
   const int tid = threadIdx.x, B = p.B;
   int u0, nu;
   row_range(idx, n_ctas, R, u0, nu);
@@ -528,10 +542,9 @@ __device__ void lstm_role(const DecParams& p, MatSmem& sm, int idx, int n_ctas, 
       float c_old = 0.f;
       if (tid < nu * nb) c_old = cell[(n0 + tid / nu) * R + u0 + tid % nu];     // only this thread ever touches it
       if (IS_ATT)
-        ok = fetch(sm, xchg_vec(xb, B, V_PRE, v0), R, v0, n0, nb, X0, ps == 0 && (p.flags & 1) ? xchg_hint(xb, B, V_PRE) : nullptr,
-                   (unsigned int)N_P2_CTAS * v0, p.s.done);
+        ok = fetch(sm, xchg_vec(xb, B, V_PRE, v0), R, v0, n0, nb, X0, nullptr, 0, p.s.done);
       else
-        ok = fetch(sm, xchg_vec(xb, B, V_CTX, v1), E, v1, n0, nb, XC, ps == 0 && (p.flags & 2) ? xchg_hint(xb, B, V_CTX) : nullptr, n_att * v1, p.s.done);
+        ok = fetch(sm, xchg_vec(xb, B, V_CTX, v1), E, v1, n0, nb, XC, nullptr, 0, p.s.done);
       prof.mark<0>();
       if (!ok) break;
       mat_part(sm, KS_LSTM, n_rows, IS_ATT ? k_in : k_ctx, none, nb, early.get(ps), true);
@@ -555,7 +568,9 @@ __device__ void lstm_role(const DecParams& p, MatSmem& sm, int idx, int n_ctas, 
 }
 
 // role P: rows [pp0, pp0 + npp) of [linear_projection | gate_layer | prenet layer 0 o projection] on hc = [h_dec | context]
-__device__ void proj_role(const DecParams& p, MatSmem& sm, int idx, int n_lstm_ctas) {
+template <bool P16>
+__device__ void proj_role(const DecParams& p, MatSmem<P16>& sm, int idx) {
+  constexpr int PASS = Cfg<P16>::PASS, XC = 0, X0 = 0;     // the context early, h_dec over it
   const int tid = threadIdx.x, B = p.B;
   int pp0, npp;
   row_range(idx, N_PP_CTAS, NPP, pp0, npp);
@@ -567,7 +582,6 @@ __device__ void proj_role(const DecParams& p, MatSmem& sm, int idx, int n_lstm_c
   unsigned long long* const xb = p.s.xchg;
   unsigned long long* const done_word = reinterpret_cast<unsigned long long*>(p.s.done + 4);
   const bool owns_gate = pp0 <= M && M < pp0 + npp;
-  const unsigned int n_lstm = (unsigned int)n_lstm_ctas;
   const SegDesc none = {0, 0, 0}, k_hdec = {0, X0, ST_SEG}, k_ctx = {SEG, XC, ST_SEGC};
   PassReg early;
 #pragma unroll
@@ -593,7 +607,7 @@ __device__ void proj_role(const DecParams& p, MatSmem& sm, int idx, int n_lstm_c
         const int row = pp0 + tid % npp;
         if (row > M && more) drop0 = p.drop[(((long long)(t + 1) * 2 + 0) * B + n0 + tid / npp) * R + row - M - 1];
       }
-      ok = fetch(sm, xchg_vec(xb, B, V_HDEC, v1), R, v1, n0, nb, X0, ps == 0 && (p.flags & 4) ? xchg_hint(xb, B, V_HDEC) : nullptr, n_lstm * v1, p.s.done);
+      ok = fetch(sm, xchg_vec(xb, B, V_HDEC, v1), R, v1, n0, nb, X0, nullptr, 0, p.s.done);
       prof.mark<0>();
       if (!ok) break;
       mat_part(sm, KS_PP, npp, k_hdec, none, nb, early.get(ps), true);
@@ -636,7 +650,9 @@ __device__ void proj_role(const DecParams& p, MatSmem& sm, int idx, int n_lstm_c
 }
 
 // role Q: rows [r0, r0 + nr) of prenet layer 1
-__device__ void prenet_role(const DecParams& p, MatSmem& sm, int idx) {
+template <bool P16>
+__device__ void prenet_role(const DecParams& p, MatSmem<P16>& sm, int idx) {
+  constexpr int PASS = Cfg<P16>::PASS, X0 = 0;
   const int tid = threadIdx.x, B = p.B;
   int r0, nr;
   row_range(idx, N_P2_CTAS, R, r0, nr);
@@ -659,8 +675,7 @@ __device__ void prenet_role(const DecParams& p, MatSmem& sm, int idx) {
         const int nb = min(PASS, B - n0);
         unsigned char drop1 = 0;
         if (tid < nr * nb) drop1 = p.drop[(((long long)(t + 1) * 2 + 1) * B + n0 + tid / nr) * R + r0 + tid % nr];
-        ok = fetch(sm, xchg_vec(xb, B, V_P1, v1), R, v1, n0, nb, X0, ps == 0 && (p.flags & 8) ? xchg_hint(xb, B, V_P1) : nullptr,
-                   (unsigned int)N_PP_CTAS * v1, p.s.done);
+        ok = fetch(sm, xchg_vec(xb, B, V_P1, v1), R, v1, n0, nb, X0, nullptr, 0, p.s.done);
         prof.mark<0>();
         if (!ok) break;
         mat_part(sm, KS_P2, nr, k_all, none, nb, 0.f, true);
@@ -928,6 +943,7 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
   prof.flush(p.prof);
 }
 
+template <bool P16>
 __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int mi = (int)blockIdx.x - p.B, GM = (int)gridDim.x - p.B;
@@ -935,11 +951,11 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
   if (mi < 0) {
     attention_role(p, *reinterpret_cast<AttSmem*>(smem_raw), blockIdx.x);
   } else {
-    MatSmem& sm = *reinterpret_cast<MatSmem*>(smem_raw);
-    if (mi < n_lstm) lstm_role<true>(p, sm, mi, n_lstm, p.B);
-    else if (mi < 2 * n_lstm) lstm_role<false>(p, sm, mi - n_lstm, n_lstm, p.B);
-    else if (mi < 2 * n_lstm + N_PP_CTAS) proj_role(p, sm, mi - 2 * n_lstm, n_lstm);
-    else if (mi < 2 * n_lstm + N_PP_CTAS + N_P2_CTAS) prenet_role(p, sm, mi - 2 * n_lstm - N_PP_CTAS);
+    MatSmem<P16>& sm = *reinterpret_cast<MatSmem<P16>*>(smem_raw);
+    if (mi < n_lstm) lstm_role<P16, true>(p, sm, mi, n_lstm, p.B);
+    else if (mi < 2 * n_lstm) lstm_role<P16, false>(p, sm, mi - n_lstm, n_lstm, p.B);
+    else if (mi < 2 * n_lstm + N_PP_CTAS) proj_role<P16>(p, sm, mi - 2 * n_lstm);
+    else if (mi < 2 * n_lstm + N_PP_CTAS + N_P2_CTAS) prenet_role<P16>(p, sm, mi - 2 * n_lstm - N_PP_CTAS);
     // (an odd CTA out, if any, has nothing to do)
   }
 }
@@ -992,7 +1008,7 @@ int taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, con
   FAC_REQUIRE(w && memory && pmem && lengths && drop && s && mel && gate, "taco_decoder: NULL argument");
   FAC_REQUIRE(s->c_att && s->c_dec && s->xchg && s->w_prev && s->w_cum && s->done && s->out_len,
               "taco_decoder: NULL state buffer");
-  FAC_REQUIRE(B <= PASS * MAXPASS, "taco_decoder: at most %d utterances per launch", PASS * MAXPASS);
+  FAC_REQUIRE(B <= 8 * MAXPASS, "taco_decoder: at most %d utterances per launch", 8 * MAXPASS);
   FAC_REQUIRE(B > 0 && T_in > 0 && max_steps > 0, "taco_decoder: empty problem");
   FAC_REQUIRE(window >= 0 && 2 * window + 1 <= MAXW, "taco_decoder: attention window %d unsupported (max %d)", window,
               (MAXW - 1) / 2);
@@ -1005,8 +1021,11 @@ int taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, con
   FAC_REQUIRE(B <= sms - MIN_MATRIX_CTAS,
               "taco_decoder: at most %d utterances per launch on this device (one attention CTA each next to >= %d "
               "matrix CTAs); split the batch", sms - MIN_MATRIX_CTAS, MIN_MATRIX_CTAS);
-  const size_t smem = sizeof(MatSmem) > sizeof(AttSmem) ? sizeof(MatSmem) : sizeof(AttSmem);
-  cudaError_t e = cudaFuncSetAttribute(taco_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool p16 = B > 8 && B <= MAX_B_P16;
+  const size_t mat_smem = p16 ? sizeof(MatSmem<true>) : sizeof(MatSmem<false>);
+  const size_t smem = mat_smem > sizeof(AttSmem) ? mat_smem : sizeof(AttSmem);
+  const void* kernel = p16 ? (const void*)taco_decoder_kernel<true> : (const void*)taco_decoder_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("taco_decoder: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
     return 2;
@@ -1018,13 +1037,9 @@ int taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, con
   p.mel = mel; p.gate = gate; p.align = align;
   p.B = B; p.T_in = T_in; p.max_steps = max_steps; p.window = window; p.gate_threshold = gate_threshold;
   p.prof = g_dec_prof;
-  {
-    const char* f = getenv("FAC_TACO_FLAGS");
-    p.flags = f ? atoi(f) : 0;
-  }
   void* args[] = {&p};
   // cooperative launch = co-residency guarantee for the CTAs that poll each other's words
-  e = cudaLaunchCooperativeKernel((void*)taco_decoder_kernel, dim3(sms), dim3(DEC_THREADS), args, smem, st);
+  e = cudaLaunchCooperativeKernel(kernel, dim3(sms), dim3(DEC_THREADS), args, smem, st);
   count_launch();
   if (e != cudaSuccess) {
     set_error("taco_decoder: cooperative launch failed: %s", cudaGetErrorString(e));

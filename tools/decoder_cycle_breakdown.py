@@ -15,8 +15,8 @@ m = Tacotron2(create_hparams_stage())
 m.load_state_dict(synth.tacotron_state())
 m = m.cuda().eval()
 m.collect_timing, m.return_alignments = True, False
-SLOTS = [("early columns", 2), ("awaited vector (wait + sweep)", 0), ("products + epilogue", 1), ("stop count", 12),
-         ("of which: arrival counters", 13), ("sweeps", 15)]
+SLOTS = [("early columns (incl. waiting for them)", 2), ("awaited vector (wait + sweep)", 0), ("products + epilogue", 1),
+         ("stop count", 12)]
 ATT = [("wait h_att", 14), ("query projection", 11), ("energies", 12), ("softmax+context", 13), ("prepare", 4),
        ("wait stop", 9)]
 args = [int(a) for a in sys.argv[1:]] or [1, 690, 8, 690, 32, 690]

@@ -26,7 +26,14 @@ __device__ __forceinline__ void split_half2(float2 x, uint32_t& hi, uint32_t& lo
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-template <int MODE>   // 0 full, 1 no split (raw bits), 2 no ldmatrix, 3 no mma
+// ~JUNK_KB KB of straight-line code nobody else executes: evicts the loop from the instruction caches
+template <int N>
+__device__ __forceinline__ float junk(float x) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) x = fmaf(x, 1.0001f + 1e-6f * i, 0.5f + i);
+  return x;
+}
+template <int MODE>   // 0 full, 1 no split (raw bits), 2 no ldmatrix, 3 no mma, 4 full + junk between repetitions
 __global__ void __launch_bounds__(512, 1) k(long long* out, float* sink, int total, int n_warps, int reps) {
   extern __shared__ __align__(16) unsigned char raw[];
   Smem& sm = *reinterpret_cast<Smem*>(raw);
@@ -36,6 +43,10 @@ __global__ void __launch_bounds__(512, 1) k(long long* out, float* sink, int tot
   long long t_mma = 0, t_red = 0;
   float res = 0.f;
   for (int rep = 0; rep < reps; ++rep) {
+    if (MODE >= 4) {
+      res = MODE == 4 ? junk<2048>(res) : MODE == 5 ? junk<8192>(res) : junk<16384>(res);
+      __syncthreads();
+    }
     const long long t0 = clock64();
     if (warp < n_warps) {
       int arow = (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -51,18 +62,18 @@ __global__ void __launch_bounds__(512, 1) k(long long* out, float* sink, int tot
         if (ls < total) {
           const int koff = 16 * ls, xo = 16 * ls;
           uint32_t ah[4] = {1, 2, 3, 4}, al[4] = {5, 6, 7, 8}, bh[2], bl[2];
-          if (MODE != 2) {
+          if (MODE != 2 || MODE >= 4) {
             ldmatrix_x4(ah, a_hi + koff * 2);
             ldmatrix_x4(al, a_lo + koff * 2);
           }
           const float2 x0 = *reinterpret_cast<const float2*>(xrow0 + xo), x1 = *reinterpret_cast<const float2*>(xrow0 + xo + 8);
-          if (MODE != 1) {
+          if (MODE != 1 || MODE >= 4) {
             split_half2(x0, bh[0], bl[0]);
             split_half2(x1, bh[1], bl[1]);
           } else {
             bh[0] = __float_as_uint(x0.x); bl[0] = __float_as_uint(x0.y); bh[1] = __float_as_uint(x1.x); bl[1] = __float_as_uint(x1.y);
           }
-          if (MODE != 3) {
+          if (MODE != 3 || MODE >= 4) {
             mma_f16(acc[0], ah, bh);
             mma_f16(acc[1], al, bh);
             mma_f16(acc[2], ah, bl);
@@ -93,13 +104,13 @@ __global__ void __launch_bounds__(512, 1) k(long long* out, float* sink, int tot
 int main() {
   long long* out; float* sink;
   cudaMalloc(&out, 16); cudaMalloc(&sink, 4);
-  const char* names[4] = {"full", "no split", "no ldmatrix", "no mma"};
+  const char* names[7] = {"full", "no split", "no ldmatrix", "no mma", "full, 32 KB of other code between", "full, 128 KB between", "full, 256 KB between"};
   auto run = [&](auto kern, int mode, int total, int nw) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     kern<<<1, 512, sizeof(Smem)>>>(out, sink, total, nw, 50);
     long long h[2];
     cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
-    printf("%-12s %2d steps on %2d warps: products %5lld cycles (warp 0), barrier + reduction %5lld\n", names[mode], total, nw, h[0], h[1]);
+    printf("%-36s %2d steps on %2d warps: products %5lld cycles (warp 0), barrier + reduction %5lld\n", names[mode], total, nw, h[0], h[1]);
   };
   for (int total : {19, 38})
     for (int nw : {4, 8, 16}) {
@@ -107,6 +118,9 @@ int main() {
       run(k<1>, 1, total, nw);
       run(k<2>, 2, total, nw);
       run(k<3>, 3, total, nw);
+      run(k<4>, 4, total, nw);
+      run(k<5>, 5, total, nw);
+      run(k<6>, 6, total, nw);
     }
   printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
