@@ -141,6 +141,7 @@ struct MatSmem {                  // matrix CTAs
   unsigned int prof[PROF_SLOTS];
   alignas(16) float xs[PASS][XSTRIDE];  // staged input vectors of a pass of utterances
 };
+constexpr int LOC_LD = NF + 8;    // halfs per row of the location features (+8: ldmatrix rows hit distinct banks)
 struct AttSmem {                  // attention CTAs
   float wq[A][R];                 // query_layer weight, resident
   float S[MAXW][A];               // exp(2 (location_dense(location_conv(.)) + processed_memory)) of the coming window
@@ -153,7 +154,7 @@ struct AttSmem {                  // attention CTAs
   int n_done, ok;
   unsigned int prof[PROF_SLOTS];
   alignas(16) union {
-    float loc[MAXW][NF];          // preparation
+    __half loc[2][MAXW][LOC_LD];  // preparation: location_conv output as half hi/lo pairs (mma operand)
     float ctxp[CTXP][E];          // critical path
   } x;
 };
@@ -735,57 +736,97 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
     window_bounds(t, p.window, len, start, end);
     nw = end - start + 1;
     // previous / cumulative weights around the window (zero outside the sequence: conv padding)
+    constexpr int NCAT = MAXW + KF - 1 + 2;
     const int c0 = start - (KF - 1) / 2, ncat = nw + KF - 1;
-    for (int i = tid; i < 2 * ncat; i += DEC_THREADS) {
-      const int c = i / ncat, q = i - c * ncat, pos = c0 + q;
+    if (tid < 2 * NCAT) {
+      const int c = tid >= NCAT, q = tid - c * NCAT, pos = c0 + q;
       float v = 0.f;
-      if (pos >= 0 && pos < p.T_in) v = c == 0 ? wprev[pos] : wcum[pos];
-      sm.cat[c][q] = v;
+      if (q < ncat && pos >= 0 && pos < p.T_in) v = c == 0 ? wprev[pos] : wcum[pos];
+      sm.cat[c][q] = v;                // zeros beyond the window: positions >= nw below are computed but never used
     }
     __syncthreads();
     prof.sub<16>(tp);
-    // location_conv (model.py:57): loc[q][f] = sum_{c,k} w[c][k][f] * cat[c][q + k]
-    for (int i = tid; i < nw * NF; i += DEC_THREADS) {
-      const int q = i / NF, f = i - q * NF;
-      float acc0 = 0.f, acc1 = 0.f;
+    // location_conv (model.py:57): loc[q][f] = sum_{c,k} w[c][k][f] * cat[c][q + k].  Lane = filter, warp = three
+    // consecutive positions: one weight and one new input per tap feed three FMAs (sliding window).
+    {
+      const int f = lane, q0 = 3 * warp;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < KF; ++k) {
-        acc0 = fmaf(__ldg(p.w.w_loc + k * NF + f), sm.cat[0][q + k], acc0);
-        acc1 = fmaf(__ldg(p.w.w_loc + (KF + k) * NF + f), sm.cat[1][q + k], acc1);
+      for (int c = 0; c < 2; ++c) {
+        float x0 = sm.cat[c][q0], x1 = sm.cat[c][q0 + 1];
+#pragma unroll
+        for (int k = 0; k < KF; ++k) {
+          const float x2 = sm.cat[c][q0 + k + 2];
+          const float w = __ldg(p.w.w_loc + (c * KF + k) * NF + f);
+          a0 = fmaf(w, x0, a0);
+          a1 = fmaf(w, x1, a1);
+          a2 = fmaf(w, x2, a2);
+          x0 = x1;
+          x1 = x2;
+        }
       }
-      sm.x.loc[q][f] = acc0 + acc1;
+      const float v[3] = {a0, a1, a2};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const __half h = __float2half_rn(v[i]);
+        sm.x.loc[0][q0 + i][f] = h;
+        sm.x.loc[1][q0 + i][f] = __float2half_rn(v[i] - __half2float(h));
+      }
     }
     __syncthreads();
     prof.sub<17>(tp);
-    // S[q][a] = location_dense(loc[q])[a] + processed_memory[q][a] (model.py:94-96): warp = 3 positions,
-    // lane = 5 channels
-    {
-      float acc[3][5];
+    // S[q][a] = exp(2 (location_dense(loc[q])[a] + processed_memory[q][a])) (model.py:94-96) on the tensor cores:
+    // [48 positions x 32 filters] x [32 x 150 channels], a warp per 8-channel n-tile (19 of them), all three
+    // m-tiles; the weights come straight from global memory (L1-resident: 19 KB), split into half hi/lo pairs
+    // like the features (three products: fp32-grade).
+    for (int nt = warp; nt < (A + 7) / 8; nt += DEC_WARPS) {
+      const int g = lane >> 2, t2 = 2 * (lane & 3), a_col = 8 * nt + t2;       // this lane's output columns a_col, + 1
+      // processed_memory of this lane's outputs (rows g, g + 8 of each m-tile): ask for it first
+      float2 pm[3][2];
 #pragma unroll
-      for (int qi = 0; qi < 3; ++qi)
+      for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const int q = warp + qi * DEC_WARPS, a = lane + 32 * j;
-          acc[qi][j] = (q < nw && a < A) ? __ldg(pmem + (long long)(start + q) * A + a) : 0.f;
+        for (int hh = 0; hh < 2; ++hh) {
+          const int q = 16 * mt + g + 8 * hh;
+          pm[mt][hh] = (q < nw && a_col < A) ? __ldg(reinterpret_cast<const float2*>(pmem + (long long)(start + q) * A + a_col))
+                                            : make_float2(0.f, 0.f);
         }
-#pragma unroll 4
-      for (int f = 0; f < NF; ++f) {
-        float wl[5], lq[3];
+      float acc[3][4];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) wl[j] = lane + 32 * j < A ? __ldg(p.w.w_ld_t + f * A + lane + 32 * j) : 0.f;
+      for (int i = 0; i < 12; ++i) (&acc[0][0])[i] = 0.f;
 #pragma unroll
-        for (int qi = 0; qi < 3; ++qi) lq[qi] = sm.x.loc[min(warp + qi * DEC_WARPS, MAXW - 1)][f];
+      for (int ks = 0; ks < 2; ++ks) {
+        // B fragment: filters (k) 16 ks + t2, + 1 and + 8, + 9 of channel 8 nt + g
+        const int an = 8 * nt + g;
+        const float* wp = p.w.w_ld_t + (16 * ks + t2) * A + an;
+        float2 w0 = make_float2(0.f, 0.f), w1 = w0;
+        if (an < A) {
+          w0 = make_float2(__ldg(wp), __ldg(wp + A));
+          w1 = make_float2(__ldg(wp + 8 * A), __ldg(wp + 9 * A));
+        }
+        uint32_t bh[2], bl[2];
+        split_half2(w0, bh[0], bl[0]);
+        split_half2(w1, bh[1], bl[1]);
+        const int arow = (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-        for (int qi = 0; qi < 3; ++qi)
-#pragma unroll
-          for (int j = 0; j < 5; ++j) acc[qi][j] = fmaf(wl[j], lq[qi], acc[qi][j]);
+        for (int mt = 0; mt < 3; ++mt) {
+          uint32_t ah[4], al[4];
+          ldmatrix_x4(ah, (uint32_t)__cvta_generic_to_shared(&sm.x.loc[0][16 * mt + arow][16 * ks + (lane >> 4) * 8]));
+          ldmatrix_x4(al, (uint32_t)__cvta_generic_to_shared(&sm.x.loc[1][16 * mt + arow][16 * ks + (lane >> 4) * 8]));
+          mma_f16(acc[mt], ah, bh);
+          mma_f16(acc[mt], al, bh);
+          mma_f16(acc[mt], ah, bl);
+        }
       }
 #pragma unroll
-      for (int qi = 0; qi < 3; ++qi)
+      for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const int q = warp + qi * DEC_WARPS, a = lane + 32 * j;
-          if (q < nw && a < A) sm.S[q][a] = exp2x(acc[qi][j]);
+        for (int hh = 0; hh < 2; ++hh) {
+          const int q = 16 * mt + g + 8 * hh;
+          if (q < nw && a_col < A) {
+            sm.S[q][a_col] = exp2x(acc[mt][2 * hh] + pm[mt][hh].x);
+            sm.S[q][a_col + 1] = exp2x(acc[mt][2 * hh + 1] + pm[mt][hh].y);
+          }
         }
     }
     prof.sub<18>(tp);
@@ -819,18 +860,27 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
       }
       if (__syncthreads_or(dead)) return false;
       prof.sub<14>(tp);
-      const float4* h4 = reinterpret_cast<const float4*>(sm.h);
-      const float4 hz = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 hv0 = h4[lane], hv1 = h4[lane + 32], hv2 = lane < 11 ? h4[lane + 64] : hz;
-#pragma unroll 2
-      for (int r = warp; r < A; r += DEC_WARPS) {
-        const float4* w4 = reinterpret_cast<const float4*>(&sm.wq[r][0]);
-        const float4 a0 = w4[lane], a1 = w4[lane + 32], a2 = lane < 11 ? w4[lane + 64] : hz;
-        float acc = a0.x * hv0.x + a0.y * hv0.y + a0.z * hv0.z + a0.w * hv0.w;
-        acc += a1.x * hv1.x + a1.y * hv1.y + a1.z * hv1.z + a1.w * hv1.w;
-        acc += a2.x * hv2.x + a2.y * hv2.y + a2.z * hv2.z + a2.w * hv2.w;
-        acc = warp_sum(acc);
-        if (lane == 0) sm.upq[r] = exp2x(acc);
+      // W_q h: a row is shared by three lanes (a third of K each: 25 float4 per lane, conflict-free in shared
+      // memory), ten rows per warp; two shuffles finish a row
+      {
+        const int rs = lane / 3, part = lane - 3 * rs, r = warp * 10 + rs;
+        float sum = 0.f;
+        if (lane < 30 && r < A) {
+          const float4* w4 = reinterpret_cast<const float4*>(&sm.wq[r][100 * part]);
+          const float4* h4 = reinterpret_cast<const float4*>(sm.h + 100 * part);
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 5
+          for (int i = 0; i < 25; ++i) {
+            const float4 a = w4[i], hv = h4[i];
+            s0 = fmaf(a.x, hv.x, s0);
+            s1 = fmaf(a.y, hv.y, s1);
+            s2 = fmaf(a.z, hv.z, s2);
+            s3 = fmaf(a.w, hv.w, s3);
+          }
+          sum = (s0 + s1) + (s2 + s3);
+        }
+        const float v1 = __shfl_down_sync(0xffffffffu, sum, 1), v2 = __shfl_down_sync(0xffffffffu, sum, 2);
+        if (lane < 30 && part == 0 && r < A) sm.upq[r] = exp2x(sum + (v1 + v2));
       }
     }
     __syncthreads();
