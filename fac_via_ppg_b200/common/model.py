@@ -153,6 +153,7 @@ class Tacotron2(nn.Module):
     # sparse form -- a pair (weights (B, T_out, 2w+1), start (B, T_out)): step t attends input positions
     # start[b, t] + [0, 2w], the only ones the attention window leaves unmasked (reference utils.py:46-78)
     return_alignments = True
+    max_utterances_per_launch = 36      # decoder launches beyond this are split (see _decode)
     ppg_prune = None             # (k, threshold): prune dense inputs on the GPU and use the gather prenet (see above)
 
     def __init__(self, hparams):
@@ -279,7 +280,8 @@ class Tacotron2(nn.Module):
         retires as soon as its own longest member has fired its stop gate; an utterance's result does not
         depend on the group it runs in (the decoder's arithmetic is batch-invariant)."""
         B = memory.shape[0]
-        limit = max(1, min(torch.cuda.get_device_properties(memory.device).multi_processor_count - 100, 36))
+        limit = max(1, min(torch.cuda.get_device_properties(memory.device).multi_processor_count - 100,
+                           self.max_utterances_per_launch))
         group = min(limit, 32)
         if B <= limit:
             return self._decode_group(packed, memory, dec_masks, n_steps, lens)

@@ -90,19 +90,26 @@ def test_exact_fp32_precision_mode_matches_oracle(model):
         model.set_precision("int8")
 
 
-@pytest.mark.parametrize("batch", [41, 50])
-def test_batches_beyond_one_launch_are_split_into_groups(model, batch):
-    """One decoder launch holds (SMs - 100) = 48 utterances on B200 (41: the fewest matrix CTAs per launch in use);
-    a larger batch runs as consecutive groups and every utterance still equals the same utterance processed
-    alone, bit for bit."""
+@pytest.mark.parametrize("batch,per_launch", [(9, 36), (20, 36), (36, 36), (41, 36), (41, 48), (50, 36)])
+def test_batches_beyond_one_launch_are_split_into_groups(model, batch, per_launch):
+    """The decoder kernel takes up to (SMs - 100) = 48 utterances per launch on B200, in passes of 8 (B <= 8 and
+    B > 36) or 16 (8 < B <= 36) through every matrix CTA; the module splits batches beyond 36 into consecutive
+    groups of 32 (two launches beat six passes).  Whatever the batch, the passes and the groups, every utterance
+    equals the same utterance processed alone, bit for bit."""
     t_in = 14
     force_length(model, t_in)
     ppg = synth.synthetic_ppg(batch, t_in, seed=4).to(DEV)
     torch.manual_seed(4)
     masks = tacotron_oracle.record_dropout_tape(batch, t_in, t_in)
-    out = model.inference(ppg, dropout_tape=masks)
+    model.max_utterances_per_launch = per_launch
+    try:
+        out = model.inference(ppg, dropout_tape=masks)
+    finally:
+        del model.max_utterances_per_launch          # back to the class default
     assert out[1].shape == (batch, 80, t_in) and out[3].shape == (batch, t_in, t_in)
-    for k in (0, 31, 32, batch - 1):
+    for k in sorted({0, 7, 8, 15, 16, 31, 32, batch - 1}):
+        if k >= batch:
+            continue
         alone = model.inference(ppg[k:k + 1].contiguous(), dropout_tape=[m[k:k + 1] for m in masks])
         assert torch.equal(out[1][k], alone[1][0]), k
         assert torch.equal(out[3][k], alone[3][0]), k
