@@ -343,13 +343,13 @@ typedef struct fac_taco_decoder_state {
   int* align_start;   /* (B, max_steps) */
 } fac_taco_decoder_state;
 
-/* Diagnostic: runs `iters` grid-wide barriers of the decoder kernel's kind on a full cooperative grid;
- * time the launch to get the per-barrier latency.  `zeroed_counter` is one zero-initialised uint32. */
+/* Diagnostic: runs `iters` grid-wide barriers (release-add + acquire spin, what round 1's decoder used between
+ * its phases) on a full cooperative grid; time the launch to get the per-barrier latency that the dataflow decoder
+ * avoids.  `zeroed_counter` is one zero-initialised uint32. */
 int fac_selftest_grid_barrier(unsigned int* zeroed_counter, int iters, void* stream);
 
-/* Optional cycle counters of the decoder kernel: device buffer of grid*16 int64 per CTA
- * ([2i] = cycles in phase i's body, [2i+1] = cycles waiting in the grid barrier after it, i = 0..4:
- * attention LSTM, attention, decoder LSTM, projection, prenet; [10] = total); NULL disables. */
+/* Optional cycle counters of the decoder kernel: device buffer of grid*32 int64 per CTA (slot meanings per role:
+ * tools/decoder_cycle_breakdown.py; [10] = total); NULL disables. */
 void fac_taco_set_profile_buffer(long long* device_buf);
 
 /* The whole autoregressive loop of Decoder.inference (reference model.py:489-535 with decode
@@ -358,8 +358,11 @@ void fac_taco_set_profile_buffer(long long* device_buf);
  *   drop (max_steps, 2, B, 300) uint8 in {0,1}: the always-on prenet dropout masks
  *   (model.py:132-135) of step t, layers 0/1;  outputs mel (B,max_steps,80), gate (B,max_steps),
  *   align (B,max_steps,T_in) pre-zeroed or NULL.  B <= (number of SMs - 100): one CTA per
- *   utterance runs the attention, the others hold the matrices.  Stops when every utterance's
- *   sigmoid(gate) > gate_threshold has fired (model.py:524) or at max_steps (model.py:526-528). */
+ *   utterance runs the attention, the others hold the rows of one matrix each and exchange vectors as
+ *   (value, version) words (no grid barrier; state->xchg).  Stops when every utterance's
+ *   sigmoid(gate) > gate_threshold has fired (model.py:524) or at max_steps (model.py:526-528).
+ *   After the kernel, state->done[7] != 0 means a hand-over timed out (the GPU was shared with a kernel
+ *   that kept CTAs of this one from running, or the state was not zero-filled): the outputs are invalid. */
 int fac_taco_decoder_run(const fac_taco_decoder_weights* w, const float* memory, const float* pmem,
                          const int* lengths, const unsigned char* drop, const fac_taco_decoder_state* state,
                          float* mel, float* gate, float* align, int B, int T_in, int max_steps,
