@@ -513,21 +513,30 @@ __device__ void lstm_role(const DecParams& p, MatSmem<P16>& sm, int idx, int n_c
   prof.init(p.prof != nullptr, sm.prof);
   // early columns of step `t` (role A: called right after the critical part of step t - 1, i.e. speculatively
   // before the stop count of that step is known -- both vectors exist by then whether or not there is a step t)
+  const unsigned int n_pass = (unsigned int)((B + PASS - 1) / PASS);   // role A announces hatt once per pass
   auto early_columns = [&](int t) -> bool {
     const unsigned int v0 = (unsigned int)t, v1 = v0 + 1;
     bool ok = true;
-    for (int ps = 0, n0 = 0; n0 < B && ok; ++ps, n0 += PASS) {
-      const int nb = min(PASS, B - n0);
-      if (IS_ATT) {
-        // ctx_t and hatt_t
-        ok = fetch(sm, xchg_vec(xb, B, V_HATT, v0), R, v0, n0, nb, X1, ps == 0 ? xchg_hint(xb, B, V_HATT) : nullptr, n_lstm * v0, p.s.done) &&
+    if (IS_ATT) {
+      // ctx_t and hatt_t
+      for (int ps = 0, n0 = 0; n0 < B && ok; ++ps, n0 += PASS) {
+        const int nb = min(PASS, B - n0);
+        ok = fetch(sm, xchg_vec(xb, B, V_HATT, v0), R, v0, n0, nb, X1, ps == 0 ? xchg_hint(xb, B, V_HATT) : nullptr, n_lstm * n_pass * v0, p.s.done) &&
              fetch(sm, xchg_vec(xb, B, V_CTX, v0), E, v0, n0, nb, XC, ps == 0 ? xchg_hint(xb, B, V_CTX) : nullptr, n_att * v0, p.s.done);
         if (ok) early.set(ps, mat_part(sm, KS_LSTM, n_rows, k_ctx, k_hid, nb));
-      } else {
-        // hatt_{t+1} (just being published by the role-A CTAs) and hdec_t
-        ok = fetch(sm, xchg_vec(xb, B, V_HDEC, v0), R, v0, n0, nb, X1, nullptr, 0, p.s.done) &&
-             fetch(sm, xchg_vec(xb, B, V_HATT, v1), R, v1, n0, nb, X0, ps == 0 ? xchg_hint(xb, B, V_HATT) : nullptr, n_lstm * v1, p.s.done);
-        if (ok) early.set(ps, mat_part(sm, KS_LSTM, n_rows, k_in, k_hid, nb));
+      }
+    } else {
+      // hdec_t first (complete since the end of the previous step), then hatt_{t+1}, pass by pass as the role-A
+      // CTAs announce it: what is left when the attention has the context ready is as little as possible
+      for (int ps = 0, n0 = 0; n0 < B && ok; ++ps, n0 += PASS) {
+        const int nb = min(PASS, B - n0);
+        ok = fetch(sm, xchg_vec(xb, B, V_HDEC, v0), R, v0, n0, nb, X1, ps == 0 ? xchg_hint(xb, B, V_HDEC) : nullptr, n_lstm * v0, p.s.done);
+        if (ok) early.set(ps, mat_part(sm, KS_LSTM, n_rows, k_hid, none, nb));
+      }
+      for (int ps = 0, n0 = 0; n0 < B && ok; ++ps, n0 += PASS) {
+        const int nb = min(PASS, B - n0);
+        ok = fetch(sm, xchg_vec(xb, B, V_HATT, v1), R, v1, n0, nb, X0, xchg_hint(xb, B, V_HATT), n_lstm * (n_pass * v0 + ps + 1), p.s.done);
+        if (ok) early.set(ps, early.get(ps) + mat_part(sm, KS_LSTM, n_rows, k_in, none, nb));
       }
     }
     prof.mark<2>();
@@ -558,10 +567,11 @@ __device__ void lstm_role(const DecParams& p, MatSmem<P16>& sm, int idx, int n_c
         cell[b * R + j] = cn;
         st_tagged(xchg_vec(xb, B, IS_ATT ? V_HATT : V_HDEC, v1) + b * R + j, sigmoidf_fast(gv[3]) * tanhf_fast(cn), v1);
       }
+      if (IS_ATT) hint_arrive(xchg_hint(xb, B, V_HATT));      // per pass: the decoder LSTM's CTAs start on it
       prof.mark<1>();
     }
     if (!ok) break;
-    hint_arrive(xchg_hint(xb, B, IS_ATT ? V_HATT : V_HDEC));
+    if (!IS_ATT) hint_arrive(xchg_hint(xb, B, V_HDEC));
     if (IS_ATT && t + 1 < p.max_steps && !early_columns(t + 1)) break;
     if (!step_continues(p, &sm.n_done, &sm.ok, v1, prof)) break;
   }
@@ -596,7 +606,8 @@ __device__ void proj_role(const DecParams& p, MatSmem<P16>& sm, int idx) {
     // ---- early: the context columns
     for (int ps = 0, n0 = 0; n0 < B && ok; ++ps, n0 += PASS) {
       const int nb = min(PASS, B - n0);
-      ok = fetch(sm, xchg_vec(xb, B, V_CTX, v1), E, v1, n0, nb, XC, ps == 0 ? xchg_hint(xb, B, V_CTX) : nullptr, (unsigned int)B * v1, p.s.done);
+      // (13 CTAs: they poll the words themselves, pass by pass, instead of waiting for all B attention CTAs)
+      ok = fetch(sm, xchg_vec(xb, B, V_CTX, v1), E, v1, n0, nb, XC, nullptr, 0, p.s.done);
       if (ok) early.set(ps, mat_part(sm, KS_PP, npp, k_ctx, none, nb));
     }
     prof.mark<2>();
