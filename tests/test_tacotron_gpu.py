@@ -115,6 +115,23 @@ def test_batches_beyond_one_launch_are_split_into_groups(model, batch, per_launc
         assert torch.equal(out[3][k], alone[3][0]), k
 
 
+@pytest.mark.parametrize("n_steps", [1, 2, 3])
+def test_shortest_decodes(model, n_steps):
+    """max_decoder_steps of 1 .. 3 (reference model.py:526-528 stops with its warning): the dataflow between the
+    decoder kernel's CTAs has to start up and wind down without a step to hide behind."""
+    batch, t_in = 2, 12
+    sd = synth.tacotron_state()
+    ppg = synth.synthetic_ppg(batch, t_in, seed=40 + n_steps)
+    torch.manual_seed(n_steps)
+    masks = tacotron_oracle.record_dropout_tape(batch, t_in, n_steps)
+    ref = tacotron_oracle.tacotron_inference(sd, synth.TACOTRON_HPARAMS, ppg, masks, 2.0, n_steps)
+    force_length(model, n_steps)
+    out = model.inference(ppg.to(DEV), dropout_tape=masks)
+    for name, a, b in zip(("mel", "mel_post", "gate", "align"), out, ref):
+        assert a.shape == b.shape, name
+        assert (a.cpu() - b).abs().max().item() <= MEL_TOL, name
+
+
 def test_gate_stops_decoding_like_reference(model):
     """Natural stop: the reference (B == 1) breaks after the first frame whose sigmoid(gate) > threshold."""
     sd = synth.tacotron_state()

@@ -20,6 +20,10 @@ __device__ __forceinline__ void load16(const unsigned long long* src, unsigned l
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(src) : "memory");
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(b) : "l"(src + 1) : "memory");
   }
+  if (V == 5) asm volatile("ld.global.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+  if (V == 6) asm volatile("ld.global.cv.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+  if (V == 7) asm volatile("ld.global.lu.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+  if (V == 8) asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
 }
 
 template <int V>
@@ -48,6 +52,29 @@ __global__ void __launch_bounds__(THREADS, 1) sweep(const unsigned long long* da
   if (acc == 0x123456789ull) *sink = acc + (unsigned long long)stage[5].x;
 }
 
+// latency of ONE dependent load per iteration (thread 0 only): the next address depends on the loaded value
+template <int V>
+__global__ void chase(const unsigned long long* data, int iters, long long* cycles, unsigned long long* sink) {
+  if (threadIdx.x != 0) return;
+  unsigned long long off = 0, a, b;
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    load16<V>(data + off, a, b);
+    off = (a & 1) * 2 + ((off + 1024) & 65535);      // a is 0: walks through 64 K words = 512 KB, always an L2 hit
+  }
+  cycles[0] = (clock64() - t0) / iters;
+  if (off == 0x12345) *sink = off;
+}
+template <int V>
+void run_chase(const char* name) {
+  unsigned long long *data, *sink; long long* cyc;
+  CK(cudaMalloc(&data, 1 << 20)); CK(cudaMemset(data, 0, 1 << 20)); CK(cudaMalloc(&sink, 8)); CK(cudaMalloc(&cyc, 8));
+  chase<V><<<1, 32>>>(data, 2000, cyc, sink); CK(cudaDeviceSynchronize());
+  chase<V><<<1, 32>>>(data, 2000, cyc, sink); CK(cudaDeviceSynchronize());
+  long long h; CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+  printf("dependent-load latency, %-30s %lld cycles\n", name, h); fflush(stdout);
+  cudaFree(data); cudaFree(sink); cudaFree(cyc);
+}
 template <int V>
 void run(const char* name, int sms, int pieces, int ctas) {
   unsigned long long *data, *sink;
@@ -73,13 +100,20 @@ void run(const char* name, int sms, int pieces, int ctas) {
 int main() {
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  run_chase<0>("ld.volatile.v2.u64"); run_chase<1>("ld.relaxed.gpu.v2.u64"); run_chase<2>("ld.global.cg.v2.u64");
+  run_chase<5>("ld.global.L1::no_allocate.v2"); run_chase<6>("ld.global.cv.v2.u64"); run_chase<7>("ld.global.lu.v2.u64");
+  run_chase<8>("ld.global.v2.u64 (L1)");
   for (int ctas : {1, sms})
-    for (int pieces : {150, 1200, 2400, 4800}) {
+    for (int pieces : {150, 1200}) {
       run<0>("ld.volatile.v2.u64", sms, pieces, ctas);
       run<1>("ld.relaxed.gpu.v2.u64", sms, pieces, ctas);
       run<2>("ld.global.cg.v2.u64", sms, pieces, ctas);
       run<3>("2 x ld.volatile.u64", sms, pieces, ctas);
       run<4>("2 x ld.relaxed.gpu.u64", sms, pieces, ctas);
+      run<5>("ld.global.L1::no_allocate.v2", sms, pieces, ctas);
+      run<6>("ld.global.cv.v2.u64", sms, pieces, ctas);
+      run<7>("ld.global.lu.v2.u64", sms, pieces, ctas);
+      run<8>("ld.global.v2.u64 (L1, stale!)", sms, pieces, ctas);
     }
   return 0;
 }
