@@ -393,7 +393,11 @@ __device__ __noinline__ float mat_part(MatSmem<P16>& sm, int ks, int n_rows, con
   float a = 0.f;
   if ((tid & (PASS - 1)) < nb && (tid >> PSHIFT) < n_rows) {
     const int r = tid >> PSHIFT, c = tid & (PASS - 1);
-    for (int w = 0; w < n_slots; ++w) a += sm.part[w][r][c];
+    float v[MAT_WARPS];
+#pragma unroll
+    for (int w = 0; w < MAT_WARPS; ++w) v[w] = w < n_slots ? sm.part[w][r][c] : 0.f;   // all loads in flight, fixed order of
+#pragma unroll
+    for (int w = 0; w < MAT_WARPS; ++w) a += v[w];                                     // the additions
     a *= 1.0f / W_SCALE;
     if (to_sums) sm.sums[r][c] = a + add;             // the epilogue's input: early columns + this piece
   }
