@@ -77,6 +77,10 @@ struct TcParams {
   float* out8;             // gate: (B, T, TC_NOUT) running end() pre-activation
   int accumulate_out8;
   int out_row_mul, out_row_off;   // residual epilogue: output row = column * mul + off (phase-strided upsampler)
+  // grouped launch (the upsampler's phases): n_phases GEMMs over the SAME activations, phase ph with the weight rows
+  // [ph * w_phase_rows, ...) of the weight map and output row offset out_row_off + ph; the tile index space is
+  // n_phases x tiles_pp (tiles_pp = the tiles of one phase rounded up to whole CTA groups).  0 = one GEMM.
+  int n_phases, tiles_pp, w_phase_rows;
   // TC_LINEAR (generic Conv1d / Linear): v = act(acc + bias) [* mask] [+ residual] on the first n_valid columns,
   // written as fp32 (out_f32, row stride out_ld) and/or as the bf16 hi/lo operand copies of the next layer
   // (out_hi/out_lo, row stride C; columns >= n_valid are exact zeros because their weights and bias are)
@@ -124,6 +128,9 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
   const int n_cols = p.n_total < TC_NHALF ? p.n_total : TC_NHALF;
   // unit schedule, identical in the three roles: the it-th unit of this CTA group is (first tile tb, block nb)
   const int n_groups = (int)gridDim.x / CG, group_id = (int)blockIdx.x / CG;
+  // grouped launch: tile index tb -> (phase, tile of the phase); a single GEMM is one phase of all tiles
+  const int n_phases = p.n_phases > 0 ? p.n_phases : 1;
+  const int tiles_pp = p.n_phases > 0 ? p.tiles_pp : ((p.n_tiles + CG - 1) / CG) * CG;
   const int total_units = ((p.n_tiles + CG - 1) / CG) * n_blocks;
   // K chunks (flat schedule only): a unit's contraction is walked in chains of chunk_steps K steps, each with its
   // own accumulator; the chains of a unit are consecutive entries of the schedule of the same CTA group
@@ -141,7 +148,7 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
     tb = tile_first + (it / n_blocks) * (int)gridDim.x;
     nb = it % n_blocks;
     ck = 0;
-    return tb < p.n_tiles;
+    return tb < n_phases * tiles_pp;
   };
 
   if (threadIdx.x == 0) {
@@ -181,7 +188,8 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
       for (int it = 0;; ++it) {
         int tb, nb, ck;
         if (!unit_at(it, tb, nb, ck)) break;
-        const int tile = tb + rank;                    // may be one past the end for the pair's second CTA:
+        const int ph = tb / tiles_pp;
+        const int tile = tb - ph * tiles_pp + rank;    // may be one past the end for the pair's second CTA:
         const int b = tile / p.tiles_per_batch;        // its loads are then fully out of bounds (zero fill)
         const int t0 = (tile % p.tiles_per_batch) * TC_BM;
         {
@@ -201,7 +209,7 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
             prod_wait += clock64() - w0;
             uint8_t* st = smem + stage * STAGE_BYTES;
             const uint32_t bytes = (uint32_t)(p.nsplit * A_BYTES) + w_bytes * (use_wlo ? 2u : 1u);
-            const int w_row = nb * TC_NHALF + rank * w_rows;
+            const int w_row = ph * p.w_phase_rows + nb * TC_NHALF + rank * w_rows;
             if (CG == 1) {
               mbar_arrive_expect_tx(&full[stage], bytes);
               tma_load_3d(st, mh, &full[stage], c0, row0, b);
@@ -296,7 +304,8 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
       int tb, nb, ck;
       if (!unit_at(it, tb, nb, ck)) break;
       const bool first_chunk = ck == 0, last_chunk = ck == n_chunks - 1;
-      const int tile = tb + rank;
+      const int ph = tb / tiles_pp;
+      const int tile = tb - ph * tiles_pp + rank;
       const int b = tile / p.tiles_per_batch;
       const int t = (tile % p.tiles_per_batch) * TC_BM + row;
       const bool valid = tile < p.n_tiles && t < p.T;
@@ -445,7 +454,7 @@ wn_gemm_tc_kernel(const __grid_constant__ CUtensorMap a0_hi, const __grid_consta
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-            const long long off = (col * p.out_row_mul + p.out_row_off) * p.C + n0;
+            const long long off = (col * p.out_row_mul + p.out_row_off + ph) * p.C + n0;
             uint4* dh = reinterpret_cast<uint4*>(p.out_hi + off);
 #pragma unroll
             for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
@@ -636,7 +645,7 @@ int launch_tc_cg(const CUtensorMap maps[6], const TcParams& p, cudaStream_t st) 
     attr_set = true;
   }
   const int n_blocks = ceil_div(p.n_total, TC_NHALF);
-  const int groups = ceil_div(p.n_tiles, CG) * (p.flat_units ? n_blocks : 1);
+  const int groups = ceil_div(p.n_tiles, CG) * (p.flat_units ? n_blocks : 1) * (p.n_phases > 0 ? p.n_phases : 1);
   const int max_groups = sm_count() / CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(CG * (groups < max_groups ? groups : max_groups)));
@@ -905,17 +914,17 @@ int wg_tc_prepare_spect(const fac_wg_model* m, const fac_wg_tc_weights* w, const
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(ws->spect_hi);
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(ws->spect_lo);
   p.out_row_mul = phases;
-  const long long w_phase = (long long)n_cond * m->upsample_taps * pad;   // elements per phase matrix
+  // all phases in ONE launch: the phase matrices are consecutive, so one weight map over phases * n_cond rows serves
+  // them all, and the tile index space is phases x (tiles rounded up to whole CTA pairs) -- 20 launches of 1.2 waves
+  // each become one of ~12 full waves
   const int cg = tc_pick_cg(nsplit);
-  for (int ph = 0; ph < phases; ++ph) {
-    const __nv_bfloat16* wh = reinterpret_cast<const __nv_bfloat16*>(w->up_hi) + ph * w_phase;
-    const __nv_bfloat16* wl = nsplit == 2 ? reinterpret_cast<const __nv_bfloat16*>(w->up_lo) + ph * w_phase : wh;
-    if (int rc = make_weight_map(&maps[4], wh, n_cond, m->upsample_taps * pad, cg, bk)) return rc;
-    if (int rc = make_weight_map(&maps[5], wl, n_cond, m->upsample_taps * pad, cg, bk)) return rc;
-    p.out_row_off = ph;
-    if (int rc = launch_tc(maps, p, st, cg)) return rc;
-  }
-  return 0;
+  if (int rc = make_weight_map(&maps[4], w->up_hi, phases * n_cond, m->upsample_taps * pad, cg, bk)) return rc;
+  if (int rc = make_weight_map(&maps[5], nsplit == 2 ? w->up_lo : w->up_hi, phases * n_cond, m->upsample_taps * pad, cg, bk)) return rc;
+  p.out_row_off = 0;
+  p.n_phases = phases;
+  p.tiles_pp = ceil_div(p.n_tiles, cg) * cg;
+  p.w_phase_rows = n_cond;
+  return launch_tc(maps, p, st, cg);
 }
 
 int wg_tc_start(const fac_wg_model* m, int flow, const float* audio, const fac_wg_tc_workspace* ws, int B, int Tg,

@@ -216,8 +216,8 @@ def test_tc_full_size_whole_tensor_and_oracle_windows():
 
 
 def test_flow_step_launch_mode_of_infer_matches_the_default(golden_dir):
-    """WaveGlow.flow_step_launch: infer() with one cooperative launch per flow step (33 launches per call instead of
-    141) produces the same bits as the default one-launch-per-layer mode, and the reference golden within 1e-4."""
+    """WaveGlow.flow_step_launch: infer() with one cooperative launch per flow step (14 launches per call instead of
+    122) produces the same bits as the default one-launch-per-layer mode, and the reference golden within 1e-4."""
     g = torch.load(os.path.join(golden_dir, "waveglow_full_b2_f5.pt"))
     model = build_model(g["cfg"], "bf16x3")
     mel = synth.synthetic_mel(g["batch"], g["frames"], seed=g["mel_seed"]).to(DEV)
@@ -228,7 +228,7 @@ def test_flow_step_launch_mode_of_infer_matches_the_default(golden_dir):
     try:
         lib.fac_reset_launch_count()
         flow = model.infer(mel, sigma=g["sigma"], noise=noise)
-        assert lib.fac_launch_count() == 20 + 1 + g["cfg"]["n_flows"]
+        assert lib.fac_launch_count() == 1 + 1 + g["cfg"]["n_flows"]      # mel split, upsampler (all phases), flows
     finally:
         model.flow_step_launch = False
     assert torch.equal(flow, base)
@@ -250,7 +250,7 @@ def test_small_inputs_replay_a_cuda_graph():
     first = model.infer(mel, sigma=0.0)            # captures
     lib.fac_reset_launch_count()
     again = model.infer(mel, sigma=0.0)            # replays
-    assert lib.fac_launch_count() >= 141          # 20 upsampler phases + mel split + 12 x (start + 8 fused layers + end)
+    assert lib.fac_launch_count() >= 122          # mel split + upsampler + 12 x (start + 8 fused layers + end)
     assert torch.equal(first, eager) and torch.equal(again, eager)
     mel2 = synth.synthetic_mel(2, 9, seed=5).to(DEV)
     assert torch.equal(model.infer(mel2, sigma=0.0), model._infer_eager(mel2, 0.0, None))   # new input, same graph
