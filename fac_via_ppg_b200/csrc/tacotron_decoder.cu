@@ -5,17 +5,18 @@
 // The reference spends ~40 kernel launches and >= 3 device->host syncs per output frame; here the
 // whole loop (up to max_steps frames, all B utterances in lock step) is a single launch of one CTA per
 // SM, and the CTAs are specialised:
-//   * MATRIX CTAs (all but B of them) keep EVERY weight matrix of the step split by output row across
-//     their shared memory for the whole sequence: the two LSTMCells (11.5 MB fp32),
-//     [mel projection | stop gate | prenet layer 0 composed with the projection] and prenet layer 1.
-//     prenet0 has no bias or nonlinearity between it and the projection (model.py:132-135, 436-438),
-//     so W_pre0 (W_proj hc + b) is evaluated as one composed matrix.  A step is four batched mat-vecs:
-//     attention LSTM | decoder LSTM | projection+gate+prenet0 | prenet1.
+//   * MATRIX CTAs (all but B of them) keep the weight matrices of the step in shared memory for the whole
+//     sequence, ONE matrix per CTA, split by output row: the two LSTMCells (11.5 MB as half hi/lo pairs, the
+//     bulk of the CTAs), [mel projection | stop gate | prenet layer 0 composed with the projection] (13 CTAs)
+//     and prenet layer 1 (11 CTAs).  prenet0 has no bias or nonlinearity between it and the projection
+//     (model.py:132-135, 436-438), so W_pre0 (W_proj hc + b) is evaluated as one composed matrix.  A step is
+//     a chain of four batched mat-vecs: attention LSTM | decoder LSTM | projection+gate+prenet0 | prenet1.
 //   * ATTENTION CTAs (one per utterance) own the location-sensitive attention of their utterance.
 //     The query matrix W_q (180 KB) is resident in their shared memory, and everything that does not
 //     depend on this step's attention-LSTM output -- location conv of the previous/cumulative weights,
 //     location_dense, processed_memory, the encoder rows of the window (held in registers) -- is
-//     prepared while the matrix CTAs run the other three mat-vecs.  On the critical path remain
+//     prepared while the matrix CTAs run the other three mat-vecs (location conv as a sliding window,
+//     location dense on mma.sync).  On the critical path remain
 //     W_q h, 41 x 150 tanh, a 41-way softmax and the 41 x 600 context sum.  Only the <= 2w+1 window
 //     positions are evaluated: everything outside [t-w, t+w] is masked to -inf by utils.py:46-78,
 //     i.e. has softmax weight exactly 0.
@@ -30,7 +31,11 @@
 //     k16 steps).  The products with vectors that are complete EARLY (the hidden states and the previous
 //     context) are accumulated while the CTA would otherwise wait for a hand-over; after the awaited vector
 //     arrives only its own segment is left: 304 of 1216 columns for the attention LSTM, 608 for the decoder
-//     LSTM, 304 of 912 for the projection.
+//     LSTM, 304 of 912 for the projection.  A CTA that runs one mat-vec per step is idle three quarters of
+//     it, so this early work is free -- with every CTA running all four mat-vecs (round 1's layout) it was not.
+//   * utterances go through a matrix CTA in passes of 8 or 16 (one or two mma n-tiles); a producer publishes
+//     pass by pass and a consumer starts on a pass as soon as its words are in, so a large batch pipelines
+//     through the chain.  The arithmetic of an utterance never depends on the batch it is in.
 //   * the stop decision (sigmoid(gate) > threshold) is taken on the device and travels as a tagged word too.
 #include "fac_common.cuh"
 #include <cuda_fp16.h>
@@ -173,6 +178,13 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
 }
+// the same for a tile that other threads have just written (the attention's location features)
+__device__ __forceinline__ void ldmatrix_x4_fresh(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr)
+               : "memory");
+}
 // D (16 x 8, fp32) += A (16 x 16, row-major halfs) * B (16 x 8, halfs; lane holds two k-pairs of one column)
 __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -200,7 +212,7 @@ __device__ __forceinline__ void put_weight(__half* hi, __half* lo, float w) {
 }
 
 struct Prof {                 // thread 0's cycles between consecutive marks, per slot (accumulators in shared memory)
-  unsigned int* acc;          // [16]: see tools/decoder_cycle_breakdown.py; [10] = total of all marks
+  unsigned int* acc;          // [PROF_SLOTS]: see tools/decoder_cycle_breakdown.py; [10] = total of all marks
   long long prev;
   bool on;
   __device__ __forceinline__ void init(bool enabled, unsigned int* smem_acc) {
@@ -442,7 +454,8 @@ __device__ __forceinline__ void row_range(int idx, int n_ctas, int n_rows, int& 
 //   role Q  prenet layer 1  (model.py:132-135)  waits for p1_{t+1}   publishes pre_{t+1}
 // A CTA is idle three quarters of a step, so the columns of its matrix that meet vectors known EARLY (hidden
 // states, the previous context) are multiplied while it waits; on the critical path of a step stay four times
-// [arrival counter | sweep of the awaited vector | its 19 or 38 k16 steps | epilogue] plus the attention.
+// [sweep of the awaited vector (polled directly) | its 19 or 38 k16 steps | epilogue] plus the attention.
+
 // the stop counter of step t (published by the CTA that owns the gate row): false = leave the loop
 __device__ __forceinline__ bool step_continues(const DecParams& p, int* n_done_s, int* ok_s, unsigned int v1, Prof& prof) {
   if (threadIdx.x == 0) {
@@ -826,8 +839,8 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
 #pragma unroll
         for (int mt = 0; mt < 3; ++mt) {
           uint32_t ah[4], al[4];
-          ldmatrix_x4(ah, (uint32_t)__cvta_generic_to_shared(&sm.x.loc[0][16 * mt + arow][16 * ks + (lane >> 4) * 8]));
-          ldmatrix_x4(al, (uint32_t)__cvta_generic_to_shared(&sm.x.loc[1][16 * mt + arow][16 * ks + (lane >> 4) * 8]));
+          ldmatrix_x4_fresh(ah, (uint32_t)__cvta_generic_to_shared(&sm.x.loc[0][16 * mt + arow][16 * ks + (lane >> 4) * 8]));
+          ldmatrix_x4_fresh(al, (uint32_t)__cvta_generic_to_shared(&sm.x.loc[1][16 * mt + arow][16 * ks + (lane >> 4) * 8]));
           mma_f16(acc[mt], ah, bh);
           mma_f16(acc[mt], al, bh);
           mma_f16(acc[mt], ah, bl);
