@@ -888,12 +888,12 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
       }
       if (__syncthreads_or(dead)) return false;
       prof.sub<14>(tp);
-      // W_q h: a row is shared by three lanes (a third of K each: 25 float4 per lane, conflict-free in shared
-      // memory), ten rows per warp; two shuffles finish a row
-      {
-        const int rs = lane / 3, part = lane - 3 * rs, r = warp * 10 + rs;
-        float sum = 0.f;
-        if (lane < 30 && r < A) {
+      // W_q h: lane = row (32 consecutive rows of W_q: their float4 reads are conflict-free, and the matching
+      // float4 of h is ONE broadcast address), warp = (row block, third of K); the three partial sums of a row
+      // meet in shared memory (the context scratch is free at this point)
+      if (warp < 15) {
+        const int part = warp % 3, r = 32 * (warp / 3) + lane;
+        if (r < A) {
           const float4* w4 = reinterpret_cast<const float4*>(&sm.wq[r][100 * part]);
           const float4* h4 = reinterpret_cast<const float4*>(sm.h + 100 * part);
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -905,11 +905,11 @@ __device__ void attention_role(const DecParams& p, AttSmem& sm, int b) {
             s2 = fmaf(a.z, hv.z, s2);
             s3 = fmaf(a.w, hv.w, s3);
           }
-          sum = (s0 + s1) + (s2 + s3);
+          sm.x.ctxp[part][r] = (s0 + s1) + (s2 + s3);
         }
-        const float v1 = __shfl_down_sync(0xffffffffu, sum, 1), v2 = __shfl_down_sync(0xffffffffu, sum, 2);
-        if (lane < 30 && part == 0 && r < A) sm.upq[r] = exp2x(sum + (v1 + v2));
       }
+      __syncthreads();
+      if (tid < A) sm.upq[tid] = exp2x(sm.x.ctxp[0][tid] + (sm.x.ctxp[1][tid] + sm.x.ctxp[2][tid]));
     }
     __syncthreads();
     prof.sub<11>(tp);
