@@ -78,7 +78,7 @@ struct FusedParams {
   int n_group, n_rem, n_half;
   __nv_bfloat16* acts_hi;    // optional (tests, single layer): the gated activations, (B, T, C)
   __nv_bfloat16* acts_lo;
-  unsigned int* grid_bar;    // zeroed by the host; arrival counter of the grid barrier
+  unsigned int* grid_bar;    // [n_tiles] zeroed by the host: finished stores of each tile's residual stream (flow_signal)
   int prefetch_steps;        // L2 prefetch distance of the producer in K steps (0 = off)
   int l2_hints;              // eviction-priority hints on the TMA loads: 1 keep re-read boxes, 2 single-use boxes first, 4 keep weights
   long long* prof;           // optional [grid][16] clock64 counters (tools/tc_cycle_breakdown.py)
@@ -157,22 +157,59 @@ struct FusedMaps {
   CUtensorMap ya_hi, ya_lo, yb_hi, yb_lo;   // the same two buffers in boxes of FU_XS_COLS channels (EG staging, TMA store)
 };
 
-// Grid-wide barrier between the phases of a flow step (cooperative launch: every CTA is resident).  The TMA stores
-// of the phase have been waited for by their issuing threads before the CTA barrier; the proxy fences order those
-// async-proxy writes with the generic-proxy release / acquire and the next phase's TMA loads.
-__device__ __forceinline__ void flow_barrier(unsigned int* counter, unsigned int& target) {
-  asm volatile("bar.sync 5, %0;" ::"n"(FU_THREADS) : "memory");
-  if (threadIdx.x == 0) {
-    target += gridDim.x;
-    asm volatile("fence.proxy.async;" ::: "memory");
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-    unsigned int seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-    } while (seen < target);
-    asm volatile("fence.proxy.async;" ::: "memory");
+// Dependencies between the phases of a flow step (cooperative launch: every CTA is resident).  No grid barrier:
+// a time tile of layer l reads the residual stream of its own rows and of the two neighbouring tiles (dilated
+// taps reach <= 128 rows), so what it has to wait for is THREE tiles of layer l - 1, not the grid.  flags[t]
+// counts the finished TMA stores of tile t's stream (two per written version: one per column half; the storing
+// thread waits for its bulk stores, fences the async proxy and adds 1 with release); a neighbour that does not
+// exist is replaced by the nearest tile that does.  The CTAs own fixed tiles and walk (layer, tile) in the
+// same order, so the waits cannot form a cycle; the write-after-read hazard of the two ping-pong buffers is
+// covered by the same waits (a tile writes version v + 1 only after its neighbours have finished the layer
+// that read version v - 1 from the buffer it overwrites).
+constexpr int FLOW_SPIN_LIMIT = 1 << 24;      // x >= 200 ns: seconds
+__device__ __forceinline__ void flow_signal(unsigned int* flags, int tile) {
+  // The caller has waited for its bulk stores (cp.async.bulk.wait_group 0: the writes are performed, they sit in
+  // L2), so the counter cannot overtake them; a release here would be a full membar that also waits for the
+  // CTA's unrelated generic stores (the out8 read-modify-writes) -- measured: ~1 k cycles per tile, 3 % of a step.
+  asm volatile("fence.proxy.async;" ::: "memory");
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(flags + tile) : "memory");
+}
+__device__ __forceinline__ void flow_wait_one(const unsigned int* flags, int idx, unsigned int need) {
+  // relaxed polls with a pause (an acquire per poll would invalidate the SM's L1 over and over under the
+  // epilogue's feet); the caller fences once when all its counters are there
+  unsigned int seen;
+  int spins = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + idx) : "memory");
+    if (seen >= need) break;
+    if (++spins > FLOW_SPIN_LIMIT) __trap();      // a lost signal must not hang the GPU
+    __nanosleep(200);
   }
-  asm volatile("bar.sync 5, %0;" ::"n"(FU_THREADS) : "memory");
+}
+// The loading threads of a CTA do not poll global memory themselves (three dependent L2 round trips per tile would
+// drain the operand ring): an otherwise idle thread, the watcher, walks the (layer, tile) items ahead of them and
+// publishes how many are cleared in a shared-memory word.
+__device__ __forceinline__ void flow_wait_cleared(const uint32_t* cleared, uint32_t item) {
+  uint32_t seen;
+  int spins = 0;
+  do {
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"((uint32_t)__cvta_generic_to_shared(cleared)) : "memory");
+    if (++spins > FLOW_SPIN_LIMIT) __trap();
+  } while (seen <= item);
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+// tile `tile` and its neighbours carry at least `writes` versions (0: nothing to wait for)
+__device__ __forceinline__ void flow_wait_tiles(const unsigned int* flags, int tile, int n_tiles, int writes, bool neighbours) {
+  if (writes <= 0) return;
+  const unsigned int need = 2u * (unsigned int)writes;
+  const int last = n_tiles - 1, idx = min(tile, last);  // a tile past the end waits for the last one
+  flow_wait_one(flags, idx, need);
+  if (neighbours) {
+    if (idx > 0) flow_wait_one(flags, idx - 1, need);
+    if (idx < last) flow_wait_one(flags, idx + 1, need);
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");      // the acquired writes came from, and go to, the async proxy
 }
 
 // FLOW = false: the single-layer form (layer_count == 1, no start / end / grid barrier): the same code with the
@@ -203,6 +240,7 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
   uint64_t* xs_full = acts_free + 1;                 // [2] x producer -> epilogue half
   uint64_t* xs_empty = xs_full + 2;                  // [2] epilogue half -> x producer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xs_empty + 2);
+  uint32_t* flow_cleared = tmem_slot + 2;            // FLOW: (layer, tile) items whose input tiles are complete (watcher)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -217,13 +255,18 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
   int my_tiles = 0;
   for (int tb = tile_first; tb < p.n_tiles; tb += (int)gridDim.x) ++my_tiles;
   const int Q = my_tiles * n_units;                                 // units of this CTA pair per layer
-  unsigned int bar_target = 0;
   // phases: [start] layer ... layer [end]; a grid barrier separates start from the first layer and a layer with a
   // residual output from the next one (`end` only touches this CTA's own columns)
   const int layer_count = FLOW ? p.layer_count : 1;
   const bool do_start = FLOW && p.do_start, do_end = FLOW && p.do_end;
   auto has_res = [&](int l) { return l < p.n_layers - 1; };
-  auto barrier_after_layer = [&](int li) { return FLOW && li + 1 < layer_count && has_res(p.layer_first + li); };
+  // versions of the residual stream written in THIS launch before layer li reads it (start + the layers with a
+  // residual output): what flags[] of a tile must have reached, halved
+  auto writes_before = [&](int li) {
+    int n = do_start ? 1 : 0;
+    for (int i = 0; i < li; ++i) n += has_res(p.layer_first + i) ? 1 : 0;
+    return FLOW ? n : 0;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -238,6 +281,7 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
     }
     mbar_init(acts_ready, FU_EPI_WARPS * 2);
     mbar_init(acts_free, 1);
+    *flow_cleared = 0;
     fence_barrier_init();
     tma_prefetch_desc(&maps.xa_hi);
     tma_prefetch_desc(&maps.w1_hi);
@@ -260,7 +304,6 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
         phase ^= 1;
       }
     };
-    if (do_start) flow_barrier(p.grid_bar, bar_target);
     long long prod_wait = 0, w_tmem0 = 0, w_full = 0, w_acts = 0, w_tmem1 = 0, issue = 0;
     const long long k_start = PROF ? clock64() : 0;
     uint32_t use[2] = {0, 0}, acts_n = 0, xph[2] = {0, 0};
@@ -304,10 +347,13 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
             ml = &maps.s_lo;
           }
         };
+        const int need_writes = writes_before(li);
         for (int q = 0; q <= Q; ++q) {
           if (q < Q) {
             const int u = q % n_units;
             const int w_row = u * TC_NHALF + rank * w1_rows;
+            if (FLOW && u == 0 && need_writes > 0)   // the stream of this tile and of its neighbours, as the previous phase left it
+              flow_wait_cleared(flow_cleared, (uint32_t)(li * my_tiles + q / n_units));
             for (int ks = 0; ks < p.k1_steps; ++ks) {
               const CUtensorMap *mh, *ml;
               int c0, row0, b;
@@ -442,9 +488,11 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
         // ===================================================== x producer: the tile's old residual stream for EG
         const CUtensorMap* ym_hi = in_a ? &maps.ya_hi : &maps.yb_hi;
         const CUtensorMap* ym_lo = in_a ? &maps.ya_lo : &maps.yb_lo;
+        const int need_writes = writes_before(li);
         for (int j = 0; j < my_tiles; ++j) {
           const int tile = tile_first + j * (int)gridDim.x + rank;
           const int b = tile / p.tiles_per_batch, t0 = (tile % p.tiles_per_batch) * TC_BM;
+          if (FLOW && need_writes > 0) flow_wait_cleared(flow_cleared, (uint32_t)(li * my_tiles + j));
           for (int cc = 0; cc < xs_chunks; ++cc)
             for (int h = 0; h < 2; ++h) {
               uint8_t* dst = xs_s + h * 2 * FU_XS_ARRAY;
@@ -462,9 +510,17 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
               xph[h] ^= 1;
             }
         }
+      } else if (FLOW && warp == 3 && lane == 0) {
+        // ===================================================== watcher: clears the (layer, tile) items in order
+        const int need_writes = writes_before(li);
+        for (int j = 0; j < my_tiles; ++j) {
+          flow_wait_tiles(p.grid_bar, tile_first + j * (int)gridDim.x + rank, p.n_tiles, need_writes, true);
+          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(flow_cleared)),
+                       "r"((uint32_t)(li * my_tiles + j + 1))
+                       : "memory");
+        }
       }
       __syncwarp();
-      if (barrier_after_layer(li)) flow_barrier(p.grid_bar, bar_target);
     }
     if (PROF && p.prof) {
       long long* pr = p.prof + blockIdx.x * 16;
@@ -494,6 +550,7 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
       else asm volatile("bar.sync 4, 128;" ::: "memory");
     };
     uint32_t xs_phase = 0, use[2] = {0, 0}, acts_n = 0;
+    int pending_tile = -1;             // storer: a tile whose stores are committed but not yet announced (FLOW)
     long long e_wfull0 = 0, e_drain = 0, e_wfree = 0, e_busy = 0, e_wfull1 = 0, eg_busy = 0;
     const long long e_start = PROF ? clock64() : 0;
     Tick tk;
@@ -544,9 +601,11 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
           }
           half_sync();                         // the staging entry may be rewritten
         }
+        if (storer && tile < p.n_tiles) {      // this half of the tile's first version is out
+          tma_store_wait_all();
+          flow_signal(p.grid_bar, tile);
+        }
       }
-      if (storer) tma_store_wait_all();
-      flow_barrier(p.grid_bar, bar_target);
     }
 
     for (int li = 0; li < layer_count; ++li) {
@@ -690,6 +749,12 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
           const int tile = tile_first + tile_j * (int)gridDim.x + rank;
           const int b = tile / p.tiles_per_batch, t0 = (tile % p.tiles_per_batch) * TC_BM;
           tk.lap(e_busy);
+          if (FLOW && storer && pending_tile >= 0) {
+            // announce the previous tile now: its stores were committed a whole tile of UMMAs ago, the wait is free
+            tma_store_wait_all();
+            flow_signal(p.grid_bar, pending_tile);
+            pending_tile = -1;
+          }
           mbar_wait(&tmem_full[1], use[1]++ & 1);
           tk.lap(e_wfull1);
           tc_fence_after();
@@ -734,14 +799,20 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
               mbar_arrive(&xs_empty[half]);
             }
           }
+          if (FLOW && storer && tile < p.n_tiles) pending_tile = tile;
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(lead_empty1);
           tk.lap(eg_busy);
         }
       }
-      if (storer) tma_store_wait_all();
-      if (barrier_after_layer(li)) flow_barrier(p.grid_bar, bar_target);
+      if (storer) {
+        tma_store_wait_all();
+        if (FLOW && pending_tile >= 0) {       // the last tile of the layer
+          flow_signal(p.grid_bar, pending_tile);
+          pending_tile = -1;
+        }
+      }
     }
 
     if (do_end && half == 0) {
@@ -961,9 +1032,10 @@ int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, c
   p.l2_hints = l2_hints;
   p.prof = prof;
   if (phases) {
-    cudaError_t e = cudaMemsetAsync(ws->flow_sync, 0, sizeof(unsigned int), st);
+    // flags[t]: finished stores of tile t's residual stream in this launch
+    cudaError_t e = cudaMemsetAsync(ws->flow_sync, 0, (size_t)p.n_tiles * sizeof(unsigned int), st);
     if (e != cudaSuccess) {
-      set_error("wn_flow_fused: cannot reset the grid barrier: %s", cudaGetErrorString(e));
+      set_error("wn_flow_fused: cannot reset the tile flags: %s", cudaGetErrorString(e));
       return 2;
     }
   }

@@ -223,7 +223,8 @@ class WaveGlow(torch.nn.Module):
                 bufs[name] = b16(c)
                 bufs[name[:-2] + "lo"] = b16(c) if nsplit == 2 else None
             bufs["out8"] = f32(8)
-            bufs["flow_sync"] = (torch.zeros(1, device=dev, dtype=torch.int32)
+            # one counter per 128-column time tile (include/fac_b200.h: flow_sync)
+            bufs["flow_sync"] = (torch.zeros(B * ((Tg + 127) // 128) + 8, device=dev, dtype=torch.int32)
                                  if fused and self.flow_step_launch else None)
             pad = self.packed().mel_pad
             bufs["mel_hi"] = torch.empty(B, F, pad, device=dev, dtype=torch.bfloat16)

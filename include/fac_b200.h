@@ -173,8 +173,10 @@ typedef struct fac_wg_tc_weights {
  * reads the stream from one pair and writes the other, because neighbouring time tiles still read the old
  * values for their dilated taps: layer i reads x when i is even and x2 when i is odd, and writes the other one
  * (fac_wn_start_tc always writes x).  acts_hi/acts_lo may then be NULL (a test hook when not).
- * flow_sync (optional, with x2): 4 bytes for the grid barrier of fac_waveglow_flow_step_tc, which then runs a
- * whole flow step -- start, every WN layer, end + coupling + invertible 1x1 -- as ONE cooperative launch. */
+ * flow_sync (optional, with x2): 4 * B * ceil(T_g / 128) bytes, one counter per 128-column time tile, for
+ * fac_waveglow_flow_step_tc, which then runs a whole flow step -- start, every WN layer, end + coupling +
+ * invertible 1x1 -- as ONE cooperative launch in which a tile of a layer waits for its own and its two neighbour
+ * tiles of the previous layer (dilated taps reach no further) instead of for the whole grid. */
 typedef struct fac_wg_tc_workspace {
   void* mel_hi; void* mel_lo;          /* (B, F, mel_pad) bf16 */
   void* spect_hi; void* spect_lo;
@@ -202,8 +204,8 @@ int fac_wn_end_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, c
 /* One step of the reverse flow (reference src/waveglow/glow.py:272-290 for flow k: WN.forward :154-175 on audio_0,
  * affine coupling inverse :278-281, Invertible1x1Conv reverse :283) in place on `audio` (B, T_g, n_group), whose
  * live channels are the last n_rem slots of every column.  With nsplit == 2 and a workspace that carries x2 and
- * flow_sync this is ONE kernel launch (csrc/waveglow_fused.cu: start -> 8 fused layers separated by grid barriers
- * -> end / coupling / W^-1, activations L2-resident between layers, weights TMA-streamed); otherwise it is the
+ * flow_sync this is ONE kernel launch (csrc/waveglow_fused.cu: start -> 8 fused layers chained by per-tile
+ * dependency counters, no grid barrier -> end / coupling / W^-1, weights TMA-streamed); otherwise it is the
  * sequence fac_wn_start_tc, fac_wn_layer_tc x n_layers, fac_wn_end_tc. */
 int fac_waveglow_flow_step_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, float* audio,
                               const fac_wg_tc_workspace* ws, int B, int Tg, int nsplit, void* stream);

@@ -102,7 +102,7 @@ def test_tc_layer_matches_fp32_layer(cfg_name, cols, precision, fused):
 @pytest.mark.parametrize("cfg_name,B,cols", [("small", 2, 300), ("full", 1, 130), ("full", 3, 1000)])
 def test_flow_step_is_one_launch_and_equals_the_layer_by_layer_sequence(cfg_name, B, cols):
     """fac_waveglow_flow_step_tc (reference glow.py:272-283 for one flow: WN.forward, coupling inverse, invertible
-    1x1) as ONE cooperative launch -- start, 8 fused layers separated by grid barriers, end -- against the same
+    1x1) as ONE cooperative launch -- start, 8 fused layers chained by per-tile dependency counters, end -- against the same
     step run as start / layer / ... / end launches: identical bits (same kernel code per tile), for the first flow
     (4 + 4 channels) and the last one (2 + 2)."""
     cfg = synth.WAVEGLOW_CONFIG_SMALL if cfg_name == "small" else synth.WAVEGLOW_CONFIG
@@ -125,7 +125,7 @@ def test_flow_step_is_one_launch_and_equals_the_layer_by_layer_sequence(cfg_name
 
     for flow in (cfg["n_flows"] - 1, 0):
         a_one, a_seq = audio0.clone(), audio0.clone()
-        ws1, keep1 = workspace(torch.zeros(1, dtype=torch.int32, device=DEV))
+        ws1, keep1 = workspace(torch.zeros(B * ((cols + 127) // 128), dtype=torch.int32, device=DEV))   # a counter per tile
         before = lib.fac_launch_count()
         _ext.check(lib.fac_waveglow_flow_step_tc(m, tcw, flow, a_one.data_ptr(), C.byref(ws1), B, cols, 2, st), "flow step")
         torch.cuda.synchronize()
