@@ -212,7 +212,7 @@ __device__ __forceinline__ void flow_wait_tiles(const unsigned int* flags, int t
   asm volatile("fence.proxy.async;" ::: "memory");      // the acquired writes came from, and go to, the async proxy
 }
 
-// FLOW = false: the single-layer form (layer_count == 1, no start / end / grid barrier): the same code with the
+// FLOW = false: the single-layer form (layer_count == 1, no start / end / tile counters): the same code with the
 // phase logic compiled out, which keeps the register allocation of the hot loops as tight as it can be.
 // NS = 2: split-bf16 operands (hi + lo pairs, 3 UMMAs per product, fp32-grade); NS = 1: plain bf16 (hi only).
 template <int BK, int NS, bool FLOW, bool PROF>
@@ -255,8 +255,8 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
   int my_tiles = 0;
   for (int tb = tile_first; tb < p.n_tiles; tb += (int)gridDim.x) ++my_tiles;
   const int Q = my_tiles * n_units;                                 // units of this CTA pair per layer
-  // phases: [start] layer ... layer [end]; a grid barrier separates start from the first layer and a layer with a
-  // residual output from the next one (`end` only touches this CTA's own columns)
+  // phases: [start] layer ... layer [end]; what a tile of a layer needs from the phase before travels through the
+  // per-tile counters (flow_signal / flow_wait_tiles); `end` only touches this CTA's own columns
   const int layer_count = FLOW ? p.layer_count : 1;
   const bool do_start = FLOW && p.do_start, do_end = FLOW && p.do_end;
   auto has_res = [&](int l) { return l < p.n_layers - 1; };
@@ -893,7 +893,7 @@ int launch_fused(const FusedMaps& maps, const FusedParams& p, cudaStream_t st) {
   cfg.dynamicSmemBytes = FU_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;      // the grid barrier between phases needs every CTA resident
+  attr[0].id = cudaLaunchAttributeCooperative;      // CTAs wait for each other's tiles: every CTA must be resident
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = FLOW ? 1 : 0;

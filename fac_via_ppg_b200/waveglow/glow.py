@@ -166,9 +166,10 @@ class WaveGlow(torch.nn.Module):
     precision = "bf16x3"      # default: tensor cores with fp32-grade results
     # bf16x3: one fused launch per WN layer (csrc/waveglow_fused.cu); False: two launches per layer
     fused_layers = os.environ.get("FAC_TC_FUSED", "1") != "0"
-    # True: a whole flow step (start, 8 layers, end / coupling / 1x1) is ONE cooperative launch with grid barriers
-    # between the layers (fac_waveglow_flow_step_tc).  Measured on B200 it is 1.5 % slower than one launch per
-    # layer at 8 x 10 s and 10 % slower for a single short utterance (profiles/README.md), so it is opt-in.
+    # True: a whole flow step (start, 8 layers, end / coupling / 1x1) is ONE cooperative launch in which a time tile
+    # of a layer waits for its own and its neighbour tiles of the previous layer (fac_waveglow_flow_step_tc).
+    # Measured on B200 it is 4-5 % slower than one launch per layer at 8 x 10 s and 8 % slower for a single short
+    # utterance (profiles/README.md), so it is opt-in.
     flow_step_launch = os.environ.get("FAC_TC_FUSED", "1") == "2"
     fused_bf16 = False        # plain bf16 through the fused kernel too (slower, see _alloc_io)
 
