@@ -825,10 +825,11 @@ int tc_set_batch_group(int n) {
 // first, 4 = keep the weights.  Measured (8 x 10 s): 3 cuts the layer's DRAM traffic from 1.67 to 1.39 GB and the step
 // by 1.3 %; adding 4 gives both back.
 int g_tc_fused = 2, g_tc_prefetch = 0, g_tc_l2_hints = 3;
-// mode & 15: 0 = two launches per layer; 1 = one fused launch per layer; 2 = one launch per flow step where possible.
+// mode & 15: 0 = two launches per layer; 1 = one fused launch per layer; 2 = one launch per flow step where possible;
+// 3 = like 2, but start and end stay separate kernels (three launches per flow step).
 // mode >> 4: L2 prefetch distance of the fused kernel's producer in K steps (experiments)
 int tc_set_fused(int mode) {
-  FAC_REQUIRE((mode & 15) <= 2 && mode >= 0, "fused mode must be 0, 1 or 2 (+ 16 x prefetch distance), got %d", mode);
+  FAC_REQUIRE((mode & 15) <= 3 && mode >= 0, "fused mode must be 0 .. 3 (+ 16 x prefetch distance), got %d", mode);
   g_tc_fused = mode & 15;
   g_tc_prefetch = (mode >> 4) & 63;
   if ((mode >> 10) & 15) g_tc_l2_hints = ((mode >> 10) & 15) - 1;     // + 1024 x (h + 1): L2 hint mask h (experiments)
@@ -1032,6 +1033,12 @@ int wg_tc_flow_step(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow,
   FAC_REQUIRE(flow >= 0 && flow < m->n_flows && audio, "waveglow_flow_step_tc: bad arguments");
   if (g_tc_fused == 2 && ws->flow_sync && tc_use_fused(m, w->flows[flow], ws, nsplit, 0))
     return wn_flow_fused(m, w, flow, ws, audio, B, Tg, nsplit, 0, m->n_layers, 1, 1, tc_fused_bk(), g_tc_prefetch & 63, g_tc_l2_hints, g_tc_prof, st);
+  if (g_tc_fused == 3 && ws->flow_sync && m->n_layers > 1 && tc_use_fused(m, w->flows[flow], ws, nsplit, 0)) {
+    // every WN layer of the step in one launch; start and end as their own (whole-chip) kernels
+    if (int rc = wg_tc_start(m, flow, audio, ws, B, Tg, nsplit, st)) return rc;
+    if (int rc = wn_flow_fused(m, w, flow, ws, audio, B, Tg, nsplit, 0, m->n_layers, 0, 0, tc_fused_bk(), g_tc_prefetch & 63, g_tc_l2_hints, g_tc_prof, st)) return rc;
+    return wg_tc_end(m, w, flow, ws->out8, audio, B, Tg, st);
+  }
   if (int rc = wg_tc_start(m, flow, audio, ws, B, Tg, nsplit, st)) return rc;
   for (int i = 0; i < m->n_layers; ++i)
     if (int rc = wg_tc_layer(m, w, flow, i, ws, B, Tg, nsplit, st)) return rc;

@@ -168,9 +168,9 @@ class WaveGlow(torch.nn.Module):
     fused_layers = os.environ.get("FAC_TC_FUSED", "1") != "0"
     # True: a whole flow step (start, 8 layers, end / coupling / 1x1) is ONE cooperative launch in which a time tile
     # of a layer waits for its own and its neighbour tiles of the previous layer (fac_waveglow_flow_step_tc).
-    # Measured on B200 it is 4-5 % slower than one launch per layer at 8 x 10 s and 8 % slower for a single short
-    # utterance (profiles/README.md), so it is opt-in.
-    flow_step_launch = os.environ.get("FAC_TC_FUSED", "1") == "2"
+    # Measured on B200 it equals one launch per layer for a single short utterance and is 8-9 % slower at 8 x 10 s
+    # (profiles/README.md), so it is opt-in.  FAC_TC_FUSED=3: the same with start and end as separate kernels.
+    flow_step_launch = os.environ.get("FAC_TC_FUSED", "1") in ("2", "3")
     fused_bf16 = False        # plain bf16 through the fused kernel too (slower, see _alloc_io)
 
     def set_precision(self, precision):
