@@ -216,7 +216,8 @@ void fac_tc_set_profile_buffer(long long* device_buf);
  * tcgen05 cta_group::2, UMMA M = 256, each CTA stages half of the weight rows). */
 int fac_tc_set_cta_group(int cta_group);
 /* 0: always the two-launch form of a layer; 1: one fused launch per layer; 2 (default): additionally one launch per
- * flow step where the workspace allows it.  Bits 4-9: L2 prefetch distance of the fused kernel's producer in K
+ * flow step where the workspace allows it (flow_sync); 3: like 2 with start and end as separate kernels (three
+ * launches per flow step).  Bits 4-9: L2 prefetch distance of the fused kernel's producer in K
  * steps; bits 10-13: 1 + mask of its L2 eviction hints (A/B measurements). */
 int fac_tc_set_fused(int enabled);
 /* Utterances per pass of fac_waveglow_infer_tc over a flow (they are independent): 0 (default) = the whole

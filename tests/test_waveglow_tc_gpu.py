@@ -215,9 +215,11 @@ def test_tc_full_size_whole_tensor_and_oracle_windows():
         assert torch.equal(alone[0], full[row]), row
 
 
-def test_flow_step_launch_mode_of_infer_matches_the_default(golden_dir):
+@pytest.mark.parametrize("mode,per_flow", [(2, 1), (3, 3)])
+def test_flow_step_launch_mode_of_infer_matches_the_default(golden_dir, mode, per_flow):
     """WaveGlow.flow_step_launch: infer() with one cooperative launch per flow step (14 launches per call instead of
-    122) produces the same bits as the default one-launch-per-layer mode, and the reference golden within 1e-4."""
+    122; fused mode 3 keeps start and end as separate kernels: 38) produces the same bits as the default
+    one-launch-per-layer mode, and the reference golden within 1e-4."""
     g = torch.load(os.path.join(golden_dir, "waveglow_full_b2_f5.pt"))
     model = build_model(g["cfg"], "bf16x3")
     mel = synth.synthetic_mel(g["batch"], g["frames"], seed=g["mel_seed"]).to(DEV)
@@ -226,11 +228,13 @@ def test_flow_step_launch_mode_of_infer_matches_the_default(golden_dir):
     base = model.infer(mel, sigma=g["sigma"], noise=noise)
     model.flow_step_launch = True
     try:
+        _ext.check(lib.fac_tc_set_fused(mode), "fac_tc_set_fused")
         lib.fac_reset_launch_count()
         flow = model.infer(mel, sigma=g["sigma"], noise=noise)
-        assert lib.fac_launch_count() == 1 + 1 + g["cfg"]["n_flows"]      # mel split, upsampler (all phases), flows
+        assert lib.fac_launch_count() == 1 + 1 + per_flow * g["cfg"]["n_flows"]   # mel split, upsampler (all phases), flows
     finally:
         model.flow_step_launch = False
+        lib.fac_tc_set_fused(2)                  # the library default (the module decides through its workspace)
     assert torch.equal(flow, base)
     assert rms(flow, g["audio"]) <= 1e-4
 
