@@ -39,6 +39,7 @@
 #include "tc_host.cuh"
 
 namespace fac {
+bool tc_pdl_enabled();      // csrc/waveglow_tc.cu
 namespace {
 
 using namespace tc;
@@ -73,6 +74,7 @@ struct FusedParams {
   const float* wc[FAC_MAX_LAYERS];      // [8][C] collapsed skip weights
   float* out8;               // (B, T, 8)
   int accumulate_out8;       // single-layer launches: layer_first > 0
+  int pdl;                   // launched with programmatic stream serialization: see grid_dep_wait()
   const float* start_w;      // [n_half][C]
   const float* start_b;      // [C]
   const float* out_bias;     // [8] end.bias + end.weight @ (sum of the skip biases)
@@ -159,6 +161,14 @@ struct FusedMaps {
   CUtensorMap w2_hi, w2_lo;                 // [layer][C][C] residual half of res_skip
   CUtensorMap ya_hi, ya_lo, yb_hi, yb_lo;   // the same two buffers in boxes of FU_XS_COLS channels (EG staging, TMA store)
 };
+
+// Programmatic dependent launch (single-layer form): a layer's kernel is allowed to start while the previous
+// layer's is still running -- on the SMs that one has already left or never used (a short utterance occupies a
+// third of the chip) -- and does everything that does not depend on it: prologue, weights, and the conditioning
+// K steps of its first unit, which come first in the K order for this reason.  Whoever touches the residual
+// stream or out8 waits for the previous grid to have completed (griddepcontrol.wait) first.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Dependencies between the phases of a flow step (cooperative launch: every CTA is resident).  No grid barrier:
 // a time tile of layer l reads the residual stream of its own rows and of the two neighbouring tiles (dilated
@@ -295,6 +305,7 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (!FLOW && p.pdl && threadIdx.x == 0) grid_dep_launch();      // the next layer's kernel may start its prologue
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FU_REGS_LOW));
@@ -363,6 +374,7 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
               const int ks = ki + steps_x < p.k1_steps ? ki + steps_x : ki + steps_x - p.k1_steps;
               if (FLOW && u == 0 && ks == 0 && need_writes > 0)
                 flow_wait_cleared(flow_cleared, (uint32_t)(li * my_tiles + q / n_units));
+              if (!FLOW && p.pdl && q == 0 && ks == 0) grid_dep_wait();     // the first read of the residual stream
               const CUtensorMap *mh, *ml;
               int c0, row0, b;
               if (p.prefetch_steps > 0) {
@@ -498,6 +510,7 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
         const CUtensorMap* ym_hi = in_a ? &maps.ya_hi : &maps.yb_hi;
         const CUtensorMap* ym_lo = in_a ? &maps.ya_lo : &maps.yb_lo;
         const int need_writes = writes_before(li);
+        if (!FLOW && p.pdl) grid_dep_wait();
         for (int j = 0; j < my_tiles; ++j) {
           const int tile = tile_first + j * (int)gridDim.x + rank;
           const int b = tile / p.tiles_per_batch, t0 = (tile % p.tiles_per_batch) * TC_BM;
@@ -540,6 +553,7 @@ wn_flow_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedParams p
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FU_REGS_HIGH));
+    if (!FLOW && p.pdl) grid_dep_wait();               // out8 and the stream are the previous kernel's
     // ===================================================== epilogue: 8 warps = TMEM lane quarter x column half
     const int qd = warp & 3;
     const int half = (warp - 4) >> 2;
@@ -902,10 +916,15 @@ int launch_fused(const FusedMaps& maps, const FusedParams& p, cudaStream_t st) {
   cfg.dynamicSmemBytes = FU_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;      // CTAs wait for each other's tiles: every CTA must be resident
-  attr[0].val.cooperative = 1;
+  if (FLOW) {
+    attr[0].id = cudaLaunchAttributeCooperative;    // CTAs wait for each other's tiles: every CTA must be resident
+    attr[0].val.cooperative = 1;
+  } else {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = FLOW ? 1 : 0;
+  cfg.numAttrs = (FLOW || p.pdl) ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, wn_flow_fused_kernel<BK, NS, FLOW, PROF>, maps, p);
   count_launch();
   if (e != cudaSuccess) {
@@ -1025,6 +1044,7 @@ int wn_flow_fused(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, c
   }
   p.out8 = ws->out8;
   p.accumulate_out8 = layer_first > 0;
+  p.pdl = tc_pdl_enabled() ? 1 : 0;
   p.start_w = f.start_w;
   p.start_b = f.start_b;
   p.out_bias = wf.out_bias;

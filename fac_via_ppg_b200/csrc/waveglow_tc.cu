@@ -22,6 +22,7 @@
 // The same kernel serves the acoustic model's Conv1d / Linear layers (TC_LINEAR epilogue, IEEE-half operand
 // pairs): there the (tile, column block) units are dealt round-robin to the CTA pairs and every unit walks its
 // contraction in chains of <= k_chunk elements that alternate the two TMEM accumulators (see conv_gemm_tc).
+#include <stdlib.h>
 #include "fac_common.cuh"
 #include "tc_common.cuh"
 #include "tc_host.cuh"
@@ -536,6 +537,10 @@ __global__ void __launch_bounds__(256) wn_start_tc_kernel(const float* __restric
                                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ x_hi,
                                                           __nv_bfloat16* __restrict__ x_lo, long long n_cols, int C,
                                                           int n_group, int off, int n_half) {
+  // programmatic dependent launch (see csrc/waveglow_fused.cu): the first layer's kernel may start its prologue and
+  // its conditioning K steps now; this kernel itself may have started before the previous flow's `end` completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int c8 = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long col0 = (idx / c8) * WN_START_COLS;
@@ -583,6 +588,8 @@ __global__ void __launch_bounds__(256) wn_start_tc_kernel(const float* __restric
 __global__ void wn_end_tc_kernel(const float* __restrict__ out8, const float* __restrict__ bias8,
                                  const float* __restrict__ w_inv, float* __restrict__ audio, long long n_cols,
                                  int n_group, int n_rem, int n_half) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the next flow's `start`
+  asm volatile("griddepcontrol.wait;" ::: "memory");                  // out8 is the last layer's
   const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= n_cols) return;
   const float4 a = __ldg(reinterpret_cast<const float4*>(out8 + col * TC_NOUT));
@@ -825,6 +832,11 @@ int tc_set_batch_group(int n) {
 // first, 4 = keep the weights.  Measured (8 x 10 s): 3 cuts the layer's DRAM traffic from 1.67 to 1.39 GB and the step
 // by 1.3 %; adding 4 gives both back.
 int g_tc_fused = 2, g_tc_prefetch = 0, g_tc_l2_hints = 3;
+// programmatic dependent launch between the kernels of a flow step (FAC_TC_PDL=0 turns it off for A/B runs)
+bool tc_pdl_enabled() {
+  static const bool on = getenv("FAC_TC_PDL") == nullptr || atoi(getenv("FAC_TC_PDL")) != 0;
+  return on;
+}
 // mode & 15: 0 = two launches per layer; 1 = one fused launch per layer; 2 = one launch per flow step where possible;
 // 3 = like 2, but start and end stay separate kernels (three launches per flow step).
 // mode >> 4: L2 prefetch distance of the fused kernel's producer in K steps (experiments)
@@ -936,11 +948,24 @@ int wg_tc_start(const fac_wg_model* m, int flow, const float* audio, const fac_w
   const long long n_cols = (long long)B * Tg;
   FAC_REQUIRE(f.n_half <= 4, "wn_start_tc: n_half %d > 4", f.n_half);
   const long long total = ((n_cols + WN_START_COLS - 1) / WN_START_COLS) * (m->n_channels / 8);
-  wn_start_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      audio, f.start_w, f.start_b, reinterpret_cast<__nv_bfloat16*>(ws->x_hi),
-      nsplit == 2 ? reinterpret_cast<__nv_bfloat16*>(ws->x_lo) : nullptr, n_cols, m->n_channels, m->n_group,
-      m->n_group - f.n_rem, f.n_half);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((total + 255) / 256));
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wn_start_tc_kernel, audio, (const float*)f.start_w, (const float*)f.start_b,
+                                     reinterpret_cast<__nv_bfloat16*>(ws->x_hi),
+                                     nsplit == 2 ? reinterpret_cast<__nv_bfloat16*>(ws->x_lo) : (__nv_bfloat16*)nullptr, n_cols,
+                                     (int)m->n_channels, (int)m->n_group, (int)(m->n_group - f.n_rem), (int)f.n_half);
   count_launch();
+  if (e != cudaSuccess) {
+    set_error("wn_start_tc_kernel: launch failed: %s", cudaGetErrorString(e));
+    return 2;
+  }
   return check_launch("wn_start_tc_kernel");
 }
 
@@ -950,9 +975,22 @@ int wg_tc_end(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, const
   FAC_REQUIRE(flow >= 0 && flow < m->n_flows && w && out8 && audio, "wn_end_tc: bad arguments");
   const fac_wg_flow& f = m->flows[flow];
   const long long n_cols = (long long)B * Tg;
-  wn_end_tc_kernel<<<(unsigned)((n_cols + 255) / 256), 256, 0, st>>>(out8, w->flows[flow].out_bias, f.w_inv, audio,
-                                                                    n_cols, m->n_group, f.n_rem, f.n_half);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((n_cols + 255) / 256));
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tc_pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wn_end_tc_kernel, out8, (const float*)w->flows[flow].out_bias, (const float*)f.w_inv,
+                                     audio, n_cols, (int)m->n_group, (int)f.n_rem, (int)f.n_half);
   count_launch();
+  if (e != cudaSuccess) {
+    set_error("wn_end_tc_kernel: launch failed: %s", cudaGetErrorString(e));
+    return 2;
+  }
   return check_launch("wn_end_tc_kernel");
 }
 

@@ -201,6 +201,9 @@ int fac_wn_layer_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow,
 /* glow.py:175 + 278-283 from out8: coupling inverse and invertible 1x1 (reverse), in place on audio. */
 int fac_wn_end_tc(const fac_wg_model* m, const fac_wg_tc_weights* w, int flow, const float* out8, float* audio,
                   int B, int Tg, void* stream);
+/* (The kernels of a flow step -- start, the fused layers, end -- are chained by programmatic dependent launch: each
+ * may start while its predecessor in the stream is still running and waits for it only before it touches the
+ * residual stream, out8 or audio.  Environment FAC_TC_PDL=0 launches them fully serialised.) */
 /* One step of the reverse flow (reference src/waveglow/glow.py:272-290 for flow k: WN.forward :154-175 on audio_0,
  * affine coupling inverse :278-281, Invertible1x1Conv reverse :283) in place on `audio` (B, T_g, n_group), whose
  * live channels are the last n_rem slots of every column.  With nsplit == 2 and a workspace that carries x2 and
