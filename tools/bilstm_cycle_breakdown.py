@@ -24,5 +24,5 @@ for B, T in zip(args[0::2], args[1::2]):
         torch.cuda.synchronize()
     lib.fac_lstm_set_profile_buffer(None)
     p = prof.view(512, 4)[:16].double().cpu() / T
-    print("B=%d T=%d: %.2f us/step | cycles/step CTA0: mma %d, cell+DSMEM %d, cluster.sync %d | CTA7: %d %d %d" %
+    print("B=%d T=%d: %.2f us/step | cycles/step CTA0: mma %d, cell+DSMEM %d, after hand-over %d | CTA7: %d %d %d" %
           (B, T, e0.elapsed_time(e1) * 1e3 / T, *p[0, :3], *p[7, :3]))
