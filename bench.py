@@ -217,13 +217,31 @@ def measure_pipeline(env, wg, batch=32, seconds=5.0):
     out_host = torch.empty(batch, frames * 160).pin_memory()
     mid = torch.cuda.Event(enable_timing=True)
     stamps = []
+    # e2e: like measure_cfg5, the PPG upload of call k + 1 runs on a copy stream behind the vocoder of call k
+    copy_stream = torch.cuda.Stream(device=dev)
+    ppg_dev = [ppg, torch.empty_like(ppg)]
+    uploaded = [torch.cuda.Event() for _ in range(2)]
+    state = {"k": 0}
+
+    def upload(b):
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream):
+            ppg_dev[b].copy_(ppg_host, non_blocking=True)
+            uploaded[b].record(copy_stream)
 
     def run(host):
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        x = ppg_host.to(dev, non_blocking=True) if host else ppg
+        x = ppg
+        if host:
+            b = state["k"] & 1
+            state["k"] += 1
+            torch.cuda.current_stream().wait_event(uploaded[b])
+            x = ppg_dev[b]
         mel = taco.inference(x)[1]
         mid.record()
+        if host:
+            upload(b ^ 1)
         wav = wg.infer(mel.clamp(-11.5, 2.0).contiguous(), 0.6)
         if host:
             out_host.copy_(wav, non_blocking=True)
@@ -235,7 +253,9 @@ def measure_pipeline(env, wg, batch=32, seconds=5.0):
             ms, clocks = env.timed_with_clocks(lambda: run(False), 3, warmup=1)
             torch.cuda.synchronize()
             ppg2mel_ms = stamps[-1][0].elapsed_time(stamps[-1][1])
+            upload(0)
             ms_e2e, _ = env.timed_with_clocks(lambda: run(True), 3, warmup=1)
+            torch.cuda.synchronize()
     finally:
         wg.set_precision(old)
     ms, ms_e2e = ms / 3, ms_e2e / 3
@@ -246,7 +266,8 @@ def measure_pipeline(env, wg, batch=32, seconds=5.0):
             "timing": "CUDA events, mean of 3 after 1 warm-up",
             "ppg2mel_ms": ppg2mel_ms, "mel2wav_ms": ms - ppg2mel_ms, "clocks": clocks,
             "e2e": {"value": n / (ms_e2e / 1e3), "unit": "samples/s", "ms": ms_e2e,
-                    "h2d_bytes_per_step": ppg_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4}}
+                    "h2d_bytes_per_step": ppg_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
+                    "note": "the PPG upload of call k+1 runs on a copy stream behind the vocoder of call k"}}
 
 
 def measure_fp32_mode(env, model, mel, peaks, samples_per_step):
