@@ -373,48 +373,31 @@ def measure_cfg5(env, model, batch=8, seconds=60.0):
     ppg_host = torch.empty(batch, 5816, F).pin_memory()                             # drawn on the device (1.5 GB)
     ppg_host.copy_(torch.softmax(logits, dim=-1).transpose(1, 2))
     del logits
-    out_host = torch.empty(batch, F * 160).pin_memory()
+    # Through the public batch-stream helper (fac_via_ppg_b200/pipeline.py): the PPG upload (1.5 GB over PCIe) of step
+    # k + 1 runs on a copy stream while step k is in the vocoder.  Every step still uploads its own input from pinned
+    # host memory inside the timed region (the upload that overlaps the last timed step is that of a step not run).
+    from fac_via_ppg_b200.pipeline import BatchStream
+    stream = BatchStream(taco, model, denoiser, sigma=0.6, denoiser_strength=0.005)
+
+    def endless():
+        while True:
+            yield ppg_host
+
+    results = stream.run(endless(), to_host=True, record_phases=True)
     marks = []
-    # The PPG upload (1.5 GB over PCIe) of step k + 1 runs on a copy stream while step k is in the vocoder: two
-    # device buffers, one event per buffer.  Every step still uploads its own input from pinned host memory inside
-    # the timed region (the upload that overlaps the last timed step belongs to a step that is not run).
-    copy_stream = torch.cuda.Stream(device=dev)
-    ppg_dev = [torch.empty(batch, 5816, F, device=dev) for _ in range(2)]
-    uploaded = [torch.cuda.Event() for _ in range(2)]
-    state = {"k": 0}
-
-    def upload(b):
-        copy_stream.wait_stream(torch.cuda.current_stream())       # buffer b is free: its last reader has been queued
-        with torch.cuda.stream(copy_stream):
-            ppg_dev[b].copy_(ppg_host, non_blocking=True)
-            uploaded[b].record(copy_stream)
-
-    upload(0)
 
     def step():
-        b = state["k"] & 1
-        state["k"] += 1
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        ev[0].record()
-        torch.cuda.current_stream().wait_event(uploaded[b])
-        mel = taco.inference(ppg_dev[b])[1]
-        ev[1].record()
-        upload(b ^ 1)                                               # next step's input, behind this step's vocoder
-        wav = model.infer(mel.clamp(-11.5, 2.0).contiguous(), sigma=0.6)
-        ev[2].record()
-        wav = denoiser(wav, strength=0.005)[:, 0]
-        out_host.copy_(wav, non_blocking=True)
-        ev[3].record()
-        torch.cuda.current_stream().synchronize()
-        marks.append(ev)
+        next(results)                       # one batch: host PPG in, host waveform out (synchronised)
+        marks.append(stream.phase_events)
 
     with quiet_stderr():
         ms, clocks = env.timed_with_clocks(step, 2, warmup=1)
     ms /= 2
     ev = marks[-1]
     n = env.world * batch * F * 160
+    results.close()
     torch.cuda.synchronize()
-    del taco, denoiser, ppg_dev
+    del taco, denoiser, stream, results
     torch.cuda.empty_cache()
     return {"workload": "PPG->Mel->WaveGlow->Denoiser end to end, %d x %.0f s per GPU = %d utterances on %d GPU(s), "
                         "host PPG in, host waveform out (BASELINE configs[4]; generate_synthesis.py:86-98)"
@@ -426,7 +409,7 @@ def measure_cfg5(env, model, batch=8, seconds=60.0):
             "phases_ms_rank0": {"ppg2mel": ev[0].elapsed_time(ev[1]), "mel2wav": ev[1].elapsed_time(ev[2]),
                                 "denoiser+d2h": ev[2].elapsed_time(ev[3])},
             "frames": F, "decoder_steps": F,
-            "h2d_bytes_per_step": ppg_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4}
+            "h2d_bytes_per_step": ppg_host.numel() * 4, "d2h_bytes_per_step": batch * F * 160 * 4}
 
 
 REF_BATCH = 2      # utterances per reference step (see run_reference)
