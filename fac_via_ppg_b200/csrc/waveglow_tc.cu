@@ -537,10 +537,12 @@ __global__ void __launch_bounds__(256) wn_start_tc_kernel(const float* __restric
                                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ x_hi,
                                                           __nv_bfloat16* __restrict__ x_lo, long long n_cols, int C,
                                                           int n_group, int off, int n_half) {
-  // programmatic dependent launch (see csrc/waveglow_fused.cu): the first layer's kernel may start its prologue and
-  // its conditioning K steps now; this kernel itself may have started before the previous flow's `end` completed
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // programmatic dependent launch (see csrc/waveglow_fused.cu): this kernel may have started before the previous
+  // flow's `end` (or the upsampler) completed; once that is certain, the first layer's kernel may start its prologue
+  // and its conditioning K steps.  (Wait BEFORE the trigger: the layer kernels read `spect` before their own wait, and
+  // every one of them starts after this point -- the upsampler's output is complete and visible by then.)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int c8 = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long col0 = (idx / c8) * WN_START_COLS;
